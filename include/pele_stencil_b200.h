@@ -1,0 +1,176 @@
+/* pele_stencil_b200.h -- C ABI of the B200-native derived-field stencil path of PeleAnalysis
+ * (ghost-cell fill -> centred-difference gradient / mean curvature, per FAB, per AMR level).
+ *
+ * The library replaces, for this path only, the AMReX C++ objects the reference tools drive between
+ * "data is in state[lev]" (Src/grad.cpp:167, Src/curvature.cpp:305) and WriteMultiLevelPlotfile
+ * (Src/grad.cpp:256, Src/curvature.cpp:843).  Each entry point cites the reference interface it stands
+ * in for (AX/ = Submodules/PelePhysics/Submodules/amrex/Src/).  INTEGRATION.md shows the call sequence a
+ * maintainer adds to grad.cpp / curvature.cpp.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every function returns 0 on success or a negative
+ * pa_status and never throws; pa_last_error() returns a thread-local message.  The library owns all device
+ * memory.  One host thread drives one pa_hier.  There is NO CPU fallback: compute entry points fail with
+ * PA_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Host buffers are FArrayBox-ordered: the VALID region of one box, one component, i fastest
+ * ([nz][ny][nx] doubles) -- what FArrayBox::dataPtr(comp) addresses for a 0-ghost FAB.
+ */
+#ifndef PELE_STENCIL_B200_H
+#define PELE_STENCIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PA_OK = 0,
+    PA_ERR_ARG = -1,        /* bad argument / inconsistent hierarchy (message says which) */
+    PA_ERR_CUDA = -2,       /* CUDA runtime error or no usable device */
+    PA_ERR_NOMEM = -3,
+    PA_ERR_UNSUPPORTED = -4,
+    PA_ERR_STATE = -5       /* call order (e.g. remote halo data not exchanged yet) */
+} pa_status;
+
+/* Domain-boundary kinds for NON-periodic directions: LinOpBCType::Neumann / reflect_odd as chosen by the
+ * tools from is_per / sym_dir (Src/grad.cpp:182-193, Src/curvature.cpp:429-441). */
+enum { PA_BC_NEUMANN = 0, PA_BC_REFLECT_ODD = 1 };
+
+/* One AMR level: Geometry + BoxArray + DistributionMapping (Src/grad.cpp:160-164). */
+typedef struct {
+    int domain_lo[3], domain_hi[3];   /* AmrData::ProbDomain()[lev], inclusive cell indices */
+    double dx[3];                     /* Geometry::CellSize(): (prob_hi-prob_lo)/N, AX/Base/AMReX_Geometry.cpp:520 */
+    int nboxes;
+    const int *boxes;                 /* nboxes x 6: lo[3], hi[3] (BoxArray) */
+    const int *owner;                 /* nboxes ranks (DistributionMapping) or NULL = everything on rank 0 */
+} pa_level_desc;
+
+typedef struct pa_hier pa_hier;
+typedef struct pa_field pa_field;
+
+/* Options of the curvature tool (ParmParse keys of Src/curvature.cpp:72-106). */
+typedef struct {
+    double prog_min, prog_max;        /* progMin / progMax (after the file min/max reduction) */
+    int do_threshold;                 /* threshold_prog */
+    double threshold;                 /* threshold_value */
+    int do_gauss;                     /* do_gaussCurv */
+    int do_strain;                    /* do_strain (StrainRate = div u, reproducing the reference's overwrite at :736-747) */
+    int get_strain_tensor;            /* getStrainTensor */
+    int do_velnormal;                 /* do_velnormal */
+    int reserved[8];
+} pa_curv_opts;
+
+/* ---- runtime ------------------------------------------------------------------------------------- */
+/* Select the CUDA device of this process (one process per GPU).  amrex::Initialize's device part. */
+int pa_init(int device);
+int pa_finalize(void);
+const char *pa_last_error(void);
+const char *pa_version(void);
+/* Stream all subsequent work of this thread's library calls is enqueued on (a cudaStream_t; NULL = default). */
+int pa_set_stream(void *cuda_stream);
+int pa_sync(void);                     /* cudaStreamSynchronize on that stream */
+/* Pinned host memory for upload/download buffers (cudaHostAlloc / cudaFreeHost). */
+int pa_host_alloc(void **p, size_t bytes);
+int pa_host_free(void *p);
+int pa_host_register(void *p, size_t bytes);   /* pin caller-owned memory, e.g. FArrayBox storage */
+int pa_host_unregister(void *p);
+
+/* ---- hierarchy: replaces MLPoisson(geoms,grids,dmaps,info) + setMaxOrder(4) + setDomainBC(lo,hi) ----
+ * (Src/grad.cpp:173-193; AX/LinearSolvers/MLMG/AMReX_MLCellLinOp.H:368-509 defineAuxData/defineBC).
+ * Builds, on the host, the copy-descriptor tables the device kernels consume: same-level/periodic halo rows
+ * (FabArrayBase::FB, AX/Base/AMReX_FabArrayBase.cpp:658-877), face masks (AX/Boundary/AMReX_MultiMask.cpp:25-71),
+ * box-face BC records (AX/LinearSolvers/MLMG/AMReX_MLMGBndry.H:107-155) and the coarse gather index of every
+ * coarse-fine face (BndryRegister, AX/Boundary/AMReX_BndryRegister.H:147-190,266-276).
+ * The refinement ratio of each level is taken from the level domains (AX/LinearSolvers/MLMG/AMReX_MLLinOp.H:856-885).
+ * rank / nranks: this process and the number of processes the boxes are distributed over (owner[] values). */
+int pa_hier_create(pa_hier **h, int nlev, const pa_level_desc *levels, const int is_per[3],
+                   const int bc_kind[3], int rank, int nranks);
+int pa_hier_destroy(pa_hier *h);
+int pa_hier_num_levels(const pa_hier *h);
+int pa_hier_num_boxes(const pa_hier *h, int lev);          /* global count */
+int64_t pa_hier_num_cells(const pa_hier *h, int lev);      /* valid cells, global; lev<0 = all levels */
+int64_t pa_hier_num_local_cells(const pa_hier *h, int lev);
+int pa_hier_box_owner(const pa_hier *h, int lev, int box);
+
+/* Morton/SFC box -> rank map balanced by cell count (DistributionMapping default strategy,
+ * AX/Base/AMReX_DistributionMapping.cpp:42,1262-1320).  owner_out has nboxes entries. */
+int pa_sfc_distribute(int nboxes, const int *boxes, int nranks, int *owner_out);
+
+/* ---- device MultiFab: replaces MultiFab(ba, dm, ncomp, nghost) (Src/grad.cpp:164) ------------------ */
+int pa_field_alloc(pa_hier *h, int ncomp, int nghost, pa_field **f);
+int pa_field_free(pa_field *f);
+int pa_field_ncomp(const pa_field *f);
+int pa_field_nghost(const pa_field *f);
+int64_t pa_field_bytes(const pa_field *f);
+/* Valid region of one (level, box, comp) <-> host, asynchronous on the library stream.  Stands in for the
+ * FillVar copy into state[lev] (Src/grad.cpp:167) and the ghost-stripping copy before VisMF::Write
+ * (AX/Base/AMReX_PlotFileUtil.cpp:227-233).  Boxes owned by other ranks are rejected with PA_ERR_ARG. */
+int pa_field_upload(pa_field *f, int lev, int box, int comp, const double *host_valid);
+int pa_field_download(const pa_field *f, int lev, int box, int comp, double *host_valid);
+/* Whole level at once: host buffer = this rank's boxes of the level concatenated in box order (each [nz][ny][nx]). */
+int pa_field_upload_level(pa_field *f, int lev, int comp, const double *host_concat);
+int pa_field_download_level(const pa_field *f, int lev, int comp, double *host_concat);
+int pa_field_set_val(pa_field *f, int comp, int ncomp, double v);     /* MultiFab::setVal incl. ghost cells */
+
+/* ---- ghost cells ------------------------------------------------------------------------------------ */
+/* FabArray::FillBoundary(scomp, ncomp, periodicity, cross) (AX/Base/AMReX_FabArrayCommI.H:7-60): same-level and
+ * periodic copies into all nghost layers; cross!=0 fills only the width-1 face layers a cross stencil reads. */
+int pa_fill_boundary(pa_field *f, int comp, int ncomp, int cross);
+/* MLCellLinOp::applyBC in inhomogeneous mode with coarse data (AX/LinearSolvers/MLMG/AMReX_MLCellLinOp.H:680-889)
+ * = FillBoundary(cross) + coarse-fine o3 interpolation (AX/Boundary/AMReX_InterpBndryData_3D_K.H:23-119) +
+ * mllinop_apply_bc (AX/LinearSolvers/MLMG/AMReX_MLLinOp_K.H:14-325) on every level in [lev_lo, lev_hi].
+ * Coarse values are the VALID cells of the same component on level-1 (what updateSolBC/setCoarseFineBC pass). */
+int pa_fill_ghosts(pa_field *f, int comp, int ncomp, int lev_lo, int lev_hi);
+
+/* ---- the two tools' hot paths ------------------------------------------------------------------------ */
+/* grad: for v in [0,nvar): (gx,gy,gz,|g|) of in[comp_in+v] -> out[comp_out+4v .. +3]; includes the ghost fill.
+ * Replaces Src/grad.cpp:169-236 (FillBoundary, setLevelBC, MLMG::apply, MLMG::getFluxes,
+ * average_face_to_cellcenter, mult(-1), magnitude lambda).  `in` needs nghost>=1. */
+int pa_grad(pa_field *in, int comp_in, int nvar, pa_field *out, int comp_out);
+/* The same in two separately callable phases, so a caller can time (or overlap) them: phases bit 0 = ghost fill
+ * (halo gather + coarse-fine / wall fill), bit 1 = stencil sweep.  pa_grad == pa_grad_phases(..., 3). */
+int pa_grad_phases(pa_field *in, int comp_in, int nvar, pa_field *out, int comp_out, int phases);
+/* curvature: S = state[comp_S]; writes Progress, MeanCurvature, FlameNormalX/Y/Z into out[comp_out..+4], then
+ * (if enabled, in this order) GaussianCurvature, StrainRate, 9 ROST comps, VelFlameNormal.
+ * Velocities (do_strain / do_velnormal) are state[comp_vel..+2].  Replaces Src/curvature.cpp:310-326,418-791.
+ * `state` needs nghost>=1; `out` may have nghost 0. */
+int pa_curvature(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out);
+int pa_curvature_num_outputs(const pa_curv_opts *opts);
+
+/* ---- multi-rank ghost exchange (one process per GPU; the transport is the caller's: NCCL send/recv) ---
+ * For exchange step `step` of an operation the library packs what each peer needs into a device send slab and
+ * unpacks the peer's slab after the caller moved it.  Sizes are in doubles.  Single-rank hierarchies have
+ * zero-length slabs and never need these calls. */
+int pa_exchange_counts(const pa_hier *h, int nghost, int ncomp, int64_t *send_counts /*nranks*/, int64_t *recv_counts /*nranks*/);
+int pa_exchange_buffers(pa_field *f, int ncomp, double **send_slab, double **recv_slab,
+                        int64_t *send_offsets /*nranks+1*/, int64_t *recv_offsets /*nranks+1*/);
+int pa_exchange_pack(pa_field *f, int comp, int ncomp);     /* valid cells peers need -> send slab */
+int pa_exchange_mark_received(pa_field *f, int comp, int ncomp);   /* recv slab now holds the peers' data */
+/* Split grad so the caller can exchange between the phases: pack (above) -> [transport] -> pa_grad. */
+
+/* ---- instrumentation --------------------------------------------------------------------------------- */
+int64_t pa_kernel_launches(void);              /* number of kernels this library launched so far (this process) */
+int pa_hier_build_seconds(const pa_hier *h, double *seconds);
+/* Algorithmic bytes of SURVEY 8(d): sum over local boxes of 8*V_in + 8*nout*V, V_in = V + 2(nx*ny+ny*nz+nx*nz). */
+int64_t pa_algorithmic_bytes(const pa_hier *h, int nout_per_cell);
+
+/* ---- debug / parity inspection (integer tables are compared bit-exactly with the oracle) ------------- */
+/* A (level, box, comp) including its ghost cells, [nz+2g][ny+2g][nx+2g]. */
+int pa_debug_download_grown(const pa_field *f, int lev, int box, int comp, double *host_grown);
+/* Expanded FillBoundary descriptor table of a level: for every cell of every local grown FAB (nghost layers),
+ * (src_box<<40 | linear index in the source box's valid region) or -1.  Same encoding as the oracle's. */
+int pa_debug_fb_source_map(pa_hier *h, int lev, int nghost, int cross, int64_t *out, int64_t out_len);
+/* Face flags of (lev, box, face): one uint16 per face-plane cell (t1 fastest): bits 0-1 = mask value at the ghost
+ * cell (0 covered, 1 not_covered, 2 outside_domain), bits 2..9 = not_covered at tangential offsets
+ * (-r,0) (+r,0) (0,-r) (0,+r) (-r,-r) (+r,-r) (-r,+r) (+r,+r).  Returns the number of cells (0 if the face
+ * has no record, i.e. it is entirely covered by same-level boxes). */
+int64_t pa_debug_face_flags(pa_hier *h, int lev, int box, int face, uint16_t *out, int64_t out_len);
+/* Polynomial coefficients and order of the coarse-fine ghost formula of (lev, box, face). */
+int pa_debug_face_coef(pa_hier *h, int lev, int box, int face, int *kind, int *nx, double coef[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -40,6 +40,8 @@ def lib():
         L.pao_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pao_curvature.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double,
                                     C.c_int, C.c_void_p, C.c_void_p]
+        L.pao_curvature_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pao_filled_fabs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.pao_fb_source_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pao_mask.restype = C.c_int64
@@ -109,6 +111,16 @@ class OracleHier:
         lib().pao_curvature(self.h, _p(S), prog_min, prog_max, int(do_threshold), threshold, crse_ratio,
                             _p(out), _p(g) if gauss else None)
         return (out, g) if gauss else out
+
+    def curvature_ex(self, S, U, prog_min, prog_max, do_threshold=False, threshold=1e-4, crse_ratio=2):
+        """All optional branches.  U: [3, total].  Returns dict of flat fields."""
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        T = self.total
+        out = np.empty((5, T)); g = np.zeros(T); sr = np.zeros(T); rost = np.zeros((9, T)); vn = np.zeros(T)
+        lib().pao_curvature_ex(self.h, _p(S), prog_min, prog_max, int(do_threshold), threshold, crse_ratio,
+                               _p(out), _p(g), _p(U), _p(sr), _p(rost), _p(vn))
+        return dict(core=out, gauss=g, strain=sr, rost=rost, veln=vn)
 
     def filled_fabs(self, lev: int, s: np.ndarray, ng: int = 1, ghost_init: float = 0.0, crse_ratio: int = 0):
         lv = self.pf.levels[lev]

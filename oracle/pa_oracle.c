@@ -435,8 +435,22 @@ int pao_grad(const pao_hier *h, const double *s, double *out)
 /* R/Src/curvature.cpp:283-326 (progress variable) and :418-572 (mean curvature), default options plus
  * threshold_prog.  out = 5 fields: Progress, MeanCurvature, FlameNormalX, FlameNormalY, FlameNormalZ.
  * Optional outputs (may be NULL): gauss (GaussianCurvature, :575-677). */
+int pao_curvature_ex(const pao_hier *h, const double *S, double progMin, double progMax,
+                     int do_threshold, double threshold, int crse_ratio, double *out, double *gauss,
+                     const double *U, double *sr, double *rost, double *veln);
+
 int pao_curvature(const pao_hier *h, const double *S, double progMin, double progMax,
                   int do_threshold, double threshold, int crse_ratio, double *out, double *gauss)
+{
+    return pao_curvature_ex(h, S, progMin, progMax, do_threshold, threshold, crse_ratio, out, gauss, NULL, NULL, NULL, NULL);
+}
+
+/* Same with the velocity-based optional branches: U = 3 fields (x,y,z velocity) of `total` cells each;
+ * sr = StrainRate (curvature.cpp:679-759; the -nn:grad u term is overwritten at :745-747, leaving div u, not clipped),
+ * rost = 9 fields dU_m/dx_n at index 3m+n (:755-757), veln = u.n with the clipped normal (:761-789). */
+int pao_curvature_ex(const pao_hier *h, const double *S, double progMin, double progMax,
+                     int do_threshold, double threshold, int crse_ratio, double *out, double *gauss,
+                     const double *U, double *sr, double *rost, double *veln)
 {
     int64_t T = h->total;
     double *c = out, *K = out+T, *n[3] = { out+2*T, out+3*T, out+4*T };
@@ -497,6 +511,23 @@ int pao_curvature(const pao_hier *h, const double *S, double progMin, double pro
         if (do_threshold)
             for (int64_t q=o0; q<o1; ++q)
                 if (c[q] < threshold || c[q] > 1.0-threshold) { K[q] = 0.0; n[0][q] = n[1][q] = n[2][q] = 0.0; }
+        if (U && (sr || rost)) {
+            double *dU = (double*)malloc(sizeof(double)*9*(size_t)(o1-o0));
+            int64_t N = o1-o0;
+            for (int m=0; m<3; ++m) {
+                grad_all_levels(h, U + (int64_t)m*T, U + (int64_t)m*T, tmp[0], tmp[1], tmp[2], l, crse_ratio);
+                for (int e=0; e<3; ++e) memcpy(dU + (size_t)(3*m+e)*(size_t)N, tmp[e]+o0, sizeof(double)*(size_t)N);
+            }
+            if (sr) for (int64_t q=0; q<N; ++q) sr[o0+q] = dU[0*N+q] + dU[4*N+q] + dU[8*N+q];
+            if (rost) for (int m=0; m<9; ++m) memcpy(rost + (int64_t)m*T + o0, dU + (size_t)m*(size_t)N, sizeof(double)*(size_t)N);
+            free(dU);
+        }
+        if (U && veln)
+            for (int64_t q=o0; q<o1; ++q) {
+                double v = U[q]*n[0][q] + U[T+q]*n[1][q] + U[2*T+q]*n[2][q];
+                if (do_threshold && (c[q] < threshold || c[q] > 1.0-threshold)) v = 0.0;
+                veln[q] = v;
+            }
     }
     for (int d=0; d<3; ++d) { free(G[d]); free(tmp[d]); }
     free(nrm);

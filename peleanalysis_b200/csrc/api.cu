@@ -1,0 +1,826 @@
+// api.cu -- implementation of the C ABI declared in include/pele_stencil_b200.h.
+// Host logic only: owns device memory, uploads the descriptor tables built by hier.cpp, sequences kernel launches.
+// There is no CPU compute fallback anywhere in this file: without a usable device every compute call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pele_stencil_b200.h"
+#include "hier.hpp"
+#include "kernels.cuh"
+
+using namespace pa;
+
+namespace {
+
+thread_local std::string t_err;
+thread_local cudaStream_t t_stream = nullptr;
+
+int fail(int code, const std::string& msg) { t_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(PA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+#define CHK(call) do { int r__ = (call); if (r__ != PA_OK) return r__; } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t st) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = v.size();
+        if (!n) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    cudaError_t reserve(size_t m) {
+        if (m <= n) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; n = 0; }
+        cudaError_t e = cudaMalloc(&p, m * sizeof(T));
+        if (e == cudaSuccess) n = m;
+        return e;
+    }
+};
+
+struct LevelDev {
+    DevBuf<PaBoxDev> boxes;
+    DevBuf<PaHaloTag> halo_cross;
+    DevBuf<long long> host_off;                        // nlocal+1 prefix of valid cells (host concat order)
+    std::vector<long long> host_off_h;
+};
+
+struct TileTable {
+    std::vector<PaTile> h;
+    DevBuf<PaTile> d;
+    std::vector<long long> level_begin;                // nlev+1
+    int max_plane_doubles = 0;                         // over tiles, for ng=1 input layout
+    bool ok = true;
+};
+
+}  // namespace
+
+struct pa_hier {
+    Hier H;
+    bool dev_ready = false;
+    std::vector<std::unique_ptr<LevelDev>> lev;
+    std::map<std::pair<int, int>, std::unique_ptr<DevBuf<PaLayDev>>> lay;         // (level, ng)
+    std::map<std::pair<int, int>, std::unique_ptr<DevBuf<PaHaloTag>>> halo_full;  // (level, ng)
+    DevBuf<PaFaceRec> face_recs;
+    DevBuf<int> face_level;
+    DevBuf<uint16_t> face_flags;
+    DevBuf<PaCrseIdx> face_cidx;
+    DevBuf<PaPackTag> pack_tags;
+    TileTable tiles_simple, tiles_tma;
+    DevBuf<double> staging;                            // upload / download staging
+    DevBuf<double> send_slab, recv_slab;               // multi-rank exchange, [cell][comp]
+    int slab_ncomp = 0;
+    // curvature temporaries (allocated on demand)
+    pa_field* tmpG = nullptr;
+    pa_field* tmpH = nullptr;
+    pa_field* tmpW = nullptr;
+};
+
+struct pa_field {
+    pa_hier* h = nullptr;
+    int ncomp = 0, ng = 0;
+    std::vector<double*> slab;                         // per level
+    std::vector<long long> cs;                         // component stride per level
+    int recv_ncomp = 0;                                // >0: recv slab holds data for that many comps of this field
+    int recv_comp0 = -1;
+};
+
+namespace {
+
+const PaLayDev* dev_layout(pa_hier* h, int l, int ng, int* err) {
+    auto key = std::make_pair(l, ng);
+    auto it = h->lay.find(key);
+    if (it != h->lay.end()) return it->second->p;
+    const Layout& Y = h->H.layout(l, ng);
+    auto buf = std::make_unique<DevBuf<PaLayDev>>();
+    cudaError_t e = buf->upload(Y.lay, t_stream);
+    if (e != cudaSuccess) { *err = cuda_fail(e, "upload layout"); return nullptr; }
+    const PaLayDev* p = buf->p;
+    h->lay.emplace(key, std::move(buf));
+    return p;
+}
+
+void build_tiles(pa_hier* h, TileTable& T, bool tma) {
+    Hier& H = h->H;
+    T.h.clear();
+    T.level_begin.assign(H.nlev + 1, 0);
+    T.max_plane_doubles = 0;
+    T.ok = true;
+    const char* ety = getenv("PA_TMA_TY");
+    const char* ezc = getenv("PA_TMA_ZC");
+    const int TY0 = ety ? std::max(1, atoi(ety)) : stencil_tma_tile_rows();
+    const int ZC0 = ezc ? std::max(1, atoi(ezc)) : 32;
+    for (int l = 0; l < H.nlev; ++l) {
+        T.level_begin[l] = (long long)T.h.size();
+        const Level& V = H.lev[l];
+        const Layout& Y = H.layout(l, 1);
+        for (size_t lb = 0; lb < V.local.size(); ++lb) {
+            const Box& B = V.boxes[V.local[lb]];
+            int nx = B.len(0), ny = B.len(1), nz = B.len(2);
+            int ty, zc;
+            if (tma) {
+                int nq = (nx + 1) / 2;
+                ty = std::min(TY0, std::max(1, 512 / nq));
+                if (nq > 512) T.ok = false;
+                // even split of the rows / planes so the last tile is not a sliver
+                int nty = (ny + ty - 1) / ty; ty = (ny + nty - 1) / nty;
+                int nzc = (nz + ZC0 - 1) / ZC0; zc = (nz + nzc - 1) / nzc;
+                T.max_plane_doubles = std::max(T.max_plane_doubles, (ty + 2) * Y.lay[lb].P);
+            } else {
+                ty = 8; zc = 8;
+            }
+            for (int z0 = 0; z0 < nz; z0 += zc)
+                for (int y0 = 0; y0 < ny; y0 += ty) {
+                    PaTile t;
+                    t.lev = l; t.box = (int)lb;
+                    t.y0 = y0; t.ny = std::min(ty, ny - y0);
+                    t.z0 = z0; t.nz = std::min(zc, nz - z0);
+                    T.h.push_back(t);
+                }
+        }
+    }
+    T.level_begin[H.nlev] = (long long)T.h.size();
+    if (tma && T.max_plane_doubles > stencil_tma_max_plane_doubles()) T.ok = false;
+}
+
+int ensure_device(pa_hier* h) {
+    if (h->dev_ready) return PA_OK;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PA_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    Hier& H = h->H;
+    h->lev.clear();
+    for (int l = 0; l < H.nlev; ++l) {
+        auto D = std::make_unique<LevelDev>();
+        const Level& V = H.lev[l];
+        std::vector<PaBoxDev> bd;
+        D->host_off_h.assign(1, 0);
+        for (int gb : V.local) {
+            PaBoxDev b;
+            for (int d = 0; d < 3; ++d) { b.lo[d] = V.boxes[gb].lo[d]; b.n[d] = V.boxes[gb].len(d); }
+            bd.push_back(b);
+            D->host_off_h.push_back(D->host_off_h.back() + V.boxes[gb].npts());
+        }
+        CU(D->boxes.upload(bd, t_stream));
+        CU(D->halo_cross.upload(H.halo_cross[l].tags, t_stream));
+        CU(D->host_off.upload(D->host_off_h, t_stream));
+        h->lev.push_back(std::move(D));
+    }
+    CU(h->face_recs.upload(H.faces.recs, t_stream));
+    CU(h->face_level.upload(H.faces.rec_level, t_stream));
+    CU(h->face_flags.upload(H.faces.flags, t_stream));
+    CU(h->face_cidx.upload(H.faces.cidx, t_stream));
+    CU(h->pack_tags.upload(H.xplan.pack, t_stream));
+    build_tiles(h, h->tiles_simple, false);
+    build_tiles(h, h->tiles_tma, true);
+    CU(h->tiles_simple.d.upload(h->tiles_simple.h, t_stream));
+    CU(h->tiles_tma.d.upload(h->tiles_tma.h, t_stream));
+    CU(cudaStreamSynchronize(t_stream));      // host vectors may be reallocated later
+    h->dev_ready = true;
+    return PA_OK;
+}
+
+int ensure_slabs(pa_hier* h, int ncomp) {
+    Hier& H = h->H;
+    if (H.nranks <= 1) return PA_OK;
+    size_t ns = (size_t)H.xplan.send_prefix[H.nranks] * ncomp, nr = (size_t)H.xplan.recv_prefix[H.nranks] * ncomp;
+    CU(h->send_slab.reserve(std::max<size_t>(ns, 1)));
+    CU(h->recv_slab.reserve(std::max<size_t>(nr, 1)));
+    return PA_OK;
+}
+
+// GridArgs with `in` = `out` = comp `comp` of field f (in-place operations: ghost fill, pack)
+int grid_args_inplace(pa_field* f, int comp, GridArgs& ga) {
+    pa_hier* h = f->h;
+    std::memset(&ga, 0, sizeof(ga));
+    for (int l = 0; l < h->H.nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* ly = dev_layout(h, l, f->ng, &err);
+        if (!ly && !h->H.lev[l].local.empty()) return err;
+        LevArgs& A = ga.L[l];
+        A.boxes = h->lev[l]->boxes.p;
+        A.lay_in = A.lay_out = ly;
+        A.in = A.out = f->slab[l] ? f->slab[l] + (long long)comp * f->cs[l] : nullptr;
+        A.cs_in = A.cs_out = f->cs[l];
+        for (int d = 0; d < 3; ++d) A.dxi[d] = h->H.lev[l].dxinv[d];
+    }
+    return PA_OK;
+}
+
+int grid_args(pa_field* in, int comp_in, pa_field* out, int comp_out, GridArgs& ga) {
+    pa_hier* h = in->h;
+    std::memset(&ga, 0, sizeof(ga));
+    for (int l = 0; l < h->H.nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* li = dev_layout(h, l, in->ng, &err);
+        if (!li && !h->H.lev[l].local.empty()) return err;
+        const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+        if (!lo && !h->H.lev[l].local.empty()) return err;
+        LevArgs& A = ga.L[l];
+        A.boxes = h->lev[l]->boxes.p;
+        A.lay_in = li; A.lay_out = lo;
+        A.in = in->slab[l] ? in->slab[l] + (long long)comp_in * in->cs[l] : nullptr;
+        A.out = out->slab[l] ? out->slab[l] + (long long)comp_out * out->cs[l] : nullptr;
+        A.cs_in = in->cs[l]; A.cs_out = out->cs[l];
+        for (int d = 0; d < 3; ++d) A.dxi[d] = h->H.lev[l].dxinv[d];
+    }
+    return PA_OK;
+}
+
+bool use_tma(pa_hier* h, int nin) {
+    const char* e = getenv("PA_STENCIL");
+    if (e && !strcmp(e, "simple")) return false;
+    if (!h->tiles_tma.ok) return false;
+    // shared memory: STAGES(4) * nin * stage_doubles * 8 bytes must fit in 227 KB
+    long long stage = (h->tiles_tma.max_plane_doubles + 15) & ~15;
+    return 4LL * nin * stage * 8 <= 200 * 1024;
+}
+
+// stencil over levels [l0, l1]
+int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex, int nvar, int l0, int l1, int in_ng) {
+    const int nin = (mode == MODE_DIV) ? 3 : 1;
+    // the TMA tile table is sized for the nghost == 1 layout (row pitch nx+4)
+    if (in_ng == 1 && use_tma(h, nin)) {
+        TileTable& T = h->tiles_tma;
+        long long a = T.level_begin[l0], b = T.level_begin[l1 + 1];
+        CU(launch_stencil_tma(mode, T.d.p + a, (int)(b - a), T.max_plane_doubles, ga, ex, nvar, t_stream));
+    } else {
+        TileTable& T = h->tiles_simple;
+        long long a = T.level_begin[l0], b = T.level_begin[l1 + 1];
+        CU(launch_stencil_simple(mode, T.d.p + a, (int)(b - a), ga, ex, nvar, t_stream));
+    }
+    return PA_OK;
+}
+
+int check_field(const pa_field* f, int comp, int ncomp, const char* who) {
+    if (!f || !f->h) return fail(PA_ERR_ARG, std::string(who) + ": null field");
+    if (comp < 0 || ncomp < 1 || comp + ncomp > f->ncomp) return fail(PA_ERR_ARG, std::string(who) + ": component range out of bounds");
+    return PA_OK;
+}
+
+// ghost fill of comps [comp, comp+ncomp) on levels [l0, l1]: halo gather per level + one BC-fill launch
+int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1) {
+    pa_hier* h = f->h;
+    Hier& H = h->H;
+    CHK(ensure_device(h));
+    if (f->ng < 1) return fail(PA_ERR_ARG, "ghost fill needs a field with nghost >= 1");
+    const double* recv = nullptr;
+    if (H.nranks > 1) {
+        if (f->recv_ncomp != ncomp || f->recv_comp0 != comp)
+            return fail(PA_ERR_STATE, "multi-rank ghost fill: exchange this component range first (pa_exchange_pack -> transport -> pa_exchange_mark_received)");
+        recv = h->recv_slab.p;
+    }
+    GridArgs ga;
+    CHK(grid_args_inplace(f, comp, ga));
+    for (int l = l0; l <= l1; ++l) {
+        const HaloTable& T = H.halo_cross[l];
+        CU(launch_halo(h->lev[l]->halo_cross.p, (int)T.tags.size(), T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out,
+                       f->cs[l], ncomp, recv, t_stream));
+    }
+    const FaceTable& F = H.faces;
+    long long r0 = F.level_rec_begin[l0], r1 = F.level_rec_begin[l1 + 1];
+    if (r1 > r0) {
+        long long c0 = F.recs[r0].start;
+        long long c1 = (r1 < (long long)F.recs.size()) ? F.recs[r1].start : F.ncells;
+        CU(launch_bcfill(h->face_recs.p, h->face_level.p, r0, r1, c0, c1, h->face_flags.p, h->face_cidx.p, ga, ncomp, recv, t_stream));
+    }
+    return PA_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+const char* pa_last_error(void) { return t_err.c_str(); }
+const char* pa_version(void) { return "pele-stencil-b200 0.1 (sm_100a)"; }
+
+int pa_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(PA_ERR_CUDA, std::string("pa_init: no usable CUDA device (no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(PA_ERR_ARG, "pa_init: device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) return fail(PA_ERR_UNSUPPORTED, "pa_init: kernels are built for sm_100a only; device is sm_" + std::to_string(p.major) + std::to_string(p.minor));
+    return PA_OK;
+}
+int pa_finalize(void) { return PA_OK; }
+int pa_set_stream(void* s) { t_stream = (cudaStream_t)s; return PA_OK; }
+int pa_sync(void) { CU(cudaStreamSynchronize(t_stream)); return PA_OK; }
+int pa_host_alloc(void** p, size_t bytes) { CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return PA_OK; }
+int pa_host_free(void* p) { CU(cudaFreeHost(p)); return PA_OK; }
+int pa_host_register(void* p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return PA_OK; }
+int pa_host_unregister(void* p) { CU(cudaHostUnregister(p)); return PA_OK; }
+int64_t pa_kernel_launches(void) { return g_launches; }
+
+int pa_hier_create(pa_hier** out, int nlev, const pa_level_desc* levels, const int is_per[3], const int bc_kind[3],
+                   int rank, int nranks) {
+    if (!out || !levels || !is_per) return fail(PA_ERR_ARG, "pa_hier_create: null argument");
+    std::vector<pa_level_desc_host> L(std::max(nlev, 0));
+    for (int l = 0; l < nlev; ++l) {
+        for (int d = 0; d < 3; ++d) {
+            L[l].domain_lo[d] = levels[l].domain_lo[d]; L[l].domain_hi[d] = levels[l].domain_hi[d];
+            L[l].dx[d] = levels[l].dx[d];
+        }
+        L[l].nboxes = levels[l].nboxes; L[l].boxes = levels[l].boxes; L[l].owner = levels[l].owner;
+        if (!L[l].boxes) return fail(PA_ERR_ARG, "pa_hier_create: level without boxes");
+    }
+    auto h = std::make_unique<pa_hier>();
+    std::string e = h->H.init(nlev, L.data(), is_per, bc_kind, rank, nranks);
+    if (!e.empty()) return fail(PA_ERR_ARG, "pa_hier_create: " + e);
+    *out = h.release();
+    return PA_OK;
+}
+
+int pa_hier_destroy(pa_hier* h) {
+    if (!h) return PA_OK;
+    if (h->tmpG) pa_field_free(h->tmpG);
+    if (h->tmpH) pa_field_free(h->tmpH);
+    if (h->tmpW) pa_field_free(h->tmpW);
+    delete h;
+    return PA_OK;
+}
+int pa_hier_num_levels(const pa_hier* h) { return h ? h->H.nlev : 0; }
+int pa_hier_num_boxes(const pa_hier* h, int lev) { return (h && lev >= 0 && lev < h->H.nlev) ? (int)h->H.lev[lev].boxes.size() : -1; }
+int64_t pa_hier_num_cells(const pa_hier* h, int lev) {
+    if (!h) return 0;
+    if (lev >= 0) return lev < h->H.nlev ? h->H.lev[lev].ncells : 0;
+    int64_t s = 0;
+    for (auto& l : h->H.lev) s += l.ncells;
+    return s;
+}
+int64_t pa_hier_num_local_cells(const pa_hier* h, int lev) {
+    if (!h) return 0;
+    if (lev >= 0) return lev < h->H.nlev ? h->H.lev[lev].ncells_local : 0;
+    int64_t s = 0;
+    for (auto& l : h->H.lev) s += l.ncells_local;
+    return s;
+}
+int pa_hier_box_owner(const pa_hier* h, int lev, int box) {
+    if (!h || lev < 0 || lev >= h->H.nlev || box < 0 || box >= (int)h->H.lev[lev].boxes.size()) return -1;
+    return h->H.lev[lev].owner[box];
+}
+int pa_hier_build_seconds(const pa_hier* h, double* s) { if (!h || !s) return fail(PA_ERR_ARG, "null"); *s = h->H.build_seconds; return PA_OK; }
+
+int pa_sfc_distribute(int nboxes, const int* boxes, int nranks, int* owner_out) {
+    if (nboxes < 1 || !boxes || nranks < 1 || !owner_out) return fail(PA_ERR_ARG, "pa_sfc_distribute: bad argument");
+    sfc_distribute(nboxes, boxes, nranks, owner_out);
+    return PA_OK;
+}
+
+int64_t pa_algorithmic_bytes(const pa_hier* h, int nout) {
+    if (!h) return 0;
+    int64_t s = 0;
+    for (auto& V : h->H.lev)
+        for (int gb : V.local) {
+            const Box& B = V.boxes[gb];
+            int64_t nx = B.len(0), ny = B.len(1), nz = B.len(2);
+            int64_t vol = nx * ny * nz;
+            s += 8 * (vol + 2 * (nx * ny + ny * nz + nx * nz)) + 8 * (int64_t)nout * vol;
+        }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------- fields
+int pa_field_alloc(pa_hier* h, int ncomp, int nghost, pa_field** out) {
+    if (!h || !out || ncomp < 1 || nghost < 0 || nghost > 4) return fail(PA_ERR_ARG, "pa_field_alloc: bad argument");
+    CHK(ensure_device(h));
+    auto f = std::make_unique<pa_field>();
+    f->h = h; f->ncomp = ncomp; f->ng = nghost;
+    f->slab.assign(h->H.nlev, nullptr);
+    f->cs.assign(h->H.nlev, 0);
+    for (int l = 0; l < h->H.nlev; ++l) {
+        const Layout& Y = h->H.layout(l, nghost);
+        f->cs[l] = Y.comp_stride;
+        size_t n = (size_t)Y.comp_stride * ncomp + 16;          // 16 doubles of slack: pair loads may touch one element past a row
+        if (Y.comp_stride == 0) continue;
+        cudaError_t e = cudaMalloc(&f->slab[l], n * sizeof(double));
+        if (e != cudaSuccess) {
+            for (double* p : f->slab) if (p) cudaFree(p);
+            return e == cudaErrorMemoryAllocation ? fail(PA_ERR_NOMEM, "pa_field_alloc: out of device memory") : cuda_fail(e, "cudaMalloc");
+        }
+        // ghost cells and pads start as zeros (never NaN garbage)
+        CU(cudaMemsetAsync(f->slab[l], 0, n * sizeof(double), t_stream));
+        int err = PA_OK;
+        if (!dev_layout(h, l, nghost, &err)) return err;
+    }
+    *out = f.release();
+    return PA_OK;
+}
+int pa_field_free(pa_field* f) {
+    if (!f) return PA_OK;
+    for (double* p : f->slab) if (p) cudaFree(p);
+    delete f;
+    return PA_OK;
+}
+int pa_field_ncomp(const pa_field* f) { return f ? f->ncomp : -1; }
+int pa_field_nghost(const pa_field* f) { return f ? f->ng : -1; }
+int64_t pa_field_bytes(const pa_field* f) {
+    if (!f) return 0;
+    int64_t s = 0;
+    for (size_t l = 0; l < f->cs.size(); ++l) s += (int64_t)f->cs[l] * f->ncomp * 8;
+    return s;
+}
+
+static int box_copy(const pa_field* f, int lev, int box, int comp, double* host, bool to_dev, bool grown) {
+    if (!f) return fail(PA_ERR_ARG, "null field");
+    pa_hier* h = f->h;
+    if (lev < 0 || lev >= h->H.nlev || comp < 0 || comp >= f->ncomp) return fail(PA_ERR_ARG, "level / component out of range");
+    const Level& V = h->H.lev[lev];
+    if (box < 0 || box >= (int)V.boxes.size()) return fail(PA_ERR_ARG, "box out of range");
+    int lb = V.g2l[box];
+    if (lb < 0) return fail(PA_ERR_ARG, "box is owned by another rank");
+    const Box& B = V.boxes[box];
+    const PaLayDev& y = h->H.layout(lev, f->ng).lay[lb];
+    const int g = grown ? f->ng : 0;
+    const int nx = B.len(0) + 2 * g, ny = B.len(1) + 2 * g, nz = B.len(2) + 2 * g;
+    double* base = f->slab[lev] + (long long)comp * f->cs[lev] + y.off + (long long)(y.ng - g) * y.PS + (long long)(y.ng - g) * y.P + (y.ng - g + y.xoff);
+    // plane by plane 2-D copies: device rows have pitch P, planes PS (not a multiple of the row count of the sub-box)
+    for (int k = 0; k < nz; ++k) {
+        double* dp = base + (long long)k * y.PS;
+        double* hp = host + (long long)k * nx * ny;
+        if (to_dev) CU(cudaMemcpy2DAsync(dp, (size_t)y.P * 8, hp, (size_t)nx * 8, (size_t)nx * 8, ny, cudaMemcpyHostToDevice, t_stream));
+        else CU(cudaMemcpy2DAsync(hp, (size_t)nx * 8, dp, (size_t)y.P * 8, (size_t)nx * 8, ny, cudaMemcpyDeviceToHost, t_stream));
+    }
+    return PA_OK;
+}
+int pa_field_upload(pa_field* f, int lev, int box, int comp, const double* host) {
+    return box_copy(f, lev, box, comp, const_cast<double*>(host), true, false);
+}
+int pa_field_download(const pa_field* f, int lev, int box, int comp, double* host) {
+    return box_copy(f, lev, box, comp, host, false, false);
+}
+int pa_debug_download_grown(const pa_field* f, int lev, int box, int comp, double* host) {
+    CHK(box_copy(f, lev, box, comp, host, false, true));
+    CU(cudaStreamSynchronize(t_stream));
+    return PA_OK;
+}
+
+int pa_field_upload_level(pa_field* f, int lev, int comp, const double* host) {
+    if (!f || lev < 0 || lev >= f->h->H.nlev || comp < 0 || comp >= f->ncomp || !host) return fail(PA_ERR_ARG, "pa_field_upload_level: bad argument");
+    pa_hier* h = f->h;
+    LevelDev& D = *h->lev[lev];
+    long long n = D.host_off_h.back();
+    if (n == 0) return PA_OK;
+    CU(h->staging.reserve((size_t)n));
+    CU(cudaMemcpyAsync(h->staging.p, host, (size_t)n * 8, cudaMemcpyHostToDevice, t_stream));
+    int err = PA_OK;
+    const PaLayDev* ly = dev_layout(h, lev, f->ng, &err);
+    if (!ly) return err;
+    CU(launch_unpack_valid(D.boxes.p, ly, D.host_off.p, (int)h->H.lev[lev].local.size(), n, h->staging.p,
+                           f->slab[lev] + (long long)comp * f->cs[lev], t_stream));
+    return PA_OK;
+}
+int pa_field_download_level(const pa_field* f, int lev, int comp, double* host) {
+    if (!f || lev < 0 || lev >= f->h->H.nlev || comp < 0 || comp >= f->ncomp || !host) return fail(PA_ERR_ARG, "pa_field_download_level: bad argument");
+    pa_hier* h = f->h;
+    LevelDev& D = *h->lev[lev];
+    long long n = D.host_off_h.back();
+    if (n == 0) return PA_OK;
+    CU(h->staging.reserve((size_t)n));
+    int err = PA_OK;
+    const PaLayDev* ly = dev_layout(h, lev, f->ng, &err);
+    if (!ly) return err;
+    CU(launch_pack_valid(D.boxes.p, ly, D.host_off.p, (int)h->H.lev[lev].local.size(), n,
+                         f->slab[lev] + (long long)comp * f->cs[lev], h->staging.p, t_stream));
+    CU(cudaMemcpyAsync(host, h->staging.p, (size_t)n * 8, cudaMemcpyDeviceToHost, t_stream));
+    return PA_OK;
+}
+int pa_field_set_val(pa_field* f, int comp, int ncomp, double v) {
+    CHK(check_field(f, comp, ncomp, "pa_field_set_val"));
+    for (int l = 0; l < f->h->H.nlev; ++l)
+        if (f->slab[l]) CU(launch_fill(f->slab[l] + (long long)comp * f->cs[l], f->cs[l] * ncomp, v, t_stream));
+    return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- ghost cells
+int pa_fill_boundary(pa_field* f, int comp, int ncomp, int cross) {
+    CHK(check_field(f, comp, ncomp, "pa_fill_boundary"));
+    pa_hier* h = f->h;
+    Hier& H = h->H;
+    CHK(ensure_device(h));
+    if (f->ng < 1) return PA_OK;
+    if (H.nranks > 1 && !cross) return fail(PA_ERR_UNSUPPORTED, "pa_fill_boundary(cross=0) is single-rank only");
+    GridArgs ga;
+    CHK(grid_args_inplace(f, comp, ga));
+    const double* recv = nullptr;
+    if (H.nranks > 1) {
+        if (f->recv_ncomp != ncomp || f->recv_comp0 != comp) return fail(PA_ERR_STATE, "exchange this component range first");
+        recv = h->recv_slab.p;
+    }
+    for (int l = 0; l < H.nlev; ++l) {
+        if (cross) {
+            const HaloTable& T = H.halo_cross[l];
+            CU(launch_halo(h->lev[l]->halo_cross.p, (int)T.tags.size(), T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out, f->cs[l], ncomp, recv, t_stream));
+        } else {
+            auto key = std::make_pair(l, f->ng);
+            const HaloTable& T = H.halo_full(l, f->ng);
+            auto it = h->halo_full.find(key);
+            if (it == h->halo_full.end()) {
+                auto buf = std::make_unique<DevBuf<PaHaloTag>>();
+                CU(buf->upload(T.tags, t_stream));
+                it = h->halo_full.emplace(key, std::move(buf)).first;
+            }
+            CU(launch_halo(it->second->p, (int)T.tags.size(), T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out, f->cs[l], ncomp, nullptr, t_stream));
+        }
+    }
+    return PA_OK;
+}
+
+int pa_fill_ghosts(pa_field* f, int comp, int ncomp, int lev_lo, int lev_hi) {
+    CHK(check_field(f, comp, ncomp, "pa_fill_ghosts"));
+    if (lev_lo < 0) lev_lo = 0;
+    if (lev_hi < 0 || lev_hi >= f->h->H.nlev) lev_hi = f->h->H.nlev - 1;
+    if (lev_lo > lev_hi) return fail(PA_ERR_ARG, "pa_fill_ghosts: empty level range");
+    return fill_ghosts_impl(f, comp, ncomp, lev_lo, lev_hi);
+}
+
+// ---------------------------------------------------------------------------------------------- exchange
+int pa_exchange_counts(const pa_hier* h, int nghost, int ncomp, int64_t* send_counts, int64_t* recv_counts) {
+    if (!h || !send_counts || !recv_counts || ncomp < 1) return fail(PA_ERR_ARG, "pa_exchange_counts: bad argument");
+    (void)nghost;
+    for (int p = 0; p < h->H.nranks; ++p) {
+        send_counts[p] = (h->H.xplan.send_prefix[p + 1] - h->H.xplan.send_prefix[p]) * ncomp;
+        recv_counts[p] = (h->H.xplan.recv_prefix[p + 1] - h->H.xplan.recv_prefix[p]) * ncomp;
+    }
+    return PA_OK;
+}
+int pa_exchange_buffers(pa_field* f, int ncomp, double** send_slab, double** recv_slab, int64_t* send_offsets, int64_t* recv_offsets) {
+    if (!f || ncomp < 1) return fail(PA_ERR_ARG, "pa_exchange_buffers: bad argument");
+    pa_hier* h = f->h;
+    CHK(ensure_device(h));
+    CHK(ensure_slabs(h, std::max(ncomp, h->slab_ncomp)));
+    h->slab_ncomp = std::max(ncomp, h->slab_ncomp);
+    if (send_slab) *send_slab = h->send_slab.p;
+    if (recv_slab) *recv_slab = h->recv_slab.p;
+    for (int p = 0; p <= h->H.nranks; ++p) {
+        if (send_offsets) send_offsets[p] = h->H.xplan.send_prefix[p] * ncomp;
+        if (recv_offsets) recv_offsets[p] = h->H.xplan.recv_prefix[p] * ncomp;
+    }
+    return PA_OK;
+}
+int pa_exchange_pack(pa_field* f, int comp, int ncomp) {
+    CHK(check_field(f, comp, ncomp, "pa_exchange_pack"));
+    pa_hier* h = f->h;
+    Hier& H = h->H;
+    CHK(ensure_device(h));
+    f->recv_ncomp = 0;
+    if (H.nranks <= 1) return PA_OK;
+    CHK(ensure_slabs(h, std::max(ncomp, h->slab_ncomp)));
+    h->slab_ncomp = std::max(ncomp, h->slab_ncomp);
+    GridArgs ga;
+    CHK(grid_args_inplace(f, comp, ga));
+    long long ntags = (long long)H.xplan.pack.size();
+    if (ntags) {
+        const PaPackTag& last = H.xplan.pack.back();
+        long long ncells = last.dense + (long long)last.n[0] * last.n[1] * last.n[2];
+        CU(launch_exchange_pack(h->pack_tags.p, 0, ntags, 0, ncells, ga, ncomp, h->send_slab.p, t_stream));
+    }
+    return PA_OK;
+}
+int pa_exchange_mark_received(pa_field* f, int comp, int ncomp) {
+    CHK(check_field(f, comp, ncomp, "pa_exchange_mark_received"));
+    f->recv_ncomp = ncomp;
+    f->recv_comp0 = comp;
+    return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- grad
+int pa_grad(pa_field* in, int comp_in, int nvar, pa_field* out, int comp_out) {
+    return pa_grad_phases(in, comp_in, nvar, out, comp_out, 3);
+}
+
+int pa_grad_phases(pa_field* in, int comp_in, int nvar, pa_field* out, int comp_out, int phases) {
+    CHK(check_field(in, comp_in, nvar, "pa_grad(in)"));
+    CHK(check_field(out, comp_out, 4 * nvar, "pa_grad(out)"));
+    if (in->h != out->h) return fail(PA_ERR_ARG, "pa_grad: fields belong to different hierarchies");
+    if (in->ng < 1) return fail(PA_ERR_ARG, "pa_grad: input field needs nghost >= 1");
+    pa_hier* h = in->h;
+    if (phases & 1) CHK(fill_ghosts_impl(in, comp_in, nvar, 0, h->H.nlev - 1));
+    if (!(phases & 2)) return PA_OK;
+    CHK(ensure_device(h));
+    GridArgs ga;
+    CHK(grid_args(in, comp_in, out, comp_out, ga));
+    StencilExtra ex;
+    std::memset(&ex, 0, sizeof(ex));
+    return run_stencil(h, MODE_GRAD, ga, ex, nvar, 0, h->H.nlev - 1, in->ng);
+}
+
+// ---------------------------------------------------------------------------------------------- curvature
+int pa_curvature_num_outputs(const pa_curv_opts* o) {
+    if (!o) return 5;
+    return 5 + (o->do_gauss ? 1 : 0) + (o->do_strain ? 1 : 0) + ((o->do_strain && o->get_strain_tensor) ? 9 : 0) + (o->do_velnormal ? 1 : 0);
+}
+
+static int tmp_field(pa_hier* h, pa_field** slot, int ncomp) {
+    if (*slot && (*slot)->ncomp >= ncomp) return PA_OK;
+    if (*slot) { pa_field_free(*slot); *slot = nullptr; }
+    return pa_field_alloc(h, ncomp, 1, slot);
+}
+
+int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out) {
+    if (!opts) return fail(PA_ERR_ARG, "pa_curvature: null options");
+    CHK(check_field(state, comp_S, 1, "pa_curvature(state)"));
+    const int nout = pa_curvature_num_outputs(opts);
+    CHK(check_field(out, comp_out, nout, "pa_curvature(out)"));
+    if (state->h != out->h) return fail(PA_ERR_ARG, "pa_curvature: fields belong to different hierarchies");
+    if (out->ng != 1) return fail(PA_ERR_ARG, "pa_curvature: the output field must have nghost == 1 (Progress and the flame normal are ghost-filled in place)");
+    if (state->ng < 1) return fail(PA_ERR_ARG, "pa_curvature: state needs nghost >= 1");
+    if (!(opts->prog_min < opts->prog_max)) return fail(PA_ERR_ARG, "progMin must be less than progMax");   // curvature.cpp:157-159
+    const bool need_vel = opts->do_strain || opts->do_velnormal;
+    if (need_vel) CHK(check_field(state, comp_vel, 3, "pa_curvature(velocity)"));
+    pa_hier* h = state->h;
+    Hier& H = h->H;
+    if (H.nranks > 1) return fail(PA_ERR_UNSUPPORTED, "pa_curvature: multi-rank exchange is driven by the host tool; use the single-rank path per GPU");
+    CHK(ensure_device(h));
+    const int nlev = H.nlev;
+    const int cP = comp_out, cK = comp_out + 1, cN = comp_out + 2;
+    int next = comp_out + 5;
+    const int cKg = opts->do_gauss ? next++ : -1;
+    const int cSR = opts->do_strain ? next++ : -1;
+    int cROST = -1;
+    if (opts->do_strain && opts->get_strain_tensor) { cROST = next; next += 9; }
+    const int cVN = opts->do_velnormal ? next++ : -1;
+
+    // 1. progress variable on valid cells of every level (curvature.cpp:310-321)
+    const double invdenom = 1.0 / (opts->prog_max - opts->prog_min);
+    for (int l = 0; l < nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* li = dev_layout(h, l, state->ng, &err);
+        if (!li) return err;
+        const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+        if (!lo) return err;
+        CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_S * state->cs[l],
+                           out->slab[l] + (long long)cP * out->cs[l], opts->prog_min, invdenom, t_stream));
+    }
+    // 2. ghost cells of c on all levels (coarse data = c on the next coarser level), then G -> nrm -> n
+    CHK(fill_ghosts_impl(out, cP, 1, 0, nlev - 1));
+    StencilExtra ex;
+    std::memset(&ex, 0, sizeof(ex));
+    if (opts->do_gauss) {
+        CHK(tmp_field(h, &h->tmpG, 3));
+        for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
+    }
+    GridArgs ga;
+    CHK(grid_args(out, cP, out, cN, ga));
+    CHK(run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, out->ng));
+    // 3. divergence of n.  Without the threshold clip every level's coarse data is final after step 2, so one
+    //    batched ghost fill + one stencil launch cover the hierarchy; with it, level l needs the CLIPPED n of l-1
+    //    (curvature.cpp:514-518 reads flame_normal[lev-1] after :549-567 modified it), so levels run in order.
+    std::memset(&ex, 0, sizeof(ex));
+    ex.do_threshold = opts->do_threshold ? 1 : 0;
+    ex.threshold = opts->threshold;
+    for (int l = 0; l < nlev; ++l) ex.prog[l] = out->slab[l] + (long long)cP * out->cs[l];
+    CHK(grid_args(out, cN, out, cK, ga));
+    if (!opts->do_threshold) {
+        CHK(fill_ghosts_impl(out, cN, 3, 0, nlev - 1));
+        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, nlev - 1, out->ng));
+    } else {
+        for (int l = 0; l < nlev; ++l) {
+            CHK(fill_ghosts_impl(out, cN, 3, l, l));
+            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng));
+            int err = PA_OK;
+            const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+            if (!lo) return err;
+            CU(launch_clip_normal(h->lev[l]->boxes.p, lo, lo, (int)H.lev[l].local.size(), out->slab[l] + (long long)cP * out->cs[l],
+                                  out->slab[l] + (long long)cN * out->cs[l], out->cs[l], opts->threshold, t_stream));
+        }
+    }
+    // 4. optional branches
+    if (opts->do_gauss) {
+        // Hessian rows: grad3 of each un-normalised gradient component, ghosts by the same rules with coarse = G on l-1
+        CHK(tmp_field(h, &h->tmpH, 9));
+        CHK(fill_ghosts_impl(h->tmpG, 0, 3, 0, nlev - 1));
+        StencilExtra e0;
+        std::memset(&e0, 0, sizeof(e0));
+        for (int d = 0; d < 3; ++d) {
+            CHK(grid_args(h->tmpG, d, h->tmpH, 3 * d, ga));
+            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, h->tmpG->ng));
+        }
+        for (int l = 0; l < nlev; ++l) {
+            int err = PA_OK;
+            const PaLayDev* ly = dev_layout(h, l, 1, &err);
+            if (!ly) return err;
+            CU(launch_gauss(h->lev[l]->boxes.p, ly, ly, (int)H.lev[l].local.size(), h->tmpG->slab[l], h->tmpG->cs[l], h->tmpH->slab[l],
+                            h->tmpH->cs[l], out->slab[l] + (long long)cP * out->cs[l], out->slab[l] + (long long)cKg * out->cs[l],
+                            opts->do_threshold ? 1 : 0, opts->threshold, t_stream));
+        }
+    }
+    if (opts->do_strain) {
+        // velocity gradients: ghosts of u_i by the same rules (curvature.cpp:686-717); needs ghost cells in `state`
+        CHK(fill_ghosts_impl(state, comp_vel, 3, 0, nlev - 1));
+        pa_field* dU = nullptr;
+        int c0 = 0;
+        if (cROST >= 0) { dU = out; c0 = cROST; }
+        else { CHK(tmp_field(h, &h->tmpW, 9)); dU = h->tmpW; }
+        StencilExtra e0;
+        std::memset(&e0, 0, sizeof(e0));
+        for (int d = 0; d < 3; ++d) {
+            CHK(grid_args(state, comp_vel + d, dU, c0 + 3 * d, ga));
+            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, state->ng));
+        }
+        for (int l = 0; l < nlev; ++l) {
+            int err = PA_OK;
+            const PaLayDev* ly = dev_layout(h, l, 1, &err);
+            if (!ly) return err;
+            CU(launch_strain(h->lev[l]->boxes.p, ly, (int)H.lev[l].local.size(), dU->slab[l] + (long long)c0 * dU->cs[l], dU->cs[l],
+                             out->slab[l] + (long long)cSR * out->cs[l], t_stream));
+        }
+    }
+    if (opts->do_velnormal) {
+        for (int l = 0; l < nlev; ++l) {
+            int err = PA_OK;
+            const PaLayDev* lu = dev_layout(h, l, state->ng, &err);
+            if (!lu) return err;
+            const PaLayDev* lo = dev_layout(h, l, 1, &err);
+            if (!lo) return err;
+            CU(launch_velnormal(h->lev[l]->boxes.p, lu, lo, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_vel * state->cs[l],
+                                state->cs[l], out->slab[l] + (long long)cN * out->cs[l], out->cs[l], out->slab[l] + (long long)cP * out->cs[l],
+                                out->slab[l] + (long long)cVN * out->cs[l], opts->do_threshold ? 1 : 0, opts->threshold, t_stream));
+        }
+    }
+    return PA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- debug
+int pa_debug_fb_source_map(pa_hier* h, int lev, int nghost, int cross, int64_t* out, int64_t out_len) {
+    if (!h || lev < 0 || lev >= h->H.nlev || !out) return fail(PA_ERR_ARG, "pa_debug_fb_source_map: bad argument");
+    Hier& H = h->H;
+    const Level& V = H.lev[lev];
+    const HaloTable* T;
+    HaloTable tmp;
+    if (cross && nghost == 1) T = &H.halo_cross[lev];
+    else if (!cross) { if (H.nranks > 1) return fail(PA_ERR_UNSUPPORTED, "single-rank only"); T = &H.halo_full(lev, nghost); }
+    else return fail(PA_ERR_ARG, "cross tables exist for nghost == 1 only");
+    std::vector<long long> off(V.local.size() + 1, 0);
+    for (size_t lb = 0; lb < V.local.size(); ++lb) off[lb + 1] = off[lb] + V.boxes[V.local[lb]].grown(nghost).npts();
+    if (out_len < off.back()) return fail(PA_ERR_ARG, "output buffer too small");
+    std::fill(out, out + off.back(), (int64_t)-1);
+    for (const PaHaloTag& t : T->tags) {
+        const Box g = V.boxes[V.local[t.dbox]].grown(nghost);
+        const int n0 = g.len(0), n1 = g.len(1);
+        for (int k = 0; k < t.n[2]; ++k)
+            for (int j = 0; j < t.n[1]; ++j)
+                for (int i = 0; i < t.n[0]; ++i) {
+                    int di = t.dlo[0] + i, dj = t.dlo[1] + j, dk = t.dlo[2] + k;
+                    int64_t v = -2;     // remote source
+                    if (t.sbox >= 0) {
+                        int gs = V.local[t.sbox];
+                        const Box& S = V.boxes[gs];
+                        int64_t lin = ((int64_t)(dk + t.shift[2] - S.lo[2]) * S.len(1) + (dj + t.shift[1] - S.lo[1])) * S.len(0) + (di + t.shift[0] - S.lo[0]);
+                        v = ((int64_t)gs << 40) | lin;
+                    }
+                    out[off[t.dbox] + ((int64_t)(dk - g.lo[2]) * n1 + (dj - g.lo[1])) * n0 + (di - g.lo[0])] = v;
+                }
+    }
+    return PA_OK;
+}
+
+static const PaFaceRec* find_face(const pa_hier* h, int lev, int box, int face) {
+    const Hier& H = h->H;
+    if (lev < 0 || lev >= H.nlev || box < 0 || box >= (int)H.lev[lev].boxes.size()) return nullptr;
+    int lb = H.lev[lev].g2l[box];
+    if (lb < 0) return nullptr;
+    for (long long r = H.faces.level_rec_begin[lev]; r < H.faces.level_rec_begin[lev + 1]; ++r)
+        if (H.faces.recs[r].box == lb && H.faces.recs[r].face == face) return &H.faces.recs[r];
+    return nullptr;
+}
+int64_t pa_debug_face_flags(pa_hier* h, int lev, int box, int face, uint16_t* out, int64_t out_len) {
+    if (!h) return 0;
+    const PaFaceRec* R = find_face(h, lev, box, face);
+    if (!R) return 0;
+    int64_t n = (int64_t)R->n1 * R->n2;
+    if (out) {
+        if (out_len < n) { fail(PA_ERR_ARG, "output buffer too small"); return -1; }
+        std::memcpy(out, h->H.faces.flags.data() + R->start, (size_t)n * sizeof(uint16_t));
+    }
+    return n;
+}
+int pa_debug_face_coef(pa_hier* h, int lev, int box, int face, int* kind, int* nx, double coef[4]) {
+    if (!h) return fail(PA_ERR_ARG, "null");
+    const PaFaceRec* R = find_face(h, lev, box, face);
+    if (!R) return fail(PA_ERR_ARG, "no record for this face");
+    if (kind) *kind = R->kind;
+    if (nx) *nx = R->nx;
+    if (coef) for (int m = 0; m < 4; ++m) coef[m] = R->coef[m];
+    return PA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,577 @@
+// hier.cpp -- builds, on the host, the integer descriptor tables of the ghost fill:
+//   * same-level / periodic halo rows            (what FabArrayBase::FB caches, AMReX_FabArrayBase.cpp:658-877)
+//   * face masks, compressed to per-cell flags   (MultiMask::define, AMReX_MultiMask.cpp:25-71; the two mask sets of
+//                                                 MLCellLinOp::defineAuxData and BndryData::define)
+//   * box-face boundary records + coefficients   (MLMGBndry::setBoxBC, AMReX_MLMGBndry.H:107-155; AMReX_MLLinOp_K.H:48-53)
+//   * coarse gather index of every c-f face      (BndryRegister on the coarsened box + copyFrom of coarse valid cells,
+//                                                 AMReX_BndryRegister.H:147-190,266-276)
+//   * the per-peer exchange plan when boxes are spread over several ranks (one process per GPU)
+// Integer work only; the arithmetic it mirrors is box algebra, so results are index-exact by construction
+// and are checked cell by cell against the oracle in tests/.
+#include "hier.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace pa {
+
+void BoxHash::build(const std::vector<Box>& boxes) {
+    boxes_ = &boxes;
+    bins_.clear();
+    for (int d = 0; d < 3; ++d) maxlen_[d] = 1;
+    for (const Box& b : boxes)
+        for (int d = 0; d < 3; ++d) maxlen_[d] = std::max(maxlen_[d], b.len(d));
+    for (int d = 0; d < 3; ++d) bin_[d] = maxlen_[d];
+    for (size_t i = 0; i < boxes.size(); ++i) {
+        const Box& b = boxes[i];
+        bins_[key(fdiv(b.lo[0], bin_[0]), fdiv(b.lo[1], bin_[1]), fdiv(b.lo[2], bin_[2]))].push_back((int)i);
+    }
+}
+
+// Periodicity::shiftIntVect (AMReX_Periodicity.cpp:8-33)
+void Hier::periodic_shifts(const Box& dom, int ng, std::vector<std::array<int, 3>>& out) const {
+    int per[3] = {0, 0, 0}, jmp[3] = {1, 1, 1};
+    for (int d = 0; d < 3; ++d)
+        if (is_per[d]) {
+            int period = dom.len(d);
+            per[d] = jmp[d] = period;
+            while (per[d] < ng) per[d] += period;
+        }
+    out.clear();
+    for (int i = -per[0]; i <= per[0]; i += jmp[0])
+        for (int j = -per[1]; j <= per[1]; j += jmp[1])
+            for (int k = -per[2]; k <= per[2]; k += jmp[2]) out.push_back({i, j, k});
+}
+
+static Box face_plane(const Box& b, int face, int out_layer /*1 = adjacent ghost layer*/, int extent) {
+    int d = face % 3;
+    Box r = b;
+    for (int t = 0; t < 3; ++t)
+        if (t != d) { r.lo[t] -= extent; r.hi[t] += extent; }
+    if (face < 3) r.lo[d] = r.hi[d] = b.lo[d] - out_layer;
+    else r.lo[d] = r.hi[d] = b.hi[d] + out_layer;
+    return r;
+}
+
+// box minus box -> up to 6 disjoint boxes (amrex::boxDiff)
+static void box_diff(const Box& a, const Box& b, std::vector<Box>& out) {
+    Box is = a.isect(b);
+    if (!is.ok()) { out.push_back(a); return; }
+    Box rem = a;
+    for (int d = 0; d < 3; ++d) {
+        if (rem.lo[d] < is.lo[d]) { Box p = rem; p.hi[d] = is.lo[d] - 1; out.push_back(p); rem.lo[d] = is.lo[d]; }
+        if (rem.hi[d] > is.hi[d]) { Box p = rem; p.lo[d] = is.hi[d] + 1; out.push_back(p); rem.hi[d] = is.hi[d]; }
+    }
+}
+
+std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, const int* bck, int rank_, int nranks_) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (nlev_ < 1 || nlev_ > PA_MAX_LEVELS) return "number of levels must be in [1," + std::to_string(PA_MAX_LEVELS) + "]";
+    if (nranks_ < 1 || rank_ < 0 || rank_ >= nranks_) return "bad rank / nranks";
+    nlev = nlev_; rank = rank_; nranks = nranks_;
+    for (int d = 0; d < 3; ++d) { is_per[d] = per[d] ? 1 : 0; bc_kind[d] = bck ? bck[d] : 0; }
+    lev.assign(nlev, Level());
+    for (int l = 0; l < nlev; ++l) {
+        Level& V = lev[l];
+        for (int d = 0; d < 3; ++d) {
+            V.dom.lo[d] = L[l].domain_lo[d]; V.dom.hi[d] = L[l].domain_hi[d];
+            V.dx[d] = L[l].dx[d];
+            if (!(V.dx[d] > 0.0)) return "dx must be positive";
+            V.dxinv[d] = 1.0 / V.dx[d];                       // Geometry: inv_dx = 1/dx (AMReX_Geometry.cpp:521)
+        }
+        if (!V.dom.ok()) return "empty domain on level " + std::to_string(l);
+        if (l > 0) {
+            // ratio from the level domains (AMReX_MLLinOp.H:856-885)
+            int r = V.dom.len(0) / lev[l - 1].dom.len(0);
+            for (int d = 0; d < 3; ++d)
+                if (lev[l - 1].dom.len(d) * r != V.dom.len(d) || V.dom.lo[d] != lev[l - 1].dom.lo[d] * r)
+                    return "level " + std::to_string(l) + " domain is not an isotropic refinement of the coarser domain";
+            if (r != 2 && r != 4) return "refinement ratio must be 2 or 4 (got " + std::to_string(r) + ")";
+            V.ratio = r;
+        }
+        if (L[l].nboxes < 1) return "level " + std::to_string(l) + " has no boxes";
+        V.boxes.resize(L[l].nboxes); V.owner.resize(L[l].nboxes); V.g2l.assign(L[l].nboxes, -1);
+        for (int b = 0; b < L[l].nboxes; ++b) {
+            Box& B = V.boxes[b];
+            for (int d = 0; d < 3; ++d) { B.lo[d] = L[l].boxes[6 * b + d]; B.hi[d] = L[l].boxes[6 * b + 3 + d]; }
+            if (!B.ok()) return "empty box";
+            for (int d = 0; d < 3; ++d) {
+                if (B.lo[d] < V.dom.lo[d] || B.hi[d] > V.dom.hi[d]) return "box outside its level domain";
+                if (B.len(d) > PA_MAX_BOX_SIDE) return "box side > " + std::to_string(PA_MAX_BOX_SIDE) + " cells is not supported";
+                if (l > 0 && (coarsen(B.lo[d], V.ratio) * V.ratio != B.lo[d] || (B.hi[d] + 1) % V.ratio != 0))
+                    return "fine box is not aligned to the refinement ratio";
+            }
+            int o = L[l].owner ? L[l].owner[b] : 0;
+            if (o < 0 || o >= nranks) return "box owner out of range";
+            V.owner[b] = o;
+            V.ncells += B.npts();
+            if (o == rank) { V.g2l[b] = (int)V.local.size(); V.local.push_back(b); V.ncells_local += B.npts(); }
+        }
+        V.hash.build(V.boxes);
+    }
+    halo_cross.assign(nlev, HaloTable());
+    xplan = ExchangePlan();
+    xplan.send_prefix.assign(nranks + 1, 0);
+    xplan.recv_prefix.assign(nranks + 1, 0);
+    xplan.pack_level_begin.assign(nlev + 1, 0);
+    if (nranks > 1) build_exchange();          // fixes recv/send slab offsets first
+    for (int l = 0; l < nlev; ++l) build_halo(l, 1, true, halo_cross[l], true);
+    std::string e = build_faces();
+    if (!e.empty()) return e;
+    build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return "";
+}
+
+const Layout& Hier::layout(int l, int ng) {
+    auto key = std::make_pair(l, ng);
+    auto it = layouts_.find(key);
+    if (it != layouts_.end()) return it->second;
+    Layout Y;
+    Y.ng = ng;
+    const Level& V = lev[l];
+    long long off = 0;
+    for (int gb : V.local) {
+        const Box& B = V.boxes[gb];
+        PaLayDev e;
+        e.ng = ng;
+        e.xoff = ng & 1;                                   // (xoff + ng) even -> first valid cell 16-byte aligned
+        int w = e.xoff + B.len(0) + 2 * ng;
+        e.P = (w + 1) & ~1;
+        e.PS = e.P * (B.len(1) + 2 * ng);
+        e.off = off;
+        long long sz = (long long)e.PS * (B.len(2) + 2 * ng);
+        off += (sz + 15) & ~15LL;                          // every box starts 128-byte aligned
+        Y.lay.push_back(e);
+    }
+    Y.comp_stride = off;
+    return layouts_.emplace(key, std::move(Y)).first->second;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Canonical enumeration of everything a destination box needs from other boxes for a width-1 cross ghost fill.
+// Both the receiver (building its tables) and the sender (building its pack list) walk this in the same order.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct HaloNeed { int face; int sbox; Box dst; int shift[3]; };        // dst region (dst index space), src = dst+shift in sbox
+struct CrseNeed { int face; int cbox; Box reg; int shift[3]; };        // register cells `reg` (coarse idx space) <- cbox cells reg+shift
+}
+
+static void sort_isects(std::vector<std::pair<int, Box>>& v) {
+    std::sort(v.begin(), v.end(), [](const std::pair<int, Box>& a, const std::pair<int, Box>& b) { return a.first < b.first; });
+}
+
+static void halo_needs_cross(const Hier& H, int l, int gb, std::vector<HaloNeed>& out) {
+    const Level& V = H.lev[l];
+    std::vector<std::array<int, 3>> sh;
+    H.periodic_shifts(V.dom, 1, sh);
+    std::vector<std::pair<int, Box>> is;
+    for (int face = 0; face < 6; ++face) {
+        Box slab = face_plane(V.boxes[gb], face, 1, 0);
+        for (auto& s : sh) {
+            is.clear();
+            V.hash.query(slab.shifted(s.data()), [&](int k, const Box& ib) { is.emplace_back(k, ib); });
+            sort_isects(is);
+            for (auto& e : is) {
+                HaloNeed n;
+                n.face = face; n.sbox = e.first;
+                int neg[3] = {-s[0], -s[1], -s[2]};
+                n.dst = e.second.shifted(neg);
+                for (int d = 0; d < 3; ++d) n.shift[d] = s[d];
+                out.push_back(n);
+            }
+        }
+    }
+}
+
+static Box crse_register_box(const Box& fine, int ratio, int face) {
+    Box cb;
+    for (int d = 0; d < 3; ++d) { cb.lo[d] = coarsen(fine.lo[d], ratio); cb.hi[d] = coarsen(fine.hi[d], ratio); }
+    return face_plane(cb, face, 1, 2);              // in 0, out 1, extent 2 (AMReX_MLCellLinOp.H:461-469)
+}
+
+static void crse_needs(const Hier& H, int l, int gb, int face, std::vector<CrseNeed>& out) {
+    const Level& V = H.lev[l];
+    const Level& C = H.lev[l - 1];
+    Box rb = crse_register_box(V.boxes[gb], V.ratio, face);
+    std::vector<std::array<int, 3>> sh;
+    H.periodic_shifts(C.dom, 0, sh);
+    std::vector<std::pair<int, Box>> is;
+    for (auto& s : sh) {
+        is.clear();
+        C.hash.query(rb.shifted(s.data()), [&](int k, const Box& ib) { is.emplace_back(k, ib); });
+        sort_isects(is);
+        for (auto& e : is) {
+            CrseNeed n;
+            n.face = face; n.cbox = e.first;
+            int neg[3] = {-s[0], -s[1], -s[2]};
+            n.reg = e.second.shifted(neg);
+            for (int d = 0; d < 3; ++d) n.shift[d] = s[d];
+            out.push_back(n);
+        }
+    }
+}
+
+// mask of a face plane grown tangentially by `extent`: 0 covered, 1 not_covered, 2 outside_domain
+static void plane_mask(const Hier& H, int l, const Box& plane, int grow_domain, std::vector<uint8_t>& m) {
+    const Level& V = H.lev[l];
+    Box dom = V.dom;
+    for (int d = 0; d < 3; ++d)
+        if (H.is_per[d]) { dom.lo[d] -= grow_domain; dom.hi[d] += grow_domain; }
+    int n0 = plane.len(0), n1 = plane.len(1);
+    m.assign((size_t)plane.npts(), 0);
+    for (int k = plane.lo[2]; k <= plane.hi[2]; ++k)
+        for (int j = plane.lo[1]; j <= plane.hi[1]; ++j)
+            for (int i = plane.lo[0]; i <= plane.hi[0]; ++i)
+                m[((size_t)(k - plane.lo[2]) * n1 + (j - plane.lo[1])) * n0 + (i - plane.lo[0])] = dom.contains(i, j, k) ? 1 : 2;
+    std::vector<std::array<int, 3>> sh;
+    H.periodic_shifts(V.dom, 0, sh);
+    for (auto& s : sh)
+        V.hash.query(plane.shifted(s.data()), [&](int, const Box& ib) {
+            for (int k = ib.lo[2]; k <= ib.hi[2]; ++k)
+                for (int j = ib.lo[1]; j <= ib.hi[1]; ++j)
+                    for (int i = ib.lo[0]; i <= ib.hi[0]; ++i)
+                        m[((size_t)(k - s[2] - plane.lo[2]) * n1 + (j - s[1] - plane.lo[1])) * n0 + (i - s[0] - plane.lo[0])] = 0;
+        });
+}
+
+// Does (level, box, face) carry a boundary record, i.e. is any adjacent ghost cell not covered by a same-level box?
+// Cheap pre-test shared by the receiver and the sender so that both enumerate the same coarse needs.
+static bool face_has_uncovered(const Hier& H, int l, int gb, int face) {
+    const Level& V = H.lev[l];
+    Box plane = face_plane(V.boxes[gb], face, 1, 0);
+    long long covered = 0;
+    std::vector<std::array<int, 3>> sh;
+    H.periodic_shifts(V.dom, 0, sh);
+    for (auto& s : sh)
+        V.hash.query(plane.shifted(s.data()), [&](int, const Box& ib) { covered += ib.npts(); });
+    return covered < plane.npts();       // valid boxes are disjoint, so the covered pieces never overlap
+}
+
+static bool face_is_physical(const Hier& H, int l, int gb, int face) {
+    const Level& V = H.lev[l];
+    int d = face % 3;
+    bool at = (face < 3) ? (V.boxes[gb].lo[d] == V.dom.lo[d]) : (V.boxes[gb].hi[d] == V.dom.hi[d]);
+    return at && !H.is_per[d];
+}
+
+void Hier::build_exchange() {
+    // Walk every (level, dst box) in canonical order; entries whose source owner differs from the dst owner are
+    // exchanged.  The stream from rank p to rank q is the subsequence with (src owner p, dst owner q); both sides
+    // enumerate it identically, so slab offsets agree without any handshake.
+    struct Ent { int lev; int peer; PaPackTag t; };
+    std::vector<Ent> sends;
+    std::vector<std::vector<long long>> send_lvl(nlev, std::vector<long long>(nranks, 0)), recv_lvl(nlev, std::vector<long long>(nranks, 0));
+    std::vector<HaloNeed> hn;
+    std::vector<CrseNeed> cn;
+    for (int l = 0; l < nlev; ++l) {
+        const Level& V = lev[l];
+        for (int gb = 0; gb < (int)V.boxes.size(); ++gb) {
+            int downer = V.owner[gb];
+            hn.clear();
+            halo_needs_cross(*this, l, gb, hn);
+            for (auto& n : hn) {
+                int sowner = V.owner[n.sbox];
+                if (sowner == downer) continue;
+                long long c = n.dst.npts();
+                if (downer == rank) recv_lvl[l][sowner] += c;
+                if (sowner == rank) {
+                    Ent e; e.lev = l; e.peer = downer;
+                    std::memset(&e.t, 0, sizeof(e.t));
+                    e.t.sbox = V.g2l[n.sbox]; e.t.slev = l;
+                    for (int d = 0; d < 3; ++d) { e.t.slo[d] = n.dst.lo[d] + n.shift[d]; e.t.n[d] = n.dst.len(d); }
+                    sends.push_back(e);
+                    send_lvl[l][downer] += c;
+                }
+            }
+            if (l > 0) {
+                const Level& C = lev[l - 1];
+                for (int face = 0; face < 6; ++face) {
+                    if (face_is_physical(*this, l, gb, face) || !face_has_uncovered(*this, l, gb, face)) continue;
+                    cn.clear();
+                    crse_needs(*this, l, gb, face, cn);
+                    for (auto& n : cn) {
+                        int sowner = C.owner[n.cbox];
+                        if (sowner == downer) continue;
+                        long long c = n.reg.npts();
+                        if (downer == rank) recv_lvl[l][sowner] += c;
+                        if (sowner == rank) {
+                            Ent e; e.lev = l; e.peer = downer;
+                            std::memset(&e.t, 0, sizeof(e.t));
+                            e.t.sbox = C.g2l[n.cbox]; e.t.slev = l - 1;
+                            for (int d = 0; d < 3; ++d) { e.t.slo[d] = n.reg.lo[d] + n.shift[d]; e.t.n[d] = n.reg.len(d); }
+                            sends.push_back(e);
+                            send_lvl[l][downer] += c;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // slab layout: per peer contiguous; inside a peer's block, fill levels ascending
+    xplan.level_send_cell0.assign(nlev + 1, std::vector<long long>(nranks, 0));
+    xplan.level_recv_cell0.assign(nlev + 1, std::vector<long long>(nranks, 0));
+    long long so = 0, ro = 0;
+    for (int p = 0; p < nranks; ++p) {
+        xplan.send_prefix[p] = so; xplan.recv_prefix[p] = ro;
+        for (int l = 0; l < nlev; ++l) {
+            xplan.level_send_cell0[l][p] = so; so += send_lvl[l][p];
+            xplan.level_recv_cell0[l][p] = ro; ro += recv_lvl[l][p];
+        }
+        xplan.level_send_cell0[nlev][p] = so;
+        xplan.level_recv_cell0[nlev][p] = ro;
+    }
+    xplan.send_prefix[nranks] = so; xplan.recv_prefix[nranks] = ro;
+    std::vector<std::vector<long long>> cur = xplan.level_send_cell0;
+    xplan.pack.clear();
+    xplan.pack_level_begin.assign(nlev + 1, 0);
+    long long dense = 0;
+    int curlev = 0;
+    for (auto& e : sends) {
+        while (curlev < e.lev) xplan.pack_level_begin[++curlev] = (long long)xplan.pack.size();
+        e.t.dense = dense;
+        e.t.start = cur[e.lev][e.peer];
+        long long c = (long long)e.t.n[0] * e.t.n[1] * e.t.n[2];
+        cur[e.lev][e.peer] += c;
+        dense += c;
+        xplan.pack.push_back(e.t);
+    }
+    while (curlev < nlev) xplan.pack_level_begin[++curlev] = (long long)xplan.pack.size();
+}
+
+void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remote) {
+    const Level& V = lev[l];
+    out.tags.clear();
+    std::vector<PaHaloTag> remote;
+    // receive cursors: position inside each peer's recv block.  Canonical order is level-major, so the cursor of
+    // level l starts after everything levels < l receive from that peer (halo + coarse needs).  Recompute by replay.
+    // receive cursors: position inside each peer's recv block for this fill level (canonical order: per dst box,
+    // halo needs first, then its coarse needs)
+    std::vector<long long> rcur;
+    if (cross && allow_remote && nranks > 1) rcur = xplan.level_recv_cell0[l];
+    if (cross) {
+        std::vector<HaloNeed> hn; std::vector<CrseNeed> cn;
+        for (int gb : V.local) {
+            hn.clear();
+            halo_needs_cross(*this, l, gb, hn);
+            for (auto& n : hn) {
+                PaHaloTag t;
+                std::memset(&t, 0, sizeof(t));
+                t.dbox = V.g2l[gb];
+                for (int d = 0; d < 3; ++d) { t.dlo[d] = n.dst.lo[d]; t.n[d] = n.dst.len(d); t.shift[d] = n.shift[d]; }
+                int so = V.owner[n.sbox];
+                if (so == rank) { t.sbox = V.g2l[n.sbox]; t.rsrc = -1; out.tags.push_back(t); }
+                else { t.sbox = -1; t.rsrc = rcur[so]; rcur[so] += n.dst.npts(); remote.push_back(t); }
+            }
+            // keep the per-peer cursor in canonical order: this box's coarse needs come next in the stream
+            if (l > 0 && !rcur.empty())
+                for (int face = 0; face < 6; ++face) {
+                    if (face_is_physical(*this, l, gb, face) || !face_has_uncovered(*this, l, gb, face)) continue;
+                    cn.clear(); crse_needs(*this, l, gb, face, cn);
+                    for (auto& n : cn) if (lev[l - 1].owner[n.cbox] != rank) rcur[lev[l - 1].owner[n.cbox]] += n.reg.npts();
+                }
+        }
+    } else {
+        // full FillBoundary: grow(vbx, ng) + p against every box, minus vbx (AMReX_FabArrayBase.cpp:739-794)
+        std::vector<std::array<int, 3>> sh;
+        periodic_shifts(V.dom, ng, sh);
+        std::vector<std::pair<int, Box>> is;
+        std::vector<Box> parts;
+        for (int gb : V.local) {
+            Box grown = V.boxes[gb].grown(ng);
+            for (auto& s : sh) {
+                is.clear();
+                V.hash.query(grown.shifted(s.data()), [&](int k, const Box& ib) { is.emplace_back(k, ib); });
+                sort_isects(is);
+                for (auto& e : is) {
+                    int neg[3] = {-s[0], -s[1], -s[2]};
+                    Box dst = e.second.shifted(neg);
+                    parts.clear();
+                    box_diff(dst, V.boxes[gb], parts);
+                    for (Box& p : parts) {
+                        PaHaloTag t;
+                        std::memset(&t, 0, sizeof(t));
+                        t.dbox = V.g2l[gb];
+                        t.sbox = V.g2l[e.first];       // caller guarantees single rank
+                        t.rsrc = -1;
+                        for (int d = 0; d < 3; ++d) { t.dlo[d] = p.lo[d]; t.n[d] = p.len(d); t.shift[d] = s[d]; }
+                        out.tags.push_back(t);
+                    }
+                }
+            }
+        }
+    }
+    out.nlocal_tags = (int)out.tags.size();
+    out.tags.insert(out.tags.end(), remote.begin(), remote.end());
+    long long c = 0;
+    for (auto& t : out.tags) { t.start = c; c += (long long)t.n[0] * t.n[1] * t.n[2]; }
+    out.ncells = c;
+}
+
+const HaloTable& Hier::halo_full(int l, int ng) {
+    auto key = std::make_pair(l, ng);
+    auto it = halo_full_.find(key);
+    if (it != halo_full_.end()) return it->second;
+    HaloTable T;
+    build_halo(l, ng, false, T, false);
+    return halo_full_.emplace(key, std::move(T)).first->second;
+}
+
+// poly_interp_coeff (AMReX_LOUtil_K.H:24-37), same loop so the last bits match
+static void poly_interp_coeff(double xInt, const double* x, int N, double* c) {
+    for (int j = 0; j < N; ++j) {
+        double num = 1.0, den = 1.0;
+        for (int i = 0; i < N; ++i)
+            if (i != j) { num *= xInt - x[i]; den *= x[j] - x[i]; }
+        c[j] = num / den;
+    }
+}
+
+std::string Hier::build_faces() {
+    faces = FaceTable();
+    faces.level_rec_begin.assign(nlev + 1, 0);
+    std::vector<uint8_t> m;
+    std::vector<CrseNeed> cn;
+    // receive cursors for the coarse needs (canonical order, see build_exchange)
+    std::vector<long long> rcur;
+    std::vector<HaloNeed> hn;
+    for (int l = 0; l < nlev; ++l) {
+        const Level& V = lev[l];
+        if (nranks > 1) rcur = xplan.level_recv_cell0[l];
+        faces.level_rec_begin[l] = (long long)faces.recs.size();
+        const int r = V.ratio;
+        const int E = (l > 0) ? r : 0;                       // tangential reach of the o3 stencil's mask tests
+        for (int gb : V.local) {
+            const Box& B = V.boxes[gb];
+            if (nranks > 1) {                                // this box's halo needs precede its coarse needs in the stream
+                hn.clear(); halo_needs_cross(*this, l, gb, hn);
+                for (auto& n : hn) if (V.owner[n.sbox] != rank) rcur[V.owner[n.sbox]] += n.dst.npts();
+            }
+            for (int face = 0; face < 6; ++face) {
+                const int d = face % 3;
+                const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+                const bool physical = face_is_physical(*this, l, gb, face);
+                if (!physical && !face_has_uncovered(*this, l, gb, face)) continue;
+                // mask plane grown tangentially by E.  Domain grown by 5 in periodic directions for the BndryData
+                // mask (NTangHalfWidth) and by 1 for m_maskvals: identical on every cell consulted here because
+                // tangential offsets never exceed the ratio (<=4) and the normal offset is 1.
+                Box plane = face_plane(B, face, 1, E);
+                plane_mask(*this, l, plane, 5, m);
+                int pn[3] = {plane.len(0), plane.len(1), plane.len(2)};
+                auto M = [&](int a1, int a2) -> int {        // a1,a2 offsets from B.lo along t1,t2 (may be negative)
+                    int c[3];
+                    c[d] = 0; c[t1] = a1 + E; c[t2] = a2 + E;
+                    return m[((size_t)c[2] * pn[1] + c[1]) * pn[0] + c[0]];
+                };
+                PaFaceRec R;
+                std::memset(&R, 0, sizeof(R));
+                R.box = V.g2l[gb]; R.face = face; R.ratio = r;
+                R.n1 = B.len(t1); R.n2 = B.len(t2);
+                R.start = (long long)faces.flags.size();
+                R.cidx = -1;
+                bool any = false;
+                for (int a2 = 0; a2 < R.n2; ++a2)
+                    for (int a1 = 0; a1 < R.n1; ++a1) {
+                        unsigned f = (unsigned)M(a1, a2);
+                        if (f) any = true;
+                        if (l > 0) {
+                            static const int o1[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+                            static const int o2[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+                            for (int b = 0; b < 8; ++b)
+                                if (M(a1 + o1[b] * r, a2 + o2[b] * r) == 1) f |= 1u << (2 + b);
+                        }
+                        faces.flags.push_back((uint16_t)f);
+                    }
+                if (!any) { faces.flags.resize((size_t)R.start); continue; }
+                if (physical) {
+                    R.kind = (bc_kind[d] == 1) ? PA_FACE_REFLECT_ODD : PA_FACE_NEUMANN;
+                    R.nx = 1;
+                } else {
+                    if (l == 0) return "level 0 does not cover the domain (box " + std::to_string(gb) + " has an interior face with no neighbour)";
+                    R.kind = PA_FACE_CF;
+                    int blen = B.len(d);
+                    R.nx = std::min(blen + 1, 4);
+                    double bcl = 0.5 * (double)r * V.dx[d];              // AMReX_MLMGBndry.H:146-148
+                    double x[4] = {-bcl * V.dxinv[d], 0.5, 1.5, 2.5};    // AMReX_MLLinOp_K.H:51
+                    poly_interp_coeff(-0.5, x, R.nx, R.coef);
+                    Box rb = crse_register_box(B, r, face);
+                    R.rlo1 = rb.lo[t1]; R.rlo2 = rb.lo[t2];
+                    R.rn1 = rb.len(t1); R.rn2 = rb.len(t2);
+                    R.cidx = (long long)faces.cidx.size();
+                    PaCrseIdx none; none.box = -1; none.rel = 0;
+                    faces.cidx.resize(faces.cidx.size() + (size_t)R.rn1 * R.rn2, none);
+                    cn.clear();
+                    crse_needs(*this, l, gb, face, cn);
+                    const Level& C = lev[l - 1];
+                    for (auto& n : cn) {
+                        const Box& cb = C.boxes[n.cbox];
+                        bool local = (C.owner[n.cbox] == rank);
+                        long long rbase = 0;
+                        if (!local) { rbase = rcur[C.owner[n.cbox]]; rcur[C.owner[n.cbox]] += n.reg.npts(); }
+                        long long q = 0;
+                        for (int k = n.reg.lo[2]; k <= n.reg.hi[2]; ++k)
+                            for (int j = n.reg.lo[1]; j <= n.reg.hi[1]; ++j)
+                                for (int i = n.reg.lo[0]; i <= n.reg.hi[0]; ++i, ++q) {
+                                    int c[3] = {i, j, k};
+                                    size_t e = (size_t)R.cidx + (size_t)(c[t2] - R.rlo2) * R.rn1 + (size_t)(c[t1] - R.rlo1);
+                                    PaCrseIdx& X = faces.cidx[e];
+                                    if (local) {
+                                        X.box = C.g2l[n.cbox];
+                                        X.rel = (unsigned)(i + n.shift[0] - cb.lo[0]) | ((unsigned)(j + n.shift[1] - cb.lo[1]) << 10) |
+                                                ((unsigned)(k + n.shift[2] - cb.lo[2]) << 20);
+                                    } else {
+                                        X.box = -2;
+                                        X.rel = (unsigned)(rbase + q);
+                                    }
+                                }
+                    }
+                }
+                faces.recs.push_back(R);
+                faces.rec_level.push_back(l);
+            }
+        }
+    }
+    faces.level_rec_begin[nlev] = (long long)faces.recs.size();
+    faces.ncells = (long long)faces.flags.size();
+    return "";
+}
+
+// Morton-order the boxes by their low corner and cut the curve into nranks chunks of ~equal cell volume
+// (the idea of DistributionMapping::SFCProcessorMap, AMReX_DistributionMapping.cpp:1262-1320).
+void sfc_distribute(int nboxes, const int* boxes, int nranks, int* owner_out) {
+    std::vector<std::pair<uint64_t, int>> keys(nboxes);
+    int mn[3] = {1 << 30, 1 << 30, 1 << 30};
+    for (int b = 0; b < nboxes; ++b)
+        for (int d = 0; d < 3; ++d) mn[d] = std::min(mn[d], boxes[6 * b + d]);
+    auto spread = [](uint64_t v) {
+        uint64_t x = v & 0x1fffff;
+        x = (x | x << 32) & 0x1f00000000ffffULL;
+        x = (x | x << 16) & 0x1f0000ff0000ffULL;
+        x = (x | x << 8) & 0x100f00f00f00f00fULL;
+        x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+        x = (x | x << 2) & 0x1249249249249249ULL;
+        return x;
+    };
+    double total = 0;
+    for (int b = 0; b < nboxes; ++b) {
+        uint64_t k = 0;
+        for (int d = 0; d < 3; ++d) k |= spread((uint64_t)(boxes[6 * b + d] - mn[d])) << d;
+        keys[b] = {k, b};
+        double v = 1;
+        for (int d = 0; d < 3; ++d) v *= boxes[6 * b + 3 + d] - boxes[6 * b + d] + 1;
+        total += v;
+    }
+    std::sort(keys.begin(), keys.end());
+    double acc = 0;
+    for (auto& kb : keys) {
+        int b = kb.second;
+        double v = 1;
+        for (int d = 0; d < 3; ++d) v *= boxes[6 * b + 3 + d] - boxes[6 * b + d] + 1;
+        int r = (int)std::floor((acc + 0.5 * v) / total * nranks);
+        owner_out[b] = std::min(std::max(r, 0), nranks - 1);
+        acc += v;
+    }
+}
+
+}  // namespace pa

@@ -1,0 +1,84 @@
+// kernels.cuh -- launch wrappers of the sm_100a kernels (definitions in kernels.cu / stencil_tma.cu).
+#ifndef PA_KERNELS_CUH
+#define PA_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "pa_types.h"
+
+namespace pa {
+
+// per-level device pointers handed to kernels by value
+struct LevArgs {
+    const PaBoxDev* boxes;      // local boxes of the level
+    const PaLayDev* lay_in;     // layout of the input field on this level
+    const PaLayDev* lay_out;    // layout of the output field
+    const double* in;           // component 0 of the input field on this level
+    double* out;                // component 0 of the output field
+    long long cs_in, cs_out;    // component strides (elements)
+    double dxi[3];              // 1/dx
+};
+struct GridArgs {
+    LevArgs L[PA_MAX_LEVELS];
+};
+
+// stencil epilogues
+enum StencilMode {
+    MODE_GRAD = 0,      // in: 1 comp            out: gx, gy, gz, |g|                          (grad tool)
+    MODE_GRAD3 = 1,     // in: 1 comp            out: gx, gy, gz                               (Hessian rows, velocity gradients)
+    MODE_NORMAL = 2,    // in: c                 out: n = G/nrm (3 comps); aux out: G (3 comps) if aux != null
+    MODE_DIV = 3        // in: n (3 comps)       out: K = 0.5*(dnx/dx + dny/dy + dnz/dz), optional clip on c
+};
+
+struct StencilExtra {
+    // MODE_NORMAL: optional un-normalised gradient output (the reference's cell_normal), per level, same layout as `out`
+    double* aux[PA_MAX_LEVELS];
+    long long cs_aux[PA_MAX_LEVELS];
+    // MODE_DIV: optional threshold clip reading the progress variable (layout = lay_in)
+    const double* prog[PA_MAX_LEVELS];
+    int do_threshold;
+    double threshold;
+};
+
+extern long long g_launches;     // kernels launched by this library
+
+cudaError_t launch_unpack_valid(const PaBoxDev* boxes, const PaLayDev* lay, const long long* host_off, int nboxes,
+                                long long ncells, const double* staging, double* comp_base, cudaStream_t st);
+cudaError_t launch_pack_valid(const PaBoxDev* boxes, const PaLayDev* lay, const long long* host_off, int nboxes,
+                              long long ncells, const double* comp_base, double* staging, cudaStream_t st);
+cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t st);
+
+cudaError_t launch_halo(const PaHaloTag* tags, int ntags, long long ncells, const PaBoxDev* boxes, const PaLayDev* lay,
+                        double* base, long long cs, int ncomp, const double* recv, cudaStream_t st);
+cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long long tag1, long long dense0, long long ncells,
+                                 const GridArgs& ga, int ncomp, double* send, cudaStream_t st);
+// BC fill over face records [rec0, rec1) whose plane cells are [cell0, cell1)
+cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, long long rec0, long long rec1, long long cell0,
+                          long long cell1, const unsigned short* flags, const PaCrseIdx* cidx, const GridArgs& ga,
+                          int ncomp, const double* recv, cudaStream_t st);
+
+// stencils: GridArgs.in/out already point at the first component to read / write
+cudaError_t launch_stencil_simple(int mode, const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex,
+                                  int nvar, cudaStream_t st);
+// TMA-staged pipeline (cp.async.bulk + mbarrier ring, 2.5-D sweep along z)
+cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, const GridArgs& ga,
+                               const StencilExtra& ex, int nvar, cudaStream_t st);
+int stencil_tma_tile_rows();     // TY the tile table must be built with
+int stencil_tma_max_plane_doubles();
+
+cudaError_t launch_progress(const PaBoxDev* boxes, const PaLayDev* lay_in, const PaLayDev* lay_out, int nboxes,
+                            const double* S, double* C, double pmin, double invdenom, cudaStream_t st);
+cudaError_t launch_clip_normal(const PaBoxDev* boxes, const PaLayDev* lay_c, const PaLayDev* lay_n, int nboxes,
+                               const double* C, double* N, long long cs_n, double thr, cudaStream_t st);
+// pointwise Gaussian curvature from G (3), H (9), c -> Kg ; strain: div u from dU (9) ; velnormal
+cudaError_t launch_gauss(const PaBoxDev* boxes, const PaLayDev* lay, const PaLayDev* lay_c, int nboxes, const double* G,
+                         long long cs_g, const double* H, long long cs_h, const double* C, double* Kg, int do_thr,
+                         double thr, cudaStream_t st);
+cudaError_t launch_strain(const PaBoxDev* boxes, const PaLayDev* lay, int nboxes, const double* dU, long long cs,
+                          double* sr, cudaStream_t st);
+cudaError_t launch_velnormal(const PaBoxDev* boxes, const PaLayDev* lay_u, const PaLayDev* lay_n, const PaLayDev* lay_o,
+                             int nboxes, const double* U, long long cs_u, const double* N, long long cs_n,
+                             const double* C, double* out, int do_thr, double thr, cudaStream_t st);
+
+}  // namespace pa
+#endif

