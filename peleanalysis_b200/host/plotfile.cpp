@@ -1,0 +1,230 @@
+#include "plotfile.hpp"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+
+namespace pltio {
+
+static std::vector<int> ints_of(const std::string& s) {
+    std::vector<int> v;
+    size_t i = 0;
+    while (i < s.size()) {
+        if (isdigit((unsigned char)s[i]) || (s[i] == '-' && i + 1 < s.size() && isdigit((unsigned char)s[i + 1]))) {
+            size_t j = i + 1;
+            while (j < s.size() && isdigit((unsigned char)s[j])) ++j;
+            v.push_back(std::atoi(s.substr(i, j - i).c_str()));
+            i = j;
+        } else ++i;
+    }
+    return v;
+}
+
+static std::vector<std::string> lines_of(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::vector<std::string> L;
+    std::string s;
+    while (std::getline(f, s)) L.push_back(s);
+    return L;
+}
+
+static void read_cell_h(const std::string& dir, LevelMeta& lv) {
+    auto L = lines_of(dir + "/" + lv.cell_path + "_H");
+    if (L.size() < 6) throw std::runtime_error("short Cell_H");
+    int vers = std::atoi(L[0].c_str());
+    lv.ncomp_on_disk = std::atoi(L[2].c_str());
+    auto nb = ints_of(L[4]);
+    int nboxes = nb.at(0);
+    lv.boxes.resize(nboxes);
+    for (int b = 0; b < nboxes; ++b) {
+        auto v = ints_of(L.at(5 + b));
+        for (int d = 0; d < 3; ++d) { lv.boxes[b].lo[d] = v.at(d); lv.boxes[b].hi[d] = v.at(3 + d); }
+    }
+    size_t p = 5 + nboxes + 1;
+    int nf = std::atoi(L.at(p).c_str());
+    ++p;
+    lv.fab_file.resize(nf); lv.fab_offset.resize(nf);
+    for (int i = 0; i < nf; ++i) {
+        std::istringstream is(L.at(p + i));
+        std::string tag;
+        is >> tag >> lv.fab_file[i] >> lv.fab_offset[i];
+    }
+    p += nf;
+    if (vers == 1) {
+        for (int t = 0; t < 2; ++t) {
+            while (p < L.size() && L[p].find_first_not_of(" \t\r") == std::string::npos) ++p;
+            if (p >= L.size()) break;
+            int n = 0, m = 0;
+            if (std::sscanf(L[p].c_str(), "%d,%d", &n, &m) != 2) break;
+            ++p;
+            auto& tab = t == 0 ? lv.fab_min : lv.fab_max;
+            tab.assign(n, std::vector<double>(m));
+            for (int i = 0; i < n; ++i) {
+                std::string s = L.at(p + i);
+                std::replace(s.begin(), s.end(), ',', ' ');
+                std::istringstream is(s);
+                for (int j = 0; j < m; ++j) is >> tab[i][j];
+            }
+            p += n;
+        }
+    }
+}
+
+Header read_header(const std::string& dir) {
+    auto L = lines_of(dir + "/Header");
+    Header h;
+    size_t p = 1;
+    int nvar = std::atoi(L.at(p++).c_str());
+    for (int i = 0; i < nvar; ++i) {
+        std::string s = L.at(p++);
+        while (!s.empty() && (s.back() == ' ' || s.back() == '\r')) s.pop_back();
+        h.names.push_back(s);
+    }
+    int dim = std::atoi(L.at(p++).c_str());
+    if (dim != 3) throw std::runtime_error("only 3-D plotfiles are supported");
+    h.time = std::atof(L.at(p++).c_str());
+    h.finest_level = std::atoi(L.at(p++).c_str());
+    { std::istringstream is(L.at(p++)); for (int d = 0; d < 3; ++d) is >> h.prob_lo[d]; }
+    { std::istringstream is(L.at(p++)); for (int d = 0; d < 3; ++d) is >> h.prob_hi[d]; }
+    h.ref_ratio = ints_of(L.at(p++));
+    auto dom = ints_of(L.at(p++));
+    ++p;  // level steps
+    h.levels.resize(h.finest_level + 1);
+    for (int l = 0; l <= h.finest_level; ++l) {
+        for (int d = 0; d < 3; ++d) { h.levels[l].domain.lo[d] = dom.at(9 * l + d); h.levels[l].domain.hi[d] = dom.at(9 * l + 3 + d); }
+        std::istringstream is(L.at(p++));
+        for (int d = 0; d < 3; ++d) is >> h.levels[l].dx[d];
+    }
+    h.coord = std::atoi(L.at(p++).c_str());
+    ++p;  // "0"
+    for (int l = 0; l <= h.finest_level; ++l) {
+        std::istringstream is(L.at(p++));
+        int lev, ng; double t;
+        is >> lev >> ng >> t;
+        ++p;  // step
+        p += 3 * (size_t)ng;
+        std::string path = L.at(p++);
+        while (!path.empty() && (path.back() == ' ' || path.back() == '\r')) path.pop_back();
+        h.levels[l].cell_path = path;
+        read_cell_h(dir, h.levels[l]);
+    }
+    return h;
+}
+
+void read_level_comp(const std::string& dir, const Header& h, int lev, int comp, double* dst) {
+    const LevelMeta& lv = h.levels.at(lev);
+    std::string ldir = dir + "/" + lv.cell_path.substr(0, lv.cell_path.find_last_of('/'));
+    std::string open_name;
+    FILE* f = nullptr;
+    for (size_t b = 0; b < lv.boxes.size(); ++b) {
+        if (lv.fab_file[b] != open_name) {
+            if (f) std::fclose(f);
+            f = std::fopen((ldir + "/" + lv.fab_file[b]).c_str(), "rb");
+            if (!f) throw std::runtime_error("cannot open " + ldir + "/" + lv.fab_file[b]);
+            open_name = lv.fab_file[b];
+        }
+        std::fseek(f, lv.fab_offset[b], SEEK_SET);
+        int c;
+        while ((c = std::fgetc(f)) != EOF && c != '\n') {}      // ASCII "FAB (...)(box) ncomp" line
+        long long n = lv.boxes[b].npts();
+        std::fseek(f, (long)(8LL * n * comp), SEEK_CUR);
+        if ((long long)std::fread(dst, 8, (size_t)n, f) != n) { std::fclose(f); throw std::runtime_error("short read in " + open_name); }
+        dst += n;
+    }
+    if (f) std::fclose(f);
+}
+
+static std::string g17(double x) { char b[64]; std::snprintf(b, sizeof b, "%.17g", x); return b; }
+static std::string boxstr(const BoxI& b) {
+    char s[160];
+    std::snprintf(s, sizeof s, "((%d,%d,%d) (%d,%d,%d) (0,0,0))", b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+    return s;
+}
+
+void write_plotfile(const std::string& dir, const Header& meta, const std::vector<std::string>& names,
+                    const std::vector<std::vector<const double*>>& data, const std::vector<int>& ref_ratio_line) {
+    struct stat sb;
+    if (::stat(dir.c_str(), &sb) == 0) {
+        auto t = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+        std::string old = dir + ".old." + std::to_string(t % 10000000000LL);
+        if (std::rename(dir.c_str(), old.c_str()) != 0) throw std::runtime_error("cannot rename existing " + dir);
+    }
+    if (::mkdir(dir.c_str(), 0755) != 0) throw std::runtime_error("cannot create " + dir);
+    const int nlev = (int)data.size();
+    const int ncomp = (int)names.size();
+    {
+        std::ofstream h(dir + "/Header");
+        h << "HyperCLaw-V1.1\n" << ncomp << '\n';
+        for (auto& n : names) h << n << '\n';
+        h << "3\n" << g17(meta.time) << '\n' << nlev - 1 << '\n';
+        for (int d = 0; d < 3; ++d) h << g17(meta.prob_lo[d]) << ' ';
+        h << '\n';
+        for (int d = 0; d < 3; ++d) h << g17(meta.prob_hi[d]) << ' ';
+        h << '\n';
+        for (int l = 0; l < nlev - 1; ++l) h << ref_ratio_line.at(l) << ' ';
+        h << '\n';
+        for (int l = 0; l < nlev; ++l) h << boxstr(meta.levels[l].domain) << ' ';
+        h << '\n';
+        for (int l = 0; l < nlev; ++l) h << "0 ";
+        h << '\n';
+        for (int l = 0; l < nlev; ++l) { for (int d = 0; d < 3; ++d) h << g17(meta.levels[l].dx[d]) << ' '; h << '\n'; }
+        h << meta.coord << "\n0\n";
+        for (int l = 0; l < nlev; ++l) {
+            const LevelMeta& lv = meta.levels[l];
+            h << l << ' ' << lv.boxes.size() << ' ' << g17(meta.time) << "\n0\n";
+            for (auto& b : lv.boxes)
+                for (int d = 0; d < 3; ++d)
+                    h << g17(meta.prob_lo[d] + lv.dx[d] * (b.lo[d] - lv.domain.lo[d])) << ' '
+                      << g17(meta.prob_lo[d] + lv.dx[d] * (b.hi[d] - lv.domain.lo[d] + 1)) << '\n';
+            h << "Level_" << l << "/Cell\n";
+        }
+    }
+    for (int l = 0; l < nlev; ++l) {
+        const LevelMeta& lv = meta.levels[l];
+        std::string ldir = dir + "/Level_" + std::to_string(l);
+        if (::mkdir(ldir.c_str(), 0755) != 0) throw std::runtime_error("cannot create " + ldir);
+        FILE* f = std::fopen((ldir + "/Cell_D_00000").c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot create Cell_D");
+        std::vector<long long> offs;
+        std::vector<std::vector<double>> mn(lv.boxes.size(), std::vector<double>(ncomp)), mx = mn;
+        long long cell0 = 0;
+        for (size_t b = 0; b < lv.boxes.size(); ++b) {
+            offs.push_back(std::ftell(f));
+            std::fprintf(f, "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))%s %d\n", boxstr(lv.boxes[b]).c_str(), ncomp);
+            long long n = lv.boxes[b].npts();
+            for (int c = 0; c < ncomp; ++c) {
+                const double* p = data[l][c] + cell0;
+                std::fwrite(p, 8, (size_t)n, f);
+                double a = std::numeric_limits<double>::max(), z = std::numeric_limits<double>::lowest();
+                for (long long q = 0; q < n; ++q) { a = std::min(a, p[q]); z = std::max(z, p[q]); }
+                mn[b][c] = a; mx[b][c] = z;
+            }
+            cell0 += n;
+        }
+        std::fclose(f);
+        std::ofstream c(ldir + "/Cell_H");
+        c << "1\n1\n" << ncomp << "\n0\n(" << lv.boxes.size() << " 0\n";
+        for (auto& b : lv.boxes) c << boxstr(b) << '\n';
+        c << ")\n" << lv.boxes.size() << '\n';
+        for (auto o : offs) c << "FabOnDisk: Cell_D_00000 " << o << '\n';
+        c << '\n';
+        for (auto* tab : {&mn, &mx}) {
+            c << lv.boxes.size() << ',' << ncomp << '\n';
+            for (auto& row : *tab) {
+                for (double v : row) { char s[64]; std::snprintf(s, sizeof s, "%.17e,", v); c << s; }
+                c << '\n';
+            }
+            c << '\n';
+        }
+    }
+}
+
+}  // namespace pltio
