@@ -170,6 +170,11 @@ int64_t pa_debug_face_flags(pa_hier *h, int lev, int box, int face, uint16_t *ou
 /* Polynomial coefficients and order of the coarse-fine ghost formula of (lev, box, face). */
 int pa_debug_face_coef(pa_hier *h, int lev, int box, int face, int *kind, int *nx, double coef[4]);
 
+/* Multi-rank exchange plan, for parity of the plan itself: identity of the cell each send-slab slot carries /
+ * each recv-slab slot expects, encoded (source level << 56 | global box << 32 | linear index in the box's valid
+ * region).  which = 0: send slab, 1: recv slab.  Returns the slab length in cells (writes min(len, out_len)). */
+int64_t pa_debug_exchange_ids(pa_hier *h, int which, int64_t *out, int64_t out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,7 @@ SYMBOLS = {
     "pa_debug_download_grown": (_i, [_vp, _i, _i, _i, _vp]),
     "pa_debug_fb_source_map": (_i, [_vp, _i, _i, _i, _vp, _i64]),
     "pa_debug_face_flags": (_i64, [_vp, _i, _i, _i, _vp, _i64]),
+    "pa_debug_exchange_ids": (_i64, [_vp, _i, _vp, _i64]),
     "pa_debug_face_coef": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d)]),
 }
 
@@ -212,6 +213,19 @@ class Hierarchy:
             res.append(out[o:o + m].reshape(n[2], n[1], n[0]))
             o += m
         return res
+
+    def exchange_ids(self, which: int) -> np.ndarray:
+        n = lib().pa_debug_exchange_ids(self.h, which, None, 0)
+        out = np.empty(n, dtype=np.int64)
+        lib().pa_debug_exchange_ids(self.h, which, _ptr(out) if n else None, n)
+        return out
+
+    def exchange_prefix(self, ncomp: int = 1):
+        """(send_counts, recv_counts) per peer, in doubles for ncomp components."""
+        s = (C.c_int64 * self.nranks)()
+        r = (C.c_int64 * self.nranks)()
+        check(lib().pa_exchange_counts(self.h, 1, ncomp, s, r))
+        return np.array(list(s)), np.array(list(r))
 
     def face_flags(self, lev: int, box: int, face: int):
         n = lib().pa_debug_face_flags(self.h, lev, box, face, None, 0)

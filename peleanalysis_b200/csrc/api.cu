@@ -823,4 +823,11 @@ int pa_debug_face_coef(pa_hier* h, int lev, int box, int face, int* kind, int* n
     return PA_OK;
 }
 
+int64_t pa_debug_exchange_ids(pa_hier* h, int which, int64_t* out, int64_t out_len) {
+    if (!h) return 0;
+    const std::vector<long long>& v = which ? h->H.xplan.recv_ids : h->H.xplan.send_ids;
+    if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < out_len; ++i) out[i] = v[i];
+    return (int64_t)v.size();
+}
+
 }  // extern "C"

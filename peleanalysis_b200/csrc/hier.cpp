@@ -256,6 +256,11 @@ static bool face_is_physical(const Hier& H, int l, int gb, int face) {
     return at && !H.is_per[d];
 }
 
+static inline long long cell_id(int lev, int gbox, const Box& B, int i, int j, int k) {
+    long long lin = ((long long)(k - B.lo[2]) * B.len(1) + (j - B.lo[1])) * B.len(0) + (i - B.lo[0]);
+    return ((long long)lev << 56) | ((long long)gbox << 32) | lin;
+}
+
 void Hier::build_exchange() {
     // Walk every (level, dst box) in canonical order; entries whose source owner differs from the dst owner are
     // exchanged.  The stream from rank p to rank q is the subsequence with (src owner p, dst owner q); both sides
@@ -338,6 +343,17 @@ void Hier::build_exchange() {
         xplan.pack.push_back(e.t);
     }
     while (curlev < nlev) xplan.pack_level_begin[++curlev] = (long long)xplan.pack.size();
+    xplan.recv_ids.assign((size_t)xplan.recv_prefix[nranks], -1);
+    xplan.send_ids.assign((size_t)xplan.send_prefix[nranks], -1);
+    for (const PaPackTag& t : xplan.pack) {
+        int gb = lev[t.slev].local[t.sbox];
+        const Box& B = lev[t.slev].boxes[gb];
+        long long q = 0;
+        for (int k = 0; k < t.n[2]; ++k)
+            for (int j = 0; j < t.n[1]; ++j)
+                for (int i = 0; i < t.n[0]; ++i, ++q)
+                    xplan.send_ids[(size_t)(t.start + q)] = cell_id(t.slev, gb, B, t.slo[0] + i, t.slo[1] + j, t.slo[2] + k);
+    }
 }
 
 void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remote) {
@@ -362,7 +378,15 @@ void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remo
                 for (int d = 0; d < 3; ++d) { t.dlo[d] = n.dst.lo[d]; t.n[d] = n.dst.len(d); t.shift[d] = n.shift[d]; }
                 int so = V.owner[n.sbox];
                 if (so == rank) { t.sbox = V.g2l[n.sbox]; t.rsrc = -1; out.tags.push_back(t); }
-                else { t.sbox = -1; t.rsrc = rcur[so]; rcur[so] += n.dst.npts(); remote.push_back(t); }
+                else {
+                    t.sbox = -1; t.pad = n.sbox; t.rsrc = rcur[so]; rcur[so] += n.dst.npts(); remote.push_back(t);
+                    const Box& SB = V.boxes[n.sbox];
+                    long long q = 0;
+                    for (int k = n.dst.lo[2]; k <= n.dst.hi[2]; ++k)
+                        for (int j = n.dst.lo[1]; j <= n.dst.hi[1]; ++j)
+                            for (int i = n.dst.lo[0]; i <= n.dst.hi[0]; ++i, ++q)
+                                xplan.recv_ids[(size_t)(t.rsrc + q)] = cell_id(l, n.sbox, SB, i + n.shift[0], j + n.shift[1], k + n.shift[2]);
+                }
             }
             // keep the per-peer cursor in canonical order: this box's coarse needs come next in the stream
             if (l > 0 && !rcur.empty())
@@ -523,6 +547,7 @@ std::string Hier::build_faces() {
                                     } else {
                                         X.box = -2;
                                         X.rel = (unsigned)(rbase + q);
+                                        xplan.recv_ids[(size_t)(rbase + q)] = cell_id(l - 1, n.cbox, cb, i + n.shift[0], j + n.shift[1], k + n.shift[2]);
                                     }
                                 }
                     }

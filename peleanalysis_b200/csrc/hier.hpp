@@ -112,6 +112,9 @@ struct ExchangePlan {
     std::vector<long long> recv_prefix;               // nranks+1, in cells
     std::vector<std::vector<long long>> level_send_cell0;  // [level][peer]: first send-slab cell of the level's block for the peer (nlev+1 rows)
     std::vector<std::vector<long long>> level_recv_cell0;  // [level][peer]: same on the receive side
+    // debug / parity: global identity (src level<<56 | global box<<32 | linear index in its valid region) of the cell every
+    // recv-slab slot expects, and of the cell every send-slab slot carries
+    std::vector<long long> recv_ids, send_ids;
 };
 
 class Hier {

@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""Run under torchrun (one process per GPU): distributed grad on SFC-partitioned boxes, cross-rank ghost cells moved
+as NCCL send/recv of the packed slabs, every rank's local boxes compared bit-for-bit with the oracle.
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import CASES  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from peleanalysis_b200 import capi, synth  # noqa: E402
+
+
+class DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def run_case(name, pf, is_per, sym, rank, world, nvar=1):
+    H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+    fin, fout = capi.Field(H, nvar, 1), capi.Field(H, 4 * nvar, 0)
+    for v in range(nvar):
+        fin.upload_fabs(v, [[f[v] for f in l.fabs] for l in pf.levels])
+    sp, rp = C.c_void_p(), C.c_void_p()
+    so, ro = (C.c_int64 * (world + 1))(), (C.c_int64 * (world + 1))()
+    capi.check(capi.lib().pa_exchange_buffers(fin.f, nvar, C.byref(sp), C.byref(rp), so, ro))
+    send_t = torch.as_tensor(DevArray(sp.value, max(so[world], 1)), device="cuda")
+    recv_t = torch.as_tensor(DevArray(rp.value, max(ro[world], 1)), device="cuda")
+    capi.check(capi.lib().pa_exchange_pack(fin.f, 0, nvar))
+    ops = []
+    for p in range(world):
+        if p != rank and ro[p + 1] > ro[p]:
+            ops.append(dist.P2POp(dist.irecv, recv_t[ro[p]:ro[p + 1]], p))
+        if p != rank and so[p + 1] > so[p]:
+            ops.append(dist.P2POp(dist.isend, send_t[so[p]:so[p + 1]], p))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    capi.check(capi.lib().pa_exchange_mark_received(fin.f, 0, nvar))
+    capi.grad(fin, 0, nvar, fout, 0)
+    capi.sync()
+    OH = O.OracleHier(pf, is_per, sym)
+    bad = 0
+    for v in range(nvar):
+        want = OH.unflatten_all(OH.grad(OH.flatten(v))) if hasattr(OH, "unflatten_all") else [OH.unflatten(g) for g in OH.grad(OH.flatten(v))]
+        for c in range(4):
+            got = fout.download_fabs(4 * v + c)
+            for l in range(len(pf.levels)):
+                for b in H.local_boxes[l]:
+                    if not np.array_equal(got[l][b], want[c][l][b]):
+                        bad += 1
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("dist_check %-18s ranks=%d local_boxes=%s remote_cells(recv)=%d mismatching boxes=%d" % (
+            name, world, [len(x) for x in H.local_boxes], ro[world] // nvar, int(t.item())), flush=True)
+    return int(t.item())
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    capi.init(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.set_stream(torch.cuda.current_stream().cuda_stream)
+    bad = 0
+    for name in ["c1_periodic", "c1_walls", "lshape", "edge_periodic", "ratio4", "c3_three_levels"]:
+        builder, is_per, sym, _, _ = CASES[name]
+        bad += run_case(name, builder(), is_per, sym, rank, world)
+    bad += run_case("config3_64", synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world)
+    bad += run_case("config1_5vars", synth.config1(32, 16, names=synth.FIELD_NAMES), (1, 1, 1), (0, 0, 0), rank, world, nvar=5)
+    bad += run_case("config5_small", synth.config5(base=32, mgs=8, ncomp=2), (1, 1, 1), (0, 0, 0), rank, world, nvar=2)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_CHECK", "OK" if bad == 0 else "FAILED (%d)" % bad, flush=True)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""CPU, world_size 2 over gloo: the multi-rank exchange plan (hier.cpp: build_exchange).  Each rank builds its own
+hierarchy tables, ships the identity of the cell in every send-slab slot to its peer with torch.distributed
+send/recv, and checks that every recv-slab slot holds exactly the cell its halo rows / coarse gather index expect.
+Also checks that single-rank tables are the union of the two ranks' local tables."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, case, ok):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cases import CASES
+        from peleanalysis_b200 import capi
+        builder, is_per, sym, _, _ = CASES[case]
+        pf = builder()
+        H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+        send_ids, want = H.exchange_ids(0), H.exchange_ids(1)
+        sc, rc = H.exchange_prefix(1)
+        assert sc[rank] == 0 and rc[rank] == 0
+        assert sc.sum() == send_ids.size and rc.sum() == want.size
+        assert (want >= 0).all() and (send_ids >= 0).all()
+        so = np.concatenate([[0], np.cumsum(sc)])
+        ro = np.concatenate([[0], np.cumsum(rc)])
+        got = np.full(want.size, -1, dtype=np.int64)
+        reqs, bufs = [], []
+        for p in range(world):
+            if p == rank:
+                continue
+            if rc[p]:
+                t = torch.empty(int(rc[p]), dtype=torch.int64)
+                bufs.append((p, t))
+                reqs.append(dist.irecv(t, p))
+            if sc[p]:
+                reqs.append(dist.isend(torch.from_numpy(send_ids[so[p]:so[p + 1]].copy()), p))
+        for r in reqs:
+            r.wait()
+        for p, t in bufs:
+            got[ro[p]:ro[p + 1]] = t.numpy()
+        assert np.array_equal(got, want), int((got != want).sum())
+        # every box is owned by exactly one rank and the local cell counts add up
+        tot = torch.tensor([H.num_local_cells], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot.item()) == H.num_cells
+        # remote ghost sources are flagged (-2) exactly where the single-rank table names a box owned by the peer
+        H1 = capi.Hierarchy(pf.levels, is_per, sym)
+        for l in range(len(pf.levels)):
+            full = H1.fb_source_map(l, 1, cross=True)
+            mine = H.fb_source_map(l, 1, cross=True)
+            for i, b in enumerate(H.local_boxes[l]):
+                f, m = full[b], mine[i]
+                src_box = np.where(f >= 0, f >> 40, -1)
+                remote = (src_box >= 0) & (H.owners[l][np.maximum(src_box, 0)] != rank)
+                assert np.array_equal(m == -2, remote)
+                assert np.array_equal(m[~remote], f[~remote])
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["c1_periodic", "c3_three_levels", "lshape", "edge_walls", "ratio4"])
+def test_exchange_plan_world2(palib, case):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0, 0])
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert list(ok) == [1, 1], [p.exitcode for p in procs]
