@@ -10,7 +10,10 @@ One "step" = one pass of the hot path (ghost fill + c-f fill + stencil) over the
             HBM copy bandwidth of MEASURED_PEAKS.json; bytes = SURVEY 8(d) algorithmic bytes
   cpu_baseline  the compiled reference (oracle/_ref/grad3d.timed.ex, all host cores) on a bounded sample
 N > 1 (torchrun, one process per GPU): the boxes of the same workload are SFC-distributed over the ranks (strong
-scaling) and the cross-rank ghost cells move as NCCL send/recv of packed slabs between the pack and fill kernels.
+scaling).  --transport peer (default): every rank maps its peers' slabs through CUDA IPC and the stencil kernel's TMA
+producer reads cross-rank neighbour planes / rows / columns in place over NVLink -- no pack, no exchange, no halo
+kernel.  --transport slab: the cross-rank ghost cells move as NCCL send/recv of packed slabs between a pack and a fill
+kernel (what an MPI code does).
 """
 import argparse
 import json
@@ -174,6 +177,51 @@ def gen_fields(torch, levels, local_boxes, names, prob_hi=(1.0, 1.0, 1.0)):
     return out
 
 
+def bench_extra(torch, capi, synth, stream, peak, kind, steps, warmup):
+    """Secondary measurements reported next to the headline line (same timing rules, N=1 only):
+    curvature3 : curvature tool (default options) on BASELINE configs[2] -- 3 levels, 256^3 base, ratio 2, 64^3 boxes
+    grad5      : grad of 12 components on a configs[4]-like 4-level hierarchy (ratios 2/4/2, 16^3 boxes)."""
+    if kind == "curvature3":
+        pf = synth.config3(256, 64, fill=False)
+        names, desc = ["temp"], "curvature (default options), 3 levels, 256^3 base, ratio 2, 64^3 boxes (BASELINE configs[2])"
+    else:
+        pf = synth.config5(128, 16, 12, fill=False)
+        names, desc = list(pf.names), "grad of 12 components, 4 levels (ratios 2/4/2), 128^3 base, 16^3 boxes (BASELINE configs[4])"
+    H = capi.Hierarchy(pf.levels)
+    host = gen_fields(torch, pf.levels, H.local_boxes, names)
+    nv = len(names)
+    fin = capi.Field(H, nv, 1)
+    for l in range(H.nlev):
+        for c in range(nv):
+            capi.check(capi.lib().pa_field_upload_level(fin.f, l, c, host[l][c].data_ptr()))
+    capi.sync()
+    if kind == "curvature3":
+        o = capi.CurvOpts()
+        o.prog_min = min(float(h[0].min()) for h in host)
+        o.prog_max = max(float(h[0].max()) for h in host)
+        out = capi.Field(H, 5, 1)
+        run = lambda: capi.curvature(fin, 0, 0, o, out, 0)
+        alg, units = H.algorithmic_bytes(5), H.num_cells
+    else:
+        out = capi.Field(H, 4 * nv, 0)
+        run = lambda: capi.grad(fin, 0, nv, out, 0)
+        alg, units = H.algorithmic_bytes(4) * nv, H.num_cells * nv
+    for _ in range(warmup):
+        run()
+    torch.cuda.synchronize()
+    l0 = capi.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": desc, "value": units / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "cells": H.num_cells,
+            "boxes": [len(l.boxes) for l in pf.levels], "launches_per_step": (capi.kernel_launches() - l0) // steps,
+            "algorithmic_bytes": alg, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "hier_build_s": H.build_seconds}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +231,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--transport", default="peer", choices=["peer", "slab"])
+    ap.add_argument("--no-links", action="store_true", help="materialise every ghost cell (reference data flow)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary curvature / small-box measurements")
+    ap.add_argument("--only-extra", default=None, choices=["curvature3", "grad5"], help="run just one secondary measurement (profiling aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     spec = workload_spec(args.workload)
@@ -191,7 +243,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from peleanalysis_b200 import build, capi, synth
+    from peleanalysis_b200 import build, capi, multigpu, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,11 +258,16 @@ def main():
     stream = torch.cuda.current_stream()
     capi.set_stream(stream.cuda_stream)
 
+    if args.only_extra:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        print(json.dumps(bench_extra(torch, capi, synth, stream, peak, args.only_extra, args.steps, args.warmup)))
+        return
     names = spec["names"]
     nvar = len(names)
     pf = synth.make_hierarchy(spec["n"], [], [], spec["mgs"], names, fill=False)
     t0 = time.perf_counter()
-    H = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, world)
+    flags = capi.NO_LINKS if args.no_links else (capi.PEER_LINKS if (world > 1 and args.transport == "peer") else 0)
+    H = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, world, flags=flags)
     hier_s = time.perf_counter() - t0
     cells_global = H.num_cells
     host_in = gen_fields(torch, pf.levels, H.local_boxes, names)
@@ -223,38 +280,19 @@ def main():
                 for c in range(nvar):
                     capi.check(capi.lib().pa_field_upload_level(fin.f, l, c, host_in[l][c].data_ptr()))
 
+    if flags & capi.PEER_LINKS:
+        multigpu.map_peers(fin)
     upload()
     capi.sync()
-
-    # cross-rank exchange plumbing (NCCL send/recv of the packed slabs)
-    send_t = recv_t = None
-    soff = roff = None
     if world > 1:
-        import ctypes as C
-        sp, rp = C.c_void_p(), C.c_void_p()
-        so = (C.c_int64 * (world + 1))()
-        ro = (C.c_int64 * (world + 1))()
-        capi.check(capi.lib().pa_exchange_buffers(fin.f, nvar, C.byref(sp), C.byref(rp), so, ro))
-        soff, roff = list(so), list(ro)
-        send_t = torch.as_tensor(DevArray(sp.value, max(soff[-1], 1)), device="cuda")
-        recv_t = torch.as_tensor(DevArray(rp.value, max(roff[-1], 1)), device="cuda")
+        dist.barrier()                 # every rank's inputs are resident before anyone reads them in place
+
+    # whatever the neighbour links do not cover moves as NCCL send/recv of packed slabs (nothing, for peer transport
+    # on a uniform grid)
+    X = multigpu.SlabExchange(fin, nvar)
 
     def exchange():
-        if world == 1:
-            return
-        capi.check(capi.lib().pa_exchange_pack(fin.f, 0, nvar))
-        ops = []
-        for p in range(world):
-            if p == rank:
-                continue
-            if roff[p + 1] > roff[p]:
-                ops.append(dist.P2POp(dist.irecv, recv_t[roff[p]:roff[p + 1]], p))
-            if soff[p + 1] > soff[p]:
-                ops.append(dist.P2POp(dist.isend, send_t[soff[p]:soff[p + 1]], p))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        capi.check(capi.lib().pa_exchange_mark_received(fin.f, 0, nvar))
+        X.run(0)
 
     def step(ev=None):
         exchange()
@@ -299,15 +337,44 @@ def main():
     host_out = [[torch.empty(max(H.local_cells[l], 1), dtype=torch.float64, pin_memory=True)[:H.local_cells[l]] for _ in range(4 * nvar)]
                 for l in range(H.nlev)]
 
-    def e2e_step():
-        upload()
-        exchange()
-        capi.grad(fin, 0, nvar, fout, 0)
-        for l in range(H.nlev):
-            if H.local_cells[l]:
-                for c in range(4 * nvar):
-                    capi.check(capi.lib().pa_field_download_level(fout.f, l, c, host_out[l][c].data_ptr()))
+    # Pipelined by variable over three streams: H2D of variable v+1 (copy engine), hot path of v (SMs) and D2H of v's
+    # four outputs (the other copy engine) overlap; PCIe is full duplex, so the step costs ~max(H2D, D2H), not the sum.
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    X1 = multigpu.SlabExchange(fin, 1) if not X.empty else None
+    ev_up = [torch.cuda.Event() for _ in range(nvar)]
+    ev_g = [torch.cuda.Event() for _ in range(nvar)]
+    ev_end = torch.cuda.Event()
+    peer = bool(flags & capi.PEER_LINKS)
 
+    def e2e_step():
+        s_up.wait_event(ev_end)             # the previous step's readers (this rank's and the peers') are done
+        capi.set_stream(s_up.cuda_stream)
+        for v in range(nvar):
+            for l in range(H.nlev):
+                if H.local_cells[l]:
+                    capi.check(capi.lib().pa_field_upload_level(fin.f, l, v, host_in[l][v].data_ptr()))
+            ev_up[v].record(s_up)
+        for v in range(nvar):
+            stream.wait_event(ev_up[v])
+            capi.set_stream(stream.cuda_stream)
+            if peer:
+                multigpu.stream_barrier()   # peers' uploads of v landed before this rank's kernel reads them over NVLink
+            if X1 is not None:
+                X1.run(v)
+            capi.grad(fin, v, 1, fout, 4 * v)
+            ev_g[v].record(stream)
+            s_dn.wait_event(ev_g[v])
+            capi.set_stream(s_dn.cuda_stream)
+            for l in range(H.nlev):
+                if H.local_cells[l]:
+                    for c in range(4 * v, 4 * v + 4):
+                        capi.check(capi.lib().pa_field_download_level(fout.f, l, c, host_out[l][c].data_ptr()))
+        capi.set_stream(stream.cuda_stream)
+        if peer:
+            multigpu.stream_barrier()       # nobody re-uploads while a peer still reads the old data
+        ev_end.record(stream)
+
+    ev_end.record(stream)
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -348,6 +415,15 @@ def main():
             dist.destroy_process_group()
         return
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        del fin, fout, host_out, host_in
+        extras = {}
+        for kind in ("curvature3", "grad5"):
+            try:
+                extras[kind] = bench_extra(torch, capi, synth, stream, peak, kind, max(5, args.steps // 2), 3)
+            except Exception as e:
+                extras[kind] = {"error": str(e).splitlines()[0][:200]}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -360,7 +436,10 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": spec["desc"], "cells": cells_global, "variables": nvar, "boxes": len(pf.levels[0].boxes),
-                   "parallelism": "boxes SFC-distributed over %d rank(s), NCCL send/recv halo slabs" % world,
+                   "parallelism": ("1 GPU" if world == 1 else "boxes SFC-distributed over %d ranks; cross-rank ghosts: %s" % (
+                       world, "read in place over NVLink (CUDA-IPC peer links, no exchange step)" if flags & capi.PEER_LINKS
+                       else "NCCL send/recv of packed slabs (%d cells/step recv on rank 0)" % (X.roff[-1] // nvar))),
+                   "ghosts": "materialised (PA_HIER_NO_LINKS)" if args.no_links else "same-level neighbours read in place by the stencil (neighbour links)",
                    "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % ((alg_bytes) / 1e9),
                    "stencil": os.environ.get("PA_STENCIL", "tma"), "hier_build_s": hier_s},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "s_per_step": e2e_s},
@@ -371,6 +450,7 @@ def main():
                      "kernel_ms": stencil_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "step_frac": value * 40.0 / peak},
         "cpu_baseline": cpu,
+        "extras": extras,
     }
     print(json.dumps(line))
     if world > 1:

@@ -87,6 +87,17 @@ int pa_host_unregister(void *p);
  * rank / nranks: this process and the number of processes the boxes are distributed over (owner[] values). */
 int pa_hier_create(pa_hier **h, int nlev, const pa_level_desc *levels, const int is_per[3],
                    const int bc_kind[3], int rank, int nranks);
+/* The same with flags.  By default every box face whose whole ghost layer lies inside ONE same-level box of equal
+ * x/y extent on the same rank gets a "neighbour link": the stencil kernels read the neighbour's valid cells in place
+ * (TMA bulk copies / scalar loads) and those ghost cells are never materialised -- the FillBoundary traffic of
+ * AX/Base/AMReX_FBI.H:211-267 disappears for them.  pa_fill_ghosts / pa_fill_boundary still materialise everything.
+ *   PA_HIER_PEER_LINKS  links may also point at boxes of OTHER ranks; their slabs are then read over NVLink through
+ *                       CUDA-IPC mappings (pa_field_ipc_handle / pa_field_map_peer), replacing the MPI send/recv of
+ *                       AX/Base/AMReX_FabArrayCommI.H:62-110 for those faces.
+ *   PA_HIER_NO_LINKS    no links at all: every ghost cell is materialised by the halo gather (reference data flow). */
+enum { PA_HIER_PEER_LINKS = 1, PA_HIER_NO_LINKS = 2 };
+int pa_hier_create2(pa_hier **h, int nlev, const pa_level_desc *levels, const int is_per[3],
+                    const int bc_kind[3], int rank, int nranks, unsigned flags);
 int pa_hier_destroy(pa_hier *h);
 int pa_hier_num_levels(const pa_hier *h);
 int pa_hier_num_boxes(const pa_hier *h, int lev);          /* global count */
@@ -104,6 +115,12 @@ int pa_field_free(pa_field *f);
 int pa_field_ncomp(const pa_field *f);
 int pa_field_nghost(const pa_field *f);
 int64_t pa_field_bytes(const pa_field *f);
+/* Peer mapping for PA_HIER_PEER_LINKS hierarchies (one process per GPU on one NVLink node).  Each rank exports a
+ * 64-byte cudaIpcMemHandle_t per level (all zero if it owns no box there), the caller moves the handles between the
+ * processes (MPI_Allgather / torch.distributed.all_gather), and every rank maps the others'.  The caller must also
+ * order the peers' writes before this rank's reads (a barrier after uploads / between dependent passes). */
+int pa_field_ipc_handle(const pa_field *f, int lev, void *handle64);
+int pa_field_map_peer(pa_field *f, int lev, int peer_rank, const void *handle64);
 /* Valid region of one (level, box, comp) <-> host, asynchronous on the library stream.  Stands in for the
  * FillVar copy into state[lev] (Src/grad.cpp:167) and the ghost-stripping copy before VisMF::Write
  * (AX/Base/AMReX_PlotFileUtil.cpp:227-233).  Boxes owned by other ranks are rejected with PA_ERR_ARG. */
@@ -169,6 +186,10 @@ int pa_debug_fb_source_map(pa_hier *h, int lev, int nghost, int cross, int64_t *
 int64_t pa_debug_face_flags(pa_hier *h, int lev, int box, int face, uint16_t *out, int64_t out_len);
 /* Polynomial coefficients and order of the coarse-fine ghost formula of (lev, box, face). */
 int pa_debug_face_coef(pa_hier *h, int lev, int box, int face, int *kind, int *nx, double coef[4]);
+
+/* Neighbour links of (lev, GLOBAL box): per face (amrex::Orientation order) 5 ints: neighbour global box id or -1,
+ * its owner rank, and rel[3] (neighbour-relative cell = own-relative cell + rel). */
+int pa_debug_links(pa_hier *h, int lev, int box, int out[30]);
 
 /* Multi-rank exchange plan, for parity of the plan itself: identity of the cell each send-slab slot carries /
  * each recv-slab slot expects, encoded (source level << 56 | global box << 32 | linear index in the box's valid

@@ -40,6 +40,8 @@ SYMBOLS = {
     "pa_host_alloc": (_i, [C.POINTER(_vp), C.c_size_t]), "pa_host_free": (_i, [_vp]),
     "pa_host_register": (_i, [_vp, C.c_size_t]), "pa_host_unregister": (_i, [_vp]),
     "pa_hier_create": (_i, [C.POINTER(_vp), _i, C.POINTER(LevelDesc), C.POINTER(_i), C.POINTER(_i), _i, _i]),
+    "pa_hier_create2": (_i, [C.POINTER(_vp), _i, C.POINTER(LevelDesc), C.POINTER(_i), C.POINTER(_i), _i, _i, C.c_uint]),
+    "pa_field_ipc_handle": (_i, [_vp, _i, _vp]), "pa_field_map_peer": (_i, [_vp, _i, _i, _vp]),
     "pa_hier_destroy": (_i, [_vp]), "pa_hier_num_levels": (_i, [_vp]), "pa_hier_num_boxes": (_i, [_vp, _i]),
     "pa_hier_num_cells": (_i64, [_vp, _i]), "pa_hier_num_local_cells": (_i64, [_vp, _i]),
     "pa_hier_box_owner": (_i, [_vp, _i, _i]),
@@ -62,6 +64,7 @@ SYMBOLS = {
     "pa_debug_fb_source_map": (_i, [_vp, _i, _i, _i, _vp, _i64]),
     "pa_debug_face_flags": (_i64, [_vp, _i, _i, _i, _vp, _i64]),
     "pa_debug_exchange_ids": (_i64, [_vp, _i, _vp, _i64]),
+    "pa_debug_links": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "pa_debug_face_coef": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d)]),
 }
 
@@ -141,7 +144,7 @@ class Hierarchy:
     """Geometry + BoxArray + DistributionMapping of all levels and the descriptor tables built from them."""
 
     def __init__(self, levels, is_per=(1, 1, 1), sym_dir=(0, 0, 0), rank: int = 0, nranks: int = 1,
-                 owners: Optional[List[np.ndarray]] = None):
+                 owners: Optional[List[np.ndarray]] = None, flags: int = 0):
         """levels: objects with domain_lo, domain_hi, dx, boxes (e.g. plotfile.Level)."""
         self.levels = levels
         self.rank, self.nranks = rank, nranks
@@ -169,7 +172,8 @@ class Hierarchy:
         per = (C.c_int * 3)(*[int(v) for v in is_per])
         bck = (C.c_int * 3)(*[int(v) for v in sym_dir])
         self.h = C.c_void_p()
-        check(lib().pa_hier_create(C.byref(self.h), nlev, descs, per, bck, rank, nranks))
+        self.flags = flags
+        check(lib().pa_hier_create2(C.byref(self.h), nlev, descs, per, bck, rank, nranks, flags))
         self.nlev = nlev
         self.local_boxes = [[b for b in range(len(lv.boxes)) if self.owners[l][b] == rank] for l, lv in enumerate(levels)]
         self.local_cells = [sum(int(np.prod([hi[d] - lo[d] + 1 for d in range(3)])) for b in self.local_boxes[l]
@@ -238,6 +242,12 @@ class Hierarchy:
         t1 = 1 if d == 0 else 0
         t2 = 1 if d == 2 else 2
         return out.reshape(hi[t2] - lo[t2] + 1, hi[t1] - lo[t1] + 1)
+
+    def links(self, lev: int, box: int) -> np.ndarray:
+        """[6,5] ints per face: neighbour global box (-1 = no link), its owner rank, rel[3]."""
+        out = np.zeros(30, dtype=np.int32)
+        check(lib().pa_debug_links(self.h, lev, box, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out.reshape(6, 5)
 
     def face_coef(self, lev: int, box: int, face: int):
         kind, nx = C.c_int(), C.c_int()
@@ -325,6 +335,18 @@ class Field:
             out.append(res)
         return out
 
+    def ipc_handles(self) -> bytes:
+        """64-byte CUDA IPC handle of every level's slab, concatenated (zeros where this rank owns no box)."""
+        buf = (C.c_ubyte * (64 * self.hier.nlev))()
+        for l in range(self.hier.nlev):
+            check(lib().pa_field_ipc_handle(self.f, l, C.byref(buf, 64 * l)))
+        return bytes(buf)
+
+    def map_peer(self, peer_rank: int, handles: bytes) -> None:
+        for l in range(self.hier.nlev):
+            h = (C.c_ubyte * 64).from_buffer_copy(handles[64 * l:64 * l + 64])
+            check(lib().pa_field_map_peer(self.f, l, peer_rank, h))
+
     def set_val(self, v: float, comp: int = 0, ncomp: Optional[int] = None) -> None:
         check(lib().pa_field_set_val(self.f, comp, ncomp or self.ncomp - comp, v))
 
@@ -333,6 +355,9 @@ class Field:
 
     def fill_ghosts(self, comp: int = 0, ncomp: int = 1, lev_lo: int = 0, lev_hi: int = -1) -> None:
         check(lib().pa_fill_ghosts(self.f, comp, ncomp, lev_lo, lev_hi))
+
+
+PEER_LINKS, NO_LINKS = 1, 2
 
 
 def grad(inp: Field, comp_in: int, nvar: int, out: Field, comp_out: int, phases: int = 3) -> None:

@@ -52,7 +52,8 @@ struct DevBuf {
 };
 
 struct LevelDev {
-    DevBuf<PaBoxDev> boxes;
+    DevBuf<PaBoxDev> boxes;                            // extended index (local boxes, then peer-owned link targets)
+    DevBuf<PaNbr> nbr;                                 // neighbour links of the local boxes
     DevBuf<PaHaloTag> halo_cross;
     DevBuf<long long> host_off;                        // nlocal+1 prefix of valid cells (host concat order)
     std::vector<long long> host_off_h;
@@ -80,7 +81,7 @@ struct pa_hier {
     DevBuf<PaCrseIdx> face_cidx;
     DevBuf<PaPackTag> pack_tags;
     TileTable tiles_simple, tiles_tma;
-    DevBuf<double> staging;                            // upload / download staging
+    std::map<cudaStream_t, std::unique_ptr<DevBuf<double>>> staging;   // upload / download staging, one per stream
     DevBuf<double> send_slab, recv_slab;               // multi-rank exchange, [cell][comp]
     int slab_ncomp = 0;
     // curvature temporaries (allocated on demand)
@@ -96,6 +97,11 @@ struct pa_field {
     std::vector<long long> cs;                         // component stride per level
     int recv_ncomp = 0;                                // >0: recv slab holds data for that many comps of this field
     int recv_comp0 = -1;
+    // per level: where every rank's slab of this field lives (own allocation, or an IPC mapping of a peer's)
+    std::vector<std::vector<PaPeerSlab>> peers_h;
+    std::vector<std::unique_ptr<DevBuf<PaPeerSlab>>> peers_d;
+    std::vector<void*> ipc_mapped;                     // pointers returned by cudaIpcOpenMemHandle
+    int peers_missing = 0;                             // (level, rank) slabs with boxes that are not mapped yet
 };
 
 namespace {
@@ -121,7 +127,7 @@ void build_tiles(pa_hier* h, TileTable& T, bool tma) {
     T.ok = true;
     const char* ety = getenv("PA_TMA_TY");
     const char* ezc = getenv("PA_TMA_ZC");
-    const int TY0 = ety ? std::max(1, atoi(ety)) : stencil_tma_tile_rows();
+    const int TY0 = ety ? std::min(std::max(1, atoi(ety)), stencil_tma_max_tile_rows()) : stencil_tma_tile_rows();
     const int ZC0 = ezc ? std::max(1, atoi(ezc)) : 32;
     for (int l = 0; l < H.nlev; ++l) {
         T.level_begin[l] = (long long)T.h.size();
@@ -169,13 +175,15 @@ int ensure_device(pa_hier* h) {
         const Level& V = H.lev[l];
         std::vector<PaBoxDev> bd;
         D->host_off_h.assign(1, 0);
-        for (int gb : V.local) {
+        for (size_t e = 0; e < V.ext.size(); ++e) {
+            const int gb = V.ext[e];
             PaBoxDev b;
             for (int d = 0; d < 3; ++d) { b.lo[d] = V.boxes[gb].lo[d]; b.n[d] = V.boxes[gb].len(d); }
             bd.push_back(b);
-            D->host_off_h.push_back(D->host_off_h.back() + V.boxes[gb].npts());
+            if (e < V.local.size()) D->host_off_h.push_back(D->host_off_h.back() + V.boxes[gb].npts());
         }
         CU(D->boxes.upload(bd, t_stream));
+        CU(D->nbr.upload(V.nbr, t_stream));
         CU(D->halo_cross.upload(H.halo_cross[l].tags, t_stream));
         CU(D->host_off.upload(D->host_off_h, t_stream));
         h->lev.push_back(std::move(D));
@@ -214,6 +222,9 @@ int grid_args_inplace(pa_field* f, int comp, GridArgs& ga) {
         LevArgs& A = ga.L[l];
         A.boxes = h->lev[l]->boxes.p;
         A.lay_in = A.lay_out = ly;
+        A.nbr = h->lev[l]->nbr.p;
+        A.peers = f->peers_d[l]->p;
+        A.in_comp = comp;
         A.in = A.out = f->slab[l] ? f->slab[l] + (long long)comp * f->cs[l] : nullptr;
         A.cs_in = A.cs_out = f->cs[l];
         for (int d = 0; d < 3; ++d) A.dxi[d] = h->H.lev[l].dxinv[d];
@@ -233,6 +244,9 @@ int grid_args(pa_field* in, int comp_in, pa_field* out, int comp_out, GridArgs& 
         LevArgs& A = ga.L[l];
         A.boxes = h->lev[l]->boxes.p;
         A.lay_in = li; A.lay_out = lo;
+        A.nbr = h->lev[l]->nbr.p;
+        A.peers = in->peers_d[l]->p;
+        A.in_comp = comp_in;
         A.in = in->slab[l] ? in->slab[l] + (long long)comp_in * in->cs[l] : nullptr;
         A.out = out->slab[l] ? out->slab[l] + (long long)comp_out * out->cs[l] : nullptr;
         A.cs_in = in->cs[l]; A.cs_out = out->cs[l];
@@ -251,8 +265,13 @@ bool use_tma(pa_hier* h, int nin) {
 }
 
 // stencil over levels [l0, l1]
-int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex, int nvar, int l0, int l1, int in_ng) {
+int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex, int nvar, int l0, int l1, int in_ng,
+                const pa_field* in) {
     const int nin = (mode == MODE_DIV) ? 3 : 1;
+    if (mode == MODE_NORMAL_S && !(in_ng == 1 && use_tma(h, 1))) return fail(PA_ERR_STATE, "internal: MODE_NORMAL_S needs the TMA pipeline");
+    if (in->peers_missing > 0)
+        return fail(PA_ERR_STATE, "this hierarchy uses peer links (PA_HIER_PEER_LINKS): map every rank's slab of the input field first "
+                                  "(pa_field_ipc_handle -> exchange -> pa_field_map_peer)");
     // the TMA tile table is sized for the nghost == 1 layout (row pitch nx+4)
     if (in_ng == 1 && use_tma(h, nin)) {
         TileTable& T = h->tiles_tma;
@@ -272,31 +291,37 @@ int check_field(const pa_field* f, int comp, int ncomp, const char* who) {
     return PA_OK;
 }
 
-// ghost fill of comps [comp, comp+ncomp) on levels [l0, l1]: halo gather per level + one BC-fill launch
-int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1) {
+// ghost fill of comps [comp, comp+ncomp) on levels [l0, l1]: halo gather per level + one BC-fill launch.
+// linked_too = false (the product path): faces with a neighbour link are skipped -- the stencil kernels read the
+// neighbour in place; true: every ghost cell of the width-1 face layers is materialised (pa_fill_ghosts).
+int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1, bool linked_too, GhostXform xf = GhostXform{0, 0.0, 1.0}) {
     pa_hier* h = f->h;
     Hier& H = h->H;
     CHK(ensure_device(h));
     if (f->ng < 1) return fail(PA_ERR_ARG, "ghost fill needs a field with nghost >= 1");
     const double* recv = nullptr;
-    if (H.nranks > 1) {
+    if (H.nranks > 1 && H.xplan.recv_prefix[H.nranks] + H.xplan.send_prefix[H.nranks] > 0) {
         if (f->recv_ncomp != ncomp || f->recv_comp0 != comp)
             return fail(PA_ERR_STATE, "multi-rank ghost fill: exchange this component range first (pa_exchange_pack -> transport -> pa_exchange_mark_received)");
         recv = h->recv_slab.p;
     }
+    if (linked_too && f->peers_missing > 0)
+        return fail(PA_ERR_STATE, "peer links: map every rank's slab of this field first (pa_field_map_peer)");
     GridArgs ga;
     CHK(grid_args_inplace(f, comp, ga));
     for (int l = l0; l <= l1; ++l) {
         const HaloTable& T = H.halo_cross[l];
-        CU(launch_halo(h->lev[l]->halo_cross.p, (int)T.tags.size(), T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out,
-                       f->cs[l], ncomp, recv, t_stream));
+        const int t1 = linked_too ? (int)T.tags.size() : T.ntags_unlinked;
+        const long long c1 = linked_too ? T.ncells : T.ncells_unlinked;
+        CU(launch_halo(h->lev[l]->halo_cross.p, 0, t1, 0, c1, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out,
+                       f->cs[l], ncomp, recv, ga.L[l].peers, comp, H.rank, xf, t_stream));
     }
     const FaceTable& F = H.faces;
     long long r0 = F.level_rec_begin[l0], r1 = F.level_rec_begin[l1 + 1];
     if (r1 > r0) {
         long long c0 = F.recs[r0].start;
         long long c1 = (r1 < (long long)F.recs.size()) ? F.recs[r1].start : F.ncells;
-        CU(launch_bcfill(h->face_recs.p, h->face_level.p, r0, r1, c0, c1, h->face_flags.p, h->face_cidx.p, ga, ncomp, recv, t_stream));
+        CU(launch_bcfill(h->face_recs.p, h->face_level.p, r0, r1, c0, c1, h->face_flags.p, h->face_cidx.p, ga, ncomp, recv, xf, t_stream));
     }
     return PA_OK;
 }
@@ -332,6 +357,12 @@ int64_t pa_kernel_launches(void) { return g_launches; }
 
 int pa_hier_create(pa_hier** out, int nlev, const pa_level_desc* levels, const int is_per[3], const int bc_kind[3],
                    int rank, int nranks) {
+    return pa_hier_create2(out, nlev, levels, is_per, bc_kind, rank, nranks, 0u);
+}
+
+int pa_hier_create2(pa_hier** out, int nlev, const pa_level_desc* levels, const int is_per[3], const int bc_kind[3],
+                    int rank, int nranks, unsigned flags) {
+    if (flags & ~(unsigned)(PA_HIER_PEER_LINKS | PA_HIER_NO_LINKS)) return fail(PA_ERR_ARG, "pa_hier_create2: unknown flag");
     if (!out || !levels || !is_per) return fail(PA_ERR_ARG, "pa_hier_create: null argument");
     std::vector<pa_level_desc_host> L(std::max(nlev, 0));
     for (int l = 0; l < nlev; ++l) {
@@ -343,7 +374,7 @@ int pa_hier_create(pa_hier** out, int nlev, const pa_level_desc* levels, const i
         if (!L[l].boxes) return fail(PA_ERR_ARG, "pa_hier_create: level without boxes");
     }
     auto h = std::make_unique<pa_hier>();
-    std::string e = h->H.init(nlev, L.data(), is_per, bc_kind, rank, nranks);
+    std::string e = h->H.init(nlev, L.data(), is_per, bc_kind, rank, nranks, flags);
     if (!e.empty()) return fail(PA_ERR_ARG, "pa_hier_create: " + e);
     *out = h.release();
     return PA_OK;
@@ -406,9 +437,15 @@ int pa_field_alloc(pa_hier* h, int ncomp, int nghost, pa_field** out) {
     f->h = h; f->ncomp = ncomp; f->ng = nghost;
     f->slab.assign(h->H.nlev, nullptr);
     f->cs.assign(h->H.nlev, 0);
+    f->peers_h.assign(h->H.nlev, std::vector<PaPeerSlab>(h->H.nranks, PaPeerSlab{nullptr, 0}));
+    for (int l = 0; l < h->H.nlev; ++l) f->peers_d.push_back(std::make_unique<DevBuf<PaPeerSlab>>());
     for (int l = 0; l < h->H.nlev; ++l) {
         const Layout& Y = h->H.layout(l, nghost);
         f->cs[l] = Y.comp_stride;
+        for (int r = 0; r < h->H.nranks; ++r) {
+            f->peers_h[l][r].cs = Y.rank_comp_stride[r];
+            if (r != h->H.rank && h->H.peer_links && Y.rank_comp_stride[r] > 0) ++f->peers_missing;
+        }
         size_t n = (size_t)Y.comp_stride * ncomp + 16;          // 16 doubles of slack: pair loads may touch one element past a row
         if (Y.comp_stride == 0) continue;
         cudaError_t e = cudaMalloc(&f->slab[l], n * sizeof(double));
@@ -421,11 +458,17 @@ int pa_field_alloc(pa_hier* h, int ncomp, int nghost, pa_field** out) {
         int err = PA_OK;
         if (!dev_layout(h, l, nghost, &err)) return err;
     }
+    for (int l = 0; l < h->H.nlev; ++l) {
+        f->peers_h[l][h->H.rank].base = f->slab[l];
+        CU(f->peers_d[l]->upload(f->peers_h[l], t_stream));
+    }
+    CU(cudaStreamSynchronize(t_stream));               // peers_h may be modified by pa_field_map_peer
     *out = f.release();
     return PA_OK;
 }
 int pa_field_free(pa_field* f) {
     if (!f) return PA_OK;
+    for (void* p : f->ipc_mapped) cudaIpcCloseMemHandle(p);
     for (double* p : f->slab) if (p) cudaFree(p);
     delete f;
     return PA_OK;
@@ -437,6 +480,38 @@ int64_t pa_field_bytes(const pa_field* f) {
     int64_t s = 0;
     for (size_t l = 0; l < f->cs.size(); ++l) s += (int64_t)f->cs[l] * f->ncomp * 8;
     return s;
+}
+
+// ---- peer mapping (one process per GPU; CUDA IPC over NVLink) --------------------------------------------------
+int pa_field_ipc_handle(const pa_field* f, int lev, void* handle64) {
+    if (!f || !handle64 || lev < 0 || lev >= f->h->H.nlev) return fail(PA_ERR_ARG, "pa_field_ipc_handle: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memset(handle64, 0, 64);
+    if (!f->slab[lev]) return PA_OK;                   // this rank owns no box of the level
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, f->slab[lev]));
+    std::memcpy(handle64, &hd, 64);
+    return PA_OK;
+}
+
+int pa_field_map_peer(pa_field* f, int lev, int peer_rank, const void* handle64) {
+    if (!f || !handle64 || lev < 0 || lev >= f->h->H.nlev || peer_rank < 0 || peer_rank >= f->h->H.nranks)
+        return fail(PA_ERR_ARG, "pa_field_map_peer: bad argument");
+    pa_hier* h = f->h;
+    if (peer_rank == h->H.rank) return PA_OK;
+    PaPeerSlab& S = f->peers_h[lev][peer_rank];
+    if (S.cs == 0) return PA_OK;                       // the peer owns no box of this level
+    if (S.base) return fail(PA_ERR_STATE, "pa_field_map_peer: this (level, rank) is already mapped");
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    f->ipc_mapped.push_back(p);
+    S.base = (const double*)p;
+    CU(f->peers_d[lev]->upload(f->peers_h[lev], t_stream));
+    CU(cudaStreamSynchronize(t_stream));
+    if (h->H.peer_links && f->peers_missing > 0) --f->peers_missing;
+    return PA_OK;
 }
 
 static int box_copy(const pa_field* f, int lev, int box, int comp, double* host, bool to_dev, bool grown) {
@@ -473,18 +548,62 @@ int pa_debug_download_grown(const pa_field* f, int lev, int box, int comp, doubl
     return PA_OK;
 }
 
+// Whole-level transfers.  Boxes with rows of >= 512 bytes go box by box as pitched 3-D DMA copies straight between the
+// caller's (pinned) buffer and the padded device layout: no staging buffer, no kernel, nothing shared between streams,
+// so uploads, compute and downloads of different components can overlap on different streams.  Levels made of small
+// boxes (short rows are slow for the copy engines) take one contiguous copy through a per-stream staging buffer plus one
+// pack / unpack kernel.
+static bool level_uses_dma(const pa_hier* h, int lev) {
+    const Level& V = h->H.lev[lev];
+    for (int gb : V.local) if (V.boxes[gb].len(0) * 8 < 512) return false;
+    return true;
+}
+
+static int level_dma(const pa_field* f, int lev, int comp, double* host, bool to_dev) {
+    pa_hier* h = f->h;
+    const Level& V = h->H.lev[lev];
+    const Layout& Y = h->H.layout(lev, f->ng);
+    long long ho = 0;
+    for (size_t lb = 0; lb < V.local.size(); ++lb) {
+        const Box& B = V.boxes[V.local[lb]];
+        const PaLayDev& y = Y.lay[lb];
+        const size_t nx = B.len(0), ny = B.len(1), nz = B.len(2);
+        cudaMemcpy3DParms p;
+        std::memset(&p, 0, sizeof(p));
+        cudaPitchedPtr hp = make_cudaPitchedPtr(host + ho, nx * 8, nx * 8, ny);
+        cudaPitchedPtr dp = make_cudaPitchedPtr(f->slab[lev] + (long long)comp * f->cs[lev] + y.off, (size_t)y.P * 8, (size_t)y.P * 8, (size_t)(y.PS / y.P));
+        cudaPos dpos = make_cudaPos((size_t)(y.ng + y.xoff) * 8, (size_t)y.ng, (size_t)y.ng);
+        if (to_dev) { p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+        else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
+        p.extent = make_cudaExtent(nx * 8, ny, nz);
+        CU(cudaMemcpy3DAsync(&p, t_stream));
+        ho += (long long)B.npts();
+    }
+    return PA_OK;
+}
+
+static int stream_staging(pa_hier* h, size_t n, double** out) {
+    auto& slot = h->staging[t_stream];
+    if (!slot) slot = std::make_unique<DevBuf<double>>();
+    CU(slot->reserve(n));
+    *out = slot->p;
+    return PA_OK;
+}
+
 int pa_field_upload_level(pa_field* f, int lev, int comp, const double* host) {
     if (!f || lev < 0 || lev >= f->h->H.nlev || comp < 0 || comp >= f->ncomp || !host) return fail(PA_ERR_ARG, "pa_field_upload_level: bad argument");
     pa_hier* h = f->h;
     LevelDev& D = *h->lev[lev];
     long long n = D.host_off_h.back();
     if (n == 0) return PA_OK;
-    CU(h->staging.reserve((size_t)n));
-    CU(cudaMemcpyAsync(h->staging.p, host, (size_t)n * 8, cudaMemcpyHostToDevice, t_stream));
+    if (level_uses_dma(h, lev)) return level_dma(f, lev, comp, const_cast<double*>(host), true);
+    double* stg = nullptr;
+    CHK(stream_staging(h, (size_t)n, &stg));
+    CU(cudaMemcpyAsync(stg, host, (size_t)n * 8, cudaMemcpyHostToDevice, t_stream));
     int err = PA_OK;
     const PaLayDev* ly = dev_layout(h, lev, f->ng, &err);
     if (!ly) return err;
-    CU(launch_unpack_valid(D.boxes.p, ly, D.host_off.p, (int)h->H.lev[lev].local.size(), n, h->staging.p,
+    CU(launch_unpack_valid(D.boxes.p, ly, D.host_off.p, (int)h->H.lev[lev].local.size(), n, stg,
                            f->slab[lev] + (long long)comp * f->cs[lev], t_stream));
     return PA_OK;
 }
@@ -494,13 +613,15 @@ int pa_field_download_level(const pa_field* f, int lev, int comp, double* host) 
     LevelDev& D = *h->lev[lev];
     long long n = D.host_off_h.back();
     if (n == 0) return PA_OK;
-    CU(h->staging.reserve((size_t)n));
+    if (level_uses_dma(h, lev)) return level_dma(f, lev, comp, host, false);
+    double* stg = nullptr;
+    CHK(stream_staging(h, (size_t)n, &stg));
     int err = PA_OK;
     const PaLayDev* ly = dev_layout(h, lev, f->ng, &err);
     if (!ly) return err;
     CU(launch_pack_valid(D.boxes.p, ly, D.host_off.p, (int)h->H.lev[lev].local.size(), n,
-                         f->slab[lev] + (long long)comp * f->cs[lev], h->staging.p, t_stream));
-    CU(cudaMemcpyAsync(host, h->staging.p, (size_t)n * 8, cudaMemcpyDeviceToHost, t_stream));
+                         f->slab[lev] + (long long)comp * f->cs[lev], stg, t_stream));
+    CU(cudaMemcpyAsync(host, stg, (size_t)n * 8, cudaMemcpyDeviceToHost, t_stream));
     return PA_OK;
 }
 int pa_field_set_val(pa_field* f, int comp, int ncomp, double v) {
@@ -521,14 +642,16 @@ int pa_fill_boundary(pa_field* f, int comp, int ncomp, int cross) {
     GridArgs ga;
     CHK(grid_args_inplace(f, comp, ga));
     const double* recv = nullptr;
-    if (H.nranks > 1) {
+    if (H.nranks > 1 && H.xplan.recv_prefix[H.nranks] + H.xplan.send_prefix[H.nranks] > 0) {
         if (f->recv_ncomp != ncomp || f->recv_comp0 != comp) return fail(PA_ERR_STATE, "exchange this component range first");
         recv = h->recv_slab.p;
     }
+    if (f->peers_missing > 0) return fail(PA_ERR_STATE, "peer links: map every rank's slab of this field first (pa_field_map_peer)");
     for (int l = 0; l < H.nlev; ++l) {
         if (cross) {
             const HaloTable& T = H.halo_cross[l];
-            CU(launch_halo(h->lev[l]->halo_cross.p, (int)T.tags.size(), T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out, f->cs[l], ncomp, recv, t_stream));
+            CU(launch_halo(h->lev[l]->halo_cross.p, 0, (int)T.tags.size(), 0, T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out, f->cs[l], ncomp, recv,
+                           ga.L[l].peers, comp, H.rank, GhostXform{0, 0.0, 1.0}, t_stream));
         } else {
             auto key = std::make_pair(l, f->ng);
             const HaloTable& T = H.halo_full(l, f->ng);
@@ -538,7 +661,8 @@ int pa_fill_boundary(pa_field* f, int comp, int ncomp, int cross) {
                 CU(buf->upload(T.tags, t_stream));
                 it = h->halo_full.emplace(key, std::move(buf)).first;
             }
-            CU(launch_halo(it->second->p, (int)T.tags.size(), T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out, f->cs[l], ncomp, nullptr, t_stream));
+            CU(launch_halo(it->second->p, 0, (int)T.tags.size(), 0, T.ncells, ga.L[l].boxes, ga.L[l].lay_in, ga.L[l].out, f->cs[l], ncomp, nullptr,
+                           ga.L[l].peers, comp, H.rank, GhostXform{0, 0.0, 1.0}, t_stream));
         }
     }
     return PA_OK;
@@ -549,7 +673,7 @@ int pa_fill_ghosts(pa_field* f, int comp, int ncomp, int lev_lo, int lev_hi) {
     if (lev_lo < 0) lev_lo = 0;
     if (lev_hi < 0 || lev_hi >= f->h->H.nlev) lev_hi = f->h->H.nlev - 1;
     if (lev_lo > lev_hi) return fail(PA_ERR_ARG, "pa_fill_ghosts: empty level range");
-    return fill_ghosts_impl(f, comp, ncomp, lev_lo, lev_hi);
+    return fill_ghosts_impl(f, comp, ncomp, lev_lo, lev_hi, true);
 }
 
 // ---------------------------------------------------------------------------------------------- exchange
@@ -613,14 +737,14 @@ int pa_grad_phases(pa_field* in, int comp_in, int nvar, pa_field* out, int comp_
     if (in->h != out->h) return fail(PA_ERR_ARG, "pa_grad: fields belong to different hierarchies");
     if (in->ng < 1) return fail(PA_ERR_ARG, "pa_grad: input field needs nghost >= 1");
     pa_hier* h = in->h;
-    if (phases & 1) CHK(fill_ghosts_impl(in, comp_in, nvar, 0, h->H.nlev - 1));
+    if (phases & 1) CHK(fill_ghosts_impl(in, comp_in, nvar, 0, h->H.nlev - 1, false));
     if (!(phases & 2)) return PA_OK;
     CHK(ensure_device(h));
     GridArgs ga;
     CHK(grid_args(in, comp_in, out, comp_out, ga));
     StencilExtra ex;
     std::memset(&ex, 0, sizeof(ex));
-    return run_stencil(h, MODE_GRAD, ga, ex, nvar, 0, h->H.nlev - 1, in->ng);
+    return run_stencil(h, MODE_GRAD, ga, ex, nvar, 0, h->H.nlev - 1, in->ng, in);
 }
 
 // ---------------------------------------------------------------------------------------------- curvature
@@ -659,19 +783,6 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     if (opts->do_strain && opts->get_strain_tensor) { cROST = next; next += 9; }
     const int cVN = opts->do_velnormal ? next++ : -1;
 
-    // 1. progress variable on valid cells of every level (curvature.cpp:310-321)
-    const double invdenom = 1.0 / (opts->prog_max - opts->prog_min);
-    for (int l = 0; l < nlev; ++l) {
-        int err = PA_OK;
-        const PaLayDev* li = dev_layout(h, l, state->ng, &err);
-        if (!li) return err;
-        const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
-        if (!lo) return err;
-        CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_S * state->cs[l],
-                           out->slab[l] + (long long)cP * out->cs[l], opts->prog_min, invdenom, t_stream));
-    }
-    // 2. ghost cells of c on all levels (coarse data = c on the next coarser level), then G -> nrm -> n
-    CHK(fill_ghosts_impl(out, cP, 1, 0, nlev - 1));
     StencilExtra ex;
     std::memset(&ex, 0, sizeof(ex));
     if (opts->do_gauss) {
@@ -679,8 +790,35 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
         for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
     }
     GridArgs ga;
-    CHK(grid_args(out, cP, out, cN, ga));
-    CHK(run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, out->ng));
+    const double invdenom = 1.0 / (opts->prog_max - opts->prog_min);
+    const char* no_fuse = getenv("PA_CURV_UNFUSED");
+    if (state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
+        // 1+2 fused.  The progress pass (curvature.cpp:310-321) rides in the stencil's loader: valid cells stay S and are
+        // normalised as they are read; the few ghost cells that must be materialised (unlinked faces) are written in
+        // progress space by the ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel
+        // writes Progress and n = G/nrm; Progress never makes a separate round trip through HBM.
+        GhostXform xf{1, opts->prog_min, invdenom};
+        CHK(fill_ghosts_impl(state, comp_S, 1, 0, nlev - 1, false, xf));
+        for (int l = 0; l < nlev; ++l) ex.cout[l] = out->slab[l] ? out->slab[l] + (long long)cP * out->cs[l] : nullptr;
+        ex.pmin = opts->prog_min; ex.inv = invdenom;
+        CHK(grid_args(state, comp_S, out, cN, ga));
+        CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
+    } else {
+        // 1. progress variable on valid cells of every level (curvature.cpp:310-321)
+        for (int l = 0; l < nlev; ++l) {
+            int err = PA_OK;
+            const PaLayDev* li = dev_layout(h, l, state->ng, &err);
+            if (!li) return err;
+            const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+            if (!lo) return err;
+            CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_S * state->cs[l],
+                               out->slab[l] + (long long)cP * out->cs[l], opts->prog_min, invdenom, t_stream));
+        }
+        // 2. ghost cells of c on all levels (coarse data = c on the next coarser level), then G -> nrm -> n
+        CHK(fill_ghosts_impl(out, cP, 1, 0, nlev - 1, false));
+        CHK(grid_args(out, cP, out, cN, ga));
+        CHK(run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, out->ng, out));
+    }
     // 3. divergence of n.  Without the threshold clip every level's coarse data is final after step 2, so one
     //    batched ghost fill + one stencil launch cover the hierarchy; with it, level l needs the CLIPPED n of l-1
     //    (curvature.cpp:514-518 reads flame_normal[lev-1] after :549-567 modified it), so levels run in order.
@@ -690,12 +828,12 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     for (int l = 0; l < nlev; ++l) ex.prog[l] = out->slab[l] + (long long)cP * out->cs[l];
     CHK(grid_args(out, cN, out, cK, ga));
     if (!opts->do_threshold) {
-        CHK(fill_ghosts_impl(out, cN, 3, 0, nlev - 1));
-        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, nlev - 1, out->ng));
+        CHK(fill_ghosts_impl(out, cN, 3, 0, nlev - 1, false));
+        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, nlev - 1, out->ng, out));
     } else {
         for (int l = 0; l < nlev; ++l) {
-            CHK(fill_ghosts_impl(out, cN, 3, l, l));
-            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng));
+            CHK(fill_ghosts_impl(out, cN, 3, l, l, false));
+            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng, out));
             int err = PA_OK;
             const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
             if (!lo) return err;
@@ -707,12 +845,12 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     if (opts->do_gauss) {
         // Hessian rows: grad3 of each un-normalised gradient component, ghosts by the same rules with coarse = G on l-1
         CHK(tmp_field(h, &h->tmpH, 9));
-        CHK(fill_ghosts_impl(h->tmpG, 0, 3, 0, nlev - 1));
+        CHK(fill_ghosts_impl(h->tmpG, 0, 3, 0, nlev - 1, false));
         StencilExtra e0;
         std::memset(&e0, 0, sizeof(e0));
         for (int d = 0; d < 3; ++d) {
             CHK(grid_args(h->tmpG, d, h->tmpH, 3 * d, ga));
-            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, h->tmpG->ng));
+            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, h->tmpG->ng, h->tmpG));
         }
         for (int l = 0; l < nlev; ++l) {
             int err = PA_OK;
@@ -725,7 +863,7 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     }
     if (opts->do_strain) {
         // velocity gradients: ghosts of u_i by the same rules (curvature.cpp:686-717); needs ghost cells in `state`
-        CHK(fill_ghosts_impl(state, comp_vel, 3, 0, nlev - 1));
+        CHK(fill_ghosts_impl(state, comp_vel, 3, 0, nlev - 1, false));
         pa_field* dU = nullptr;
         int c0 = 0;
         if (cROST >= 0) { dU = out; c0 = cROST; }
@@ -734,7 +872,7 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
         std::memset(&e0, 0, sizeof(e0));
         for (int d = 0; d < 3; ++d) {
             CHK(grid_args(state, comp_vel + d, dU, c0 + 3 * d, ga));
-            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, state->ng));
+            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, state->ng, state));
         }
         for (int l = 0; l < nlev; ++l) {
             int err = PA_OK;
@@ -782,7 +920,7 @@ int pa_debug_fb_source_map(pa_hier* h, int lev, int nghost, int cross, int64_t* 
                     int di = t.dlo[0] + i, dj = t.dlo[1] + j, dk = t.dlo[2] + k;
                     int64_t v = -2;     // remote source
                     if (t.sbox >= 0) {
-                        int gs = V.local[t.sbox];
+                        int gs = V.ext[t.sbox];
                         const Box& S = V.boxes[gs];
                         int64_t lin = ((int64_t)(dk + t.shift[2] - S.lo[2]) * S.len(1) + (dj + t.shift[1] - S.lo[1])) * S.len(0) + (di + t.shift[0] - S.lo[0]);
                         v = ((int64_t)gs << 40) | lin;
@@ -820,6 +958,19 @@ int pa_debug_face_coef(pa_hier* h, int lev, int box, int face, int* kind, int* n
     if (kind) *kind = R->kind;
     if (nx) *nx = R->nx;
     if (coef) for (int m = 0; m < 4; ++m) coef[m] = R->coef[m];
+    return PA_OK;
+}
+
+int pa_debug_links(pa_hier* h, int lev, int box, int out[30]) {
+    if (!h || !out || lev < 0 || lev >= h->H.nlev || box < 0 || box >= (int)h->H.lev[lev].boxes.size())
+        return fail(PA_ERR_ARG, "pa_debug_links: bad argument");
+    const Level& V = h->H.lev[lev];
+    for (int f = 0; f < 6; ++f) {
+        const Level::Link& K = V.link[box][f];
+        out[5 * f] = K.nb;
+        out[5 * f + 1] = K.nb >= 0 ? V.owner[K.nb] : -1;
+        for (int d = 0; d < 3; ++d) out[5 * f + 2 + d] = K.nb >= 0 ? V.boxes[box].lo[d] + K.shift[d] - V.boxes[K.nb].lo[d] : 0;
+    }
     return PA_OK;
 }
 

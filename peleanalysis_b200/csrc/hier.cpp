@@ -66,8 +66,11 @@ static void box_diff(const Box& a, const Box& b, std::vector<Box>& out) {
     }
 }
 
-std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, const int* bck, int rank_, int nranks_) {
+std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, const int* bck, int rank_, int nranks_,
+                       unsigned flags) {
     auto t0 = std::chrono::steady_clock::now();
+    peer_links = (flags & 1u) != 0;
+    no_links = (flags & 2u) != 0;
     if (nlev_ < 1 || nlev_ > PA_MAX_LEVELS) return "number of levels must be in [1," + std::to_string(PA_MAX_LEVELS) + "]";
     if (nranks_ < 1 || rank_ < 0 || rank_ >= nranks_) return "bad rank / nranks";
     nlev = nlev_; rank = rank_; nranks = nranks_;
@@ -111,6 +114,7 @@ std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, c
         }
         V.hash.build(V.boxes);
     }
+    build_links();
     halo_cross.assign(nlev, HaloTable());
     xplan = ExchangePlan();
     xplan.send_prefix.assign(nranks + 1, 0);
@@ -131,9 +135,12 @@ const Layout& Hier::layout(int l, int ng) {
     Layout Y;
     Y.ng = ng;
     const Level& V = lev[l];
-    long long off = 0;
-    for (int gb : V.local) {
+    // every rank packs ITS boxes (ascending global id) back to back, so any rank can compute any other rank's layout
+    std::vector<PaLayDev> all(V.boxes.size());
+    Y.rank_comp_stride.assign(nranks, 0);
+    for (size_t gb = 0; gb < V.boxes.size(); ++gb) {
         const Box& B = V.boxes[gb];
+        long long& off = Y.rank_comp_stride[V.owner[gb]];
         PaLayDev e;
         e.ng = ng;
         e.xoff = ng & 1;                                   // (xoff + ng) even -> first valid cell 16-byte aligned
@@ -143,9 +150,10 @@ const Layout& Hier::layout(int l, int ng) {
         e.off = off;
         long long sz = (long long)e.PS * (B.len(2) + 2 * ng);
         off += (sz + 15) & ~15LL;                          // every box starts 128-byte aligned
-        Y.lay.push_back(e);
+        all[gb] = e;
     }
-    Y.comp_stride = off;
+    for (int gb : V.ext) Y.lay.push_back(all[gb]);
+    Y.comp_stride = Y.rank_comp_stride[rank];
     return layouts_.emplace(key, std::move(Y)).first->second;
 }
 
@@ -162,12 +170,15 @@ static void sort_isects(std::vector<std::pair<int, Box>>& v) {
     std::sort(v.begin(), v.end(), [](const std::pair<int, Box>& a, const std::pair<int, Box>& b) { return a.first < b.first; });
 }
 
-static void halo_needs_cross(const Hier& H, int l, int gb, std::vector<HaloNeed>& out) {
+enum { NEED_ALL = 0, NEED_UNLINKED = 1, NEED_LINKED = 2 };
+
+static void halo_needs_cross(const Hier& H, int l, int gb, std::vector<HaloNeed>& out, int which = NEED_ALL) {
     const Level& V = H.lev[l];
     std::vector<std::array<int, 3>> sh;
     H.periodic_shifts(V.dom, 1, sh);
     std::vector<std::pair<int, Box>> is;
     for (int face = 0; face < 6; ++face) {
+        if (which != NEED_ALL && H.linked(l, gb, face) != (which == NEED_LINKED)) continue;
         Box slab = face_plane(V.boxes[gb], face, 1, 0);
         for (auto& s : sh) {
             is.clear();
@@ -261,6 +272,60 @@ static inline long long cell_id(int lev, int gbox, const Box& B, int i, int j, i
     return ((long long)lev << 56) | ((long long)gbox << 32) | lin;
 }
 
+// Neighbour links (see PaNbrFace): face `f` of box gb is linked when its width-1 ghost layer, under exactly one
+// periodic shift, lies inside exactly one same-level box with the same x and y extent (=> same row pitch and plane
+// stride, so "ghost address + constant" addresses the neighbour's cell), owned by the same rank unless peer links
+// are enabled.  Computed for every box of the level because senders must know which of a peer's faces are linked.
+void Hier::build_links() {
+    for (int l = 0; l < nlev; ++l) {
+        Level& V = lev[l];
+        V.link.assign(V.boxes.size(), std::array<Level::Link, 6>());
+        V.ext = V.local;
+        V.g2e.assign(V.boxes.size(), -1);
+        for (size_t lb = 0; lb < V.local.size(); ++lb) V.g2e[V.local[lb]] = (int)lb;
+        if (no_links) { V.nbr.assign(V.local.size(), PaNbr()); for (auto& n : V.nbr) for (auto& f : n.f) { f.nb = -1; f.rank = rank; f.rel[0] = f.rel[1] = f.rel[2] = 0; f.pad = 0; } continue; }
+        std::vector<std::array<int, 3>> sh;
+        periodic_shifts(V.dom, 1, sh);
+        for (int gb = 0; gb < (int)V.boxes.size(); ++gb) {
+            const Box& B = V.boxes[gb];
+            for (int face = 0; face < 6; ++face) {
+                Box plane = face_plane(B, face, 1, 0);
+                int hits = 0, hk = -1;
+                std::array<int, 3> hs{0, 0, 0};
+                long long hn = 0;
+                for (auto& s : sh)
+                    V.hash.query(plane.shifted(s.data()), [&](int k, const Box& ib) { ++hits; hk = k; hs = s; hn = ib.npts(); });
+                if (hits != 1 || hn != plane.npts()) continue;
+                const Box& N = V.boxes[hk];
+                if (N.len(0) != B.len(0) || N.len(1) != B.len(1)) continue;
+                if (face % 3 == 0 && B.len(0) < 3) continue;        // the x-pair kernels want distinct first / last pairs
+                if (V.owner[hk] != V.owner[gb] && !peer_links) continue;
+                Level::Link& K = V.link[gb][face];
+                K.nb = hk;
+                for (int d = 0; d < 3; ++d) K.shift[d] = hs[d];
+            }
+        }
+        // extended index: peer-owned link targets of local boxes
+        for (int gb : V.local)
+            for (int face = 0; face < 6; ++face) {
+                int k = V.link[gb][face].nb;
+                if (k >= 0 && V.g2e[k] < 0) { V.g2e[k] = (int)V.ext.size(); V.ext.push_back(k); }
+            }
+        V.nbr.assign(V.local.size(), PaNbr());
+        for (size_t lb = 0; lb < V.local.size(); ++lb) {
+            const Box& B = V.boxes[V.local[lb]];
+            for (int face = 0; face < 6; ++face) {
+                const Level::Link& K = V.link[V.local[lb]][face];
+                PaNbrFace& F = V.nbr[lb].f[face];
+                F.nb = (K.nb >= 0) ? V.g2e[K.nb] : -1;
+                F.rank = (K.nb >= 0) ? V.owner[K.nb] : rank;
+                for (int d = 0; d < 3; ++d) F.rel[d] = (K.nb >= 0) ? B.lo[d] + K.shift[d] - V.boxes[K.nb].lo[d] : 0;
+                F.pad = 0;
+            }
+        }
+    }
+}
+
 void Hier::build_exchange() {
     // Walk every (level, dst box) in canonical order; entries whose source owner differs from the dst owner are
     // exchanged.  The stream from rank p to rank q is the subsequence with (src owner p, dst owner q); both sides
@@ -275,7 +340,7 @@ void Hier::build_exchange() {
         for (int gb = 0; gb < (int)V.boxes.size(); ++gb) {
             int downer = V.owner[gb];
             hn.clear();
-            halo_needs_cross(*this, l, gb, hn);
+            halo_needs_cross(*this, l, gb, hn, NEED_UNLINKED);     // linked faces are read in place, never exchanged
             for (auto& n : hn) {
                 int sowner = V.owner[n.sbox];
                 if (sowner == downer) continue;
@@ -366,20 +431,22 @@ void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remo
     // halo needs first, then its coarse needs)
     std::vector<long long> rcur;
     if (cross && allow_remote && nranks > 1) rcur = xplan.level_recv_cell0[l];
+    std::vector<PaHaloTag> linked;
     if (cross) {
         std::vector<HaloNeed> hn; std::vector<CrseNeed> cn;
         for (int gb : V.local) {
             hn.clear();
-            halo_needs_cross(*this, l, gb, hn);
+            halo_needs_cross(*this, l, gb, hn, NEED_UNLINKED);
             for (auto& n : hn) {
                 PaHaloTag t;
                 std::memset(&t, 0, sizeof(t));
                 t.dbox = V.g2l[gb];
                 for (int d = 0; d < 3; ++d) { t.dlo[d] = n.dst.lo[d]; t.n[d] = n.dst.len(d); t.shift[d] = n.shift[d]; }
                 int so = V.owner[n.sbox];
+                t.srank = so;
                 if (so == rank) { t.sbox = V.g2l[n.sbox]; t.rsrc = -1; out.tags.push_back(t); }
                 else {
-                    t.sbox = -1; t.pad = n.sbox; t.rsrc = rcur[so]; rcur[so] += n.dst.npts(); remote.push_back(t);
+                    t.sbox = -1; t.rsrc = rcur[so]; rcur[so] += n.dst.npts(); remote.push_back(t);
                     const Box& SB = V.boxes[n.sbox];
                     long long q = 0;
                     for (int k = n.dst.lo[2]; k <= n.dst.hi[2]; ++k)
@@ -395,6 +462,19 @@ void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remo
                     cn.clear(); crse_needs(*this, l, gb, face, cn);
                     for (auto& n : cn) if (lev[l - 1].owner[n.cbox] != rank) rcur[lev[l - 1].owner[n.cbox]] += n.reg.npts();
                 }
+            // linked faces: materialised only on request, straight from the neighbour (local or peer-mapped)
+            hn.clear();
+            halo_needs_cross(*this, l, gb, hn, NEED_LINKED);
+            for (auto& n : hn) {
+                PaHaloTag t;
+                std::memset(&t, 0, sizeof(t));
+                t.dbox = V.g2l[gb];
+                for (int d = 0; d < 3; ++d) { t.dlo[d] = n.dst.lo[d]; t.n[d] = n.dst.len(d); t.shift[d] = n.shift[d]; }
+                t.srank = V.owner[n.sbox];
+                t.sbox = V.g2e[n.sbox];
+                t.rsrc = -1;
+                linked.push_back(t);
+            }
         }
     } else {
         // full FillBoundary: grow(vbx, ng) + p against every box, minus vbx (AMReX_FabArrayBase.cpp:739-794)
@@ -418,6 +498,7 @@ void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remo
                         std::memset(&t, 0, sizeof(t));
                         t.dbox = V.g2l[gb];
                         t.sbox = V.g2l[e.first];       // caller guarantees single rank
+                        t.srank = rank;
                         t.rsrc = -1;
                         for (int d = 0; d < 3; ++d) { t.dlo[d] = p.lo[d]; t.n[d] = p.len(d); t.shift[d] = s[d]; }
                         out.tags.push_back(t);
@@ -428,8 +509,16 @@ void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remo
     }
     out.nlocal_tags = (int)out.tags.size();
     out.tags.insert(out.tags.end(), remote.begin(), remote.end());
+    out.ntags_unlinked = (int)out.tags.size();
+    out.tags.insert(out.tags.end(), linked.begin(), linked.end());
     long long c = 0;
-    for (auto& t : out.tags) { t.start = c; c += (long long)t.n[0] * t.n[1] * t.n[2]; }
+    out.ncells_unlinked = 0;
+    for (size_t i = 0; i < out.tags.size(); ++i) {
+        if ((int)i == out.ntags_unlinked) out.ncells_unlinked = c;
+        PaHaloTag& t = out.tags[i];
+        t.start = c; c += (long long)t.n[0] * t.n[1] * t.n[2];
+    }
+    if (out.ntags_unlinked == (int)out.tags.size()) out.ncells_unlinked = c;
     out.ncells = c;
 }
 
@@ -469,7 +558,7 @@ std::string Hier::build_faces() {
         for (int gb : V.local) {
             const Box& B = V.boxes[gb];
             if (nranks > 1) {                                // this box's halo needs precede its coarse needs in the stream
-                hn.clear(); halo_needs_cross(*this, l, gb, hn);
+                hn.clear(); halo_needs_cross(*this, l, gb, hn, NEED_UNLINKED);
                 for (auto& n : hn) if (V.owner[n.sbox] != rank) rcur[V.owner[n.sbox]] += n.dst.npts();
             }
             for (int face = 0; face < 6; ++face) {

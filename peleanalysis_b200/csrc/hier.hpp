@@ -76,6 +76,14 @@ struct Level {
     std::vector<int> owner;           // global DistributionMapping
     std::vector<int> local;           // global ids of this rank's boxes, ascending
     std::vector<int> g2l;             // global id -> local index or -1
+    // extended box index: this rank's boxes first (same order as `local`), then the boxes of other ranks that are
+    // neighbour-link targets of local boxes (read in place through peer-mapped memory)
+    std::vector<int> ext;             // extended index -> global id
+    std::vector<int> g2e;             // global id -> extended index or -1
+    // neighbour links of EVERY box of the level (global id x 6 faces): sender and receiver must agree on them
+    struct Link { int nb = -1; int shift[3] = {0, 0, 0}; };
+    std::vector<std::array<Link, 6>> link;
+    std::vector<PaNbr> nbr;           // device form, per local box
     BoxHash hash;
     long long ncells = 0, ncells_local = 0;
 };
@@ -83,15 +91,21 @@ struct Level {
 // Layout of one component of every local box of a level for a given ghost width.
 struct Layout {
     int ng = 0;
-    std::vector<PaLayDev> lay;        // per local box
-    long long comp_stride = 0;        // elements per component of the whole level (multiple of 16)
+    std::vector<PaLayDev> lay;        // per box of the extended index (peer boxes: offsets inside THEIR rank's slab)
+    long long comp_stride = 0;        // elements per component of this rank's level slab (multiple of 16)
+    std::vector<long long> rank_comp_stride;   // the same for every rank
 };
 
 // Everything the ghost-fill kernels need for one level at one "mode".
 struct HaloTable {
-    std::vector<PaHaloTag> tags;      // sorted: local-source tags first, then remote-source
+    // order: [faces without a neighbour link: local sources, then recv-slab sources][linked faces]
+    // The product path copies only the first group (the stencil reads linked faces in place); pa_fill_ghosts /
+    // pa_fill_boundary materialise both.
+    std::vector<PaHaloTag> tags;
     long long ncells = 0;             // total cells over all tags
     int nlocal_tags = 0;
+    int ntags_unlinked = 0;
+    long long ncells_unlinked = 0;
 };
 
 struct FaceTable {                    // all levels concatenated, level-major
@@ -121,6 +135,8 @@ class Hier {
 public:
     int nlev = 0;
     int rank = 0, nranks = 1;
+    bool peer_links = false;          // links may cross ranks (every rank's slabs are peer-mapped, PA_HIER_PEER_LINKS)
+    bool no_links = false;            // PA_HIER_NO_LINKS: materialise every ghost cell (reference-style data flow)
     int is_per[3] = {1, 1, 1};
     int bc_kind[3] = {0, 0, 0};
     std::vector<Level> lev;
@@ -131,7 +147,9 @@ public:
     FaceTable faces;
     ExchangePlan xplan;
 
-    std::string init(int nlev, const struct pa_level_desc_host* L, const int* is_per, const int* bc_kind, int rank, int nranks);
+    std::string init(int nlev, const struct pa_level_desc_host* L, const int* is_per, const int* bc_kind, int rank, int nranks,
+                     unsigned flags = 0);
+    bool linked(int l, int gb, int face) const { return lev[l].link[gb][face].nb >= 0; }
 
     const Layout& layout(int l, int ng);      // lazily built, cached
     // full FillBoundary table (all ng layers incl. edges/corners) -- debug / pa_fill_boundary(cross=0); local sources only
@@ -142,6 +160,7 @@ public:
 private:
     std::map<std::pair<int, int>, Layout> layouts_;
     std::map<std::pair<int, int>, HaloTable> halo_full_;
+    void build_links();
     void build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remote);
     std::string build_faces();
     void build_exchange();

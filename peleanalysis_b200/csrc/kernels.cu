@@ -85,11 +85,12 @@ cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t st) {
 // halo_gather: same-level + periodic ghost copies, one launch per level over the precomputed tag table.
 // A tag whose source box lives on another rank reads the recv slab ([cell][comp] order) instead.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_halo(const PaHaloTag* __restrict__ tags, int ntags, long long ncells, const PaBoxDev* __restrict__ boxes,
-                       const PaLayDev* __restrict__ lay, double* __restrict__ base, long long cs, int ncomp,
-                       const double* __restrict__ recv) {
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
-        const PaHaloTag t = tags[upper_idx(tags, 0, ntags, c)];
+__global__ void k_halo(const PaHaloTag* __restrict__ tags, int tag0, int tag1, long long cell0, long long cell1,
+                       const PaBoxDev* __restrict__ boxes, const PaLayDev* __restrict__ lay, double* __restrict__ base,
+                       long long cs, int ncomp, const double* __restrict__ recv, const PaPeerSlab* __restrict__ peers,
+                       int comp0, int rank, GhostXform xf) {
+    for (long long c = cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cell1; c += (long long)gridDim.x * blockDim.x) {
+        const PaHaloTag t = tags[upper_idx(tags, tag0, tag1, c)];
         long long q = c - t.start;
         int i = (int)(q % t.n[0]);
         long long r = q / t.n[0];
@@ -101,17 +102,24 @@ __global__ void k_halo(const PaHaloTag* __restrict__ tags, int ntags, long long 
         if (t.sbox >= 0) {
             const PaBoxDev sb = boxes[t.sbox];
             long long sa = cell_addr(lay[t.sbox], di + t.shift[0] - sb.lo[0], dj + t.shift[1] - sb.lo[1], dk + t.shift[2] - sb.lo[2]);
-            for (int m = 0; m < ncomp; ++m) base[da + m * cs] = base[sa + m * cs];
+            if (t.srank == rank) {
+                for (int m = 0; m < ncomp; ++m) { double v = base[sa + m * cs]; base[da + m * cs] = xf.on ? (v - xf.pmin) * xf.inv : v; }
+            } else {                                   // peer-owned link target: read its slab in place (NVLink)
+                const PaPeerSlab ps = peers[t.srank];
+                const double* s = ps.base + (long long)comp0 * ps.cs + sa;
+                for (int m = 0; m < ncomp; ++m) { double v = s[m * ps.cs]; base[da + m * cs] = xf.on ? (v - xf.pmin) * xf.inv : v; }
+            }
         } else {
             const double* s = recv + (t.rsrc + q) * ncomp;
-            for (int m = 0; m < ncomp; ++m) base[da + m * cs] = s[m];
+            for (int m = 0; m < ncomp; ++m) { double v = s[m]; base[da + m * cs] = xf.on ? (v - xf.pmin) * xf.inv : v; }
         }
     }
 }
-cudaError_t launch_halo(const PaHaloTag* tags, int ntags, long long ncells, const PaBoxDev* boxes, const PaLayDev* lay,
-                        double* base, long long cs, int ncomp, const double* recv, cudaStream_t st) {
-    if (ncells <= 0) return cudaSuccess;
-    k_halo<<<grid_for(ncells, 256), 256, 0, st>>>(tags, ntags, ncells, boxes, lay, base, cs, ncomp, recv);
+cudaError_t launch_halo(const PaHaloTag* tags, int tag0, int tag1, long long cell0, long long cell1, const PaBoxDev* boxes,
+                        const PaLayDev* lay, double* base, long long cs, int ncomp, const double* recv,
+                        const PaPeerSlab* peers, int comp0, int rank, GhostXform xf, cudaStream_t st) {
+    if (cell1 <= cell0 || tag1 <= tag0) return cudaSuccess;
+    k_halo<<<grid_for(cell1 - cell0, 256), 256, 0, st>>>(tags, tag0, tag1, cell0, cell1, boxes, lay, base, cs, ncomp, recv, peers, comp0, rank, xf);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -153,21 +161,23 @@ cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long lon
 // Coarse values are gathered straight from the coarse level's valid cells through the precomputed index
 // (no BndryRegister copy); an index of -1 means the reference's register cell was never filled (NaN).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xform(const GhostXform& xf, double v) { return xf.on ? (v - xf.pmin) * xf.inv : v; }
+
 __device__ __forceinline__ double crse_val(const PaCrseIdx* __restrict__ cidx, long long e, const LevArgs& LC, int comp,
-                                           const double* __restrict__ recv, int ncomp) {
+                                           const double* __restrict__ recv, int ncomp, const GhostXform& xf) {
     const PaCrseIdx x = cidx[e];
     if (x.box >= 0) {
         const PaLayDev y = LC.lay_in[x.box];
         long long a = cell_addr(y, (int)(x.rel & 1023u), (int)((x.rel >> 10) & 1023u), (int)(x.rel >> 20));
-        return LC.in[a + comp * LC.cs_in];
+        return xform(xf, LC.in[a + comp * LC.cs_in]);
     }
     if (x.box == -1) return PA_NAN;
-    return recv[(long long)x.rel * ncomp + comp];
+    return xform(xf, recv[(long long)x.rel * ncomp + comp]);
 }
 
 __global__ void k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restrict__ rec_level, long long rec0, long long rec1,
                          long long cell0, long long cell1, const unsigned short* __restrict__ flags,
-                         const PaCrseIdx* __restrict__ cidx, GridArgs ga, int ncomp, const double* __restrict__ recv) {
+                         const PaCrseIdx* __restrict__ cidx, GridArgs ga, int ncomp, const double* __restrict__ recv, GhostXform xf) {
     for (long long c = cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cell1; c += (long long)gridDim.x * blockDim.x) {
         const unsigned fl = flags[c];
         if ((fl & 3u) == 0u) continue;                             // covered: the halo copy owns this cell
@@ -190,16 +200,16 @@ __global__ void k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restri
         for (int m = 0; m < ncomp; ++m) {
             double* p = L.out + ga_ + m * L.cs_in;
             if (R.kind == PA_FACE_NEUMANN) {
-                *p = p[s * sd];
+                *p = xform(xf, p[s * sd]);
             } else if (R.kind == PA_FACE_REFLECT_ODD) {
-                *p = -p[s * sd];
+                *p = -xform(xf, p[s * sd]);
             } else {
                 const LevArgs& LC = ga.L[lev - 1];
                 const int r = R.ratio;
                 const int j = bx.lo[t1] + a1, k = bx.lo[t2] + a2;
                 const int jc = fdiv_dev(j, r), kc = fdiv_dev(k, r);
                 const long long e0 = R.cidx + (long long)(kc - R.rlo2) * R.rn1 + (jc - R.rlo1);
-#define CR(o1, o2) crse_val(cidx, e0 + (long long)(o2) * R.rn1 + (o1), LC, m, recv, ncomp)
+#define CR(o1, o2) crse_val(cidx, e0 + (long long)(o2) * R.rn1 + (o1), LC, m, recv, ncomp, xf)
                 const double c00 = CR(0, 0);
                 int lo = PA_FLAG_NC(fl, 0) ? -1 : 0;
                 int hi = PA_FLAG_NC(fl, 1) ? 1 : 0;
@@ -218,7 +228,7 @@ __global__ void k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restri
                 const double x2 = -0.5 + (k - kc * r + 0.5) / r;
                 const double bcval = c00 + x1 * d1 + (x1 * x1) * d11 + x2 * d2 + (x2 * x2) * d22 + x1 * x2 * d12;
                 double tmp = 0.0;
-                for (int mm = 1; mm < R.nx; ++mm) tmp += p[mm * s * sd] * R.coef[mm];
+                for (int mm = 1; mm < R.nx; ++mm) tmp += xform(xf, p[mm * s * sd]) * R.coef[mm];
                 double v = tmp;
                 v += bcval * R.coef[0];
                 *p = v;
@@ -228,9 +238,9 @@ __global__ void k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restri
 }
 cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, long long rec0, long long rec1, long long cell0,
                           long long cell1, const unsigned short* flags, const PaCrseIdx* cidx, const GridArgs& ga,
-                          int ncomp, const double* recv, cudaStream_t st) {
+                          int ncomp, const double* recv, GhostXform xf, cudaStream_t st) {
     if (cell1 <= cell0 || rec1 <= rec0) return cudaSuccess;
-    k_bcfill<<<grid_for(cell1 - cell0, 128), 128, 0, st>>>(recs, rec_level, rec0, rec1, cell0, cell1, flags, cidx, ga, ncomp, recv);
+    k_bcfill<<<grid_for(cell1 - cell0, 128), 128, 0, st>>>(recs, rec_level, rec0, rec1, cell0, cell1, flags, cidx, ga, ncomp, recv, xf);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -245,6 +255,25 @@ __device__ __forceinline__ double cdiff(double dxi, double m, double c, double p
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// Address of input cell (i,j,k) of local box `box` (box-relative; at most one cell outside the valid region, through
+// one face).  A ghost cell of a LINKED face is the neighbour's valid cell, read in place (own slab or a peer's);
+// otherwise it is this box's materialised ghost cell.  `comp` counts from the first input component.
+__device__ __forceinline__ const double* in_ptr(const LevArgs& L, int box, const PaLayDev& li, const PaBoxDev& bx, int comp,
+                                                int i, int j, int k) {
+    int face = -1;
+    if (i < 0) face = 0; else if (i >= bx.n[0]) face = 3;
+    else if (j < 0) face = 1; else if (j >= bx.n[1]) face = 4;
+    else if (k < 0) face = 2; else if (k >= bx.n[2]) face = 5;
+    if (face >= 0) {
+        const PaNbrFace F = L.nbr[box].f[face];
+        if (F.nb >= 0) {
+            const PaPeerSlab ps = L.peers[F.rank];
+            return ps.base + (long long)(L.in_comp + comp) * ps.cs + cell_addr(L.lay_in[F.nb], i + F.rel[0], j + F.rel[1], k + F.rel[2]);
+        }
+    }
+    return L.in + (long long)comp * L.cs_in + cell_addr(li, i, j, k);
+}
 
 // One tile = rows [y0,y0+ny) x planes [z0,z0+nz) of a box, full x extent.  Each thread handles x pairs with
 // 128-bit loads; neighbours come through L1/L2.  This is the general fallback path (any box width) and the
@@ -273,12 +302,14 @@ __global__ void __launch_bounds__(256) k_stencil_simple(const PaTile* __restrict
         const long long o = cell_addr(lo, i, jy, kz);
         const bool two = (i + 1 < nx);
         double r0[4], r1[4];
+        const int xe = two ? i + 2 : i + 1;                 // x index of the cell right of this item's last valid cell
         if (MODE != MODE_DIV) {
             const double* p = in0 + a;
-            const double2 c = ld2(p);
-            const double xm = p[-1], xp = p[2];
-            const double2 ym = ld2(p - li.P), yp = ld2(p + li.P);
-            const double2 zm = ld2(p - li.PS), zp = ld2(p + li.PS);
+            double2 c = ld2(p);
+            if (!two) c.y = *in_ptr(L, t.box, li, bx, v, i + 1, jy, kz);
+            const double xm = *in_ptr(L, t.box, li, bx, v, i - 1, jy, kz), xp = *in_ptr(L, t.box, li, bx, v, xe, jy, kz);
+            const double2 ym = ld2(in_ptr(L, t.box, li, bx, v, i, jy - 1, kz)), yp = ld2(in_ptr(L, t.box, li, bx, v, i, jy + 1, kz));
+            const double2 zm = ld2(in_ptr(L, t.box, li, bx, v, i, jy, kz - 1)), zp = ld2(in_ptr(L, t.box, li, bx, v, i, jy, kz + 1));
             const double gx0 = cdiff(dxi, xm, c.x, c.y), gx1 = cdiff(dxi, c.x, c.y, xp);
             const double gy0 = cdiff(dyi, ym.x, c.x, yp.x), gy1 = cdiff(dyi, ym.y, c.y, yp.y);
             const double gz0 = cdiff(dzi, zm.x, c.x, zp.x), gz1 = cdiff(dzi, zm.y, c.y, zp.y);
@@ -304,10 +335,11 @@ __global__ void __launch_bounds__(256) k_stencil_simple(const PaTile* __restrict
             const double* px = in0 + a;
             const double* py = px + L.cs_in;
             const double* pz = py + L.cs_in;
-            const double2 cx = ld2(px);
-            const double xm = px[-1], xp = px[2];
-            const double2 cy = ld2(py), ym = ld2(py - li.P), yp = ld2(py + li.P);
-            const double2 cz = ld2(pz), zm = ld2(pz - li.PS), zp = ld2(pz + li.PS);
+            double2 cx = ld2(px);
+            if (!two) cx.y = *in_ptr(L, t.box, li, bx, 0, i + 1, jy, kz);
+            const double xm = *in_ptr(L, t.box, li, bx, 0, i - 1, jy, kz), xp = *in_ptr(L, t.box, li, bx, 0, xe, jy, kz);
+            const double2 cy = ld2(py), ym = ld2(in_ptr(L, t.box, li, bx, 1, i, jy - 1, kz)), yp = ld2(in_ptr(L, t.box, li, bx, 1, i, jy + 1, kz));
+            const double2 cz = ld2(pz), zm = ld2(in_ptr(L, t.box, li, bx, 2, i, jy, kz - 1)), zp = ld2(in_ptr(L, t.box, li, bx, 2, i, jy, kz + 1));
             const double dx0 = cdiff(dxi, xm, cx.x, cx.y), dx1 = cdiff(dxi, cx.x, cx.y, xp);
             const double dy0 = cdiff(dyi, ym.x, cy.x, yp.x), dy1 = cdiff(dyi, ym.y, cy.y, yp.y);
             const double dz0 = cdiff(dzi, zm.x, cz.x, zp.x), dz1 = cdiff(dzi, zm.y, cz.y, zp.y);

@@ -10,9 +10,12 @@ namespace pa {
 
 // per-level device pointers handed to kernels by value
 struct LevArgs {
-    const PaBoxDev* boxes;      // local boxes of the level
-    const PaLayDev* lay_in;     // layout of the input field on this level
+    const PaBoxDev* boxes;      // boxes of the level, extended index (local boxes, then peer-owned link targets)
+    const PaLayDev* lay_in;     // layout of the input field on this level (extended index)
     const PaLayDev* lay_out;    // layout of the output field
+    const PaNbr* nbr;           // neighbour links of the local boxes
+    const PaPeerSlab* peers;    // per rank: where that rank's slab of the INPUT field lives (comp 0 of the field)
+    int in_comp;                // index of the first input component inside its field (peer slabs start at comp 0)
     const double* in;           // component 0 of the input field on this level
     double* out;                // component 0 of the output field
     long long cs_in, cs_out;    // component strides (elements)
@@ -27,7 +30,19 @@ enum StencilMode {
     MODE_GRAD = 0,      // in: 1 comp            out: gx, gy, gz, |g|                          (grad tool)
     MODE_GRAD3 = 1,     // in: 1 comp            out: gx, gy, gz                               (Hessian rows, velocity gradients)
     MODE_NORMAL = 2,    // in: c                 out: n = G/nrm (3 comps); aux out: G (3 comps) if aux != null
-    MODE_DIV = 3        // in: n (3 comps)       out: K = 0.5*(dnx/dx + dny/dy + dnz/dz), optional clip on c
+    MODE_DIV = 3,       // in: n (3 comps)       out: K = 0.5*(dnx/dx + dny/dy + dnz/dz), optional clip on c
+    MODE_NORMAL_S = 4   // in: raw scalar S      out: n as MODE_NORMAL, plus Progress c = (S - pmin)*inv into cout[] --
+                        // the progress pass fused into the loader.  Valid cells and linked neighbours hold S and are
+                        // normalised on the fly; MATERIALISED ghost cells already hold c (see GhostXform)   (TMA kernel only)
+};
+
+// Ghost fill "in progress space" for MODE_NORMAL_S: the field holds the raw scalar S in its valid cells; every ghost
+// cell the fill writes receives what the reference's Progress MultiFab would hold there -- a copied neighbour value is
+// normalised on the way, and the Neumann / reflect_odd / coarse-fine formulas are evaluated on normalised inputs
+// (curvature.cpp:310-322 then :447-457), so the results are bit-identical to normalise-then-fill.
+struct GhostXform {
+    int on;
+    double pmin, inv;
 };
 
 struct StencilExtra {
@@ -38,6 +53,9 @@ struct StencilExtra {
     const double* prog[PA_MAX_LEVELS];
     int do_threshold;
     double threshold;
+    // MODE_NORMAL_S: Progress output (one component, same layout as `out`) and the normalisation
+    double* cout[PA_MAX_LEVELS];
+    double pmin, inv;
 };
 
 extern long long g_launches;     // kernels launched by this library
@@ -48,14 +66,17 @@ cudaError_t launch_pack_valid(const PaBoxDev* boxes, const PaLayDev* lay, const 
                               long long ncells, const double* comp_base, double* staging, cudaStream_t st);
 cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t st);
 
-cudaError_t launch_halo(const PaHaloTag* tags, int ntags, long long ncells, const PaBoxDev* boxes, const PaLayDev* lay,
-                        double* base, long long cs, int ncomp, const double* recv, cudaStream_t st);
+// halo tags [tag0, tag1) covering cells [cell0, cell1) of the table's flattened enumeration; `comp0` = first component
+// of the field being filled (peer slabs are addressed from the field's component 0)
+cudaError_t launch_halo(const PaHaloTag* tags, int tag0, int tag1, long long cell0, long long cell1, const PaBoxDev* boxes,
+                        const PaLayDev* lay, double* base, long long cs, int ncomp, const double* recv,
+                        const PaPeerSlab* peers, int comp0, int rank, GhostXform xf, cudaStream_t st);
 cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long long tag1, long long dense0, long long ncells,
                                  const GridArgs& ga, int ncomp, double* send, cudaStream_t st);
 // BC fill over face records [rec0, rec1) whose plane cells are [cell0, cell1)
 cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, long long rec0, long long rec1, long long cell0,
                           long long cell1, const unsigned short* flags, const PaCrseIdx* cidx, const GridArgs& ga,
-                          int ncomp, const double* recv, cudaStream_t st);
+                          int ncomp, const double* recv, GhostXform xf, cudaStream_t st);
 
 // stencils: GridArgs.in/out already point at the first component to read / write
 cudaError_t launch_stencil_simple(int mode, const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex,
@@ -64,6 +85,7 @@ cudaError_t launch_stencil_simple(int mode, const PaTile* tiles, int ntiles, con
 cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, const GridArgs& ga,
                                const StencilExtra& ex, int nvar, cudaStream_t st);
 int stencil_tma_tile_rows();     // TY the tile table must be built with
+int stencil_tma_max_tile_rows();
 int stencil_tma_max_plane_doubles();
 
 cudaError_t launch_progress(const PaBoxDev* boxes, const PaLayDev* lay_in, const PaLayDev* lay_out, int nboxes,

@@ -28,13 +28,34 @@ struct PaLayDev {
 // (AMReX_FabArrayBase.H:193-201): dst cell d in [dlo, dlo+n) of local box `dbox` <- src cell d+shift of `sbox`.
 struct PaHaloTag {
     int dbox;         // local index of the receiving box
-    int sbox;         // local index of the source box, or -1 if the source box lives on another rank
+    int sbox;         // source box in the level's EXTENDED box index (local boxes first, then the peer-owned link
+                      // targets, read through peer-mapped memory), or -1 if its data arrives in the recv slab
     int dlo[3];
     int n[3];
     int shift[3];
-    int pad;
+    int srank;        // rank that owns the source box
     long long start;  // first cell of this tag in the flattened cell enumeration of the table
     long long rsrc;   // sbox<0: first cell of this tag's data inside the recv slab (per component)
+};
+
+// Neighbour link of one (box, face): the whole width-1 ghost layer of the face lies inside ONE same-level box
+// whose row pitch and plane stride equal this box's.  The stencil kernels then read the neighbour's valid cells
+// in place (TMA bulk copies for y rows / z planes, scalar loads for x columns) and the ghost cells of that face
+// are never materialised.  Neighbour-relative cell = own-relative cell + rel.
+struct PaNbrFace {
+    int nb;           // extended box index of the neighbour, -1 = face not linked (ghosts are materialised)
+    int rank;         // owner of the neighbour (== own rank unless the hierarchy was created with peer links)
+    int rel[3];
+    int pad;
+};
+struct PaNbr {
+    PaNbrFace f[6];   // amrex::Orientation order: low x,y,z, high x,y,z
+};
+
+// where rank r's slab of a (field, level) lives in this process' address space (own allocation or an IPC mapping)
+struct PaPeerSlab {
+    const double* base;   // component 0
+    long long cs;         // component stride of that rank's slab
 };
 
 // what a rank must pack for a peer: src cells [slo, slo+n) of local box sbox -> send slab at soff

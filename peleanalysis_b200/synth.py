@@ -136,7 +136,7 @@ def config2(n: int = 512, mgs: int = 128, names=tuple(FIELD_NAMES), fill: bool =
     return make_hierarchy(n, [], [], mgs, names, fill=fill)
 
 
-def config3(base: int = 256, mgs: int = 64, names=("temp",), nlev: int = 3) -> Plotfile:
+def config3(base: int = 256, mgs: int = 64, names=("temp",), nlev: int = 3, fill: bool = True) -> Plotfile:
     """BASELINE config 3: 3 levels ratio 2, each level refines the central half of the previous one."""
     regs = []
     lo = (0, 0, 0)
@@ -149,7 +149,7 @@ def config3(base: int = 256, mgs: int = 64, names=("temp",), nlev: int = 3) -> P
         fhi = tuple(flo[d] + fn[d] - 1 for d in range(3))
         regs.append([(flo, fhi)])
         lo, n = flo, fn
-    return make_hierarchy(base, regs, [2] * (nlev - 1), mgs, names)
+    return make_hierarchy(base, regs, [2] * (nlev - 1), mgs, names, fill=fill)
 
 
 def config4(n: int = 1024, mgs: int = 128, names=("temp",), fill: bool = True) -> Plotfile:

@@ -15,37 +15,24 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from cases import CASES  # noqa: E402
 from oracle import oracle as O  # noqa: E402
-from peleanalysis_b200 import capi, synth  # noqa: E402
+from peleanalysis_b200 import capi, multigpu, synth  # noqa: E402
 
 
-class DevArray:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
-
-
-def run_case(name, pf, is_per, sym, rank, world, nvar=1):
-    H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+def run_case(name, pf, is_per, sym, rank, world, nvar=1, mode="slab"):
+    H = capi.Hierarchy(pf.levels, is_per, sym, rank, world, flags=capi.PEER_LINKS if mode == "peer" else 0)
     fin, fout = capi.Field(H, nvar, 1), capi.Field(H, 4 * nvar, 0)
+    if mode == "peer":
+        multigpu.map_peers(fin)
     for v in range(nvar):
         fin.upload_fabs(v, [[f[v] for f in l.fabs] for l in pf.levels])
-    sp, rp = C.c_void_p(), C.c_void_p()
-    so, ro = (C.c_int64 * (world + 1))(), (C.c_int64 * (world + 1))()
-    capi.check(capi.lib().pa_exchange_buffers(fin.f, nvar, C.byref(sp), C.byref(rp), so, ro))
-    send_t = torch.as_tensor(DevArray(sp.value, max(so[world], 1)), device="cuda")
-    recv_t = torch.as_tensor(DevArray(rp.value, max(ro[world], 1)), device="cuda")
-    capi.check(capi.lib().pa_exchange_pack(fin.f, 0, nvar))
-    ops = []
-    for p in range(world):
-        if p != rank and ro[p + 1] > ro[p]:
-            ops.append(dist.P2POp(dist.irecv, recv_t[ro[p]:ro[p + 1]], p))
-        if p != rank and so[p + 1] > so[p]:
-            ops.append(dist.P2POp(dist.isend, send_t[so[p]:so[p + 1]], p))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    capi.check(capi.lib().pa_exchange_mark_received(fin.f, 0, nvar))
+    capi.sync()
+    dist.barrier()                      # peers' uploads are complete before anyone reads them in place
+    X = multigpu.SlabExchange(fin, nvar)
+    ro = X.roff
+    X.run(0)
     capi.grad(fin, 0, nvar, fout, 0)
     capi.sync()
+    dist.barrier()                      # nobody frees / overwrites a slab a peer may still be reading
     OH = O.OracleHier(pf, is_per, sym)
     bad = 0
     for v in range(nvar):
@@ -59,8 +46,8 @@ def run_case(name, pf, is_per, sym, rank, world, nvar=1):
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print("dist_check %-18s ranks=%d local_boxes=%s remote_cells(recv)=%d mismatching boxes=%d" % (
-            name, world, [len(x) for x in H.local_boxes], ro[world] // nvar, int(t.item())), flush=True)
+        print("dist_check %-18s %-4s ranks=%d local_boxes=%s slab_cells(recv)=%d mismatching boxes=%d" % (
+            name, mode, world, [len(x) for x in H.local_boxes], ro[-1] // nvar, int(t.item())), flush=True)
     return int(t.item())
 
 
@@ -72,12 +59,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.set_stream(torch.cuda.current_stream().cuda_stream)
     bad = 0
-    for name in ["c1_periodic", "c1_walls", "lshape", "edge_periodic", "ratio4", "c3_three_levels"]:
-        builder, is_per, sym, _, _ = CASES[name]
-        bad += run_case(name, builder(), is_per, sym, rank, world)
-    bad += run_case("config3_64", synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world)
-    bad += run_case("config1_5vars", synth.config1(32, 16, names=synth.FIELD_NAMES), (1, 1, 1), (0, 0, 0), rank, world, nvar=5)
-    bad += run_case("config5_small", synth.config5(base=32, mgs=8, ncomp=2), (1, 1, 1), (0, 0, 0), rank, world, nvar=2)
+    for mode in ("slab", "peer"):
+        for name in ["c1_periodic", "c1_walls", "lshape", "edge_periodic", "ratio4", "c3_three_levels"]:
+            builder, is_per, sym, _, _ = CASES[name]
+            bad += run_case(name, builder(), is_per, sym, rank, world, mode=mode)
+        bad += run_case("config3_64", synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+        bad += run_case("config1_5vars", synth.config1(32, 16, names=synth.FIELD_NAMES), (1, 1, 1), (0, 0, 0), rank, world, nvar=5, mode=mode)
+        bad += run_case("config5_small", synth.config5(base=32, mgs=8, ncomp=2), (1, 1, 1), (0, 0, 0), rank, world, nvar=2, mode=mode)
+        bad += run_case("uniform_64", synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
     dist.destroy_process_group()
     if rank == 0:
         print("DIST_CHECK", "OK" if bad == 0 else "FAILED (%d)" % bad, flush=True)

@@ -21,9 +21,9 @@ def _flat(pf, name):
     return np.concatenate([f[c].ravel() for l in pf.levels for f in l.fabs])
 
 
-def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma"):
+def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
     os.environ["PA_STENCIL"] = stencil
-    H = capi.Hierarchy(pf.levels, is_per, sym)
+    H = capi.Hierarchy(pf.levels, is_per, sym, flags=flags)
     fin = capi.Field(H, len(names), 1)
     fout = capi.Field(H, 4 * len(names), 0)
     for v, n in enumerate(names):
@@ -34,9 +34,9 @@ def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma"):
     return out, H, fin
 
 
-def _gpu_curv(capi, pf, is_per, sym, pmin, pmax, kw, stencil="tma"):
+def _gpu_curv(capi, pf, is_per, sym, pmin, pmax, kw, stencil="tma", flags=0):
     os.environ["PA_STENCIL"] = stencil
-    H = capi.Hierarchy(pf.levels, is_per, sym)
+    H = capi.Hierarchy(pf.levels, is_per, sym, flags=flags)
     o = capi.CurvOpts()
     o.prog_min, o.prog_max = pmin, pmax
     o.do_threshold = int(kw.get("threshold_prog", 0))
@@ -58,21 +58,29 @@ def _gpu_curv(capi, pf, is_per, sym, pmin, pmax, kw, stencil="tma"):
     return np.stack([flat_from_fabs(out.download_fabs(c)) for c in range(nout)]), o
 
 
+# "links": same-level neighbours are read in place by the stencil (default); "nolinks": every ghost cell is
+# materialised by the halo gather first (PA_HIER_NO_LINKS, the reference's data flow).  Both must be bit-exact.
+LINK_MODES = {"links": 0, "nolinks": 2}
+
+
+@pytest.mark.parametrize("links", list(LINK_MODES))
 @pytest.mark.parametrize("stencil", ["tma", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "grad" in c[3]])
-def test_grad_matches_reference_golden(gpu, name, stencil):
+def test_grad_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
-    out, _, _ = _gpu_grad(gpu, pf, tuple(z["is_per"]), tuple(z["sym_dir"]), stencil=stencil)
+    out, _, _ = _gpu_grad(gpu, pf, tuple(z["is_per"]), tuple(z["sym_dir"]), stencil=stencil, flags=LINK_MODES[links])
     for c, k in enumerate(["gx", "gy", "gz", "mag"]):
         assert bit_equal(out[c], z["grad_" + k]), (name, stencil, k, max_rel(out[c], z["grad_" + k]))
 
 
+@pytest.mark.parametrize("links", list(LINK_MODES))
 @pytest.mark.parametrize("stencil", ["tma", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
-def test_curvature_matches_reference_golden(gpu, name, stencil):
+def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
     kw = dict(s.split("=") for s in z["curv_opts"]) if len(z["curv_opts"]) else {}
-    out, o = _gpu_curv(gpu, pf, tuple(z["is_per"]), tuple(z["sym_dir"]), float(z["prog_min"]), float(z["prog_max"]), kw, stencil)
+    out, o = _gpu_curv(gpu, pf, tuple(z["is_per"]), tuple(z["sym_dir"]), float(z["prog_min"]), float(z["prog_max"]), kw, stencil,
+                       flags=LINK_MODES[links])
     names = ["Progress", "MeanCurvature_temp", "FlameNormalX_temp", "FlameNormalY_temp", "FlameNormalZ_temp"]
     c = 5
     if o.do_gauss:

@@ -85,6 +85,51 @@ def test_face_masks_and_coefficients(palib, name):
                     assert np.array_equal(want, got), (name, l, b, face, bit)
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_neighbour_links_agree_with_fill_boundary(palib, name):
+    """A linked face must name exactly the cells FillBoundary would copy into that face's ghost layer (oracle's
+    expanded copy rule), and every face that is one same-shaped neighbour's territory must be linked."""
+    pf, OH, PH = _hiers(name)
+    nlinked = 0
+    for l, lv in enumerate(pf.levels):
+        want = OH.fb_source_map(l, 1)
+        for b, (lo, hi) in enumerate(lv.boxes):
+            n = [hi[d] - lo[d] + 1 for d in range(3)]
+            L = PH.links(l, b)
+            src = want[b]                                    # [nz+2, ny+2, nx+2], (box<<40 | linear idx) or -1
+            for face in range(6):
+                d = face % 3
+                sl = [slice(1, -1)] * 3                      # numpy axes are (z, y, x)
+                sl[2 - d] = 0 if face < 3 else -1
+                layer = src[tuple(sl)]
+                # ghost cell coordinates (box-relative) of the layer
+                idx = [np.arange(n[2]), np.arange(n[1]), np.arange(n[0])]
+                idx[2 - d] = np.array([-1 if face < 3 else n[d]])
+                K, J, I = np.meshgrid(*idx, indexing="ij")
+                K, J, I = [np.squeeze(a, axis=2 - d) for a in (K, J, I)]
+                boxes = np.where(layer >= 0, layer >> 40, -1)
+                single = (boxes >= 0).all() and (boxes == boxes.flat[0]).all()
+                nb = int(L[face][0])
+                if nb >= 0:
+                    nlinked += 1
+                    nlo, nhi = lv.boxes[nb]
+                    nn = [nhi[t] - nlo[t] + 1 for t in range(3)]
+                    assert nn[0] == n[0] and nn[1] == n[1]
+                    rel = L[face][2:5]
+                    lin = ((K + rel[2]) * nn[1] + (J + rel[1])) * nn[0] + (I + rel[0])
+                    assert single and boxes.flat[0] == nb, (name, l, b, face)
+                    assert np.array_equal(layer & ((1 << 40) - 1), lin), (name, l, b, face)
+                elif single:
+                    nlo, nhi = lv.boxes[int(boxes.flat[0])]
+                    same = (nhi[0] - nlo[0] == hi[0] - lo[0]) and (nhi[1] - nlo[1] == hi[1] - lo[1])
+                    assert not same or (d == 0 and n[0] < 3), (name, l, b, face, "face should have been linked")
+    assert nlinked > 0
+    # PA_HIER_NO_LINKS turns them all off
+    builder, is_per, sym, _, _ = CASES[name]
+    H0 = capi.Hierarchy(pf.levels, is_per, sym, flags=capi.NO_LINKS)
+    assert all((H0.links(l, b)[:, 0] == -1).all() for l, lv in enumerate(pf.levels) for b in range(len(lv.boxes)))
+
+
 def test_hierarchy_validation(palib):
     from peleanalysis_b200 import synth
     pf = synth.config1(16, 8)

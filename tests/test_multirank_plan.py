@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, case, ok):
+def _worker(rank, world, port, case, ok, flags=0):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -25,7 +25,7 @@ def _worker(rank, world, port, case, ok):
         from peleanalysis_b200 import capi
         builder, is_per, sym, _, _ = CASES[case]
         pf = builder()
-        H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+        H = capi.Hierarchy(pf.levels, is_per, sym, rank, world, flags=flags)
         send_ids, want = H.exchange_ids(0), H.exchange_ids(1)
         sc, rc = H.exchange_prefix(1)
         assert sc[rank] == 0 and rc[rank] == 0
@@ -62,11 +62,65 @@ def _worker(rank, world, port, case, ok):
                 f, m = full[b], mine[i]
                 src_box = np.where(f >= 0, f >> 40, -1)
                 remote = (src_box >= 0) & (H.owners[l][np.maximum(src_box, 0)] != rank)
-                assert np.array_equal(m == -2, remote)
-                assert np.array_equal(m[~remote], f[~remote])
+                if flags & capi.PEER_LINKS:
+                    # peer-linked faces name the peer's box directly (read in place); only unlinked remote cells use the slab
+                    lk = H.links(l, b)
+                    g = 1
+                    linked = np.zeros(f.shape, dtype=bool)
+                    for face in range(6):
+                        if lk[face][0] >= 0:
+                            sl = [slice(g, -g)] * 3
+                            sl[2 - face % 3] = 0 if face < 3 else -1
+                            linked[tuple(sl)] = True
+                    assert np.array_equal(m == -2, remote & ~linked)
+                    assert np.array_equal(m[m != -2], f[m != -2])
+                    assert (H.owners[l][lk[lk[:, 0] >= 0, 0]] == lk[lk[:, 0] >= 0, 1]).all()
+                else:
+                    assert np.array_equal(m == -2, remote)
+                    assert np.array_equal(m[~remote], f[~remote])
         ok[rank] = 1
     finally:
         dist.destroy_process_group()
+
+
+def _spawn2(case, flags):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0, 0])
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, ok, flags)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert list(ok) == [1, 1], [p.exitcode for p in procs]
+
+
+@pytest.mark.parametrize("case", ["c1_periodic", "c3_three_levels", "edge_walls"])
+def test_exchange_plan_world2_peer_links(palib, case):
+    """PA_HIER_PEER_LINKS: faces linked to a peer's box leave the exchange plan; what remains is still consistent."""
+    _spawn2(case, 1)
+
+
+def test_uniform_grid_with_peer_links_needs_no_exchange(palib):
+    from peleanalysis_b200 import capi, synth
+    pf = synth.make_hierarchy(32, [], [], 16, fill=False)
+    for rank in range(2):
+        H = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, 2, flags=capi.PEER_LINKS)
+        sc, rc = H.exchange_prefix(1)
+        assert sc.sum() == 0 and rc.sum() == 0
+        remote = 0
+        for b in range(len(pf.levels[0].boxes)):
+            lk = H.links(0, b)
+            assert (lk[:, 0] >= 0).all()
+            remote += int((lk[:, 1] != H.owners[0][b]).sum())
+        assert remote > 0
+        H0 = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, 2)
+        sc, rc = H0.exchange_prefix(1)
+        assert sc.sum() > 0 and rc.sum() > 0
 
 
 @pytest.mark.parametrize("case", ["c1_periodic", "c3_three_levels", "lshape", "edge_walls", "ratio4"])
