@@ -78,7 +78,8 @@ struct pa_hier {
     DevBuf<PaFaceRec> face_recs;
     DevBuf<int> face_level;
     DevBuf<uint16_t> face_flags;
-    DevBuf<PaCrseIdx> face_cidx;
+    DevBuf<PaFaceBlock> face_blocks;
+    std::map<int, std::unique_ptr<DevBuf<long long>>> face_coff;   // coarse gather offsets per ghost width
     DevBuf<PaPackTag> pack_tags;
     TileTable tiles_simple, tiles_tma;
     std::map<cudaStream_t, std::unique_ptr<DevBuf<double>>> staging;   // upload / download staging, one per stream
@@ -191,7 +192,7 @@ int ensure_device(pa_hier* h) {
     CU(h->face_recs.upload(H.faces.recs, t_stream));
     CU(h->face_level.upload(H.faces.rec_level, t_stream));
     CU(h->face_flags.upload(H.faces.flags, t_stream));
-    CU(h->face_cidx.upload(H.faces.cidx, t_stream));
+    CU(h->face_blocks.upload(H.faces.blocks, t_stream));
     CU(h->pack_tags.upload(H.xplan.pack, t_stream));
     build_tiles(h, h->tiles_simple, false);
     build_tiles(h, h->tiles_tma, true);
@@ -317,11 +318,17 @@ int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1, bool link
                        f->cs[l], ncomp, recv, ga.L[l].peers, comp, H.rank, xf, t_stream));
     }
     const FaceTable& F = H.faces;
-    long long r0 = F.level_rec_begin[l0], r1 = F.level_rec_begin[l1 + 1];
-    if (r1 > r0) {
-        long long c0 = F.recs[r0].start;
-        long long c1 = (r1 < (long long)F.recs.size()) ? F.recs[r1].start : F.ncells;
-        CU(launch_bcfill(h->face_recs.p, h->face_level.p, r0, r1, c0, c1, h->face_flags.p, h->face_cidx.p, ga, ncomp, recv, xf, t_stream));
+    const long long b0 = F.level_blk_begin[l0], b1 = F.level_blk_begin[l1 + 1];
+    if (b1 > b0) {
+        auto it = h->face_coff.find(f->ng);
+        if (it == h->face_coff.end()) {
+            auto buf = std::make_unique<DevBuf<long long>>();
+            std::vector<long long> v = H.crse_offsets(f->ng);
+            CU(buf->upload(v, t_stream));
+            CU(cudaStreamSynchronize(t_stream));           // v dies at the end of this scope
+            it = h->face_coff.emplace(f->ng, std::move(buf)).first;
+        }
+        CU(launch_bcfill(h->face_recs.p, h->face_level.p, h->face_blocks.p, b0, b1, h->face_flags.p, it->second->p, ga, ncomp, recv, xf, t_stream));
     }
     return PA_OK;
 }

@@ -648,7 +648,39 @@ std::string Hier::build_faces() {
     }
     faces.level_rec_begin[nlev] = (long long)faces.recs.size();
     faces.ncells = (long long)faces.flags.size();
+    faces.level_blk_begin.assign(nlev + 1, 0);
+    for (int l = 0; l < nlev; ++l) {
+        faces.level_blk_begin[l] = (long long)faces.blocks.size();
+        for (long long r = faces.level_rec_begin[l]; r < faces.level_rec_begin[l + 1]; ++r) {
+            const int n = faces.recs[r].n1 * faces.recs[r].n2;
+            for (int c = 0; c < n; c += PA_FACE_CHUNK) faces.blocks.push_back(PaFaceBlock{(int)r, c});
+        }
+    }
+    faces.level_blk_begin[nlev] = (long long)faces.blocks.size();
     return "";
+}
+
+std::vector<long long> Hier::crse_offsets(int ng) {
+    std::vector<long long> out(faces.cidx.size(), -1);
+    for (size_t r = 0; r < faces.recs.size(); ++r) {
+        const PaFaceRec& R = faces.recs[r];
+        if (R.cidx < 0) continue;
+        const Layout& Y = layout(faces.rec_level[r] - 1, ng);
+        const long long n = (long long)R.rn1 * R.rn2;
+        for (long long e = R.cidx; e < R.cidx + n; ++e) {
+            const PaCrseIdx& X = faces.cidx[(size_t)e];
+            if (X.box >= 0) {
+                const PaLayDev& y = Y.lay[X.box];
+                const int i = (int)(X.rel & 1023u), j = (int)((X.rel >> 10) & 1023u), k = (int)(X.rel >> 20);
+                out[(size_t)e] = y.off + (long long)(k + y.ng) * y.PS + (long long)(j + y.ng) * y.P + (i + y.ng + y.xoff);
+            } else if (X.box == -1) {
+                out[(size_t)e] = -1;
+            } else {
+                out[(size_t)e] = -2 - (long long)X.rel;
+            }
+        }
+    }
+    return out;
 }
 
 // Morton-order the boxes by their low corner and cut the curve into nranks chunks of ~equal cell volume

@@ -114,6 +114,8 @@ struct FaceTable {                    // all levels concatenated, level-major
     std::vector<uint16_t> flags;
     std::vector<PaCrseIdx> cidx;
     std::vector<long long> level_rec_begin;   // nlev+1
+    std::vector<PaFaceBlock> blocks;          // chunks of <= PA_FACE_CHUNK plane cells, record-major (hence level-major)
+    std::vector<long long> level_blk_begin;   // nlev+1
     long long ncells = 0;
 };
 
@@ -152,6 +154,9 @@ public:
     bool linked(int l, int gb, int face) const { return lev[l].link[gb][face].nb >= 0; }
 
     const Layout& layout(int l, int ng);      // lazily built, cached
+    // coarse gather index resolved against the ng-ghost layout: element offset inside the coarse level's component slab,
+    // -1 = never filled (NaN in the reference), <= -2: recv-slab slot -(v+2)
+    std::vector<long long> crse_offsets(int ng);
     // full FillBoundary table (all ng layers incl. edges/corners) -- debug / pa_fill_boundary(cross=0); local sources only
     const HaloTable& halo_full(int l, int ng);
 

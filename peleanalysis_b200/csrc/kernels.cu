@@ -163,84 +163,81 @@ cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long lon
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double xform(const GhostXform& xf, double v) { return xf.on ? (v - xf.pmin) * xf.inv : v; }
 
-__device__ __forceinline__ double crse_val(const PaCrseIdx* __restrict__ cidx, long long e, const LevArgs& LC, int comp,
-                                           const double* __restrict__ recv, int ncomp, const GhostXform& xf) {
-    const PaCrseIdx x = cidx[e];
-    if (x.box >= 0) {
-        const PaLayDev y = LC.lay_in[x.box];
-        long long a = cell_addr(y, (int)(x.rel & 1023u), (int)((x.rel >> 10) & 1023u), (int)(x.rel >> 20));
-        return xform(xf, LC.in[a + comp * LC.cs_in]);
-    }
-    if (x.box == -1) return PA_NAN;
-    return xform(xf, recv[(long long)x.rel * ncomp + comp]);
+__device__ __forceinline__ double crse_val(const long long* __restrict__ coff, long long e, const double* __restrict__ cbase,
+                                           const double* __restrict__ recv, int ncomp, int comp, const GhostXform& xf) {
+    const long long a = coff[e];
+    if (a >= 0) return xform(xf, cbase[a]);
+    if (a == -1) return PA_NAN;
+    return xform(xf, recv[(-2 - a) * ncomp + comp]);
 }
 
-__global__ void k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restrict__ rec_level, long long rec0, long long rec1,
-                         long long cell0, long long cell1, const unsigned short* __restrict__ flags,
-                         const PaCrseIdx* __restrict__ cidx, GridArgs ga, int ncomp, const double* __restrict__ recv, GhostXform xf) {
-    for (long long c = cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cell1; c += (long long)gridDim.x * blockDim.x) {
-        const unsigned fl = flags[c];
-        if ((fl & 3u) == 0u) continue;                             // covered: the halo copy owns this cell
-        const long long ri = upper_idx(recs, rec0, rec1, c);
-        const PaFaceRec R = recs[ri];
-        const int lev = rec_level[ri];
-        const LevArgs& L = ga.L[lev];
-        const PaBoxDev bx = L.boxes[R.box];
-        const PaLayDev ly = L.lay_in[R.box];
-        const long long q = c - R.start;
-        const int a1 = (int)(q % R.n1), a2 = (int)(q / R.n1);
-        const int d = R.face % 3;
-        const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
-        const int s = (R.face < 3) ? 1 : -1;
-        int g[3];
-        g[d] = (R.face < 3) ? -1 : bx.n[d];
-        g[t1] = a1; g[t2] = a2;
-        const long long ga_ = cell_addr(ly, g[0], g[1], g[2]);
-        const long long sd = (d == 0) ? 1 : (d == 1) ? (long long)ly.P : (long long)ly.PS;
-        for (int m = 0; m < ncomp; ++m) {
-            double* p = L.out + ga_ + m * L.cs_in;
-            if (R.kind == PA_FACE_NEUMANN) {
-                *p = xform(xf, p[s * sd]);
-            } else if (R.kind == PA_FACE_REFLECT_ODD) {
-                *p = -xform(xf, p[s * sd]);
-            } else {
-                const LevArgs& LC = ga.L[lev - 1];
-                const int r = R.ratio;
-                const int j = bx.lo[t1] + a1, k = bx.lo[t2] + a2;
-                const int jc = fdiv_dev(j, r), kc = fdiv_dev(k, r);
-                const long long e0 = R.cidx + (long long)(kc - R.rlo2) * R.rn1 + (jc - R.rlo1);
-#define CR(o1, o2) crse_val(cidx, e0 + (long long)(o2) * R.rn1 + (o1), LC, m, recv, ncomp, xf)
-                const double c00 = CR(0, 0);
-                int lo = PA_FLAG_NC(fl, 0) ? -1 : 0;
-                int hi = PA_FLAG_NC(fl, 1) ? 1 : 0;
-                double fac = (hi == lo + 1) ? 1.0 : 0.5;
-                const double d1 = fac * (CR(hi, 0) - CR(lo, 0));
-                const double d11 = (hi == lo + 2) ? 0.5 * (CR(1, 0) - 2. * c00 + CR(-1, 0)) : 0.;
-                lo = PA_FLAG_NC(fl, 2) ? -1 : 0;
-                hi = PA_FLAG_NC(fl, 3) ? 1 : 0;
-                fac = (hi == lo + 1) ? 1.0 : 0.5;
-                const double d2 = fac * (CR(0, hi) - CR(0, lo));
-                const double d22 = (hi == lo + 2) ? 0.5 * (CR(0, 1) - 2. * c00 + CR(0, -1)) : 0.;
-                const double d12 = (((fl >> 6) & 15u) == 15u)
-                                       ? 0.25 * (CR(1, 1) - CR(-1, 1) + CR(-1, -1) - CR(1, -1)) : 0.0;
+__global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restrict__ rec_level,
+                                                          const PaFaceBlock* __restrict__ blocks, const unsigned short* __restrict__ flags,
+                                                          const long long* __restrict__ coff, GridArgs ga, int ncomp,
+                                                          const double* __restrict__ recv, GhostXform xf) {
+    const PaFaceBlock fb = blocks[blockIdx.x];
+    const PaFaceRec R = recs[fb.rec];
+    const int q = fb.cell0 + threadIdx.x;
+    if (q >= R.n1 * R.n2) return;
+    const unsigned fl = flags[R.start + q];
+    if ((fl & 3u) == 0u) return;                                   // covered: the halo copy (or a neighbour link) owns this cell
+    const int lev = rec_level[fb.rec];
+    const LevArgs& L = ga.L[lev];
+    const PaBoxDev bx = L.boxes[R.box];
+    const PaLayDev ly = L.lay_in[R.box];
+    const int a1 = q % R.n1, a2 = q / R.n1;
+    const int d = R.face % 3;
+    const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+    const int s = (R.face < 3) ? 1 : -1;
+    int g[3];
+    g[d] = (R.face < 3) ? -1 : bx.n[d];
+    g[t1] = a1; g[t2] = a2;
+    const long long ga_ = cell_addr(ly, g[0], g[1], g[2]);
+    const long long sd = (d == 0) ? 1 : (d == 1) ? (long long)ly.P : (long long)ly.PS;
+    for (int m = 0; m < ncomp; ++m) {
+        double* p = L.out + ga_ + m * L.cs_in;
+        if (R.kind == PA_FACE_NEUMANN) {
+            *p = xform(xf, p[s * sd]);
+        } else if (R.kind == PA_FACE_REFLECT_ODD) {
+            *p = -xform(xf, p[s * sd]);
+        } else {
+            const LevArgs& LC = ga.L[lev - 1];
+            const double* cbase = LC.in + m * LC.cs_in;
+            const int r = R.ratio;
+            const int j = bx.lo[t1] + a1, k = bx.lo[t2] + a2;
+            const int jc = fdiv_dev(j, r), kc = fdiv_dev(k, r);
+            const long long e0 = R.cidx + (long long)(kc - R.rlo2) * R.rn1 + (jc - R.rlo1);
+#define CR(o1, o2) crse_val(coff, e0 + (long long)(o2) * R.rn1 + (o1), cbase, recv, ncomp, m, xf)
+            const double c00 = CR(0, 0);
+            int lo = PA_FLAG_NC(fl, 0) ? -1 : 0;
+            int hi = PA_FLAG_NC(fl, 1) ? 1 : 0;
+            double fac = (hi == lo + 1) ? 1.0 : 0.5;
+            const double d1 = fac * (CR(hi, 0) - CR(lo, 0));
+            const double d11 = (hi == lo + 2) ? 0.5 * (CR(1, 0) - 2. * c00 + CR(-1, 0)) : 0.;
+            lo = PA_FLAG_NC(fl, 2) ? -1 : 0;
+            hi = PA_FLAG_NC(fl, 3) ? 1 : 0;
+            fac = (hi == lo + 1) ? 1.0 : 0.5;
+            const double d2 = fac * (CR(0, hi) - CR(0, lo));
+            const double d22 = (hi == lo + 2) ? 0.5 * (CR(0, 1) - 2. * c00 + CR(0, -1)) : 0.;
+            const double d12 = (((fl >> 6) & 15u) == 15u)
+                                   ? 0.25 * (CR(1, 1) - CR(-1, 1) + CR(-1, -1) - CR(1, -1)) : 0.0;
 #undef CR
-                const double x1 = -0.5 + (j - jc * r + 0.5) / r;
-                const double x2 = -0.5 + (k - kc * r + 0.5) / r;
-                const double bcval = c00 + x1 * d1 + (x1 * x1) * d11 + x2 * d2 + (x2 * x2) * d22 + x1 * x2 * d12;
-                double tmp = 0.0;
-                for (int mm = 1; mm < R.nx; ++mm) tmp += xform(xf, p[mm * s * sd]) * R.coef[mm];
-                double v = tmp;
-                v += bcval * R.coef[0];
-                *p = v;
-            }
+            const double x1 = -0.5 + (j - jc * r + 0.5) / r;
+            const double x2 = -0.5 + (k - kc * r + 0.5) / r;
+            const double bcval = c00 + x1 * d1 + (x1 * x1) * d11 + x2 * d2 + (x2 * x2) * d22 + x1 * x2 * d12;
+            double tmp = 0.0;
+            for (int mm = 1; mm < R.nx; ++mm) tmp += xform(xf, p[mm * s * sd]) * R.coef[mm];
+            double v = tmp;
+            v += bcval * R.coef[0];
+            *p = v;
         }
     }
 }
-cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, long long rec0, long long rec1, long long cell0,
-                          long long cell1, const unsigned short* flags, const PaCrseIdx* cidx, const GridArgs& ga,
+cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaFaceBlock* blocks, long long blk0, long long blk1,
+                          const unsigned short* flags, const long long* coff, const GridArgs& ga,
                           int ncomp, const double* recv, GhostXform xf, cudaStream_t st) {
-    if (cell1 <= cell0 || rec1 <= rec0) return cudaSuccess;
-    k_bcfill<<<grid_for(cell1 - cell0, 128), 128, 0, st>>>(recs, rec_level, rec0, rec1, cell0, cell1, flags, cidx, ga, ncomp, recv, xf);
+    if (blk1 <= blk0) return cudaSuccess;
+    k_bcfill<<<(unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st>>>(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
     ++g_launches;
     return cudaGetLastError();
 }

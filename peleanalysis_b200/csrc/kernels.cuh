@@ -73,9 +73,10 @@ cudaError_t launch_halo(const PaHaloTag* tags, int tag0, int tag1, long long cel
                         const PaPeerSlab* peers, int comp0, int rank, GhostXform xf, cudaStream_t st);
 cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long long tag1, long long dense0, long long ncells,
                                  const GridArgs& ga, int ncomp, double* send, cudaStream_t st);
-// BC fill over face records [rec0, rec1) whose plane cells are [cell0, cell1)
-cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, long long rec0, long long rec1, long long cell0,
-                          long long cell1, const unsigned short* flags, const PaCrseIdx* cidx, const GridArgs& ga,
+// BC fill over the face chunks [blk0, blk1) (one thread block per chunk); coff = coarse gather offsets for the field's
+// ghost width (Hier::crse_offsets)
+cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaFaceBlock* blocks, long long blk0, long long blk1,
+                          const unsigned short* flags, const long long* coff, const GridArgs& ga,
                           int ncomp, const double* recv, GhostXform xf, cudaStream_t st);
 
 // stencils: GridArgs.in/out already point at the first component to read / write

@@ -92,6 +92,14 @@ struct PaCrseIdx {
     unsigned rel;     // i | j<<10 | k<<20 relative to the coarse box's low corner (or remote slot offset)
 };
 
+// BC-fill work item: up to PA_FACE_CHUNK consecutive plane cells of one face record (one thread block each), so the
+// kernel never searches for "which record does this cell belong to"
+#define PA_FACE_CHUNK 128
+struct PaFaceBlock {
+    int rec;          // index into the face record table
+    int cell0;        // first plane cell of the chunk, relative to the record's start
+};
+
 // stencil work item: rows [y0, y0+ny) x planes [z0, z0+nz) of a local box, full x extent
 struct PaTile {
     int lev;

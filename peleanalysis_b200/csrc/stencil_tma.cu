@@ -1,14 +1,25 @@
-// stencil_tma.cu -- the hot stencil kernels as a TMA-staged shared-memory pipeline for sm_100a.
+// stencil_tma.cu -- the hot stencil kernels as a persistent, TMA-staged shared-memory pipeline for sm_100a.
 //
-// One CTA owns a tile = rows [y0,y0+ny) x planes [z0,z0+nz) of one box, full x extent, and sweeps it along z
-// (2.5-D blocking).  Because a tile spans whole rows, the (ny+2) rows of one z-plane -- y halo and x ghosts
-// included -- are ONE contiguous, 16-byte aligned run in the box's slab, so each plane is staged with a single
-// cp.async.bulk (TMA, SASS UBLKCP) that completes on an mbarrier.  A producer warp keeps STAGES planes in flight;
-// eight consumer warps read a plane exactly once (128-bit LDS for the centre and y neighbours, warp shuffles for
-// the x neighbours), keep the z-1 / z / z+1 centre values in a register queue, and release the stage back to the
-// producer through a second mbarrier -- no __syncthreads in the steady state.
+// Work item = (tile, variable); a tile = rows [y0,y0+ny) x planes [z0,z0+nz) of one box, full x extent, swept along z
+// (2.5-D blocking).  Because a tile spans whole rows, the (ny+2) rows of one z-plane -- y halo and x ghosts included --
+// are ONE contiguous, 16-byte aligned run in the box's slab, so a plane is staged with a single cp.async.bulk (TMA,
+// SASS UBLKCP) that completes on an mbarrier.  Faces with a neighbour link (PaNbrFace) are staged straight from the
+// neighbour box -- this rank's slab or a peer GPU's over NVLink: a z-ghost plane is one bulk copy from the
+// neighbour's plane, a y-ghost row one row copy, an x-ghost column one 8-byte cp.async (LDGSTS) per row.
+//
+// The kernel is PERSISTENT: the grid is 2 CTAs per SM, each CTA draws work items from a global ticket counter (SMs do
+// not all see the same HBM bandwidth, so a static split would wait for the slowest) and the S-stage ring of planes
+// runs continuously across item boundaries -- the producer warp is already streaming the next
+// tile while the consumers finish the current one, so there is no per-tile pipeline fill / drain and the descriptor
+// loads of the next tile are off the consumers' critical path (the tile record travels through the ring with the
+// tile's first plane).  Eight consumer warps read each plane from shared memory (128-bit LDS for the centre pair and
+// the y neighbours, warp shuffles for the x neighbours), keep the z-1 / z / z+1 centre values in a register queue, and
+// hand stages back to the producer through a second mbarrier -- no __syncthreads in the steady state.
 // Arithmetic is the reference's expression order with separate IEEE mul/add (-fmad=false): bit-exact.
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <map>
 
 #include "kernels.cuh"
 
@@ -16,13 +27,14 @@ namespace pa {
 
 namespace {
 
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 16;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int THREADS = CONSUMER_THREADS + 32;       // + 1 producer warp
 constexpr int MAX_ITEMS = 2;                          // x-pairs per consumer thread per plane
-constexpr int TILE_ROWS = 8;                          // default TY
-constexpr int MAX_TILE_ROWS = 15;                     // 2 * rows x-ghost lanes must fit in the producer warp next to lane 0
+constexpr int MAX_TILE_ROWS = 30;                     // rows per tile: as many as MAX_ITEMS * CONSUMER_THREADS x-pairs allow, up to this
+constexpr int XG_LANES = 30;                          // producer lanes 1 .. 30 fetch the x ghosts: (side, row) cells lane-1 and lane-1+30
+constexpr int STATIC_SMEM = 8 * 1024;                 // upper bound of the static shared memory below
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -53,7 +65,6 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-
 // 8-byte asynchronous global -> shared copy (SASS LDGSTS) and its completion hooked to an mbarrier arrival
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -75,284 +86,401 @@ template <> struct ModeTraits<MODE_NORMAL> { static constexpr int NIN = 1, NOUT 
 template <> struct ModeTraits<MODE_DIV> { static constexpr int NIN = 3, NOUT = 1; };
 template <> struct ModeTraits<MODE_NORMAL_S> { static constexpr int NIN = 1, NOUT = 3; };
 
-// per-item register state carried from plane to plane
-struct ItemState {
-    double2 cm, c0;       // centre values of planes p-2 and p-1 (MODE_DIV: of the z component)
-    double2 a0, b0;       // in-plane derivatives of plane p-1 (x and y)
+// what the consumers need to know about a work item; written by producer lane 0 into the ring slot of the item's
+// first plane, so it is protected by that stage's full / empty barriers like the plane data itself
+struct TileRec {
+    PaTile t;
+    int v;                   // variable (blockIdx.y of the non-persistent formulation)
+    int links;               // bit f set: face f has a neighbour link
+    PaBoxDev bx;
+    PaLayDev li, lo;
+};
+
+// per-item flags (one register)
+enum : unsigned {
+    F_ACTIVE = 1u, F_TWO = 2u,           // item exists; its second cell is a valid cell (not the x-hi ghost of an odd row)
+    F_EDGE_LO = 4u, F_EDGE_HI = 8u,      // x-1 / x+2 must come from shared memory (lane or row boundary), not from a shuffle
+    F_XLO_LINK = 16u, F_XHI_LINK = 32u,  // first / last pair of a row whose x ghost comes from a linked neighbour (xg_s)
+    F_XM_RAW = 64u, F_XP_RAW = 128u,     // MODE_NORMAL_S: that neighbour is a materialised ghost (already progress space)
+    F_YM_RAW = 256u, F_YP_RAW = 512u, F_CY_RAW = 1024u,   // ... same for the y neighbours / the pair's second cell
+    F_ROW_SHIFT = 16
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __restrict__ tiles, GridArgs ga, StencilExtra ex,
-                                                         int stage_doubles /* per input component, multiple of 16 */) {
+__global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
+                                                            StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
+                                                            int S /* ring depth in planes */,
+                                                            unsigned long long* __restrict__ ticket, unsigned long long ticket_base) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
     constexpr int NOUT = ModeTraits<MODE>::NOUT;
+    constexpr bool XS = (MODE == MODE_NORMAL_S);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sm = reinterpret_cast<double*>(smem_raw);                 // [STAGES][NIN][stage_doubles]
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    __shared__ __align__(16) double xg_s[STAGES][2][16];              // x ghosts of linked x faces: [stage][lo/hi][row]
+    double* sm = reinterpret_cast<double*>(smem_raw);                 // [S][NIN][stage_doubles]
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(16) double xg_s[MAX_STAGES][2][32];          // x ghosts of linked x faces: [stage][lo/hi][row]
+    __shared__ __align__(16) TileRec rec_s[MAX_STAGES];
 
-    const PaTile t = tiles[blockIdx.x];
-    const LevArgs& L = ga.L[t.lev];
-    const PaBoxDev bx = L.boxes[t.box];
-    const PaLayDev li = L.lay_in[t.box];
-    const PaLayDev lo = L.lay_out[t.box];
-    const int v = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long stage_stride = (long long)NIN * stage_doubles;
 
-    const int rows = t.ny + 2;                         // y0-1 .. y0+ny
-    const int plane_elems = rows * li.P;               // contiguous in global memory
-    const uint32_t plane_bytes = (uint32_t)plane_elems * 8u;
-    const int nplanes = t.nz + 2;                      // z0-1 .. z0+nz
-    const double* __restrict__ in0 = L.in + (MODE == MODE_DIV ? 0 : (long long)v * L.cs_in);
-
-    // x faces with a neighbour link: their ghost column is fetched cell by cell from the neighbour by producer lanes
-    const bool xlo_link = L.nbr[t.box].f[0].nb >= 0, xhi_link = L.nbr[t.box].f[3].nb >= 0;
     if (threadIdx.x == 0) {
-        // a stage is full when the TMA bytes have landed (lane 0's arrive.expect_tx) and every x-ghost lane's copy has
-        const uint32_t nfull = 1u + (xlo_link ? t.ny : 0) + (xhi_link ? t.ny : 0);
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], nfull); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        // a stage is full when the TMA bytes have landed (lane 0's arrive.expect_tx) and every x-ghost lane has arrived
+        for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1u + XG_LANES); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == CONSUMER_WARPS) {
-        // ===== producer warp =====
-        // lane 0 drives the TMA ring.  Linked faces (PaNbrFace) are staged straight from the neighbour box -- this
-        // rank's slab or a peer's over NVLink: a z-ghost plane is one bulk copy from the neighbour's plane, a y-ghost
-        // row one row copy.  Unlinked faces come from this box's own (materialised) ghost cells inside the main run.
-        // lanes 1 .. 2*ny each own one x-ghost cell per plane (side, row) of a linked x face and fetch it with an
-        // 8-byte cp.async (LDGSTS) into xg_s; its completion is one more arrival on the stage's full barrier.
-        const PaNbr nb = L.nbr[t.box];
-        const int c0 = L.in_comp + (MODE == MODE_DIV ? 0 : v);
-        // per linked face: address of the neighbour element matching (row 0 of the padded block, plane 0) of
-        // component c0, and the component stride of the slab it lives in
-        auto link_src = [&](int face, long long& cs) -> const double* {
-            const PaNbrFace F = nb.f[face];
-            cs = 0;
-            if (F.nb < 0) return nullptr;
-            const PaPeerSlab ps = L.peers[F.rank];
-            const PaLayDev ln = L.lay_in[F.nb];
-            cs = ps.cs;
-            // neighbour-relative (x, y, z) = own-relative + rel
-            return ps.base + (long long)c0 * ps.cs + ln.off + (long long)(F.rel[2] + ln.ng) * ln.PS + (long long)(F.rel[1] + ln.ng) * ln.P + F.rel[0];
-        };
-        const int nyb = bx.n[1], nzb = bx.n[2];
-        if (lane == 0) {
-            long long cs_ylo, cs_zlo, cs_yhi, cs_zhi;
-            const double* s_ylo = link_src(1, cs_ylo);        // rel[0] == 0 for y and z faces: rows are x-aligned
-            const double* s_zlo = link_src(2, cs_zlo);
-            const double* s_yhi = link_src(4, cs_yhi);
-            const double* s_zhi = link_src(5, cs_zhi);
-            const uint32_t row_bytes = (uint32_t)li.P * 8u;
-            for (int p = 0; p < nplanes; ++p) {
-                const int s = p % STAGES;
-                const int n = p / STAGES;
-                if (n > 0) mbar_wait(&empty_bar[s], (uint32_t)((n - 1) & 1));
-                mbar_expect_tx(&full_bar[s], plane_bytes * NIN);
-                const int z = t.z0 - 1 + p;
-                const double* zs = (z < 0) ? s_zlo : (z >= nzb ? s_zhi : nullptr);
-                const long long zcs = (z < 0) ? cs_zlo : cs_zhi;
+        // ===================================== producer warp =====================================
+        // lane 0 drives the TMA ring; lanes 1 .. 2*ny each own one x-ghost cell (side, row) per plane of a linked x face;
+        // lanes without such a cell just arrive, so the full barrier's arrival count is the same for every tile.
+        if (lane > XG_LANES) return;
+        int stage = 0;
+        uint32_t ephase = 1;                            // parity that lets the first pass through the ring go without waiting
+        for (;;) {
+            // next work item: the counter is never reset -- the host advances ticket_base by (nwork + grid) per launch,
+            // exactly what the CTAs of one launch draw in total (every CTA overdraws once, then stops)
+            unsigned long long tk = 0;
+            if (lane == 0) tk = atomicAdd(ticket, 1ULL) - ticket_base;
+            tk = __shfl_sync(0x7fffffffu, tk, 0);
+            if (tk >= (unsigned long long)nwork) {
+                // end marker for the consumers: an empty record in one more ring slot
+                mbar_wait(&empty_bar[stage], ephase);
+                if (lane == 0) { rec_s[stage].t.lev = -1; mbar_arrive(&full_bar[stage]); }
+                else cp_async_arrive_noinc(&full_bar[stage]);
+                break;
+            }
+            const int wi = (int)tk;
+            const int v = wi / ntiles;
+            const PaTile t = tiles[wi - v * ntiles];
+            const LevArgs& L = ga.L[t.lev];
+            const PaBoxDev bx = L.boxes[t.box];
+            const PaLayDev li = L.lay_in[t.box];
+            const PaNbr nb = L.nbr[t.box];
+            const int c0 = L.in_comp + (MODE == MODE_DIV ? 0 : v);
+            const int rows = t.ny + 2, nplanes = t.nz + 2;
+            const uint32_t row_bytes = (uint32_t)li.P * 8u, plane_bytes = (uint32_t)rows * row_bytes;
+            // per linked face: address of the neighbour element matching (row 0 of the padded block, plane 0, x pad 0) of
+            // component c0, and the component stride of the slab it lives in.  neighbour-relative cell = own-relative + rel
+            auto link_src = [&](int face, long long& cs) -> const double* {
+                const PaNbrFace F = nb.f[face];
+                cs = 0;
+                if (F.nb < 0) return nullptr;
+                const PaPeerSlab ps = L.peers[F.rank];
+                const PaLayDev ln = L.lay_in[F.nb];
+                cs = ps.cs;
+                return ps.base + (long long)c0 * ps.cs + ln.off + (long long)(F.rel[2] + ln.ng) * ln.PS + (long long)(F.rel[1] + ln.ng) * ln.P + F.rel[0];
+            };
+            const double* own = L.in + (MODE == MODE_DIV ? 0 : (long long)v * L.cs_in) + li.off + (long long)li.ng * li.PS + (long long)li.ng * li.P;
+            // lane 0: sources of the linked y / z faces; lanes 1..: source of this lane's x-ghost cell at plane 0
+            long long cs_ylo = 0, cs_zlo = 0, cs_yhi = 0, cs_zhi = 0;
+            const double *s_ylo = nullptr, *s_zlo = nullptr, *s_yhi = nullptr, *s_zhi = nullptr;
+            const double* xsrc[2] = {nullptr, nullptr};            // this lane's (up to two) x-ghost cells at plane 0
+            double* xdst[2] = {nullptr, nullptr};                  // ... and where they go inside stage 0's xg_s block
+            if (lane == 0) {
+                s_ylo = link_src(1, cs_ylo);                       // rel[0] == 0 for y and z faces: rows are x-aligned
+                s_zlo = link_src(2, cs_zlo);
+                s_yhi = link_src(4, cs_yhi);
+                s_zhi = link_src(5, cs_zhi);
+            } else {
 #pragma unroll
-                for (int c = 0; c < NIN; ++c) {
-                    double* dst = sm + ((long long)s * NIN + c) * stage_doubles;
-                    if (zs) {
-                        tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[s]);
-                        continue;
+                for (int k = 0; k < 2; ++k) {
+                    const int idx = lane - 1 + XG_LANES * k;
+                    const int side = idx / t.ny, xr = idx - side * t.ny;   // side 0 = x-lo, 1 = x-hi
+                    if (side < 2) {
+                        long long cs;
+                        const double* s0 = link_src(side ? 3 : 0, cs);
+                        // own-relative ghost cell (gi, y0 + xr, z0 - 1 + p): gi = -1 (lo) or nx (hi)
+                        if (s0) {
+                            xsrc[k] = s0 + (long long)(t.z0 - 1) * li.PS + (long long)(t.y0 + xr) * li.P + ((side ? bx.n[0] : -1) + li.ng + li.xoff);
+                            xdst[k] = &xg_s[0][side][xr];
+                        }
                     }
-                    int r0 = t.y0 - 1, r1 = t.y0 + t.ny;                     // first / last staged row (box-relative)
-                    if (r0 < 0 && s_ylo) {
-                        tma_load_1d(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[s]);
-                        r0 = 0;
-                    }
-                    if (r1 >= nyb && s_yhi) {
-                        tma_load_1d(dst + (long long)(rows - 1) * li.P, s_yhi + (long long)c * cs_yhi + (long long)z * li.PS + (long long)nyb * li.P,
-                                    row_bytes, &full_bar[s]);
-                        r1 = nyb - 1;
-                    }
-                    tma_load_1d(dst + (long long)(r0 - (t.y0 - 1)) * li.P,
-                                in0 + (long long)c * L.cs_in + li.off + (long long)(z + li.ng) * li.PS + (long long)(r0 + li.ng) * li.P,
-                                (uint32_t)(r1 - r0 + 1) * row_bytes, &full_bar[s]);
                 }
             }
-        } else {
-            const int idx = lane - 1;
-            const int side = idx / t.ny, r = idx - side * t.ny;              // side 0 = x-lo, 1 = x-hi
-            if (side < 2 && (side ? xhi_link : xlo_link)) {
-                long long cs;
-                // own-relative ghost cell (gi, y0 + r, z0 - 1 + p): gi = -1 (lo) or nx (hi)
-                const int gi = side ? bx.n[0] : -1;
-                const double* src = link_src(side ? 3 : 0, cs) + (long long)(t.z0 - 1) * li.PS + (long long)(t.y0 + r) * li.P + (gi + li.ng + li.xoff);
-                for (int p = 0; p < nplanes; ++p) {
-                    const int s = p % STAGES;
-                    const int n = p / STAGES;
-                    if (n > 0) mbar_wait(&empty_bar[s], (uint32_t)((n - 1) & 1));
-                    cp_async_8(&xg_s[s][side][r], src + (long long)p * li.PS);
-                    cp_async_arrive_noinc(&full_bar[s]);
+            const int nyb = bx.n[1], nzb = bx.n[2];
+            for (int p = 0; p < nplanes; ++p) {
+                mbar_wait(&empty_bar[stage], ephase);
+                if (lane == 0) {
+                    if (p == 0) {                                  // the tile record rides with the tile's first plane
+                        TileRec& R = rec_s[stage];
+                        R.t = t; R.v = v; R.bx = bx; R.li = li; R.lo = L.lay_out[t.box];
+                        int lk = 0;
+#pragma unroll
+                        for (int f = 0; f < 6; ++f) lk |= (nb.f[f].nb >= 0) ? (1 << f) : 0;
+                        R.links = lk;
+                    }
+                    mbar_expect_tx(&full_bar[stage], plane_bytes * NIN);
+                    const int z = t.z0 - 1 + p;
+                    const double* zs = (z < 0) ? s_zlo : (z >= nzb ? s_zhi : nullptr);
+                    const long long zcs = (z < 0) ? cs_zlo : cs_zhi;
+#pragma unroll
+                    for (int c = 0; c < NIN; ++c) {
+                        double* dst = sm + (long long)stage * stage_stride + (long long)c * stage_doubles;
+                        if (zs) {
+                            tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
+                            continue;
+                        }
+                        int r0 = t.y0 - 1, r1 = t.y0 + t.ny;             // first / last staged row (box-relative)
+                        if (r0 < 0 && s_ylo) {
+                            tma_load_1d(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[stage]);
+                            r0 = 0;
+                        }
+                        if (r1 >= nyb && s_yhi) {
+                            tma_load_1d(dst + (long long)(rows - 1) * li.P, s_yhi + (long long)c * cs_yhi + (long long)z * li.PS + (long long)nyb * li.P,
+                                        row_bytes, &full_bar[stage]);
+                            r1 = nyb - 1;
+                        }
+                        tma_load_1d(dst + (long long)(r0 - (t.y0 - 1)) * li.P, own + (long long)c * L.cs_in + (long long)z * li.PS + (long long)r0 * li.P,
+                                    (uint32_t)(r1 - r0 + 1) * row_bytes, &full_bar[stage]);
+                    }
+                } else {
+                    if (xsrc[0]) cp_async_8(xdst[0] + stage * 64, xsrc[0] + (long long)p * li.PS);
+                    if (xsrc[1]) cp_async_8(xdst[1] + stage * 64, xsrc[1] + (long long)p * li.PS);
+                    cp_async_arrive_noinc(&full_bar[stage]);
                 }
+                if (++stage == S) { stage = 0; ephase ^= 1u; }
             }
         }
         return;
     }
 
-    // ===== consumer warps =====
-    const int nx = bx.n[0];
-    const int nq = (nx + 1) >> 1;
-    const int items = nq * t.ny;                       // <= MAX_ITEMS * CONSUMER_THREADS by tile construction
-    const double dxi = L.dxi[0], dyi = L.dxi[1], dzi = L.dxi[2];
-    const int xbase = li.ng + li.xoff;                 // even
-    double* __restrict__ out0 = L.out + (long long)v * NOUT * L.cs_out;
-
-    // MODE_NORMAL_S: staged values are the raw scalar S wherever they come from valid cells (own or a linked neighbour's)
-    // and already-normalised progress values c where they are this box's materialised ghost cells.  n?_raw = "the
-    // ghost layer of that face is materialised" (face not linked).
-    constexpr bool XS = (MODE == MODE_NORMAL_S);
-    bool xlo_raw = false, xhi_raw = false, ylo_raw = false, yhi_raw = false, zlo_raw = false, zhi_raw = false;
-    if (XS) {
-        const PaNbr nb = L.nbr[t.box];
-        xlo_raw = nb.f[0].nb < 0; ylo_raw = nb.f[1].nb < 0; zlo_raw = nb.f[2].nb < 0;
-        xhi_raw = nb.f[3].nb < 0; yhi_raw = nb.f[4].nb < 0; zhi_raw = nb.f[5].nb < 0;
-    }
+    // ===================================== consumer warps =====================================
+    int sc = 0;                    // stage of the plane being received
+    uint32_t fphase = 0;
     const double pmin = ex.pmin, pinv = ex.inv;
     auto prog = [&](double sv) { return (sv - pmin) * pinv; };          // curvature.cpp:316-320
 
-    ItemState st[MAX_ITEMS];
-#pragma unroll
-    for (int it = 0; it < MAX_ITEMS; ++it) st[it].cm = st[it].c0 = st[it].a0 = st[it].b0 = make_double2(0., 0.);
+    for (;;) {
+        // ---- plane 0 of the tile (z = z0-1) and the tile record ----
+        mbar_wait(&full_bar[sc], fphase);
+        const TileRec& R = rec_s[sc];
+        const PaTile t = R.t;
+        if (t.lev < 0) break;                          // end marker
+        const int v = R.v, links = R.links;
+        const int nx = R.bx.n[0], nyb = R.bx.n[1], nzb = R.bx.n[2];
+        const int P = R.li.P;
+        const int lo_P = R.lo.P;
+        const long long lo_PS = R.lo.PS;
+        const LevArgs& L = ga.L[t.lev];
+        const double dxi = L.dxi[0], dyi = L.dxi[1], dzi = L.dxi[2];
+        const long long cs_out = L.cs_out;
+        double* __restrict__ out0 = L.out + (long long)v * NOUT * cs_out;
+        const int nq = (nx + 1) >> 1;
+        const int items = nq * t.ny;                   // <= MAX_ITEMS * CONSUMER_THREADS by tile construction
+        const int xbase = R.li.ng + R.li.xoff;         // even
+        const int nplanes = t.nz + 2;
+        // MODE_NORMAL_S: staged values are the raw scalar S wherever they come from valid cells (own or a linked
+        // neighbour's) and already-normalised progress values where they are this box's materialised ghost cells
+        const bool z0_raw = XS && t.z0 == 0 && !(links & 4);
+        const bool zl_raw = XS && t.z0 + t.nz == nzb && !(links & 32);
 
-    for (int p = 0; p < nplanes; ++p) {
-        const int s = p % STAGES;
-        mbar_wait(&full_bar[s], (uint32_t)((p / STAGES) & 1));
-        const double* S0 = sm + (long long)s * NIN * stage_doubles;
+        int soff[MAX_ITEMS];                           // centre pair inside one component block of a stage
+        unsigned fl[MAX_ITEMS];
+        long long oo[MAX_ITEMS];                       // output element offset of the item in the plane being written
+        double2 cm[MAX_ITEMS], c0[MAX_ITEMS];          // register queue: centre pairs of planes p-2 and p-1
+        long long pi[MAX_ITEMS];                       // MODE_DIV threshold: the item's cell in the input layout (progress variable)
+        const int li_PS = R.li.PS;
 #pragma unroll
         for (int it = 0; it < MAX_ITEMS; ++it) {
             const int w = threadIdx.x + it * CONSUMER_THREADS;
             const bool active = w < items;
             const int q = active ? (w % nq) : 0;
             const int r = active ? (w / nq) : 0;
-            const int xi = xbase + 2 * q;
-            const double* Sc = S0 + (r + 1) * li.P + xi;               // centre row of this item, component 0
-            // centre pair of the component whose x derivative we take
-            double2 c = lds2(Sc);
-            const bool last_odd = (nx & 1) && (q == nq - 1);              // the pair's second cell is the x-hi ghost
+            soff[it] = (r + 1) * P + xbase + 2 * q;
+            oo[it] = R.lo.off + (long long)(t.z0 + R.lo.ng) * lo_PS + (long long)(t.y0 + r + R.lo.ng) * lo_P + (2 * q + R.lo.ng + R.lo.xoff);
+            unsigned f = (unsigned)r << F_ROW_SHIFT;
+            if (active) f |= F_ACTIVE;
+            if (2 * q + 1 < nx) f |= F_TWO;
+            if (lane == 0 || q == 0) f |= F_EDGE_LO;
+            if (lane == 31 || q == nq - 1 || !active || w + 1 >= items) f |= F_EDGE_HI;
+            if (q == 0 && (links & 1)) f |= F_XLO_LINK;
+            if (q == nq - 1 && (links & 8)) f |= F_XHI_LINK;
             if (XS) {
-                // a z-ghost plane of an unlinked face is materialised (already c); everything else staged here is S
-                const int z = t.z0 - 1 + p;
-                const bool plane_raw = (z < 0 && zlo_raw) || (z >= bx.n[2] && zhi_raw);
-                if (!plane_raw) { c.x = prog(c.x); if (!(last_odd && xhi_raw)) c.y = prog(c.y); }
+                if (q == 0 && !(links & 1)) f |= F_XM_RAW;
+                if (q == nq - 1 && !(links & 8)) f |= (nx & 1) ? F_CY_RAW : F_XP_RAW;
+                if (t.y0 + r == 0 && !(links & 2)) f |= F_YM_RAW;
+                if (t.y0 + r == nyb - 1 && !(links & 16)) f |= F_YP_RAW;
             }
-            // x neighbours: from the adjacent lanes when they hold the same row, else from shared memory
-            double xm = __shfl_up_sync(0xffffffffu, c.y, 1);
-            double xp = __shfl_down_sync(0xffffffffu, c.x, 1);
-            if (lane == 0 || q == 0) { xm = Sc[-1]; if (XS && !(q == 0 && xlo_raw)) xm = prog(xm); }
-            if (lane == 31 || q == nq - 1 || !active || (w + 1 >= items)) { xp = Sc[2]; if (XS && !(q == nq - 1 && xhi_raw)) xp = prog(xp); }
-            if (q == 0 && xlo_link) {                                     // ghost = the linked neighbour's last valid cell
-                xm = xg_s[s][0][r]; if (XS) xm = prog(xm);
-            }
-            if (q == nq - 1 && xhi_link) {
-                double xg = xg_s[s][1][r]; if (XS) xg = prog(xg);
-                if (nx & 1) c.y = xg;                                     // odd row length: the pair's second cell IS the ghost
-                else xp = xg;
-            }
-            double2 a1, b1, cp;
-            a1.x = cdiff(dxi, xm, c.x, c.y);
-            a1.y = cdiff(dxi, c.x, c.y, xp);
-            if (MODE != MODE_DIV) {
-                double2 ym = lds2(Sc - li.P), yp = lds2(Sc + li.P);
-                if (XS) {
-                    if (!(t.y0 + r == 0 && ylo_raw)) { ym.x = prog(ym.x); ym.y = prog(ym.y); }
-                    if (!(t.y0 + r == bx.n[1] - 1 && yhi_raw)) { yp.x = prog(yp.x); yp.y = prog(yp.y); }
-                }
-                b1.x = cdiff(dyi, ym.x, c.x, yp.x);
-                b1.y = cdiff(dyi, ym.y, c.y, yp.y);
-                cp = c;
-            } else {
-                const double* Sy = Sc + stage_doubles;                  // component 1 (n_y)
-                const double2 cy = lds2(Sy), ym = lds2(Sy - li.P), yp = lds2(Sy + li.P);
-                b1.x = cdiff(dyi, ym.x, cy.x, yp.x);
-                b1.y = cdiff(dyi, ym.y, cy.y, yp.y);
-                cp = lds2(Sc + 2 * stage_doubles);                      // component 2 (n_z) centre
-            }
-            // finish plane p-1 (needs centre of p-2, p-1, p) once it is an interior plane of the tile
-            if (p >= 2 && active) {
-                const int jy = t.y0 + r, kz = t.z0 + p - 2;
-                const double g0 = cdiff(dzi, st[it].cm.x, st[it].c0.x, cp.x);
-                const double g1 = cdiff(dzi, st[it].cm.y, st[it].c0.y, cp.y);
-                const long long o = lo.off + (long long)(kz + lo.ng) * lo.PS + (long long)(jy + lo.ng) * lo.P + (2 * q + lo.ng + lo.xoff);
-                const bool two = (2 * q + 1 < nx);
-                double r0[4], r1[4];
-                const double ax = st[it].a0.x, ay = st[it].a0.y, bx0 = st[it].b0.x, by0 = st[it].b0.y;
-                if (MODE == MODE_GRAD) {
-                    r0[0] = ax; r0[1] = bx0; r0[2] = g0; r0[3] = sqrt(ax * ax + bx0 * bx0 + g0 * g0);
-                    r1[0] = ay; r1[1] = by0; r1[2] = g1; r1[3] = sqrt(ay * ay + by0 * by0 + g1 * g1);
-                } else if (MODE == MODE_GRAD3) {
-                    r0[0] = ax; r0[1] = bx0; r0[2] = g0;
-                    r1[0] = ay; r1[1] = by0; r1[2] = g1;
-                } else if (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
-                    if (XS) {                                                // Progress of plane p-1 (curvature.cpp:310-321)
-                        double* pc = ex.cout[t.lev] + o;
-                        if (two) stg2(pc, st[it].c0.x, st[it].c0.y); else pc[0] = st[it].c0.x;
-                    }
-                    const double n0 = -fmax(1e-14, sqrt(ax * ax + bx0 * bx0 + g0 * g0));
-                    const double n1 = -fmax(1e-14, sqrt(ay * ay + by0 * by0 + g1 * g1));
-                    r0[0] = ax / n0; r0[1] = bx0 / n0; r0[2] = g0 / n0;
-                    r1[0] = ay / n1; r1[1] = by0 / n1; r1[2] = g1 / n1;
-                    if (ex.aux[t.lev]) {
-                        double* g = ex.aux[t.lev] + o;
-                        const long long cg = ex.cs_aux[t.lev];
-                        if (two) { stg2(g, ax, ay); stg2(g + cg, bx0, by0); stg2(g + 2 * cg, g0, g1); }
-                        else { g[0] = ax; g[cg] = bx0; g[2 * cg] = g0; }
-                    }
-                } else {
-                    r0[0] = 0.5 * (((0.0 + ax) + bx0) + g0);
-                    r1[0] = 0.5 * (((0.0 + ay) + by0) + g1);
-                    if (ex.do_threshold) {
-                        const long long ai = li.off + (long long)(kz + li.ng) * li.PS + (long long)(jy + li.ng) * li.P + (2 * q + xbase);
-                        const double2 pc = *reinterpret_cast<const double2*>(ex.prog[t.lev] + ai);
-                        if (pc.x < ex.threshold || pc.x > 1.0 - ex.threshold) r0[0] = 0.0;
-                        if (pc.y < ex.threshold || pc.y > 1.0 - ex.threshold) r1[0] = 0.0;
-                    }
-                }
-                double* po = out0 + o;
-#pragma unroll
-                for (int m = 0; m < NOUT; ++m) {
-                    if (two) stg2(po + m * L.cs_out, r0[m], r1[m]); else po[m * L.cs_out] = r0[m];
-                }
-            }
-            st[it].cm = st[it].c0;
-            st[it].c0 = cp;
-            st[it].a0 = a1;
-            st[it].b0 = b1;
+            fl[it] = f;
+            pi[it] = R.li.off + (long long)(t.z0 + R.li.ng) * li_PS + (long long)(t.y0 + r + R.li.ng) * P + (2 * q + xbase);
+            cm[it] = c0[it] = make_double2(0., 0.);
         }
-        // this warp is done reading stage s
+        // centre pair of the z-derivative component of a freshly landed plane (MODE_DIV: n_z), fixed up so that the
+        // register queue always holds final values: linked x-hi ghost of an odd row, progress normalisation
+        auto load_centre = [&](int st, int it, bool plane_raw) -> double2 {
+            const double* Sq = sm + (long long)st * stage_stride + (MODE == MODE_DIV ? 2 * stage_doubles : 0) + soff[it];
+            double2 c = lds2(Sq);
+            if (MODE != MODE_DIV) {
+                if ((fl[it] & F_XHI_LINK) && (nx & 1)) c.y = xg_s[st][1][fl[it] >> F_ROW_SHIFT];    // the pair's second cell IS the ghost
+                if (XS && !plane_raw) { c.x = prog(c.x); if (!(fl[it] & F_CY_RAW)) c.y = prog(c.y); }
+            }
+            return c;
+        };
+#pragma unroll
+        for (int it = 0; it < MAX_ITEMS; ++it) c0[it] = load_centre(sc, it, z0_raw);
+        int sp = sc;                                   // stage of plane p-1
+        if (++sc == S) { sc = 0; fphase ^= 1u; }
+
+        for (int p = 1; p < nplanes; ++p) {
+            mbar_wait(&full_bar[sc], fphase);
+            const double* Sp = sm + (long long)sp * stage_stride;
+            const bool last_raw = zl_raw && p == nplanes - 1;
+#pragma unroll
+            for (int it = 0; it < MAX_ITEMS; ++it) {
+                const unsigned f = fl[it];
+                const double2 cp = load_centre(sc, it, last_raw);
+                if (p >= 2) {
+                    // ---- finish plane p-1: in-plane derivatives from its stage, z derivative from the register queue ----
+                    const double* Sc = Sp + soff[it];
+                    double2 c = c0[it];
+                    if (MODE == MODE_DIV) {
+                        c = lds2(Sc);                                      // n_x centre pair
+                        if ((f & F_XHI_LINK) && (nx & 1)) c.y = xg_s[sp][1][f >> F_ROW_SHIFT];
+                    }
+                    // x neighbours: from the adjacent lanes when they hold the same row, else from shared memory
+                    double xm = __shfl_up_sync(0xffffffffu, c.y, 1);
+                    double xp = __shfl_down_sync(0xffffffffu, c.x, 1);
+                    if (f & F_EDGE_LO) { xm = Sc[-1]; if (XS && !(f & F_XM_RAW)) xm = prog(xm); }
+                    if (f & F_EDGE_HI) { xp = Sc[2]; if (XS && !(f & F_XP_RAW)) xp = prog(xp); }
+                    if (f & F_XLO_LINK) { xm = xg_s[sp][0][f >> F_ROW_SHIFT]; if (XS) xm = prog(xm); }
+                    if ((f & F_XHI_LINK) && !(nx & 1)) { xp = xg_s[sp][1][f >> F_ROW_SHIFT]; if (XS) xp = prog(xp); }
+                    const double ax = cdiff(dxi, xm, c.x, c.y);
+                    const double ay = cdiff(dxi, c.x, c.y, xp);
+                    double bx0, by0;
+                    if (MODE != MODE_DIV) {
+                        double2 ym = lds2(Sc - P), yp = lds2(Sc + P);
+                        if (XS) {
+                            if (!(f & F_YM_RAW)) { ym.x = prog(ym.x); ym.y = prog(ym.y); }
+                            if (!(f & F_YP_RAW)) { yp.x = prog(yp.x); yp.y = prog(yp.y); }
+                        }
+                        bx0 = cdiff(dyi, ym.x, c.x, yp.x);
+                        by0 = cdiff(dyi, ym.y, c.y, yp.y);
+                    } else {
+                        const double* Sy = Sc + stage_doubles;              // component 1 (n_y)
+                        const double2 cy = lds2(Sy), ym = lds2(Sy - P), yp = lds2(Sy + P);
+                        bx0 = cdiff(dyi, ym.x, cy.x, yp.x);
+                        by0 = cdiff(dyi, ym.y, cy.y, yp.y);
+                    }
+                    const double g0 = cdiff(dzi, cm[it].x, c0[it].x, cp.x);
+                    const double g1 = cdiff(dzi, cm[it].y, c0[it].y, cp.y);
+                    if (f & F_ACTIVE) {
+                        const long long o = oo[it];
+                        const bool two = (f & F_TWO) != 0;
+                        double r0[4], r1[4];
+                        if (MODE == MODE_GRAD) {
+                            r0[0] = ax; r0[1] = bx0; r0[2] = g0; r0[3] = sqrt(ax * ax + bx0 * bx0 + g0 * g0);
+                            r1[0] = ay; r1[1] = by0; r1[2] = g1; r1[3] = sqrt(ay * ay + by0 * by0 + g1 * g1);
+                        } else if (MODE == MODE_GRAD3) {
+                            r0[0] = ax; r0[1] = bx0; r0[2] = g0;
+                            r1[0] = ay; r1[1] = by0; r1[2] = g1;
+                        } else if (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
+                            if (XS) {                                        // Progress of plane p-1 (curvature.cpp:310-321)
+                                double* pc = ex.cout[t.lev] + o;
+                                if (two) stg2(pc, c.x, c.y); else pc[0] = c.x;
+                            }
+                            const double n0 = -fmax(1e-14, sqrt(ax * ax + bx0 * bx0 + g0 * g0));
+                            const double n1 = -fmax(1e-14, sqrt(ay * ay + by0 * by0 + g1 * g1));
+                            r0[0] = ax / n0; r0[1] = bx0 / n0; r0[2] = g0 / n0;
+                            r1[0] = ay / n1; r1[1] = by0 / n1; r1[2] = g1 / n1;
+                            if (ex.aux[t.lev]) {
+                                double* g = ex.aux[t.lev] + o;
+                                const long long cg = ex.cs_aux[t.lev];
+                                if (two) { stg2(g, ax, ay); stg2(g + cg, bx0, by0); stg2(g + 2 * cg, g0, g1); }
+                                else { g[0] = ax; g[cg] = bx0; g[2 * cg] = g0; }
+                            }
+                        } else {
+                            r0[0] = 0.5 * (((0.0 + ax) + bx0) + g0);
+                            r1[0] = 0.5 * (((0.0 + ay) + by0) + g1);
+                            if (ex.do_threshold) {
+                                const double2 pc = *reinterpret_cast<const double2*>(ex.prog[t.lev] + pi[it]);
+                                if (pc.x < ex.threshold || pc.x > 1.0 - ex.threshold) r0[0] = 0.0;
+                                if (pc.y < ex.threshold || pc.y > 1.0 - ex.threshold) r1[0] = 0.0;
+                            }
+                        }
+                        double* po = out0 + o;
+#pragma unroll
+                        for (int m = 0; m < NOUT; ++m) {
+                            if (two) stg2(po, r0[m], r1[m]); else po[0] = r0[m];
+                            po += cs_out;
+                        }
+                    }
+                    oo[it] += lo_PS;
+                    if (MODE == MODE_DIV) pi[it] += li_PS;
+                }
+                cm[it] = c0[it];
+                c0[it] = cp;
+            }
+            // this warp no longer needs plane p-1
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[sp]);
+            sp = sc;
+            if (++sc == S) { sc = 0; fphase ^= 1u; }
+        }
+        // ... nor the tile's last plane
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive(&empty_bar[sp]);
     }
 }
+
+int g_num_sms = 0;
+// work-item ticket counters, one per stream (launches on one stream are ordered, so they can share a counter that is
+// never reset; kernels on different streams may overlap and must not)
+struct Ticket { unsigned long long* dev = nullptr; unsigned long long base = 0; };
+std::map<cudaStream_t, Ticket> g_tickets;
+int g_stage_cap = 0;
+size_t g_inflight_bytes = 0;
 
 template <int MODE>
 cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                         int nvar, cudaStream_t st) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
-    size_t smem = (size_t)STAGES * NIN * stage_doubles * sizeof(double);
+    const size_t stage_bytes = (size_t)NIN * stage_doubles * sizeof(double);
+    // Ring depth.  The consumers hold two planes (p-1 and p); the rest of the ring is data in flight.  Measured on B200
+    // (config 2): ~20 KB in flight per CTA (2 CTAs/SM, ~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
+    // ring is SLOWER (the read stream runs far ahead of the write stream and the two fight for DRAM pages / L2).
+    if (g_inflight_bytes == 0) { const char* e = getenv("PA_TMA_INFLIGHT_KB"); g_inflight_bytes = (size_t)(e ? std::max(1, atoi(e)) : 20) * 1024; }
+    const size_t budget2 = (227 * 1024 - 2 * STATIC_SMEM - 2 * 1024) / 2, budget1 = 227 * 1024 - STATIC_SMEM - 1024;
+    int S = 2 + (int)((g_inflight_bytes + stage_bytes - 1) / stage_bytes), per_sm = 2;
+    if ((size_t)S * stage_bytes > budget2) S = (int)(budget2 / stage_bytes);
+    if (S < 4) { S = std::min(4, (int)(budget1 / stage_bytes)); per_sm = 1; }
+    if (S < 3) return cudaErrorInvalidConfiguration;
+    if (S > MAX_STAGES) S = MAX_STAGES;
+    if (g_stage_cap == 0) { const char* e = getenv("PA_TMA_STAGES"); g_stage_cap = e ? std::max(3, atoi(e)) : MAX_STAGES; }
+    if (S > g_stage_cap) S = g_stage_cap;
+    const size_t smem = (size_t)S * stage_bytes;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_stencil_tma<MODE><<<dim3(ntiles, nvar), THREADS, smem, st>>>(tiles, ga, ex, stage_doubles);
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    const long long nwork = (long long)ntiles * nvar;
+    const int grid = (int)std::min<long long>(nwork, (long long)g_num_sms * per_sm);
+    Ticket& T = g_tickets[st];
+    if (!T.dev) {
+        cudaError_t e = cudaMalloc(&T.dev, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+    }
+    k_stencil_tma<MODE><<<grid, THREADS, smem, st>>>(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
 
 }  // namespace
 
-int stencil_tma_tile_rows() { return TILE_ROWS; }
+int stencil_tma_tile_rows() { return MAX_TILE_ROWS; }
 int stencil_tma_max_tile_rows() { return MAX_TILE_ROWS; }
-int stencil_tma_max_items() { return MAX_ITEMS * CONSUMER_THREADS; }
-// largest staged plane ((TY+2) rows x pitch) the pipeline accepts per input component
-int stencil_tma_max_plane_doubles() { return (200 * 1024) / (STAGES * 3 * 8); }
+// largest staged plane ((TY+2) rows x pitch) the pipeline accepts per input component (3 stages of 3 components must fit)
+int stencil_tma_max_plane_doubles() { return (227 * 1024 - STATIC_SMEM - 1024) / (3 * 3 * 8); }
 
 cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, const GridArgs& ga,
                                const StencilExtra& ex, int nvar, cudaStream_t st) {
