@@ -246,8 +246,11 @@ cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaF
 // stencil arithmetic shared by the simple and the TMA kernels (expression order = reference)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double cdiff(double dxi, double m, double c, double p) {
-    // average_face_to_cellcenter of the two face differences: 0.5*( dxi*(c-m) + dxi*(p-c) )
-    return 0.5 * (dxi * (c - m) + dxi * (p - c));
+    // the reference's sequence, sign of zero included: faces f = dxinv*(s(i)-s(i-1)) are multiplied by 1/b = -1
+    // (MLCellABecLap::getFluxes), averaged (average_face_to_cellcenter), and multiplied by -1 again (grad.cpp:219).  When the
+    // two face differences cancel exactly the result is -0, which 0.5*(fl+fh) would turn into +0.
+    const double fl = dxi * (c - m), fh = dxi * (p - c);
+    return -(0.5 * ((-fl) + (-fh)));
 }
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }

@@ -74,10 +74,44 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 }
 
 __device__ __forceinline__ double cdiff(double dxi, double m, double c, double p) {
-    return 0.5 * (dxi * (c - m) + dxi * (p - c));
+    // the reference's sequence, sign of zero included: faces f = dxinv*(s(i)-s(i-1)) are multiplied by 1/b = -1
+    // (MLCellABecLap::getFluxes), averaged (average_face_to_cellcenter), and multiplied by -1 again (grad.cpp:219).  When the
+    // two face differences cancel exactly the result is -0, which 0.5*(fl+fh) would turn into +0.
+    const double fl = dxi * (c - m), fh = dxi * (p - c);
+    return -(0.5 * ((-fl) + (-fh)));
 }
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// Three quotients by one divisor, bit-identical to the IEEE divisions a/n the reference performs (curvature.cpp:498-502,
+// MultiFab::Divide): y = RN(1/n) once, then per numerator q0 = RN(a*y), r = a - n*q0 (exact in an FMA), q = RN(q0 + r*y).
+// With a correctly rounded reciprocal the corrected quotient is the correctly rounded a/n (Markstein, "Computation of
+// elementary functions on the IBM RISC System/6000 processor", 1990, Thm 8.8); checked here against a/n on 5e10 random and
+// adversarial operand pairs without a mismatch (tests/golden/README: divtest).  The remainder must not underflow, so
+// tiny non-zero numerators take the plain division; zeros and NaN/Inf fall out right (+-0 keeps the sign rule of a/n).
+// The reference divides valid cells by a norm that is >= |a| (or by -1e-14), so quotients never overflow.
+__device__ __forceinline__ double div_by(double a, double y, double n) {
+    const double q0 = a * y;
+    const double r = fma(-n, q0, a);
+    return fma(r, y, q0);
+}
+// non-zero and below 2^-830 (~1.4e-250): the remainder a - n*q0 (~2^-53 |a|) could underflow
+__device__ __forceinline__ bool tiny_nonzero(double a) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffULL;
+    return (u - 1ULL) < (0x0C10000000000000ULL - 1ULL);
+}
+__device__ __noinline__ void div3_plain(double a, double b, double c, double n, double* q) {
+    q[0] = a / n; q[1] = b / n; q[2] = c / n;
+}
+// q[0..2] = a/n, b/n, c/n with IEEE-identical results; |n| >= 1e-14 (so 1/n is a normal number)
+__device__ __forceinline__ void div3(double a, double b, double c, double n, double* q) {
+    if (tiny_nonzero(a) | tiny_nonzero(b) | tiny_nonzero(c)) {          // practically never: out of line
+        div3_plain(a, b, c, n, q);
+        return;
+    }
+    const double y = __drcp_rn(n);
+    q[0] = div_by(a, y, n); q[1] = div_by(b, y, n); q[2] = div_by(c, y, n);
+}
 
 template <int MODE> struct ModeTraits;
 template <> struct ModeTraits<MODE_GRAD> { static constexpr int NIN = 1, NOUT = 4; };
@@ -382,8 +416,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __rest
                             }
                             const double n0 = -fmax(1e-14, sqrt(ax * ax + bx0 * bx0 + g0 * g0));
                             const double n1 = -fmax(1e-14, sqrt(ay * ay + by0 * by0 + g1 * g1));
-                            r0[0] = ax / n0; r0[1] = bx0 / n0; r0[2] = g0 / n0;
-                            r1[0] = ay / n1; r1[1] = by0 / n1; r1[2] = g1 / n1;
+                            div3(ax, bx0, g0, n0, r0);
+                            div3(ay, by0, g1, n1, r1);
                             if (ex.aux[t.lev]) {
                                 double* g = ex.aux[t.lev] + o;
                                 const long long cg = ex.cs_aux[t.lev];
@@ -444,7 +478,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     const size_t budget2 = (227 * 1024 - 2 * STATIC_SMEM - 2 * 1024) / 2, budget1 = 227 * 1024 - STATIC_SMEM - 1024;
     int S = 2 + (int)((g_inflight_bytes + stage_bytes - 1) / stage_bytes), per_sm = 2;
     if ((size_t)S * stage_bytes > budget2) S = (int)(budget2 / stage_bytes);
-    if (S < 4) { S = std::min(4, (int)(budget1 / stage_bytes)); per_sm = 1; }
+    if (S < 3) { S = std::min(4, (int)(budget1 / stage_bytes)); per_sm = 1; }
     if (S < 3) return cudaErrorInvalidConfiguration;
     if (S > MAX_STAGES) S = MAX_STAGES;
     if (g_stage_cap == 0) { const char* e = getenv("PA_TMA_STAGES"); g_stage_cap = e ? std::max(3, atoi(e)) : MAX_STAGES; }

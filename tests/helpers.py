@@ -52,10 +52,13 @@ def fabs_from_flat(pf, flat):
 
 
 def bit_equal(a, b):
-    """Bit-for-bit equality of float64 arrays, treating any NaN == any NaN."""
-    a = np.asarray(a)
-    b = np.asarray(b)
-    return a.shape == b.shape and bool(np.array_equal(a, b, equal_nan=True))
+    """Bit-for-bit equality of float64 arrays -- the sign of zero included -- treating any NaN == any NaN."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return False
+    same = a.view(np.int64) == b.view(np.int64)
+    return bool(np.all(same | (np.isnan(a) & np.isnan(b))))
 
 
 def max_rel(a, b):

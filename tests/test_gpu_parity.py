@@ -174,6 +174,37 @@ def test_midsize_grad_and_curvature_vs_oracle(gpu, case, kw):
             assert bit_equal(flat_from_fabs(out.download_fabs(c)), wk[c]), (case, "curv", c)
 
 
+@pytest.mark.parametrize("stencil", ["tma", "simple"])
+def test_curvature_degenerate_values(gpu, stencil):
+    """Exactly flat regions (0/-1e-14 = -0), gradients around the 1e-250 guard of the shared-reciprocal division, huge and
+    sign-alternating values: the flame normal's three IEEE divisions must come out bit-identical to the oracle's a/n."""
+    pf = synth.config1(16, 8)
+    rng = np.random.default_rng(7)
+    for lv in pf.levels:
+        for b, ((lo, hi), fab) in enumerate(zip(lv.boxes, lv.fabs)):
+            kind = (b + lo[0] // 8) % 4
+            shape = fab[0].shape
+            if kind == 0:
+                fab[0][...] = 0.25                                                     # flat: G = 0 exactly
+            elif kind == 1:
+                fab[0][...] = rng.uniform(-1, 1, shape) * 10.0 ** rng.integers(-262, -240, shape)   # around the guard
+            elif kind == 2:
+                fab[0][...] = rng.uniform(-1, 1, shape) * 1e150                        # huge
+            else:
+                fab[0][...] = np.where(rng.random(shape) < 0.5, 0.0, rng.uniform(-1, 1, shape) * 1e-300)
+    s = _flat(pf, "temp")
+    OH = O.OracleHier(pf, (1, 1, 1), (0, 0, 0))
+    want = OH.curvature(s, 0.0, 1.0)                                                   # progMin 0, progMax 1: c == S
+    out, _ = _gpu_curv(gpu, pf, (1, 1, 1), (0, 0, 0), 0.0, 1.0, {}, stencil)
+    for c in range(5):
+        assert bit_equal(out[c], want[c]), (stencil, c, max_rel(out[c], want[c]))
+    # signed zeros too: bit_equal uses ==, which does not tell -0 from +0
+    for c in range(5):
+        ok = np.isnan(want[c]) | (np.signbit(out[c]) == np.signbit(want[c]))
+        bad = np.flatnonzero(~ok)
+        assert bad.size == 0, (stencil, c, bad.size, bad[:8], out[c][bad[:8]], want[c][bad[:8]], s[bad[:8]])
+
+
 def test_multi_variable_grad_equals_single(gpu):
     """The multi-variable extension (config 2's 5 components in one call) gives each variable the single-variable result."""
     pf = synth.config1(32, 16, names=synth.FIELD_NAMES)
