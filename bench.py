@@ -180,10 +180,15 @@ def gen_fields(torch, levels, local_boxes, names, prob_hi=(1.0, 1.0, 1.0)):
 def bench_extra(torch, capi, synth, stream, peak, kind, steps, warmup):
     """Secondary measurements reported next to the headline line (same timing rules, N=1 only):
     curvature3 : curvature tool (default options) on BASELINE configs[2] -- 3 levels, 256^3 base, ratio 2, 64^3 boxes
+    target_grad / target_curv : grad / curvature of temp on the north-star target hierarchy (3 levels, 512^3 base, 128^3 boxes)
     grad5      : grad of 12 components on a configs[4]-like 4-level hierarchy (ratios 2/4/2, 16^3 boxes)."""
     if kind == "curvature3":
         pf = synth.config3(256, 64, fill=False)
         names, desc = ["temp"], "curvature (default options), 3 levels, 256^3 base, ratio 2, 64^3 boxes (BASELINE configs[2])"
+    elif kind in ("target_grad", "target_curv"):
+        pf = synth.config3(512, 128, fill=False)
+        names = ["temp"]
+        desc = "%s, 3 levels, 512^3 base, ratio 2, 128^3 boxes (the north-star target hierarchy)" % ("grad of temp" if kind == "target_grad" else "curvature (default options)")
     else:
         pf = synth.config5(128, 16, 12, fill=False)
         names, desc = list(pf.names), "grad of 12 components, 4 levels (ratios 2/4/2), 128^3 base, 16^3 boxes (BASELINE configs[4])"
@@ -195,7 +200,7 @@ def bench_extra(torch, capi, synth, stream, peak, kind, steps, warmup):
         for c in range(nv):
             capi.check(capi.lib().pa_field_upload_level(fin.f, l, c, host[l][c].data_ptr()))
     capi.sync()
-    if kind == "curvature3":
+    if kind in ("curvature3", "target_curv"):
         o = capi.CurvOpts()
         o.prog_min = min(float(h[0].min()) for h in host)
         o.prog_max = max(float(h[0].max()) for h in host)
@@ -234,7 +239,7 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "slab"])
     ap.add_argument("--no-links", action="store_true", help="materialise every ghost cell (reference data flow)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary curvature / small-box measurements")
-    ap.add_argument("--only-extra", default=None, choices=["curvature3", "grad5"], help="run just one secondary measurement (profiling aid)")
+    ap.add_argument("--only-extra", default=None, choices=["curvature3", "grad5", "target_grad", "target_curv"], help="run just one secondary measurement (profiling aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     spec = workload_spec(args.workload)
@@ -419,7 +424,7 @@ def main():
     if world == 1 and not args.no_extras:
         del fin, fout, host_out, host_in
         extras = {}
-        for kind in ("curvature3", "grad5"):
+        for kind in ("curvature3", "grad5", "target_grad", "target_curv"):
             try:
                 extras[kind] = bench_extra(torch, capi, synth, stream, peak, kind, max(5, args.steps // 2), 3)
             except Exception as e:
