@@ -155,6 +155,17 @@ int pa_grad_phases(pa_field *in, int comp_in, int nvar, pa_field *out, int comp_
  * `state` needs nghost>=1; `out` may have nghost 0. */
 int pa_curvature(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out);
 int pa_curvature_num_outputs(const pa_curv_opts *opts);
+/* The same in its two passes, so a multi-rank caller can put the cross-rank step between them (the reference does the
+ * same thing with MPI inside FillBoundary / ParallelCopy of the flame normal, Src/curvature.cpp:487-502,514-520):
+ *   phases bit 0: progress variable + ghost fill of S + flame normal (writes Progress, FlameNormalX/Y/Z);
+ *                 multi-rank: the caller has exchanged state[comp_S] (pa_exchange_pack -> transport -> mark_received)
+ *   phases bit 1: ghost fill of the normal + MeanCurvature + the optional branches;
+ *                 multi-rank: the caller has exchanged out[comp_out+2 .. +4], and with peer links has ordered every
+ *                 rank's pass 1 before this call (a cross-rank barrier on the stream).
+ * pa_curvature == pa_curvature_phases(..., 3) and is single-rank only.  Multi-rank hierarchies support the default
+ * options and do_velnormal; threshold_prog / do_gaussCurv / do_strain return PA_ERR_UNSUPPORTED there. */
+int pa_curvature_phases(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out,
+                        int phases);
 
 /* ---- multi-rank ghost exchange (one process per GPU; the transport is the caller's: NCCL send/recv) ---
  * For exchange step `step` of an operation the library packs what each peer needs into a device send slab and
@@ -195,6 +206,12 @@ int pa_debug_links(pa_hier *h, int lev, int box, int out[30]);
  * each recv-slab slot expects, encoded (source level << 56 | global box << 32 | linear index in the box's valid
  * region).  which = 0: send slab, 1: recv slab.  Returns the slab length in cells (writes min(len, out_len)). */
 int64_t pa_debug_exchange_ids(pa_hier *h, int which, int64_t *out, int64_t out_len);
+
+/* Device self-test of the stencil kernels' branch-free IEEE sqrt / reciprocal / quotient forms (the flame normal's
+ * nrm = -max(1e-14, sqrt(G.G)), n = G / nrm of Src/curvature.cpp:467-502) against the plain operators on n pseudo-random
+ * operand sets covering every exponent of their ranges, zeros, denormals and overflow.  Returns the number of results
+ * that differ in any bit (0 = identical), or -1 on error. */
+int64_t pa_debug_selftest_math(int64_t n, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ SYMBOLS = {
     "pa_grad": (_i, [_vp, _i, _i, _vp, _i]), "pa_grad_phases": (_i, [_vp, _i, _i, _vp, _i, _i]),
     "pa_curvature": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i]),
     "pa_curvature_num_outputs": (_i, [C.POINTER(CurvOpts)]),
+    "pa_debug_selftest_math": (C.c_int64, [C.c_int64, C.c_uint64]),
+    "pa_curvature_phases": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i, _i]),
     "pa_exchange_counts": (_i, [_vp, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "pa_exchange_buffers": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "pa_exchange_pack": (_i, [_vp, _i, _i]), "pa_exchange_mark_received": (_i, [_vp, _i, _i]),
@@ -366,6 +368,10 @@ def grad(inp: Field, comp_in: int, nvar: int, out: Field, comp_out: int, phases:
 
 def curvature(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, out: Field, comp_out: int = 0) -> None:
     check(lib().pa_curvature(state.f, comp_S, comp_vel, C.byref(opts), out.f, comp_out))
+
+
+def curvature_phases(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, out: Field, comp_out: int, phases: int) -> None:
+    check(lib().pa_curvature_phases(state.f, comp_S, comp_vel, C.byref(opts), out.f, comp_out, phases))
 
 
 def curvature_num_outputs(opts: CurvOpts) -> int:

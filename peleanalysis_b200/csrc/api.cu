@@ -767,7 +767,15 @@ static int tmp_field(pa_hier* h, pa_field** slot, int ncomp) {
 }
 
 int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out) {
+    if (state && state->h && state->h->H.nranks > 1)
+        return fail(PA_ERR_UNSUPPORTED, "pa_curvature: on a multi-rank hierarchy the two passes are separated by a cross-rank step the caller "
+                                        "owns; use pa_curvature_phases (1, exchange / barrier, 2)");
+    return pa_curvature_phases(state, comp_S, comp_vel, opts, out, comp_out, 3);
+}
+
+int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out, int phases) {
     if (!opts) return fail(PA_ERR_ARG, "pa_curvature: null options");
+    if (phases < 1 || phases > 3) return fail(PA_ERR_ARG, "pa_curvature_phases: phases must be 1, 2 or 3");
     CHK(check_field(state, comp_S, 1, "pa_curvature(state)"));
     const int nout = pa_curvature_num_outputs(opts);
     CHK(check_field(out, comp_out, nout, "pa_curvature(out)"));
@@ -779,7 +787,9 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     if (need_vel) CHK(check_field(state, comp_vel, 3, "pa_curvature(velocity)"));
     pa_hier* h = state->h;
     Hier& H = h->H;
-    if (H.nranks > 1) return fail(PA_ERR_UNSUPPORTED, "pa_curvature: multi-rank exchange is driven by the host tool; use the single-rank path per GPU");
+    if (H.nranks > 1 && (opts->do_threshold || opts->do_gauss || opts->do_strain))
+        return fail(PA_ERR_UNSUPPORTED, "pa_curvature_phases: threshold_prog / do_gaussCurv / do_strain need further cross-rank exchanges "
+                                        "(per level, of internal fields) that the multi-rank path does not sequence yet");
     CHK(ensure_device(h));
     const int nlev = H.nlev;
     const int cP = comp_out, cK = comp_out + 1, cN = comp_out + 2;
@@ -799,7 +809,9 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     GridArgs ga;
     const double invdenom = 1.0 / (opts->prog_max - opts->prog_min);
     const char* no_fuse = getenv("PA_CURV_UNFUSED");
-    if (state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
+    if (!(phases & 1)) {
+        // pass 1 already ran (previous call)
+    } else if (state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
         // 1+2 fused.  The progress pass (curvature.cpp:310-321) rides in the stencil's loader: valid cells stay S and are
         // normalised as they are read; the few ghost cells that must be materialised (unlinked faces) are written in
         // progress space by the ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel
@@ -811,6 +823,9 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
         CHK(grid_args(state, comp_S, out, cN, ga));
         CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
     } else {
+        if (H.nranks > 1)
+            return fail(PA_ERR_UNSUPPORTED, "pa_curvature_phases: the multi-rank path needs the fused progress pass (state with nghost == 1, "
+                                            "TMA-eligible boxes); the unfused route would exchange an intermediate field");
         // 1. progress variable on valid cells of every level (curvature.cpp:310-321)
         for (int l = 0; l < nlev; ++l) {
             int err = PA_OK;
@@ -829,6 +844,7 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     // 3. divergence of n.  Without the threshold clip every level's coarse data is final after step 2, so one
     //    batched ghost fill + one stencil launch cover the hierarchy; with it, level l needs the CLIPPED n of l-1
     //    (curvature.cpp:514-518 reads flame_normal[lev-1] after :549-567 modified it), so levels run in order.
+    if (!(phases & 2)) return PA_OK;
     std::memset(&ex, 0, sizeof(ex));
     ex.do_threshold = opts->do_threshold ? 1 : 0;
     ex.threshold = opts->threshold;
@@ -979,6 +995,14 @@ int pa_debug_links(pa_hier* h, int lev, int box, int out[30]) {
         for (int d = 0; d < 3; ++d) out[5 * f + 2 + d] = K.nb >= 0 ? V.boxes[box].lo[d] + K.shift[d] - V.boxes[K.nb].lo[d] : 0;
     }
     return PA_OK;
+}
+
+int64_t pa_debug_selftest_math(int64_t n, uint64_t seed) {
+    if (n < 1) { fail(PA_ERR_ARG, "pa_debug_selftest_math: n < 1"); return -1; }
+    unsigned long long bad = 0;
+    cudaError_t e = selftest_math((long long)n, (unsigned long long)seed, &bad, t_stream);
+    if (e != cudaSuccess) { cuda_fail(e, "pa_debug_selftest_math"); return -1; }
+    return (int64_t)bad;
 }
 
 int64_t pa_debug_exchange_ids(pa_hier* h, int which, int64_t* out, int64_t out_len) {

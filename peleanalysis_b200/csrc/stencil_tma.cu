@@ -28,10 +28,12 @@ namespace pa {
 namespace {
 
 constexpr int MAX_STAGES = 16;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
-constexpr int THREADS = CONSUMER_THREADS + 32;       // + 1 producer warp
-constexpr int MAX_ITEMS = 2;                          // x-pairs per consumer thread per plane
+// Two CTA shapes (template parameter CW = consumer warps; + 1 producer warp each):
+//   CW = 8,  2 CTAs/SM, 2 x-pairs per consumer thread per plane : the bandwidth-bound modes (two independent rings per SM)
+//   CW = 16, 1 CTA/SM,  1 x-pair  per consumer thread per plane : the FP64-heavy flame-normal modes -- the same 16 consumer
+//            warps per SM, but half the per-thread state and a 112-register budget (9 warps are allocated as 10, which
+//            caps the 2-CTA shape at 96 registers and made the normal epilogue spill)
+constexpr int TILE_ITEMS = 512;                       // x-pairs per tile plane: CW * 32 * ITEMS for both shapes
 constexpr int MAX_TILE_ROWS = 30;                     // rows per tile: as many as MAX_ITEMS * CONSUMER_THREADS x-pairs allow, up to this
 constexpr int XG_LANES = 30;                          // producer lanes 1 .. 30 fetch the x ghosts: (side, row) cells lane-1 and lane-1+30
 constexpr int STATIC_SMEM = 8 * 1024;                 // upper bound of the static shared memory below
@@ -97,20 +99,67 @@ __device__ __forceinline__ double div_by(double a, double y, double n) {
 }
 // non-zero and below 2^-830 (~1.4e-250): the remainder a - n*q0 (~2^-53 |a|) could underflow
 __device__ __forceinline__ bool tiny_nonzero(double a) {
-    const unsigned long long u = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffULL;
-    return (u - 1ULL) < (0x0C10000000000000ULL - 1ULL);
+    const unsigned h = (unsigned)__double2hiint(a) & 0x7fffffffu;
+    return (h < 0x0C100000u) & ((h | (unsigned)__double2loint(a)) != 0u);
 }
-__device__ __noinline__ void div3_plain(double a, double b, double c, double n, double* q) {
-    q[0] = a / n; q[1] = b / n; q[2] = c / n;
+
+// ---- branch-free IEEE sqrt / reciprocal -------------------------------------------------------------------------
+// The two cells of a pair (and the two pairs of a thread) carry independent sqrt -> reciprocal -> quotient chains; the
+// compiler only overlaps them inside one basic block, and CUDA's sqrt() / __drcp_rn() each end in a branch to a slow
+// path.  These are the FAST paths of exactly those two routines -- the instruction sequences nvcc 12.9 emits for
+// sm_100a, transcribed operation by operation (MUFU seed incl. its low word, the FMA refinements, the final
+// correction) -- without the branch; the caller checks the operand range once for all chains and sends the rare
+// out-of-range case to the plain operators.  pa_debug_selftest_math compares them bit for bit with sqrt() and
+// __drcp_rn() on the device over every exponent of their range (tests/test_gpu_parity.py::test_fast_math_selftest).
+__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
+// valid for hi32(x) in [0x03500000, 0x7ff00000): 2^-970 <= x < inf
+__device__ __forceinline__ double sqrt_fast(double x) {
+    double seed;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(x));          // MUFU.RSQ64H on the high word
+    const double y = __hiloint2double(hi32(seed), hi32(x) - 0x03500000);
+    const double e = fma(x, -(y * y), 1.0);
+    const double h = fma(e, 0.375, 0.5);
+    const double y1 = fma(h, y * e, y);                                 // refined 1/sqrt(x)
+    const double g = x * y1;
+    const double d = fma(g, -g, x);
+    const double hy = __hiloint2double(hi32(y1) - 0x00100000, __double2loint(y1));   // y1 / 2
+    return fma(d, hy, g);
 }
-// q[0..2] = a/n, b/n, c/n with IEEE-identical results; |n| >= 1e-14 (so 1/n is a normal number)
-__device__ __forceinline__ void div3(double a, double b, double c, double n, double* q) {
-    if (tiny_nonzero(a) | tiny_nonzero(b) | tiny_nonzero(c)) {          // practically never: out of line
-        div3_plain(a, b, c, n, q);
-        return;
+__device__ __forceinline__ bool sqrt_fast_ok(double x) { return (unsigned)(hi32(x) - 0x03500000) < 0x7ca00000u; }
+// valid while |float(hi32(n) + 0x300402)| >= 2^-127, i.e. for every n whose exponent is neither tiny nor huge; the
+// callers' divisors lie in [1e-14, 2^513]
+__device__ __forceinline__ double rcp_fast(double n) {
+    double seed;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(n));            // MUFU.RCP64H on the high word
+    const double y = __hiloint2double(hi32(seed), hi32(n) + 0x300402);
+    const double e = fma(-n, y, 1.0);
+    const double y1 = fma(y, fma(e, e, e), y);
+    return fma(y1, fma(-n, y1, 1.0), y1);
+}
+__device__ __forceinline__ bool rcp_fast_ok(double n) { return fabsf(__int_as_float(hi32(n) + 0x300402)) >= 5.8789094863358348022e-39f; }
+
+// Flame normal of the two cells of a pair (curvature.cpp:467-502): nrm = -max(1e-14, sqrt(G.G)), n = G / nrm, IEEE
+// results.  Both chains run branch-free side by side; one joint predicate covers everything the fast forms exclude.
+//  * G.G below 2^-970 (exact zeros -- flat regions -- included): sqrt <= 2^-485 < 1e-14, the clamp decides, nrm = -1e-14
+//    whatever the exact root (a NaN with the sign bit set lands here too: std::max(1e-14, NaN) = 1e-14, same result)
+//  * G.G = inf / NaN, or a tiny non-zero numerator (remainder underflow in div_by): plain operators, out of line of
+//    the hot path
+__device__ __forceinline__ void normal_pair(double ax, double bx, double gx, double ay, double by, double gy, double* __restrict__ r0,
+                                            double* __restrict__ r1) {
+    const double s0 = ax * ax + bx * bx + gx * gx, s1 = ay * ay + by * by + gy * gy;
+    double n0 = -fmax(1e-14, sqrt_fast(s0)), n1 = -fmax(1e-14, sqrt_fast(s1));
+    if (hi32(s0) < 0x03500000) n0 = -1e-14;
+    if (hi32(s1) < 0x03500000) n1 = -1e-14;
+    const bool cold = (hi32(s0) >= 0x7ff00000) | (hi32(s1) >= 0x7ff00000) | tiny_nonzero(ax) | tiny_nonzero(bx) | tiny_nonzero(gx) |
+                      tiny_nonzero(ay) | tiny_nonzero(by) | tiny_nonzero(gy);
+    const double y0 = rcp_fast(n0), y1 = rcp_fast(n1);
+    r0[0] = div_by(ax, y0, n0); r0[1] = div_by(bx, y0, n0); r0[2] = div_by(gx, y0, n0);
+    r1[0] = div_by(ay, y1, n1); r1[1] = div_by(by, y1, n1); r1[2] = div_by(gy, y1, n1);
+    if (__builtin_expect(cold, 0)) {
+        n0 = -fmax(1e-14, sqrt(s0)); n1 = -fmax(1e-14, sqrt(s1));
+        r0[0] = ax / n0; r0[1] = bx / n0; r0[2] = gx / n0;
+        r1[0] = ay / n1; r1[1] = by / n1; r1[2] = gy / n1;
     }
-    const double y = __drcp_rn(n);
-    q[0] = div_by(a, y, n); q[1] = div_by(b, y, n); q[2] = div_by(c, y, n);
 }
 
 template <int MODE> struct ModeTraits;
@@ -140,14 +189,15 @@ enum : unsigned {
     F_ROW_SHIFT = 16
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
+template <int MODE, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
                                                             StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
                                                             int S /* ring depth in planes */,
                                                             unsigned long long* __restrict__ ticket, unsigned long long ticket_base) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
     constexpr int NOUT = ModeTraits<MODE>::NOUT;
     constexpr bool XS = (MODE == MODE_NORMAL_S);
+    constexpr int CONSUMER_WARPS = CW, CONSUMER_THREADS = CW * 32, MAX_ITEMS = TILE_ITEMS / CONSUMER_THREADS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);                 // [S][NIN][stage_doubles]
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -357,6 +407,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __rest
         int sp = sc;                                   // stage of plane p-1
         if (++sc == S) { sc = 0; fphase ^= 1u; }
 
+        // per-tile invariants of the epilogues (kernel parameters indexed by the level: one load per tile, not per plane)
+        double* const cout_base = XS ? ex.cout[t.lev] : nullptr;
+        double* const aux_base = (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) ? ex.aux[t.lev] : nullptr;
+        const long long cg = (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) ? ex.cs_aux[t.lev] : 0;
+        const double* const prog_base = (MODE == MODE_DIV && ex.do_threshold) ? ex.prog[t.lev] : nullptr;
+        const bool xlo_link = (links & 1) != 0, xhi_link_even = (links & 8) != 0 && !(nx & 1);
+
         for (int p = 1; p < nplanes; ++p) {
             mbar_wait(&full_bar[sc], fphase);
             const double* Sp = sm + (long long)sp * stage_stride;
@@ -367,27 +424,38 @@ __global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __rest
                 const double2 cp = load_centre(sc, it, last_raw);
                 if (p >= 2) {
                     // ---- finish plane p-1: in-plane derivatives from its stage, z derivative from the register queue ----
+                    // Everything up to the stores is branch-free (selects, not divergent branches: lanes 0 and 31 of every
+                    // warp are "edge" lanes), so the two items' chains can be scheduled side by side.
                     const double* Sc = Sp + soff[it];
+                    const int row = (int)(f >> F_ROW_SHIFT);
                     double2 c = c0[it];
                     if (MODE == MODE_DIV) {
                         c = lds2(Sc);                                      // n_x centre pair
-                        if ((f & F_XHI_LINK) && (nx & 1)) c.y = xg_s[sp][1][f >> F_ROW_SHIFT];
+                        if ((f & F_XHI_LINK) && (nx & 1)) c.y = xg_s[sp][1][row];
                     }
-                    // x neighbours: from the adjacent lanes when they hold the same row, else from shared memory
+                    // x neighbours: from the adjacent lanes when they hold the same row, else from shared memory -- the
+                    // staged row (own cells / materialised ghost) or, on a linked x face, the neighbour's column in xg_s
                     double xm = __shfl_up_sync(0xffffffffu, c.y, 1);
                     double xp = __shfl_down_sync(0xffffffffu, c.x, 1);
-                    if (f & F_EDGE_LO) { xm = Sc[-1]; if (XS && !(f & F_XM_RAW)) xm = prog(xm); }
-                    if (f & F_EDGE_HI) { xp = Sc[2]; if (XS && !(f & F_XP_RAW)) xp = prog(xp); }
-                    if (f & F_XLO_LINK) { xm = xg_s[sp][0][f >> F_ROW_SHIFT]; if (XS) xm = prog(xm); }
-                    if ((f & F_XHI_LINK) && !(nx & 1)) { xp = xg_s[sp][1][f >> F_ROW_SHIFT]; if (XS) xp = prog(xp); }
+                    double el = Sc[-1], eh = Sc[2];
+                    if (xlo_link) { const double gl = xg_s[sp][0][row]; el = (f & F_XLO_LINK) ? gl : el; }
+                    if (xhi_link_even) { const double gh = xg_s[sp][1][row]; eh = (f & F_XHI_LINK) ? gh : eh; }
+                    if (XS) {
+                        const double pl = prog(el), ph = prog(eh);
+                        el = (f & F_XM_RAW) ? el : pl;
+                        eh = (f & F_XP_RAW) ? eh : ph;
+                    }
+                    xm = (f & F_EDGE_LO) ? el : xm;
+                    xp = (f & F_EDGE_HI) ? eh : xp;
                     const double ax = cdiff(dxi, xm, c.x, c.y);
                     const double ay = cdiff(dxi, c.x, c.y, xp);
                     double bx0, by0;
                     if (MODE != MODE_DIV) {
                         double2 ym = lds2(Sc - P), yp = lds2(Sc + P);
                         if (XS) {
-                            if (!(f & F_YM_RAW)) { ym.x = prog(ym.x); ym.y = prog(ym.y); }
-                            if (!(f & F_YP_RAW)) { yp.x = prog(yp.x); yp.y = prog(yp.y); }
+                            const double a0 = prog(ym.x), a1 = prog(ym.y), b0 = prog(yp.x), b1 = prog(yp.y);
+                            ym.x = (f & F_YM_RAW) ? ym.x : a0; ym.y = (f & F_YM_RAW) ? ym.y : a1;
+                            yp.x = (f & F_YP_RAW) ? yp.x : b0; yp.y = (f & F_YP_RAW) ? yp.y : b1;
                         }
                         bx0 = cdiff(dyi, ym.x, c.x, yp.x);
                         by0 = cdiff(dyi, ym.y, c.y, yp.y);
@@ -399,39 +467,35 @@ __global__ void __launch_bounds__(THREADS, 2) k_stencil_tma(const PaTile* __rest
                     }
                     const double g0 = cdiff(dzi, cm[it].x, c0[it].x, cp.x);
                     const double g1 = cdiff(dzi, cm[it].y, c0[it].y, cp.y);
-                    if (f & F_ACTIVE) {
-                        const long long o = oo[it];
-                        const bool two = (f & F_TWO) != 0;
-                        double r0[4], r1[4];
-                        if (MODE == MODE_GRAD) {
-                            r0[0] = ax; r0[1] = bx0; r0[2] = g0; r0[3] = sqrt(ax * ax + bx0 * bx0 + g0 * g0);
-                            r1[0] = ay; r1[1] = by0; r1[2] = g1; r1[3] = sqrt(ay * ay + by0 * by0 + g1 * g1);
-                        } else if (MODE == MODE_GRAD3) {
-                            r0[0] = ax; r0[1] = bx0; r0[2] = g0;
-                            r1[0] = ay; r1[1] = by0; r1[2] = g1;
-                        } else if (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
-                            if (XS) {                                        // Progress of plane p-1 (curvature.cpp:310-321)
-                                double* pc = ex.cout[t.lev] + o;
-                                if (two) stg2(pc, c.x, c.y); else pc[0] = c.x;
-                            }
-                            const double n0 = -fmax(1e-14, sqrt(ax * ax + bx0 * bx0 + g0 * g0));
-                            const double n1 = -fmax(1e-14, sqrt(ay * ay + by0 * by0 + g1 * g1));
-                            div3(ax, bx0, g0, n0, r0);
-                            div3(ay, by0, g1, n1, r1);
-                            if (ex.aux[t.lev]) {
-                                double* g = ex.aux[t.lev] + o;
-                                const long long cg = ex.cs_aux[t.lev];
-                                if (two) { stg2(g, ax, ay); stg2(g + cg, bx0, by0); stg2(g + 2 * cg, g0, g1); }
-                                else { g[0] = ax; g[cg] = bx0; g[2 * cg] = g0; }
-                            }
-                        } else {
-                            r0[0] = 0.5 * (((0.0 + ax) + bx0) + g0);
-                            r1[0] = 0.5 * (((0.0 + ay) + by0) + g1);
-                            if (ex.do_threshold) {
-                                const double2 pc = *reinterpret_cast<const double2*>(ex.prog[t.lev] + pi[it]);
-                                if (pc.x < ex.threshold || pc.x > 1.0 - ex.threshold) r0[0] = 0.0;
-                                if (pc.y < ex.threshold || pc.y > 1.0 - ex.threshold) r1[0] = 0.0;
-                            }
+                    const bool act = (f & F_ACTIVE) != 0, two = (f & F_TWO) != 0;
+                    const long long o = oo[it];
+                    double r0[4], r1[4];
+                    if (MODE == MODE_GRAD) {
+                        r0[0] = ax; r0[1] = bx0; r0[2] = g0; r0[3] = sqrt(ax * ax + bx0 * bx0 + g0 * g0);
+                        r1[0] = ay; r1[1] = by0; r1[2] = g1; r1[3] = sqrt(ay * ay + by0 * by0 + g1 * g1);
+                    } else if (MODE == MODE_GRAD3) {
+                        r0[0] = ax; r0[1] = bx0; r0[2] = g0;
+                        r1[0] = ay; r1[1] = by0; r1[2] = g1;
+                    } else if (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
+                        normal_pair(ax, bx0, g0, ay, by0, g1, r0, r1);
+                    } else {
+                        r0[0] = 0.5 * (((0.0 + ax) + bx0) + g0);
+                        r1[0] = 0.5 * (((0.0 + ay) + by0) + g1);
+                    }
+                    if (act) {
+                        if (XS) {                                            // Progress of plane p-1 (curvature.cpp:310-321)
+                            double* pc = cout_base + o;
+                            if (two) stg2(pc, c.x, c.y); else pc[0] = c.x;
+                        }
+                        if ((MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) && aux_base) {
+                            double* g = aux_base + o;
+                            if (two) { stg2(g, ax, ay); stg2(g + cg, bx0, by0); stg2(g + 2 * cg, g0, g1); }
+                            else { g[0] = ax; g[cg] = bx0; g[2 * cg] = g0; }
+                        }
+                        if (MODE == MODE_DIV && prog_base) {
+                            const double2 pc = *reinterpret_cast<const double2*>(prog_base + pi[it]);
+                            if (pc.x < ex.threshold || pc.x > 1.0 - ex.threshold) r0[0] = 0.0;
+                            if (pc.y < ex.threshold || pc.y > 1.0 - ex.threshold) r1[0] = 0.0;
                         }
                         double* po = out0 + o;
 #pragma unroll
@@ -466,18 +530,21 @@ std::map<cudaStream_t, Ticket> g_tickets;
 int g_stage_cap = 0;
 size_t g_inflight_bytes = 0;
 
-template <int MODE>
+template <int MODE, int CW>
 cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                         int nvar, cudaStream_t st) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
+    constexpr int PER_SM = CW == 8 ? 2 : 1;
     const size_t stage_bytes = (size_t)NIN * stage_doubles * sizeof(double);
     // Ring depth.  The consumers hold two planes (p-1 and p); the rest of the ring is data in flight.  Measured on B200
-    // (config 2): ~20 KB in flight per CTA (2 CTAs/SM, ~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
+    // (config 2): ~20 KB in flight per CTA at 2 CTAs/SM (~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
     // ring is SLOWER (the read stream runs far ahead of the write stream and the two fight for DRAM pages / L2).
     if (g_inflight_bytes == 0) { const char* e = getenv("PA_TMA_INFLIGHT_KB"); g_inflight_bytes = (size_t)(e ? std::max(1, atoi(e)) : 20) * 1024; }
+    const size_t inflight = g_inflight_bytes * (2 / PER_SM);
     const size_t budget2 = (227 * 1024 - 2 * STATIC_SMEM - 2 * 1024) / 2, budget1 = 227 * 1024 - STATIC_SMEM - 1024;
-    int S = 2 + (int)((g_inflight_bytes + stage_bytes - 1) / stage_bytes), per_sm = 2;
-    if ((size_t)S * stage_bytes > budget2) S = (int)(budget2 / stage_bytes);
+    int S = 2 + (int)((inflight + stage_bytes - 1) / stage_bytes), per_sm = PER_SM;
+    if (per_sm == 2 && (size_t)S * stage_bytes > budget2) S = (int)(budget2 / stage_bytes);
+    if (per_sm == 1 && (size_t)S * stage_bytes > budget1) S = (int)(budget1 / stage_bytes);
     if (S < 3) { S = std::min(4, (int)(budget1 / stage_bytes)); per_sm = 1; }
     if (S < 3) return cudaErrorInvalidConfiguration;
     if (S > MAX_STAGES) S = MAX_STAGES;
@@ -486,7 +553,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     const size_t smem = (size_t)S * stage_bytes;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -504,12 +571,90 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    k_stencil_tma<MODE><<<grid, THREADS, smem, st>>>(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    k_stencil_tma<MODE, CW><<<grid, (CW + 1) * 32, smem, st>>>(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
 
+// which modes run in the 16-consumer-warp shape: bit m = mode m (PA_TMA_CW16 overrides; default: the two flame-normal modes)
+int g_cw16_mask = -1;
+template <int MODE>
+cudaError_t launch_shape(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
+                         int nvar, cudaStream_t st) {
+    if (g_cw16_mask < 0) { const char* e = getenv("PA_TMA_CW16"); g_cw16_mask = e ? atoi(e) : ((1 << MODE_NORMAL) | (1 << MODE_NORMAL_S)); }
+    if (g_cw16_mask & (1 << MODE)) return launch_mode<MODE, 16>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    return launch_mode<MODE, 8>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+}
+
+// ---- device self-test of the branch-free math against the plain operators --------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {          // splitmix64 finaliser
+    z += 0x9E3779B97F4A7C15ULL; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ bool same_bits(double a, double b) {
+    return (a != a && b != b) || __double_as_longlong(a) == __double_as_longlong(b);
+}
+// a double with a random sign / mantissa and an exponent drawn uniformly from [e0, e1]; every 16th mantissa is 0 or all ones
+__device__ __forceinline__ double rnd_double(unsigned long long r, int e0, int e1, bool neg_ok) {
+    unsigned long long m = r & 0x000FFFFFFFFFFFFFULL;
+    const unsigned sel = (unsigned)(r >> 52) & 15u;
+    if (sel == 0) m = 0; else if (sel == 1) m = 0x000FFFFFFFFFFFFFULL;
+    const unsigned long long e = (unsigned long long)(e0 + (int)((r >> 20) % (unsigned long long)(e1 - e0 + 1)));
+    const unsigned long long sg = neg_ok ? (r >> 63) : 0ULL;
+    return __longlong_as_double((long long)((sg << 63) | (e << 52) | m));
+}
+__global__ void k_selftest_math(long long n, unsigned long long seed, unsigned long long* __restrict__ bad) {
+    unsigned long long local = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long r0 = mix64(seed + 4ULL * (unsigned long long)i), r1 = mix64(r0), r2 = mix64(r1), r3 = mix64(r2);
+        // sqrt_fast on its whole range [2^-970, inf), and on near-squares (the hard rounding cases)
+        double x = rnd_double(r0, 0x035, 0x7fe, false);
+        if (sqrt_fast_ok(x) && !same_bits(sqrt_fast(x), sqrt(x))) ++local;
+        const double y = rnd_double(r1, 0x200, 0x5ff, false);
+        x = __longlong_as_double(__double_as_longlong(y * y) + (long long)(r1 % 5ULL) - 2);
+        if (sqrt_fast_ok(x) && !same_bits(sqrt_fast(x), sqrt(x))) ++local;
+        // rcp_fast on the divisors the flame normal produces: 1e-14 <= |n| <= 2^513 (and the fast-path guard agrees)
+        const double d = rnd_double(r2, 0x3d0, 0x600, true);
+        if (!rcp_fast_ok(d) || !same_bits(rcp_fast(d), __drcp_rn(d))) ++local;
+        // the whole flame-normal pair against the plain formula, components spread over 2^-1074 .. 2^600, zeros included
+        double g[6];
+        unsigned long long r = r3;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            r = mix64(r);
+            const unsigned cls = (unsigned)(r >> 40) & 15u;
+            if (cls == 0) g[k] = (r >> 63) ? -0.0 : 0.0;
+            else if (cls == 1) g[k] = rnd_double(r, 0x000, 0x0d0, true);             // denormals and tiny normals
+            else if (cls == 2) g[k] = rnd_double(r, 0x600, 0x658, true);             // G.G overflows for the largest
+            else if (cls < 6) g[k] = rnd_double(r, 0x3c0, 0x3e0, true);              // around the 1e-14 clamp
+            else g[k] = rnd_double(r, 0x3f0 - (int)((r >> 8) & 63u), 0x410, true);   // ordinary gradients, mixed magnitudes
+        }
+        double q0[3], q1[3];
+        normal_pair(g[0], g[1], g[2], g[3], g[4], g[5], q0, q1);
+        const double n0 = -fmax(1e-14, sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]));
+        const double n1 = -fmax(1e-14, sqrt(g[3] * g[3] + g[4] * g[4] + g[5] * g[5]));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!same_bits(q0[k], g[k] / n0)) ++local;
+            if (!same_bits(q1[k], g[3 + k] / n1)) ++local;
+        }
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 }  // namespace
+
+cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long long* bad_host, cudaStream_t st) {
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) { k_selftest_math<<<148 * 8, 256, 0, st>>>(n, seed, d); ++g_launches; e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bad_host, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return e;
+}
 
 int stencil_tma_tile_rows() { return MAX_TILE_ROWS; }
 int stencil_tma_max_tile_rows() { return MAX_TILE_ROWS; }
@@ -522,11 +667,11 @@ cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int ma
     int stage_doubles = (max_plane_doubles + 15) & ~15;
     cudaError_t e;
     switch (mode) {
-        case MODE_GRAD: e = launch_mode<MODE_GRAD>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_GRAD3: e = launch_mode<MODE_GRAD3>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_NORMAL: e = launch_mode<MODE_NORMAL>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_DIV: e = launch_mode<MODE_DIV>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_NORMAL_S: e = launch_mode<MODE_NORMAL_S>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
+        case MODE_GRAD: e = launch_shape<MODE_GRAD>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
+        case MODE_GRAD3: e = launch_shape<MODE_GRAD3>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
+        case MODE_NORMAL: e = launch_shape<MODE_NORMAL>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
+        case MODE_DIV: e = launch_shape<MODE_DIV>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
+        case MODE_NORMAL_S: e = launch_shape<MODE_NORMAL_S>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
         default: return cudaErrorInvalidValue;
     }
     ++g_launches;

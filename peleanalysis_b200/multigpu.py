@@ -21,8 +21,9 @@ class _DevArray:
 def map_peers(field: capi.Field) -> None:
     """Collective: every rank maps every other rank's slabs of `field` (PA_HIER_PEER_LINKS hierarchies)."""
     H = field.hier
-    if H.nranks == 1:
+    if H.nranks == 1 or getattr(field, "_peers_mapped", False):
         return
+    field._peers_mapped = True
     mine = field.ipc_handles()
     got = [None] * H.nranks
     dist.all_gather_object(got, mine)
@@ -78,3 +79,37 @@ class SlabExchange:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         capi.check(capi.lib().pa_exchange_mark_received(f.f, comp, self.ncomp))
+
+
+class Curvature:
+    """pa_curvature on a multi-rank hierarchy: the two passes with the cross-rank steps between them.
+
+        [barrier]  exchange S  ->  pass 1 (ghost fill of S, Progress, flame normal)
+        [barrier]  exchange n  ->  pass 2 (ghost fill of n, MeanCurvature, VelFlameNormal)
+
+    The barriers (1-element all-reduce on the stream) are only needed with peer links, where a rank's kernels read the
+    other ranks' slabs in place: pass 2 must not start before every peer finished writing n, and the next step's
+    pass 1 must not overwrite n while a peer still reads it.  The reference reaches the same ordering through MPI inside
+    FillBoundary / ParallelCopy (Src/curvature.cpp:487-502, 514-520)."""
+
+    def __init__(self, state: capi.Field, comp_S: int, opts: capi.CurvOpts, out: capi.Field, comp_out: int = 0, comp_vel: int = 0):
+        self.state, self.comp_S, self.opts, self.out, self.comp_out, self.comp_vel = state, comp_S, opts, out, comp_out, comp_vel
+        H = state.hier
+        self.peer = bool(H.flags & capi.PEER_LINKS) and H.nranks > 1
+        # the 3-component exchange first: the library grows its slabs to the largest request, and the tensors below
+        # wrap raw slab pointers
+        self.Xn = SlabExchange(out, 3)
+        self.Xs = SlabExchange(state, 1)
+        if self.peer:
+            map_peers(state)
+            map_peers(out)
+
+    def run(self) -> None:
+        if self.peer:
+            stream_barrier()
+        self.Xs.run(self.comp_S)
+        capi.curvature_phases(self.state, self.comp_S, self.comp_vel, self.opts, self.out, self.comp_out, 1)
+        if self.peer:
+            stream_barrier()
+        self.Xn.run(self.comp_out + 2)
+        capi.curvature_phases(self.state, self.comp_S, self.comp_vel, self.opts, self.out, self.comp_out, 2)

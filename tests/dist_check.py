@@ -51,6 +51,51 @@ def run_case(name, pf, is_per, sym, rank, world, nvar=1, mode="slab"):
     return int(t.item())
 
 
+def run_curv(name, pf, is_per, sym, rank, world, mode="slab", velnormal=False):
+    """Default-option curvature (optionally + VelFlameNormal) through multigpu.Curvature, two steps back to back (the
+    second one checks the cross-step ordering), every local box against the oracle bit for bit."""
+    H = capi.Hierarchy(pf.levels, is_per, sym, rank, world, flags=capi.PEER_LINKS if mode == "peer" else 0)
+    names = list(pf.names)
+    cS = names.index("temp")
+    state = capi.Field(H, len(names), 1)
+    for v in range(len(names)):
+        state.upload_fabs(v, [[f[v] for f in l.fabs] for l in pf.levels])
+    OH = O.OracleHier(pf, is_per, sym)
+    s = OH.flatten(cS)
+    o = capi.CurvOpts()
+    o.prog_min, o.prog_max = float(s.min()), float(s.max())
+    o.do_velnormal = 1 if velnormal else 0
+    nout = capi.curvature_num_outputs(o)
+    out = capi.Field(H, nout, 1)
+    cv = names.index("x_velocity") if velnormal else 0
+    op = multigpu.Curvature(state, cS, o, out, 0, comp_vel=cv)
+    capi.sync()
+    dist.barrier()
+    op.run()
+    op.run()
+    capi.sync()
+    dist.barrier()
+    if velnormal:
+        r = OH.curvature_ex(s, np.stack([OH.flatten(cv + d) for d in range(3)]), o.prog_min, o.prog_max)
+        want = list(r["core"]) + [r["veln"]]
+    else:
+        want = list(OH.curvature(s, o.prog_min, o.prog_max))
+    bad = 0
+    for c in range(nout):
+        w = OH.unflatten(want[c])
+        got = out.download_fabs(c)
+        for l in range(len(pf.levels)):
+            for b in H.local_boxes[l]:
+                if not np.array_equal(got[l][b], w[l][b]):
+                    bad += 1
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("dist_check curvature %-14s %-4s ranks=%d local_boxes=%s mismatching boxes=%d" % (
+            name, mode, world, [len(x) for x in H.local_boxes], int(t.item())), flush=True)
+    return int(t.item())
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -67,6 +112,10 @@ def main():
         bad += run_case("config1_5vars", synth.config1(32, 16, names=synth.FIELD_NAMES), (1, 1, 1), (0, 0, 0), rank, world, nvar=5, mode=mode)
         bad += run_case("config5_small", synth.config5(base=32, mgs=8, ncomp=2), (1, 1, 1), (0, 0, 0), rank, world, nvar=2, mode=mode)
         bad += run_case("uniform_64", synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+        bad += run_curv("config1", synth.config1(32, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+        bad += run_curv("config3_64", synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+        bad += run_curv("c1_walls_vn", synth.config1(32, 16, names=synth.FIELD_NAMES, corner=True), (0, 0, 0), (1, 0, 0), rank, world, mode=mode, velnormal=True)
+        bad += run_curv("uniform_64", synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
     dist.destroy_process_group()
     if rank == 0:
         print("DIST_CHECK", "OK" if bad == 0 else "FAILED (%d)" % bad, flush=True)

@@ -252,3 +252,46 @@ def test_full_size_properties_config2(gpu):
             assert bit_equal(got[dst], res["tma"][c][i]), (c, i)
     # checksum of checksums, recorded for the log
     print("config2 temp grad checksum", float(sum(np.sum(a, dtype=np.float64) for a in res["tma"][3])))
+
+
+def test_fast_math_selftest(gpu):
+    """The stencil kernel's branch-free sqrt / reciprocal / flame-normal forms against the plain IEEE operators, on the
+    device, over every exponent of their ranges (zeros, denormals, the 1e-14 clamp, overflow): not one differing bit."""
+    from peleanalysis_b200 import capi
+    for seed in (1, 0x5EED5EED, 2 ** 63 + 12345):
+        bad = capi.lib().pa_debug_selftest_math(1 << 26, seed)
+        assert bad == 0, (seed, bad)
+
+
+@pytest.mark.parametrize("name", ["c1_periodic", "c3_three_levels"])
+def test_curvature_two_phases_equal_one_call(gpu, name):
+    """pa_curvature_phases(1) then (2) == pa_curvature (the split a multi-rank caller puts its exchange into)."""
+    builder, is_per, sym, _, _ = CASES[name]
+    pf = builder()
+    s = _flat(pf, "temp")
+    one, o = _gpu_curv(gpu, pf, is_per, sym, float(s.min()), float(s.max()), {})
+    H = gpu.Hierarchy(pf.levels, is_per, sym)
+    state = gpu.Field(H, 1, 1)
+    state.upload_fabs(0, [[f[pf.comp("temp")] for f in l.fabs] for l in pf.levels])
+    out = gpu.Field(H, 5, 1)
+    gpu.curvature_phases(state, 0, 0, o, out, 0, 1)
+    gpu.curvature_phases(state, 0, 0, o, out, 0, 2)
+    gpu.sync()
+    two = np.stack([flat_from_fabs(out.download_fabs(c)) for c in range(5)])
+    assert bit_equal(one, two)
+
+
+def test_flat_field_takes_the_clamp(gpu):
+    """A field with exactly flat regions: G.G = 0 there, nrm = -1e-14 by the clamp, n = -0 (curvature.cpp:467-502) -- the
+    branch-free normal decides this without a square root; compare with the oracle bit for bit (signed zeros included)."""
+    pf = synth.make_hierarchy(32, [], [], 16, ("temp",))
+    for lv in pf.levels:
+        for f in lv.fabs:
+            f[0] = np.where(f[0] > 900.0, 900.0, f[0])           # plateau: exact zeros in the gradient
+    s = _flat(pf, "temp")
+    out, o = _gpu_curv(gpu, pf, (1, 1, 1), (0, 0, 0), float(s.min()), float(s.max()), {})
+    OH = O.OracleHier(pf, (1, 1, 1), (0, 0, 0))
+    want = OH.curvature(s, float(s.min()), float(s.max()))
+    assert (want[2:5] == 0).sum() > 1000
+    for c in range(5):
+        assert bit_equal(out[c], want[c]), c
