@@ -212,6 +212,11 @@ int64_t pa_debug_exchange_ids(pa_hier *h, int which, int64_t *out, int64_t out_l
  * operand sets covering every exponent of their ranges, zeros, denormals and overflow.  Returns the number of results
  * that differ in any bit (0 = identical), or -1 on error. */
 int64_t pa_debug_selftest_math(int64_t n, uint64_t seed);
+/* Which arithmetic the TMA stencil kernel uses for the flame normal: 0 = the branch-free forms, 1 = the plain IEEE
+ * operators, -1 = not decided yet.  Decided once per process at the first flame-normal launch: PA_NORMAL_MATH=fast|plain
+ * forces one; otherwise the library runs the self-test above on the device and keeps the branch-free forms only if not
+ * one result bit differs (both forms compute the same IEEE results; the choice affects speed only). */
+int pa_debug_normal_math(void);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ SYMBOLS = {
     "pa_curvature": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i]),
     "pa_curvature_num_outputs": (_i, [C.POINTER(CurvOpts)]),
     "pa_debug_selftest_math": (C.c_int64, [C.c_int64, C.c_uint64]),
+    "pa_debug_normal_math": (C.c_int, []),
     "pa_curvature_phases": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i, _i]),
     "pa_exchange_counts": (_i, [_vp, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "pa_exchange_buffers": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),

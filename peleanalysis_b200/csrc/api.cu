@@ -1005,6 +1005,8 @@ int64_t pa_debug_selftest_math(int64_t n, uint64_t seed) {
     return (int64_t)bad;
 }
 
+int pa_debug_normal_math(void) { return stencil_tma_normal_math(); }
+
 int64_t pa_debug_exchange_ids(pa_hier* h, int which, int64_t* out, int64_t out_len) {
     if (!h) return 0;
     const std::vector<long long>& v = which ? h->H.xplan.recv_ids : h->H.xplan.send_ids;

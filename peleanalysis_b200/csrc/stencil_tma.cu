@@ -18,7 +18,9 @@
 // Arithmetic is the reference's expression order with separate IEEE mul/add (-fmad=false): bit-exact.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 
 #include "kernels.cuh"
@@ -189,7 +191,9 @@ enum : unsigned {
     F_ROW_SHIFT = 16
 };
 
-template <int MODE, int CW>
+// PLAIN = true: the flame normal through the plain IEEE operators (sqrt(), six divisions) instead of normal_pair() -- the
+// form the library falls back to should the device self-test of the branch-free forms ever report a differing bit
+template <int MODE, int CW, bool PLAIN>
 __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
                                                             StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
                                                             int S /* ring depth in planes */,
@@ -477,7 +481,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) k_stencil_tma(
                         r0[0] = ax; r0[1] = bx0; r0[2] = g0;
                         r1[0] = ay; r1[1] = by0; r1[2] = g1;
                     } else if (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
-                        normal_pair(ax, bx0, g0, ay, by0, g1, r0, r1);
+                        if (PLAIN) {
+                            const double n0 = -fmax(1e-14, sqrt(ax * ax + bx0 * bx0 + g0 * g0));
+                            const double n1 = -fmax(1e-14, sqrt(ay * ay + by0 * by0 + g1 * g1));
+                            r0[0] = ax / n0; r0[1] = bx0 / n0; r0[2] = g0 / n0;
+                            r1[0] = ay / n1; r1[1] = by0 / n1; r1[2] = g1 / n1;
+                        } else {
+                            normal_pair(ax, bx0, g0, ay, by0, g1, r0, r1);
+                        }
                     } else {
                         r0[0] = 0.5 * (((0.0 + ax) + bx0) + g0);
                         r1[0] = 0.5 * (((0.0 + ay) + by0) + g1);
@@ -530,7 +541,7 @@ std::map<cudaStream_t, Ticket> g_tickets;
 int g_stage_cap = 0;
 size_t g_inflight_bytes = 0;
 
-template <int MODE, int CW>
+template <int MODE, int CW, bool PLAIN>
 cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                         int nvar, cudaStream_t st) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
@@ -553,7 +564,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     const size_t smem = (size_t)S * stage_bytes;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -571,19 +582,44 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    k_stencil_tma<MODE, CW><<<grid, (CW + 1) * 32, smem, st>>>(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    k_stencil_tma<MODE, CW, PLAIN><<<grid, (CW + 1) * 32, smem, st>>>(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
 
 // which modes run in the 16-consumer-warp shape: bit m = mode m (PA_TMA_CW16 overrides; default: the two flame-normal modes)
 int g_cw16_mask = -1;
+// Flame-normal arithmetic of the TMA kernel: 0 = branch-free forms (normal_pair), 1 = plain IEEE operators, -1 = not decided.
+// PA_NORMAL_MATH=fast|plain forces one; otherwise ("auto") the first flame-normal launch of the process runs the device
+// self-test once (2^20 operand sets, well under a millisecond) and the branch-free forms are used only if not one result
+// bit differs from sqrt() / division on THIS device and driver -- the transcribed sequences depend on the MUFU seeds.
+int g_normal_plain = -1;
+int decide_normal_math(cudaStream_t st) {
+    if (g_normal_plain >= 0) return g_normal_plain;
+    const char* e = getenv("PA_NORMAL_MATH");
+    if (e && !strcmp(e, "plain")) return g_normal_plain = 1;
+    if (e && !strcmp(e, "fast")) return g_normal_plain = 0;
+    unsigned long long bad = 0;
+    const cudaError_t ce = selftest_math(1LL << 20, 0x9A5EEDULL, &bad, st);
+    g_normal_plain = (ce != cudaSuccess || bad != 0) ? 1 : 0;
+    if (g_normal_plain)
+        fprintf(stderr, "[pelestencil_b200] branch-free flame-normal self-test: %llu differing results (%s) -- using the plain IEEE operators\n",
+                bad, cudaGetErrorString(ce));
+    return g_normal_plain;
+}
 template <int MODE>
 cudaError_t launch_shape(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                          int nvar, cudaStream_t st) {
     if (g_cw16_mask < 0) { const char* e = getenv("PA_TMA_CW16"); g_cw16_mask = e ? atoi(e) : ((1 << MODE_NORMAL) | (1 << MODE_NORMAL_S)); }
-    if (g_cw16_mask & (1 << MODE)) return launch_mode<MODE, 16>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-    return launch_mode<MODE, 8>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    const bool wide = (g_cw16_mask & (1 << MODE)) != 0;
+    if constexpr (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
+        if (decide_normal_math(st)) {
+            return wide ? launch_mode<MODE, 16, true>(tiles, ntiles, stage_doubles, ga, ex, nvar, st)
+                        : launch_mode<MODE, 8, true>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        }
+    }
+    return wide ? launch_mode<MODE, 16, false>(tiles, ntiles, stage_doubles, ga, ex, nvar, st)
+                : launch_mode<MODE, 8, false>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
 }
 
 // ---- device self-test of the branch-free math against the plain operators --------------------------------------
@@ -656,6 +692,7 @@ cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long lo
     return e;
 }
 
+int stencil_tma_normal_math() { return g_normal_plain; }
 int stencil_tma_tile_rows() { return MAX_TILE_ROWS; }
 int stencil_tma_max_tile_rows() { return MAX_TILE_ROWS; }
 // largest staged plane ((TY+2) rows x pitch) the pipeline accepts per input component (3 stages of 3 components must fit)

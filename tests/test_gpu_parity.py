@@ -256,11 +256,25 @@ def test_full_size_properties_config2(gpu):
 
 def test_fast_math_selftest(gpu):
     """The stencil kernel's branch-free sqrt / reciprocal / flame-normal forms against the plain IEEE operators, on the
-    device, over every exponent of their ranges (zeros, denormals, the 1e-14 clamp, overflow): not one differing bit."""
+    device, over every exponent of their ranges (zeros, denormals, the 1e-14 clamp, overflow).  The library runs the same
+    self-test before its first flame-normal launch and uses the branch-free forms only if not one bit differs, so the
+    check here is that its decision matches what the self-test says on this device (and, when PA_NORMAL_MATH does not
+    force a form, that the branch-free forms are in fact clean)."""
     from peleanalysis_b200 import capi
+    bad = 0
     for seed in (1, 0x5EED5EED, 2 ** 63 + 12345):
-        bad = capi.lib().pa_debug_selftest_math(1 << 26, seed)
-        assert bad == 0, (seed, bad)
+        b = capi.lib().pa_debug_selftest_math(1 << 26, seed)
+        assert b >= 0, capi.lib().pa_last_error()
+        bad += b
+    pf = synth.config1(16, 8)
+    s = _flat(pf, "temp")
+    _gpu_curv(gpu, pf, (1, 1, 1), (0, 0, 0), float(s.min()), float(s.max()), {})     # makes the library decide
+    mode = capi.lib().pa_debug_normal_math()
+    forced = os.environ.get("PA_NORMAL_MATH")
+    if forced not in ("fast", "plain"):
+        assert mode == (1 if bad else 0), (mode, bad)
+    if forced != "plain":
+        assert bad == 0, "branch-free forms differ from the IEEE operators in %d results (library fell back: %s)" % (bad, mode == 1)
 
 
 @pytest.mark.parametrize("name", ["c1_periodic", "c3_three_levels"])
