@@ -64,6 +64,7 @@ struct TileTable {
     DevBuf<PaTile> d;
     std::vector<long long> level_begin;                // nlev+1
     int max_plane_doubles = 0;                         // over tiles, for ng=1 input layout
+    std::vector<int> lev_plane_doubles, lev_items;     // per level: largest staged plane / most x-pairs per tile plane
     bool ok = true;
 };
 
@@ -125,6 +126,8 @@ void build_tiles(pa_hier* h, TileTable& T, bool tma) {
     T.h.clear();
     T.level_begin.assign(H.nlev + 1, 0);
     T.max_plane_doubles = 0;
+    T.lev_plane_doubles.assign(H.nlev, 0);
+    T.lev_items.assign(H.nlev, 0);
     T.ok = true;
     const char* ety = getenv("PA_TMA_TY");
     const char* ezc = getenv("PA_TMA_ZC");
@@ -146,6 +149,8 @@ void build_tiles(pa_hier* h, TileTable& T, bool tma) {
                 int nty = (ny + ty - 1) / ty; ty = (ny + nty - 1) / nty;
                 int nzc = (nz + ZC0 - 1) / ZC0; zc = (nz + nzc - 1) / nzc;
                 T.max_plane_doubles = std::max(T.max_plane_doubles, (ty + 2) * Y.lay[lb].P);
+                T.lev_plane_doubles[l] = std::max(T.lev_plane_doubles[l], (ty + 2) * Y.lay[lb].P);
+                T.lev_items[l] = std::max(T.lev_items[l], nq * ty);
             } else {
                 ty = 8; zc = 8;
             }
@@ -277,7 +282,10 @@ int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex
     if (in_ng == 1 && use_tma(h, nin)) {
         TileTable& T = h->tiles_tma;
         long long a = T.level_begin[l0], b = T.level_begin[l1 + 1];
-        CU(launch_stencil_tma(mode, T.d.p + a, (int)(b - a), T.max_plane_doubles, ga, ex, nvar, t_stream));
+        // stage size and CTA shape follow the largest tile of the levels in this launch
+        int plane = 0, items = 0;
+        for (int l = l0; l <= l1; ++l) { plane = std::max(plane, T.lev_plane_doubles[l]); items = std::max(items, T.lev_items[l]); }
+        CU(launch_stencil_tma(mode, T.d.p + a, (int)(b - a), plane, items, ga, ex, nvar, t_stream));
     } else {
         TileTable& T = h->tiles_simple;
         long long a = T.level_begin[l0], b = T.level_begin[l1 + 1];

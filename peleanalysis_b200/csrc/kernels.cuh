@@ -82,8 +82,9 @@ cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaF
 // stencils: GridArgs.in/out already point at the first component to read / write
 cudaError_t launch_stencil_simple(int mode, const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex,
                                   int nvar, cudaStream_t st);
-// TMA-staged pipeline (cp.async.bulk + mbarrier ring, 2.5-D sweep along z)
-cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, const GridArgs& ga,
+// TMA-staged pipeline (cp.async.bulk + mbarrier ring, 2.5-D sweep along z).  max_plane_doubles / max_items = the largest staged
+// plane (doubles, one component) and the largest number of x-pairs per plane over the given tiles (picks the CTA shape)
+cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, int max_items, const GridArgs& ga,
                                const StencilExtra& ex, int nvar, cudaStream_t st);
 // device self-test: the branch-free sqrt / reciprocal / flame-normal forms of the TMA kernel against the plain operators on
 // n pseudo-random operand sets; *bad_host = number of results that differ in any bit

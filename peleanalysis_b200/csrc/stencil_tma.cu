@@ -35,10 +35,19 @@ constexpr int MAX_STAGES = 16;
 //   CW = 16, 1 CTA/SM,  1 x-pair  per consumer thread per plane : the FP64-heavy flame-normal modes -- the same 16 consumer
 //            warps per SM, but half the per-thread state and a 112-register budget (9 warps are allocated as 10, which
 //            caps the 2-CTA shape at 96 registers and made the normal epilogue spill)
-constexpr int TILE_ITEMS = 512;                       // x-pairs per tile plane: CW * 32 * ITEMS for both shapes
+//   CW = 4 / 2 : tiles of small boxes (at most 256 / 128 x-pairs per plane, e.g. 32^3 / 16^3 boxes).  In the big shapes such
+//            a tile would leave half / three quarters of the consumer threads idle while they still execute every
+//            instruction; here the CTA is as wide as the tile and more CTAs (3-6) share an SM, so more tiles are in flight
+constexpr int TILE_ITEMS = 512;                       // x-pairs per tile plane of the two big shapes: CW * 32 * ITEMS
+template <int CW, bool HEAVY> struct Shape {
+    static constexpr int NI = CW >= 16 ? 1 : 2;                                           // x-pairs per consumer thread
+    static constexpr int CAP = CW * 32 * NI;                                              // x-pairs per tile plane
+    // CTAs per SM; HEAVY = the flame-normal modes, which want ~112 registers
+    static constexpr int PER_SM = CW >= 16 ? 1 : CW == 8 ? 2 : CW == 4 ? (HEAVY ? 3 : 4) : (HEAVY ? 5 : 6);
+};
 constexpr int MAX_TILE_ROWS = 30;                     // rows per tile: as many as MAX_ITEMS * CONSUMER_THREADS x-pairs allow, up to this
 constexpr int XG_LANES = 30;                          // producer lanes 1 .. 30 fetch the x ghosts: (side, row) cells lane-1 and lane-1+30
-constexpr int STATIC_SMEM = 8 * 1024;                 // upper bound of the static shared memory below
+constexpr int STATIC_SMEM = 10 * 1024 + 256;          // upper bound of the static shared memory below (10112 bytes)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -194,14 +203,14 @@ enum : unsigned {
 // PLAIN = true: the flame normal through the plain IEEE operators (sqrt(), six divisions) instead of normal_pair() -- the
 // form the library falls back to should the device self-test of the branch-free forms ever report a differing bit
 template <int MODE, int CW, bool PLAIN>
-__global__ void __launch_bounds__((CW + 1) * 32, CW == 8 ? 2 : 1) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
+__global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
                                                             StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
                                                             int S /* ring depth in planes */,
                                                             unsigned long long* __restrict__ ticket, unsigned long long ticket_base) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
     constexpr int NOUT = ModeTraits<MODE>::NOUT;
     constexpr bool XS = (MODE == MODE_NORMAL_S);
-    constexpr int CONSUMER_WARPS = CW, CONSUMER_THREADS = CW * 32, MAX_ITEMS = TILE_ITEMS / CONSUMER_THREADS;
+    constexpr int CONSUMER_WARPS = CW, CONSUMER_THREADS = CW * 32, MAX_ITEMS = Shape<CW, false>::NI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);                 // [S][NIN][stage_doubles]
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -545,17 +554,16 @@ template <int MODE, int CW, bool PLAIN>
 cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                         int nvar, cudaStream_t st) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
-    constexpr int PER_SM = CW == 8 ? 2 : 1;
+    constexpr int PER_SM = Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM;
     const size_t stage_bytes = (size_t)NIN * stage_doubles * sizeof(double);
     // Ring depth.  The consumers hold two planes (p-1 and p); the rest of the ring is data in flight.  Measured on B200
-    // (config 2): ~20 KB in flight per CTA at 2 CTAs/SM (~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
+    // (config 2): ~40 KB in flight per SM (~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
     // ring is SLOWER (the read stream runs far ahead of the write stream and the two fight for DRAM pages / L2).
     if (g_inflight_bytes == 0) { const char* e = getenv("PA_TMA_INFLIGHT_KB"); g_inflight_bytes = (size_t)(e ? std::max(1, atoi(e)) : 20) * 1024; }
-    const size_t inflight = g_inflight_bytes * (2 / PER_SM);
-    const size_t budget2 = (227 * 1024 - 2 * STATIC_SMEM - 2 * 1024) / 2, budget1 = 227 * 1024 - STATIC_SMEM - 1024;
+    const size_t inflight = g_inflight_bytes * 2 / PER_SM;
+    const size_t budget = (size_t)(227 * 1024) / PER_SM - STATIC_SMEM - 1024, budget1 = 227 * 1024 - STATIC_SMEM - 1024;
     int S = 2 + (int)((inflight + stage_bytes - 1) / stage_bytes), per_sm = PER_SM;
-    if (per_sm == 2 && (size_t)S * stage_bytes > budget2) S = (int)(budget2 / stage_bytes);
-    if (per_sm == 1 && (size_t)S * stage_bytes > budget1) S = (int)(budget1 / stage_bytes);
+    if ((size_t)S * stage_bytes > budget) S = (int)(budget / stage_bytes);
     if (S < 3) { S = std::min(4, (int)(budget1 / stage_bytes)); per_sm = 1; }
     if (S < 3) return cudaErrorInvalidConfiguration;
     if (S > MAX_STAGES) S = MAX_STAGES;
@@ -607,19 +615,31 @@ int decide_normal_math(cudaStream_t st) {
                 bad, cudaGetErrorString(ce));
     return g_normal_plain;
 }
+// PA_TMA_SMALL=0 switches the small-tile shapes (4 / 2 consumer warps) off (read at every launch: the tests flip it)
+template <int MODE, bool PLAIN>
+cudaError_t launch_cw(int cw, const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
+                      int nvar, cudaStream_t st) {
+    switch (cw) {
+        case 2: return launch_mode<MODE, 2, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        case 4: return launch_mode<MODE, 4, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        case 16: return launch_mode<MODE, 16, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        default: return launch_mode<MODE, 8, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    }
+}
 template <int MODE>
-cudaError_t launch_shape(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
+cudaError_t launch_shape(const PaTile* tiles, int ntiles, int stage_doubles, int max_items, const GridArgs& ga, const StencilExtra& ex,
                          int nvar, cudaStream_t st) {
     if (g_cw16_mask < 0) { const char* e = getenv("PA_TMA_CW16"); g_cw16_mask = e ? atoi(e) : ((1 << MODE_NORMAL) | (1 << MODE_NORMAL_S)); }
-    const bool wide = (g_cw16_mask & (1 << MODE)) != 0;
-    if constexpr (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
-        if (decide_normal_math(st)) {
-            return wide ? launch_mode<MODE, 16, true>(tiles, ntiles, stage_doubles, ga, ex, nvar, st)
-                        : launch_mode<MODE, 8, true>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        }
+    const char* es = getenv("PA_TMA_SMALL");
+    int cw = (g_cw16_mask & (1 << MODE)) ? 16 : 8;
+    if (!(es && es[0] == '0') && max_items > 0) {
+        if (max_items <= Shape<2, false>::CAP) cw = 2;
+        else if (max_items <= Shape<4, false>::CAP) cw = 4;
     }
-    return wide ? launch_mode<MODE, 16, false>(tiles, ntiles, stage_doubles, ga, ex, nvar, st)
-                : launch_mode<MODE, 8, false>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    if constexpr (MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) {
+        if (decide_normal_math(st)) return launch_cw<MODE, true>(cw, tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    }
+    return launch_cw<MODE, false>(cw, tiles, ntiles, stage_doubles, ga, ex, nvar, st);
 }
 
 // ---- device self-test of the branch-free math against the plain operators --------------------------------------
@@ -698,17 +718,17 @@ int stencil_tma_max_tile_rows() { return MAX_TILE_ROWS; }
 // largest staged plane ((TY+2) rows x pitch) the pipeline accepts per input component (3 stages of 3 components must fit)
 int stencil_tma_max_plane_doubles() { return (227 * 1024 - STATIC_SMEM - 1024) / (3 * 3 * 8); }
 
-cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, const GridArgs& ga,
+cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int max_plane_doubles, int max_items, const GridArgs& ga,
                                const StencilExtra& ex, int nvar, cudaStream_t st) {
     if (ntiles <= 0) return cudaSuccess;
     int stage_doubles = (max_plane_doubles + 15) & ~15;
     cudaError_t e;
     switch (mode) {
-        case MODE_GRAD: e = launch_shape<MODE_GRAD>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_GRAD3: e = launch_shape<MODE_GRAD3>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_NORMAL: e = launch_shape<MODE_NORMAL>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_DIV: e = launch_shape<MODE_DIV>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
-        case MODE_NORMAL_S: e = launch_shape<MODE_NORMAL_S>(tiles, ntiles, stage_doubles, ga, ex, nvar, st); break;
+        case MODE_GRAD: e = launch_shape<MODE_GRAD>(tiles, ntiles, stage_doubles, max_items, ga, ex, nvar, st); break;
+        case MODE_GRAD3: e = launch_shape<MODE_GRAD3>(tiles, ntiles, stage_doubles, max_items, ga, ex, nvar, st); break;
+        case MODE_NORMAL: e = launch_shape<MODE_NORMAL>(tiles, ntiles, stage_doubles, max_items, ga, ex, nvar, st); break;
+        case MODE_DIV: e = launch_shape<MODE_DIV>(tiles, ntiles, stage_doubles, max_items, ga, ex, nvar, st); break;
+        case MODE_NORMAL_S: e = launch_shape<MODE_NORMAL_S>(tiles, ntiles, stage_doubles, max_items, ga, ex, nvar, st); break;
         default: return cudaErrorInvalidValue;
     }
     ++g_launches;

@@ -21,8 +21,15 @@ def _flat(pf, name):
     return np.concatenate([f[c].ravel() for l in pf.levels for f in l.fabs])
 
 
+def _set_stencil(stencil):
+    """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps); tma_big: TMA pipeline in the
+    8 / 16-warp shapes whatever the tile size; simple: the plain-load kernel."""
+    os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
+    os.environ["PA_TMA_SMALL"] = "0" if stencil == "tma_big" else "1"
+
+
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
-    os.environ["PA_STENCIL"] = stencil
+    _set_stencil(stencil)
     H = capi.Hierarchy(pf.levels, is_per, sym, flags=flags)
     fin = capi.Field(H, len(names), 1)
     fout = capi.Field(H, 4 * len(names), 0)
@@ -35,7 +42,7 @@ def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
 
 
 def _gpu_curv(capi, pf, is_per, sym, pmin, pmax, kw, stencil="tma", flags=0):
-    os.environ["PA_STENCIL"] = stencil
+    _set_stencil(stencil)
     H = capi.Hierarchy(pf.levels, is_per, sym, flags=flags)
     o = capi.CurvOpts()
     o.prog_min, o.prog_max = pmin, pmax
@@ -64,7 +71,7 @@ LINK_MODES = {"links": 0, "nolinks": 2}
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "grad" in c[3]])
 def test_grad_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -74,7 +81,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -147,14 +154,15 @@ def test_ghost_cells_match_oracle(gpu, name):
     ("config5", dict(base=32, mgs=8, ncomp=3, ratios=(2, 4, 2))),
     ("lshape", dict(base=32, mgs=16)),
 ])
-def test_midsize_grad_and_curvature_vs_oracle(gpu, case, kw):
+@pytest.mark.parametrize("stencil", ["tma", "tma_big"])
+def test_midsize_grad_and_curvature_vs_oracle(gpu, case, kw, stencil):
     """Mid-size hierarchies (hundreds of boxes) against the oracle run on the GPU box's host."""
     pf = synth.CASES[case](**kw)
     var = pf.names[0]
     OH = O.OracleHier(pf, (1, 1, 1), (0, 0, 0))
     s = _flat(pf, var)
     want = OH.grad(s)
-    os.environ["PA_STENCIL"] = "tma"
+    _set_stencil(stencil)
     H = gpu.Hierarchy(pf.levels)
     fin, fout = gpu.Field(H, 1, 1), gpu.Field(H, 4, 0)
     fin.upload_fabs(0, [[f[0] for f in l.fabs] for l in pf.levels])
@@ -174,7 +182,7 @@ def test_midsize_grad_and_curvature_vs_oracle(gpu, case, kw):
             assert bit_equal(flat_from_fabs(out.download_fabs(c)), wk[c]), (case, "curv", c)
 
 
-@pytest.mark.parametrize("stencil", ["tma", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
 def test_curvature_degenerate_values(gpu, stencil):
     """Exactly flat regions (0/-1e-14 = -0), gradients around the 1e-250 guard of the shared-reciprocal division, huge and
     sign-alternating values: the flame normal's three IEEE divisions must come out bit-identical to the oracle's a/n."""
