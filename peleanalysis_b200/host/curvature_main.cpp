@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
     }
     // variable index management (curvature.cpp:163-224)
     std::vector<std::string> inNames{progressName};
-    const int idVst = 1;
+    // (the reference's idVst = 1: velocities follow the progress variable, curvature.cpp:172)
     if (do_strain) for (const char* v : {"x_velocity", "y_velocity", "z_velocity"}) inNames.push_back(v);
     for (auto& a : aux) { if (H.comp(a) < 0) pa_abort("Unknown auxiliary variable name: " + a); inNames.push_back(a); }
     const int nCompIn = (int)inNames.size();

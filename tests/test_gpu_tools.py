@@ -18,7 +18,12 @@ HOST = os.path.join(ROOT, "peleanalysis_b200", "host")
 
 @pytest.fixture(scope="module")
 def exes(gpu):
-    subprocess.check_call(["make", "-s", "-C", HOST])
+    # one make at a time: with pytest-xdist a second worker's relink would otherwise hit "Text file busy" on an
+    # executable the first worker is already running
+    import fcntl
+    with open(os.path.join(HOST, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        subprocess.check_call(["make", "-s", "-C", HOST])
     return os.path.join(HOST, "grad3d.b200.ex"), os.path.join(HOST, "curvature3d.b200.ex")
 
 
