@@ -411,7 +411,10 @@ def main():
     achieved = alg_bytes / (stencil_ms * 1e-3) / 1e9
     traffic = None
     try:
+        # ncu capture of one launch at N=1; a rank's launch covers its share of the boxes
         traffic = json.load(open(os.path.join(ROOT, "profiles", "stencil_traffic.json"))).get(args.workload)
+        if traffic is not None and world > 1:
+            traffic = int(traffic * H.num_local_cells / max(cells_global, 1))
     except Exception:
         pass
 
@@ -453,7 +456,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_stencil_tma<MODE_GRAD>" if os.environ.get("PA_STENCIL", "tma") != "simple" else "k_stencil_simple<MODE_GRAD>",
                      "kernel_ms": stencil_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                     "step_frac": value * 40.0 / peak},
+                     "step_frac": value / world * (alg_bytes / max(H.num_local_cells * nvar, 1)) / peak},
         "cpu_baseline": cpu,
         "extras": extras,
     }
