@@ -59,14 +59,14 @@ __global__ void k_valid_copy(const PaBoxDev* __restrict__ boxes, const PaLayDev*
 cudaError_t launch_unpack_valid(const PaBoxDev* boxes, const PaLayDev* lay, const long long* host_off, int nboxes,
                                 long long ncells, const double* staging, double* comp_base, cudaStream_t st) {
     if (ncells <= 0) return cudaSuccess;
-    k_valid_copy<true><<<grid_for(ncells, 256), 256, 0, st>>>(boxes, lay, host_off, nboxes, ncells, comp_base, const_cast<double*>(staging));
+    PA_LAUNCH(grid_for(ncells, 256), 256, 0, st, k_valid_copy<true>)(boxes, lay, host_off, nboxes, ncells, comp_base, const_cast<double*>(staging));
     ++g_launches;
     return cudaGetLastError();
 }
 cudaError_t launch_pack_valid(const PaBoxDev* boxes, const PaLayDev* lay, const long long* host_off, int nboxes,
                               long long ncells, const double* comp_base, double* staging, cudaStream_t st) {
     if (ncells <= 0) return cudaSuccess;
-    k_valid_copy<false><<<grid_for(ncells, 256), 256, 0, st>>>(boxes, lay, host_off, nboxes, ncells, const_cast<double*>(comp_base), staging);
+    PA_LAUNCH(grid_for(ncells, 256), 256, 0, st, k_valid_copy<false>)(boxes, lay, host_off, nboxes, ncells, const_cast<double*>(comp_base), staging);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -76,7 +76,7 @@ __global__ void k_fill(double* __restrict__ p, long long n, double v) {
 }
 cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    k_fill<<<grid_for(n, 256), 256, 0, st>>>(p, n, v);
+    PA_LAUNCH(grid_for(n, 256), 256, 0, st, k_fill)(p, n, v);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -119,7 +119,7 @@ cudaError_t launch_halo(const PaHaloTag* tags, int tag0, int tag1, long long cel
                         const PaLayDev* lay, double* base, long long cs, int ncomp, const double* recv,
                         const PaPeerSlab* peers, int comp0, int rank, GhostXform xf, cudaStream_t st) {
     if (cell1 <= cell0 || tag1 <= tag0) return cudaSuccess;
-    k_halo<<<grid_for(cell1 - cell0, 256), 256, 0, st>>>(tags, tag0, tag1, cell0, cell1, boxes, lay, base, cs, ncomp, recv, peers, comp0, rank, xf);
+    PA_LAUNCH(grid_for(cell1 - cell0, 256), 256, 0, st, k_halo)(tags, tag0, tag1, cell0, cell1, boxes, lay, base, cs, ncomp, recv, peers, comp0, rank, xf);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -148,7 +148,7 @@ __global__ void k_xpack(const PaPackTag* __restrict__ tags, long long tag0, long
 cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long long tag1, long long dense0, long long ncells,
                                  const GridArgs& ga, int ncomp, double* send, cudaStream_t st) {
     if (ncells <= 0 || tag1 <= tag0) return cudaSuccess;
-    k_xpack<<<grid_for(ncells, 256), 256, 0, st>>>(tags, tag0, tag1, dense0, ncells, ga, ncomp, send);
+    PA_LAUNCH(grid_for(ncells, 256), 256, 0, st, k_xpack)(tags, tag0, tag1, dense0, ncells, ga, ncomp, send);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -237,7 +237,7 @@ cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaF
                           const unsigned short* flags, const long long* coff, const GridArgs& ga,
                           int ncomp, const double* recv, GhostXform xf, cudaStream_t st) {
     if (blk1 <= blk0) return cudaSuccess;
-    k_bcfill<<<(unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st>>>(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
+    PA_LAUNCH((unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st, k_bcfill)(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -364,10 +364,10 @@ cudaError_t launch_stencil_simple(int mode, const PaTile* tiles, int ntiles, con
     if (ntiles <= 0) return cudaSuccess;
     dim3 grid(ntiles, nvar), block(256);
     switch (mode) {
-        case MODE_GRAD: k_stencil_simple<MODE_GRAD><<<grid, block, 0, st>>>(tiles, ga, ex); break;
-        case MODE_GRAD3: k_stencil_simple<MODE_GRAD3><<<grid, block, 0, st>>>(tiles, ga, ex); break;
-        case MODE_NORMAL: k_stencil_simple<MODE_NORMAL><<<grid, block, 0, st>>>(tiles, ga, ex); break;
-        case MODE_DIV: k_stencil_simple<MODE_DIV><<<grid, block, 0, st>>>(tiles, ga, ex); break;
+        case MODE_GRAD: PA_LAUNCH(grid, block, 0, st, k_stencil_simple<MODE_GRAD>)(tiles, ga, ex); break;
+        case MODE_GRAD3: PA_LAUNCH(grid, block, 0, st, k_stencil_simple<MODE_GRAD3>)(tiles, ga, ex); break;
+        case MODE_NORMAL: PA_LAUNCH(grid, block, 0, st, k_stencil_simple<MODE_NORMAL>)(tiles, ga, ex); break;
+        case MODE_DIV: PA_LAUNCH(grid, block, 0, st, k_stencil_simple<MODE_DIV>)(tiles, ga, ex); break;
         default: return cudaErrorInvalidValue;
     }
     ++g_launches;
@@ -399,7 +399,7 @@ __global__ void k_progress(const PaBoxDev* __restrict__ boxes, const PaLayDev* _
 cudaError_t launch_progress(const PaBoxDev* boxes, const PaLayDev* lay_in, const PaLayDev* lay_out, int nboxes,
                             const double* S, double* C, double pmin, double invdenom, cudaStream_t st) {
     if (nboxes <= 0) return cudaSuccess;
-    k_progress<<<dim3(32, nboxes), 256, 0, st>>>(boxes, lay_in, lay_out, S, C, pmin, invdenom);
+    PA_LAUNCH(dim3(32, nboxes), 256, 0, st, k_progress)(boxes, lay_in, lay_out, S, C, pmin, invdenom);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -421,7 +421,7 @@ __global__ void k_clip_normal(const PaBoxDev* __restrict__ boxes, const PaLayDev
 cudaError_t launch_clip_normal(const PaBoxDev* boxes, const PaLayDev* lay_c, const PaLayDev* lay_n, int nboxes,
                                const double* C, double* N, long long cs_n, double thr, cudaStream_t st) {
     if (nboxes <= 0) return cudaSuccess;
-    k_clip_normal<<<dim3(32, nboxes), 256, 0, st>>>(boxes, lay_c, lay_n, C, N, cs_n, thr);
+    PA_LAUNCH(dim3(32, nboxes), 256, 0, st, k_clip_normal)(boxes, lay_c, lay_n, C, N, cs_n, thr);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -462,7 +462,7 @@ cudaError_t launch_gauss(const PaBoxDev* boxes, const PaLayDev* lay, const PaLay
                          long long cs_g, const double* H, long long cs_h, const double* C, double* Kg, int do_thr,
                          double thr, cudaStream_t st) {
     if (nboxes <= 0) return cudaSuccess;
-    k_gauss<<<dim3(32, nboxes), 256, 0, st>>>(boxes, lay, lay_c, G, cs_g, H, cs_h, C, Kg, do_thr, thr);
+    PA_LAUNCH(dim3(32, nboxes), 256, 0, st, k_gauss)(boxes, lay, lay_c, G, cs_g, H, cs_h, C, Kg, do_thr, thr);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -481,7 +481,7 @@ __global__ void k_strain(const PaBoxDev* __restrict__ boxes, const PaLayDev* __r
 cudaError_t launch_strain(const PaBoxDev* boxes, const PaLayDev* lay, int nboxes, const double* dU, long long cs,
                           double* sr, cudaStream_t st) {
     if (nboxes <= 0) return cudaSuccess;
-    k_strain<<<dim3(32, nboxes), 256, 0, st>>>(boxes, lay, dU, cs, sr);
+    PA_LAUNCH(dim3(32, nboxes), 256, 0, st, k_strain)(boxes, lay, dU, cs, sr);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -507,7 +507,7 @@ cudaError_t launch_velnormal(const PaBoxDev* boxes, const PaLayDev* lay_u, const
                              int nboxes, const double* U, long long cs_u, const double* N, long long cs_n,
                              const double* C, double* out, int do_thr, double thr, cudaStream_t st) {
     if (nboxes <= 0) return cudaSuccess;
-    k_velnormal<<<dim3(32, nboxes), 256, 0, st>>>(boxes, lay_u, lay_n, lay_o, U, cs_u, N, cs_n, C, out, do_thr, thr);
+    PA_LAUNCH(dim3(32, nboxes), 256, 0, st, k_velnormal)(boxes, lay_u, lay_n, lay_o, U, cs_u, N, cs_n, C, out, do_thr, thr);
     ++g_launches;
     return cudaGetLastError();
 }

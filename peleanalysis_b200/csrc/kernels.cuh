@@ -6,6 +6,14 @@
 
 #include "pa_types.h"
 
+// Kernel launch and dynamic shared memory, spelled as macros so that tests/emu can compile these same sources for its
+// CPU emulation of the CUDA execution model (PA_HOST_EMULATION: a test-only build that checks indexing and the
+// producer/consumer protocol without a GPU; it is never part of libpelestencil_b200.so and nothing in the product loads it).
+#ifndef PA_HOST_EMULATION
+#define PA_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
+#define PA_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 namespace pa {
 
 // per-level device pointers handed to kernels by value

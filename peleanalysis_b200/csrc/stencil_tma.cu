@@ -49,6 +49,7 @@ constexpr int MAX_TILE_ROWS = 30;                     // rows per tile: as many 
 constexpr int XG_LANES = 30;                          // producer lanes 1 .. 30 fetch the x ghosts: (side, row) cells lane-1 and lane-1+30
 constexpr int STATIC_SMEM = 10 * 1024 + 256;          // upper bound of the static shared memory below (10112 bytes)
 
+#ifndef PA_HOST_EMULATION
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -85,6 +86,19 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// seeds of the IEEE sqrt / reciprocal refinements (MUFU.RSQ64H / MUFU.RCP64H on the high word)
+__device__ __forceinline__ double mufu_rsq64h(double x) { double s; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x)); return s; }
+__device__ __forceinline__ double mufu_rcp64h(double x) { double s; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x)); return s; }
+#else   // tests/emu: the emulator's mbarrier / async-copy model instead of PTX (see tests/emu/cuda_runtime.h)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { cuemu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { cuemu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { cuemu::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { cuemu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { cuemu::tma_load_1d(smem_dst, gsrc, bytes, bar); }
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) { cuemu::cp_async_8(smem_dst, gsrc); }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) { cuemu::cp_async_arrive_noinc(bar); }
+#endif
 
 __device__ __forceinline__ double cdiff(double dxi, double m, double c, double p) {
     // the reference's sequence, sign of zero included: faces f = dxinv*(s(i)-s(i-1)) are multiplied by 1/b = -1
@@ -125,8 +139,10 @@ __device__ __forceinline__ bool tiny_nonzero(double a) {
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 // valid for hi32(x) in [0x03500000, 0x7ff00000): 2^-970 <= x < inf
 __device__ __forceinline__ double sqrt_fast(double x) {
-    double seed;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(x));          // MUFU.RSQ64H on the high word
+#ifdef PA_HOST_EMULATION
+    return sqrt(x);                                                     // the emulator has no MUFU: the value the fast path must equal
+#else
+    const double seed = mufu_rsq64h(x);
     const double y = __hiloint2double(hi32(seed), hi32(x) - 0x03500000);
     const double e = fma(x, -(y * y), 1.0);
     const double h = fma(e, 0.375, 0.5);
@@ -135,17 +151,21 @@ __device__ __forceinline__ double sqrt_fast(double x) {
     const double d = fma(g, -g, x);
     const double hy = __hiloint2double(hi32(y1) - 0x00100000, __double2loint(y1));   // y1 / 2
     return fma(d, hy, g);
+#endif
 }
 __device__ __forceinline__ bool sqrt_fast_ok(double x) { return (unsigned)(hi32(x) - 0x03500000) < 0x7ca00000u; }
 // valid while |float(hi32(n) + 0x300402)| >= 2^-127, i.e. for every n whose exponent is neither tiny nor huge; the
 // callers' divisors lie in [1e-14, 2^513]
 __device__ __forceinline__ double rcp_fast(double n) {
-    double seed;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(n));            // MUFU.RCP64H on the high word
+#ifdef PA_HOST_EMULATION
+    return 1.0 / n;
+#else
+    const double seed = mufu_rcp64h(n);
     const double y = __hiloint2double(hi32(seed), hi32(n) + 0x300402);
     const double e = fma(-n, y, 1.0);
     const double y1 = fma(y, fma(e, e, e), y);
     return fma(y1, fma(-n, y1, 1.0), y1);
+#endif
 }
 __device__ __forceinline__ bool rcp_fast_ok(double n) { return fabsf(__int_as_float(hi32(n) + 0x300402)) >= 5.8789094863358348022e-39f; }
 
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
     constexpr int NOUT = ModeTraits<MODE>::NOUT;
     constexpr bool XS = (MODE == MODE_NORMAL_S);
     constexpr int CONSUMER_WARPS = CW, CONSUMER_THREADS = CW * 32, MAX_ITEMS = Shape<CW, false>::NI;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PA_DYN_SMEM(smem_raw);
     double* sm = reinterpret_cast<double*>(smem_raw);                 // [S][NIN][stage_doubles]
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -224,7 +244,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
     if (threadIdx.x == 0) {
         // a stage is full when the TMA bytes have landed (lane 0's arrive.expect_tx) and every x-ghost lane has arrived
         for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1u + XG_LANES); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+#ifndef PA_HOST_EMULATION
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     }
     __syncthreads();
 
@@ -590,7 +612,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    k_stencil_tma<MODE, CW, PLAIN><<<grid, (CW + 1) * 32, smem, st>>>(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    PA_LAUNCH(grid, (CW + 1) * 32, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
@@ -705,7 +727,7 @@ cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long lo
     cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), st);
-    if (e == cudaSuccess) { k_selftest_math<<<148 * 8, 256, 0, st>>>(n, seed, d); ++g_launches; e = cudaGetLastError(); }
+    if (e == cudaSuccess) { PA_LAUNCH(148 * 8, 256, 0, st, k_selftest_math)(n, seed, d); ++g_launches; e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(bad_host, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);

@@ -39,6 +39,28 @@ def test_product_does_not_import_oracle():
                 assert not bad.search(txt), (dirpath, f, bad.search(txt).group(0))
 
 
+def test_product_cannot_reach_the_emulator(palib):
+    """tests/emu (the CPU emulation of the CUDA execution model used by tests/test_emu_parity.py) is test infrastructure:
+    the product library is built by nvcc without PA_HOST_EMULATION and exports no emulator symbol, no product file names
+    the emulated library or its directory, and the binding opens exactly lib/libpelestencil_b200.so."""
+    import subprocess
+    from peleanalysis_b200 import build, capi
+    assert capi.LIB_PATH == build.LIB and capi.LIB_PATH.endswith(os.path.join("peleanalysis_b200", "lib", "libpelestencil_b200.so"))
+    assert "PA_HOST_EMULATION" not in " ".join(build.FLAGS)
+    syms = subprocess.run(["nm", "-D", "--defined-only", build.LIB], capture_output=True, text=True).stdout
+    assert "cuemu" not in syms
+    bad = re.compile(r"(libpelestencil_emu|tests/emu|build_emu|cuemu\.cpp)")
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "peleanalysis_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                # the two kernel sources say, in comments, which test build defines PA_HOST_EMULATION
+                txt = "\n".join(l for l in txt.splitlines() if not l.lstrip().startswith("//") and "// tests/emu" not in l)
+                assert not bad.search(txt), (dirpath, f, bad.search(txt).group(0))
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert not bad.search(open(os.path.join(ROOT, f)).read()), f
+
+
 def test_no_device_fails_loudly(palib):
     import torch
     if torch.cuda.is_available():

@@ -1,0 +1,102 @@
+"""CPU tier: the kernel SOURCES of peleanalysis_b200/csrc, compiled by g++ against the CUDA execution-model emulator of
+tests/emu (fibers for threads, mbarrier / bulk-copy / shuffle semantics, deadlock detection), run the same parity
+checks as the GPU tests -- same C ABI, same oracle, same golden vectors of the compiled reference.
+
+This is test infrastructure: it checks descriptor use, indexing, the TMA ring's producer/consumer protocol and the
+host-side sequencing before any GPU time is spent.  It is NOT a CPU path of the product: the emulated library lives under
+tests/emu/_build, only this file loads it (through a private copy of the ctypes binding), and capi.py can open nothing but
+lib/libpelestencil_b200.so (tests/test_capi_surface.py).  PTX semantics, the MUFU-seeded sqrt / reciprocal forms and
+performance are GPU-only matters (tests/test_gpu_parity.py)."""
+import importlib.util
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+import test_gpu_parity as G  # noqa: E402  (the GPU tests' bodies are reused as plain functions)
+from cases import CASES  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    from peleanalysis_b200 import capi as product_capi
+    lib = build_emu.build()
+    spec = importlib.util.spec_from_file_location("capi_emulated", product_capi.__file__)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.LIB_PATH = lib                     # a private module instance: the product binding itself is untouched
+    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "CUEMU_SEED")}
+    os.environ["PA_NORMAL_MATH"] = "fast"   # no device self-test: the emulator has no MUFU (sqrt_fast == sqrt there)
+    m.init(0)
+    yield m
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.fixture(params=[0, 20261017], ids=["inorder", "shuffled"])
+def schedule(request):
+    """inorder: threads run round-robin and async copies land within the round; shuffled: a fresh pseudo-random thread
+    order every scheduler round and async copies that land 0-3 rounds late."""
+    os.environ["CUEMU_SEED"] = str(request.param)
+    yield request.param
+    os.environ["CUEMU_SEED"] = "0"
+
+
+GRAD_CASES = [n for n, c in CASES.items() if "grad" in c[3]]
+CURV_CASES = [n for n, c in CASES.items() if "curvature" in c[3]]
+
+
+@pytest.mark.parametrize("links", list(G.LINK_MODES))
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, links):
+    if schedule and (stencil == "simple" or links == "nolinks"):
+        pytest.skip("the shuffled schedule matters for the TMA pipeline only")
+    G.test_grad_matches_reference_golden(emu, name, stencil, links)
+
+
+@pytest.mark.parametrize("links", list(G.LINK_MODES))
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
+@pytest.mark.parametrize("name", CURV_CASES)
+def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
+    if schedule and (stencil == "simple" or links == "nolinks"):
+        pytest.skip("the shuffled schedule matters for the TMA pipeline only")
+    G.test_curvature_matches_reference_golden(emu, name, stencil, links)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_ghost_cells_match_oracle(emu, name):
+    os.environ["CUEMU_SEED"] = "0"
+    G.test_ghost_cells_match_oracle(emu, name)
+
+
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
+def test_emulated_curvature_degenerate_values(emu, stencil):
+    os.environ["CUEMU_SEED"] = "0"
+    G.test_curvature_degenerate_values(emu, stencil)
+
+
+def test_emulated_multi_variable_and_phases(emu, schedule):
+    G.test_multi_variable_grad_equals_single(emu)
+    G.test_curvature_two_phases_equal_one_call(emu, "c1_periodic")
+    G.test_flat_field_takes_the_clamp(emu)
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("config3", dict(base=32, mgs=16)),
+    ("config5", dict(base=16, mgs=8, ncomp=2, ratios=(2, 4, 2))),
+    ("lshape", dict(base=32, mgs=16)),
+])
+def test_emulated_midsize_vs_oracle(emu, case, kw):
+    os.environ["CUEMU_SEED"] = "7"
+    try:
+        G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma")
+    finally:
+        os.environ["CUEMU_SEED"] = "0"
