@@ -18,6 +18,11 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
+def _wrap_device(ptr: int, n: int) -> torch.Tensor:
+    """The library's send / recv slab (a raw device pointer) as a CUDA tensor NCCL can send from / receive into."""
+    return torch.as_tensor(_DevArray(ptr, n), device="cuda")
+
+
 def map_peers(field: capi.Field) -> None:
     """Collective: every rank maps every other rank's slabs of `field` (PA_HIER_PEER_LINKS hierarchies)."""
     H = field.hier
@@ -45,7 +50,8 @@ class SlabExchange:
     """NCCL send/recv of the packed ghost slabs for ncomp components of one field (everything the neighbour links do
     not cover: ragged same-level neighbours and coarse cells of coarse-fine faces owned by other ranks)."""
 
-    def __init__(self, field: capi.Field, ncomp: int):
+    def __init__(self, field: capi.Field, ncomp: int, wrap=_wrap_device):
+        """wrap(ptr, n): raw slab pointer -> tensor for the process group's backend (CUDA tensors for NCCL)."""
         H = field.hier
         self.field, self.ncomp, self.rank, self.world = field, ncomp, H.rank, H.nranks
         self.soff = self.roff = [0]
@@ -57,8 +63,8 @@ class SlabExchange:
         ro = (C.c_int64 * (self.world + 1))()
         capi.check(capi.lib().pa_exchange_buffers(field.f, ncomp, C.byref(sp), C.byref(rp), so, ro))
         self.soff, self.roff = list(so), list(ro)
-        self.send_t = torch.as_tensor(_DevArray(sp.value, max(self.soff[-1], 1)), device="cuda")
-        self.recv_t = torch.as_tensor(_DevArray(rp.value, max(self.roff[-1], 1)), device="cuda")
+        self.send_t = wrap(sp.value, max(self.soff[-1], 1))
+        self.recv_t = wrap(rp.value, max(self.roff[-1], 1))
         # a rank with nothing to send or receive still takes part if any peer does (batch_isend_irecv is pairwise)
         self.empty = (self.soff[-1] == 0 and self.roff[-1] == 0)
 
@@ -92,14 +98,15 @@ class Curvature:
     pass 1 must not overwrite n while a peer still reads it.  The reference reaches the same ordering through MPI inside
     FillBoundary / ParallelCopy (Src/curvature.cpp:487-502, 514-520)."""
 
-    def __init__(self, state: capi.Field, comp_S: int, opts: capi.CurvOpts, out: capi.Field, comp_out: int = 0, comp_vel: int = 0):
+    def __init__(self, state: capi.Field, comp_S: int, opts: capi.CurvOpts, out: capi.Field, comp_out: int = 0, comp_vel: int = 0,
+                 wrap=_wrap_device):
         self.state, self.comp_S, self.opts, self.out, self.comp_out, self.comp_vel = state, comp_S, opts, out, comp_out, comp_vel
         H = state.hier
         self.peer = bool(H.flags & capi.PEER_LINKS) and H.nranks > 1
         # the 3-component exchange first: the library grows its slabs to the largest request, and the tensors below
         # wrap raw slab pointers
-        self.Xn = SlabExchange(out, 3)
-        self.Xs = SlabExchange(state, 1)
+        self.Xn = SlabExchange(out, 3, wrap)
+        self.Xs = SlabExchange(state, 1, wrap)
         if self.peer:
             map_peers(state)
             map_peers(out)

@@ -1,0 +1,130 @@
+"""CPU tier, world_size 2 over gloo: the multi-rank SLAB transport end to end -- pack kernel, send/recv of the packed ghost
+slabs, halo / coarse-fine fill from the recv slab, stencil -- with the kernel sources running under the CUDA
+execution-model emulator of tests/emu (test infrastructure, see tests/test_emu_parity.py), every rank's boxes compared
+bit for bit with the oracle.  grad and the two-pass curvature driver (multigpu.Curvature), the same checks
+tests/dist_check.py makes on real GPUs over NCCL.  Peer links (CUDA IPC) are a GPU-only matter."""
+import ctypes as C
+import importlib.util
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_emulated():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from peleanalysis_b200 import capi as product_capi, multigpu as product_multigpu
+
+    def private(mod, name):
+        spec = importlib.util.spec_from_file_location("peleanalysis_b200." + name, mod.__file__)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    capi = private(product_capi, "_capi_emulated")
+    capi.LIB_PATH = build_emu.build()
+    mg = private(product_multigpu, "_multigpu_emulated")
+    mg.capi = capi
+    os.environ["PA_NORMAL_MATH"] = "fast"
+    return capi, mg
+
+
+def _wrap_host(ptr, n):
+    return torch.from_numpy(np.ctypeslib.as_array((C.c_double * int(n)).from_address(int(ptr))))
+
+
+def _worker(rank, world, port, ok):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["CUEMU_SEED"] = str(1 + rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cases import CASES
+        from oracle import oracle as O
+        from peleanalysis_b200 import synth
+        capi, mg = _load_emulated()
+        capi.init(0)
+        bad = []
+        exchanged = 0
+
+        def check(name, out, want_flat, OH, pf, H, comps):
+            for c in comps:
+                w = OH.unflatten(want_flat[c])
+                got = out.download_fabs(c)
+                for l in range(len(pf.levels)):
+                    for b in H.local_boxes[l]:
+                        if not np.array_equal(got[l][b], w[l][b]):
+                            bad.append((name, c, l, b))
+
+        grad_cases = [(n,) + tuple(CASES[n][:3]) for n in ("c1_periodic", "c1_walls", "lshape", "ratio4", "c3_three_levels")]
+        grad_cases = [(n, b(), per, sym) for n, b, per, sym in grad_cases]
+        grad_cases.append(("config5_small", synth.config5(base=16, mgs=8, ncomp=2), (1, 1, 1), (0, 0, 0)))
+        for name, pf, is_per, sym in grad_cases:
+            H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+            fin, fout = capi.Field(H, 1, 1), capi.Field(H, 4, 0)
+            fin.upload_fabs(0, [[f[pf.comp(pf.names[0])] for f in l.fabs] for l in pf.levels])
+            X = mg.SlabExchange(fin, 1, _wrap_host)
+            exchanged += 0 if X.empty else 1      # (ratio4: one box per level, everything on rank 0)
+            X.run(0)
+            capi.grad(fin, 0, 1, fout, 0)
+            capi.sync()
+            OH = O.OracleHier(pf, is_per, sym)
+            check("grad " + name, fout, OH.grad(OH.flatten(pf.comp(pf.names[0]))), OH, pf, H, range(4))
+
+        curv_cases = [("config1", synth.config1(32, 16), (1, 1, 1), (0, 0, 0), False),
+                      ("config3", synth.config3(32, 16), (1, 1, 1), (0, 0, 0), False),
+                      ("c1_walls_vn", synth.config1(32, 16, names=synth.FIELD_NAMES, corner=True), (0, 0, 0), (1, 0, 0), True)]
+        for name, pf, is_per, sym, veln in curv_cases:
+            H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+            names = list(pf.names)
+            cS = names.index("temp")
+            state = capi.Field(H, len(names), 1)
+            for v in range(len(names)):
+                state.upload_fabs(v, [[f[v] for f in l.fabs] for l in pf.levels])
+            OH = O.OracleHier(pf, is_per, sym)
+            s = OH.flatten(cS)
+            o = capi.CurvOpts()
+            o.prog_min, o.prog_max = float(s.min()), float(s.max())
+            o.do_velnormal = 1 if veln else 0
+            nout = capi.curvature_num_outputs(o)
+            out = capi.Field(H, nout, 1)
+            cv = names.index("x_velocity") if veln else 0
+            op = mg.Curvature(state, cS, o, out, 0, comp_vel=cv, wrap=_wrap_host)
+            op.run()
+            op.run()                      # twice: the second step checks nothing stale survives in the slabs
+            capi.sync()
+            if veln:
+                r = OH.curvature_ex(s, np.stack([OH.flatten(cv + d) for d in range(3)]), o.prog_min, o.prog_max)
+                want = list(r["core"]) + [r["veln"]]
+            else:
+                want = list(OH.curvature(s, o.prog_min, o.prog_max))
+            check("curvature " + name, out, want, OH, pf, H, range(nout))
+        assert not bad, bad[:10]
+        assert exchanged >= 4
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_emulated_slab_transport_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0, 0])
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+    assert list(ok) == [1, 1], [p.exitcode for p in procs]
