@@ -59,12 +59,17 @@ struct LevelDev {
     std::vector<long long> host_off_h;
 };
 
+// Tiles are stored class-major, level-minor: a "class" groups the boxes one CTA shape of the TMA pipeline serves
+// (x-pairs per tile plane <= 128, <= 256, more), so a stencil pass over levels [l0, l1] is one contiguous tile range --
+// one launch -- per class that occurs, each in the shape that fits its tiles.  The simple kernel has one class.
+constexpr int N_TILE_CLASSES = 3;
 struct TileTable {
     std::vector<PaTile> h;
     DevBuf<PaTile> d;
-    std::vector<long long> level_begin;                // nlev+1
-    int max_plane_doubles = 0;                         // over tiles, for ng=1 input layout
-    std::vector<int> lev_plane_doubles, lev_items;     // per level: largest staged plane / most x-pairs per tile plane
+    long long begin[N_TILE_CLASSES][PA_MAX_LEVELS + 1];        // first tile of (class, level); [c][nlev] = end of the class
+    int plane_doubles[N_TILE_CLASSES][PA_MAX_LEVELS];          // largest staged plane (ng = 1 input layout, one component)
+    int items[N_TILE_CLASSES][PA_MAX_LEVELS];                  // most x-pairs per tile plane
+    int max_plane_doubles = 0;                                 // over all tiles
     bool ok = true;
 };
 
@@ -124,47 +129,51 @@ const PaLayDev* dev_layout(pa_hier* h, int l, int ng, int* err) {
 void build_tiles(pa_hier* h, TileTable& T, bool tma) {
     Hier& H = h->H;
     T.h.clear();
-    T.level_begin.assign(H.nlev + 1, 0);
     T.max_plane_doubles = 0;
-    T.lev_plane_doubles.assign(H.nlev, 0);
-    T.lev_items.assign(H.nlev, 0);
     T.ok = true;
+    std::memset(T.begin, 0, sizeof(T.begin));
+    std::memset(T.plane_doubles, 0, sizeof(T.plane_doubles));
+    std::memset(T.items, 0, sizeof(T.items));
     const char* ety = getenv("PA_TMA_TY");
     const char* ezc = getenv("PA_TMA_ZC");
     const int TY0 = ety ? std::min(std::max(1, atoi(ety)), stencil_tma_max_tile_rows()) : stencil_tma_tile_rows();
     const int ZC0 = ezc ? std::max(1, atoi(ezc)) : 32;
-    for (int l = 0; l < H.nlev; ++l) {
-        T.level_begin[l] = (long long)T.h.size();
-        const Level& V = H.lev[l];
-        const Layout& Y = H.layout(l, 1);
-        for (size_t lb = 0; lb < V.local.size(); ++lb) {
-            const Box& B = V.boxes[V.local[lb]];
-            int nx = B.len(0), ny = B.len(1), nz = B.len(2);
-            int ty, zc;
-            if (tma) {
-                int nq = (nx + 1) / 2;
-                ty = std::min(TY0, std::max(1, 512 / nq));
-                if (nq > 512) T.ok = false;
-                // even split of the rows / planes so the last tile is not a sliver
-                int nty = (ny + ty - 1) / ty; ty = (ny + nty - 1) / nty;
-                int nzc = (nz + ZC0 - 1) / ZC0; zc = (nz + nzc - 1) / nzc;
-                T.max_plane_doubles = std::max(T.max_plane_doubles, (ty + 2) * Y.lay[lb].P);
-                T.lev_plane_doubles[l] = std::max(T.lev_plane_doubles[l], (ty + 2) * Y.lay[lb].P);
-                T.lev_items[l] = std::max(T.lev_items[l], nq * ty);
-            } else {
-                ty = 8; zc = 8;
-            }
-            for (int z0 = 0; z0 < nz; z0 += zc)
-                for (int y0 = 0; y0 < ny; y0 += ty) {
-                    PaTile t;
-                    t.lev = l; t.box = (int)lb;
-                    t.y0 = y0; t.ny = std::min(ty, ny - y0);
-                    t.z0 = z0; t.nz = std::min(zc, nz - z0);
-                    T.h.push_back(t);
+    for (int c = 0; c < (tma ? N_TILE_CLASSES : 1); ++c)
+        for (int l = 0; l < H.nlev; ++l) {
+            T.begin[c][l] = (long long)T.h.size();
+            const Level& V = H.lev[l];
+            const Layout& Y = H.layout(l, 1);
+            for (size_t lb = 0; lb < V.local.size(); ++lb) {
+                const Box& B = V.boxes[V.local[lb]];
+                int nx = B.len(0), ny = B.len(1), nz = B.len(2);
+                int ty, zc;
+                if (tma) {
+                    int nq = (nx + 1) / 2;
+                    ty = std::min(TY0, std::max(1, 512 / nq));
+                    if (nq > 512) T.ok = false;
+                    // even split of the rows / planes so the last tile is not a sliver
+                    int nty = (ny + ty - 1) / ty; ty = (ny + nty - 1) / nty;
+                    int nzc = (nz + ZC0 - 1) / ZC0; zc = (nz + nzc - 1) / nzc;
+                    const int it = nq * ty;
+                    if (c != (it <= 128 ? 0 : it <= 256 ? 1 : 2)) continue;
+                    const int plane = (ty + 2) * Y.lay[lb].P;
+                    T.max_plane_doubles = std::max(T.max_plane_doubles, plane);
+                    T.plane_doubles[c][l] = std::max(T.plane_doubles[c][l], plane);
+                    T.items[c][l] = std::max(T.items[c][l], it);
+                } else {
+                    ty = 8; zc = 8;
                 }
+                for (int z0 = 0; z0 < nz; z0 += zc)
+                    for (int y0 = 0; y0 < ny; y0 += ty) {
+                        PaTile t;
+                        t.lev = l; t.box = (int)lb;
+                        t.y0 = y0; t.ny = std::min(ty, ny - y0);
+                        t.z0 = z0; t.nz = std::min(zc, nz - z0);
+                        T.h.push_back(t);
+                    }
+            }
+            T.begin[c][l + 1] = (long long)T.h.size();
         }
-    }
-    T.level_begin[H.nlev] = (long long)T.h.size();
     if (tma && T.max_plane_doubles > stencil_tma_max_plane_doubles()) T.ok = false;
 }
 
@@ -281,14 +290,17 @@ int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex
     // the TMA tile table is sized for the nghost == 1 layout (row pitch nx+4)
     if (in_ng == 1 && use_tma(h, nin)) {
         TileTable& T = h->tiles_tma;
-        long long a = T.level_begin[l0], b = T.level_begin[l1 + 1];
-        // stage size and CTA shape follow the largest tile of the levels in this launch
-        int plane = 0, items = 0;
-        for (int l = l0; l <= l1; ++l) { plane = std::max(plane, T.lev_plane_doubles[l]); items = std::max(items, T.lev_items[l]); }
-        CU(launch_stencil_tma(mode, T.d.p + a, (int)(b - a), plane, items, ga, ex, nvar, t_stream));
+        for (int c = 0; c < N_TILE_CLASSES; ++c) {
+            const long long a = T.begin[c][l0], b = T.begin[c][l1 + 1];
+            if (b <= a) continue;
+            // stage size and CTA shape follow the largest tile of this class on the levels of the launch
+            int plane = 0, items = 0;
+            for (int l = l0; l <= l1; ++l) { plane = std::max(plane, T.plane_doubles[c][l]); items = std::max(items, T.items[c][l]); }
+            CU(launch_stencil_tma(mode, T.d.p + a, (int)(b - a), plane, items, ga, ex, nvar, t_stream));
+        }
     } else {
         TileTable& T = h->tiles_simple;
-        long long a = T.level_begin[l0], b = T.level_begin[l1 + 1];
+        long long a = T.begin[0][l0], b = T.begin[0][l1 + 1];
         CU(launch_stencil_simple(mode, T.d.p + a, (int)(b - a), ga, ex, nvar, t_stream));
     }
     return PA_OK;

@@ -212,7 +212,15 @@ def case_thin(names=("temp",)) -> Plotfile:
     return pf
 
 
+def case_mixed(names=("temp",)) -> Plotfile:
+    """Boxes of three different sizes on one level (64x16x16, 32x16x16, 8^3, abutting raggedly) over a single 32x16x16
+    coarse box: every CTA-shape class of the TMA stencil occurs in one hierarchy, so one stencil pass is several launches."""
+    reg = [((0, 0, 0), (63, 15, 15)), ((0, 16, 0), (7, 23, 7)), ((8, 16, 0), (39, 31, 15))]
+    return make_hierarchy((32, 16, 16), [reg], [2], 64, names)
+
+
 CASES: Dict[str, Callable[..., Plotfile]] = {
     "config1": config1, "config2": config2, "config3": config3, "config4": config4, "config5": config5,
     "lshape": case_lshape, "ratio4": case_ratio4, "np2": case_np2, "edge": case_edge, "thin": case_thin,
+    "mixed": case_mixed,
 }

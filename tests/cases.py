@@ -20,6 +20,7 @@ CASES = {
     "edge_periodic": (lambda: synth.case_edge(16, 8), (1, 1, 1), (0, 0, 0), ("grad", "curvature"), {}),
     "np2": (_np2_small, (1, 1, 1), (0, 0, 0), ("grad", "curvature"), {}),
     "thin": (synth.case_thin, (1, 1, 1), (0, 0, 0), ("grad", "curvature"), {}),
+    "mixed_boxes": (synth.case_mixed, (1, 1, 1), (0, 0, 0), ("grad", "curvature"), {}),
     "ratio4": (lambda: synth.case_ratio4(8, 16), (1, 1, 1), (0, 0, 0), ("grad",), {}),
     "c3_three_levels": (lambda: synth.config3(16, 8), (1, 1, 1), (0, 0, 0), ("grad", "curvature"), {}),
     "c3_threshold": (lambda: synth.config3(16, 8), (1, 1, 1), (0, 0, 0), ("curvature",),

@@ -2,7 +2,7 @@
 """Generate tests/golden/*.npz by running the compiled, unmodified reference (oracle/_ref, built by
 oracle/build_ref.py from /root/reference) on the synthetic cases of tests/cases.py.
 
-Run in the build container (needs oracle/_ref):  python tests/golden/make_golden.py
+Run in the build container (needs oracle/_ref):  python tests/golden/make_golden.py [case ...]
 Each fixture stores the hierarchy metadata, the input component(s) and the reference's output components as the
 flat concatenation (level-major, box order, [k][j][i]) of the valid regions -- bit-exact float64."""
 import os
@@ -28,6 +28,8 @@ def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     with tempfile.TemporaryDirectory() as tmp:
         for name, (builder, is_per, sym, tools, ckw) in CASES.items():
+            if len(sys.argv) > 1 and name not in sys.argv[1:]:
+                continue
             pf = builder()
             d = os.path.join(tmp, "plt_" + name)
             plotfile.write_plotfile(d, pf, clean="remove")
