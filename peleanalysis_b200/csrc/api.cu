@@ -91,6 +91,9 @@ struct pa_hier {
     std::map<cudaStream_t, std::unique_ptr<DevBuf<double>>> staging;   // upload / download staging, one per stream
     DevBuf<double> send_slab, recv_slab;               // multi-rank exchange, [cell][comp]
     int slab_ncomp = 0;
+    // side stream on which the ghost fill of the refined levels overlaps the stencil of level 0 (created on demand)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // curvature temporaries (allocated on demand)
     pa_field* tmpG = nullptr;
     pa_field* tmpH = nullptr;
@@ -353,6 +356,44 @@ int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1, bool link
     return PA_OK;
 }
 
+// ---- overlap of the refined levels' ghost fill with the stencil of level 0 -----------------------------------------
+// The BC fill of levels >= 1 is a latency-bound gather (coarse VALID cells + fine interior cells -> fine ghost cells) that
+// depends on nothing the level-0 stencil writes, and level 0 is a third or more of the cells of a hierarchy.  So one pass is
+//     caller's stream:  fill(level 0)  | stencil(level 0)            | wait | stencil(levels >= 1)
+//     side stream:      wait(fork)     | fill(levels >= 1)  record   |
+// PA_STREAM_OVERLAP=0 keeps everything on the caller's stream in the plain order fill(all) -> stencil(all).
+bool overlap_enabled(const pa_hier* h) {
+    if (h->H.nlev < 2) return false;
+    const char* e = getenv("PA_STREAM_OVERLAP");
+    return !(e && e[0] == '0');
+}
+int ensure_side(pa_hier* h) {
+    if (h->side) return PA_OK;
+    CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    return PA_OK;
+}
+// run `fill_fine` (a ghost fill of levels >= 1) on the side stream, ordered after everything already enqueued on the
+// caller's stream; the caller's stream goes on and must call join_side() before it touches what the fill wrote
+template <class F>
+int fork_side(pa_hier* h, F&& fill_fine) {
+    CHK(ensure_side(h));
+    cudaStream_t main_stream = t_stream;
+    CU(cudaEventRecord(h->ev_fork, main_stream));
+    CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    t_stream = h->side;
+    const int rc = fill_fine();
+    t_stream = main_stream;
+    CHK(rc);
+    CU(cudaEventRecord(h->ev_join, h->side));
+    return PA_OK;
+}
+int join_side(pa_hier* h) {
+    CU(cudaStreamWaitEvent(t_stream, h->ev_join, 0));
+    return PA_OK;
+}
+
 }  // namespace
 
 // =============================================================================================================
@@ -412,6 +453,9 @@ int pa_hier_destroy(pa_hier* h) {
     if (h->tmpG) pa_field_free(h->tmpG);
     if (h->tmpH) pa_field_free(h->tmpH);
     if (h->tmpW) pa_field_free(h->tmpW);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     delete h;
     return PA_OK;
 }
@@ -764,14 +808,23 @@ int pa_grad_phases(pa_field* in, int comp_in, int nvar, pa_field* out, int comp_
     if (in->h != out->h) return fail(PA_ERR_ARG, "pa_grad: fields belong to different hierarchies");
     if (in->ng < 1) return fail(PA_ERR_ARG, "pa_grad: input field needs nghost >= 1");
     pa_hier* h = in->h;
-    if (phases & 1) CHK(fill_ghosts_impl(in, comp_in, nvar, 0, h->H.nlev - 1, false));
-    if (!(phases & 2)) return PA_OK;
+    const int nlev = h->H.nlev;
     CHK(ensure_device(h));
     GridArgs ga;
-    CHK(grid_args(in, comp_in, out, comp_out, ga));
     StencilExtra ex;
     std::memset(&ex, 0, sizeof(ex));
-    return run_stencil(h, MODE_GRAD, ga, ex, nvar, 0, h->H.nlev - 1, in->ng, in);
+    if (phases == 3 && overlap_enabled(h)) {
+        CHK(grid_args(in, comp_in, out, comp_out, ga));            // (also puts both layouts on the device before the fork)
+        CHK(fill_ghosts_impl(in, comp_in, nvar, 0, 0, false));
+        CHK(fork_side(h, [&]() { return fill_ghosts_impl(in, comp_in, nvar, 1, nlev - 1, false); }));
+        CHK(run_stencil(h, MODE_GRAD, ga, ex, nvar, 0, 0, in->ng, in));
+        CHK(join_side(h));
+        return run_stencil(h, MODE_GRAD, ga, ex, nvar, 1, nlev - 1, in->ng, in);
+    }
+    if (phases & 1) CHK(fill_ghosts_impl(in, comp_in, nvar, 0, nlev - 1, false));
+    if (!(phases & 2)) return PA_OK;
+    CHK(grid_args(in, comp_in, out, comp_out, ga));
+    return run_stencil(h, MODE_GRAD, ga, ex, nvar, 0, nlev - 1, in->ng, in);
 }
 
 // ---------------------------------------------------------------------------------------------- curvature
@@ -837,11 +890,19 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
         // progress space by the ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel
         // writes Progress and n = G/nrm; Progress never makes a separate round trip through HBM.
         GhostXform xf{1, opts->prog_min, invdenom};
-        CHK(fill_ghosts_impl(state, comp_S, 1, 0, nlev - 1, false, xf));
         for (int l = 0; l < nlev; ++l) ex.cout[l] = out->slab[l] ? out->slab[l] + (long long)cP * out->cs[l] : nullptr;
         ex.pmin = opts->prog_min; ex.inv = invdenom;
         CHK(grid_args(state, comp_S, out, cN, ga));
-        CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
+        if (overlap_enabled(h)) {
+            CHK(fill_ghosts_impl(state, comp_S, 1, 0, 0, false, xf));
+            CHK(fork_side(h, [&]() { return fill_ghosts_impl(state, comp_S, 1, 1, nlev - 1, false, xf); }));
+            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, 0, state->ng, state));
+            CHK(join_side(h));
+            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 1, nlev - 1, state->ng, state));
+        } else {
+            CHK(fill_ghosts_impl(state, comp_S, 1, 0, nlev - 1, false, xf));
+            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
+        }
     } else {
         if (H.nranks > 1)
             return fail(PA_ERR_UNSUPPORTED, "pa_curvature_phases: the multi-rank path needs the fused progress pass (state with nghost == 1, "
@@ -870,7 +931,14 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
     ex.threshold = opts->threshold;
     for (int l = 0; l < nlev; ++l) ex.prog[l] = out->slab[l] + (long long)cP * out->cs[l];
     CHK(grid_args(out, cN, out, cK, ga));
-    if (!opts->do_threshold) {
+    if (!opts->do_threshold && overlap_enabled(h)) {
+        // n of every level is final (pass 1 is complete on the caller's stream, which the fork orders the side stream after)
+        CHK(fill_ghosts_impl(out, cN, 3, 0, 0, false));
+        CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, cN, 3, 1, nlev - 1, false); }));
+        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
+        CHK(join_side(h));
+        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 1, nlev - 1, out->ng, out));
+    } else if (!opts->do_threshold) {
         CHK(fill_ghosts_impl(out, cN, 3, 0, nlev - 1, false));
         CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, nlev - 1, out->ng, out));
     } else {

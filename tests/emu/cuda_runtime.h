@@ -50,6 +50,8 @@ enum cudaError_t {
     cudaErrorNotSupported = 801
 };
 typedef struct CUstream_st* cudaStream_t;
+typedef struct CUevent_st* cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaHostAllocDefault = 0, cudaHostRegisterDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
@@ -86,6 +88,13 @@ cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st);
 cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k, cudaStream_t st);
 cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t st);
 cudaError_t cudaStreamSynchronize(cudaStream_t st);
+// streams and events: the emulator executes everything in issue order, which is one of the orders the events allow
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned flags);
+cudaError_t cudaStreamDestroy(cudaStream_t st);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* ev, unsigned flags);
+cudaError_t cudaEventDestroy(cudaEvent_t ev);
+cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t st);
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t ev, unsigned flags);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void* p);
@@ -97,6 +106,10 @@ extern uint3 g_threadIdx, g_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 unsigned char* dyn_smem();
 void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+// run `work` now, or -- CUEMU_DEFER_SIDE=1 and `st` was made by cudaStreamCreate* -- when something waits for that stream
+// (cudaStreamWaitEvent on an event recorded in it, cudaStreamSynchronize): the LATEST order the events allow, where the
+// default is the earliest.  A pass that is correct under both has its cross-stream dependencies covered by events.
+void submit(cudaStream_t st, std::function<void()> work);
 void syncthreads();
 void syncwarp(unsigned mask);
 // every participating lane publishes `bytes` bytes; returns a pointer to the 32 published slots (8 bytes each)
@@ -114,23 +127,26 @@ template <class... KA>
 struct Launcher {
     dim3 g, b;
     size_t smem;
+    cudaStream_t st;
     void (*k)(KA...);
     template <class... A>
     void operator()(A&&... a) const {
-        std::tuple<KA...> args(std::forward<A>(a)...);
+        std::tuple<std::decay_t<KA>...> args(std::forward<A>(a)...);
         void (*fn)(KA...) = k;
-        launch_impl(g, b, smem, [fn, &args]() { std::apply(fn, args); });
+        const dim3 gg = g, bb = b;
+        const size_t sm = smem;
+        submit(st, [fn, args, gg, bb, sm]() { launch_impl(gg, bb, sm, [&]() { std::apply(fn, args); }); });
     }
 };
 template <class... KA>
-Launcher<KA...> launcher(dim3 g, dim3 b, size_t smem, void (*k)(KA...)) { return Launcher<KA...>{g, b, smem, k}; }
+Launcher<KA...> launcher(dim3 g, dim3 b, size_t smem, cudaStream_t st, void (*k)(KA...)) { return Launcher<KA...>{g, b, smem, st, k}; }
 }  // namespace cuemu
 
 #define threadIdx (::cuemu::g_threadIdx)
 #define blockIdx (::cuemu::g_blockIdx)
 #define blockDim (::cuemu::g_blockDim)
 #define gridDim (::cuemu::g_gridDim)
-#define PA_LAUNCH(grid, block, smem, stream, ...) ::cuemu::launcher((grid), (block), (smem), __VA_ARGS__)
+#define PA_LAUNCH(grid, block, smem, stream, ...) ::cuemu::launcher((grid), (block), (smem), (stream), __VA_ARGS__)
 #define PA_DYN_SMEM(name) unsigned char* name = ::cuemu::dyn_smem()
 
 inline void __syncthreads() { cuemu::syncthreads(); }

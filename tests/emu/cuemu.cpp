@@ -161,6 +161,25 @@ void run_block() {
 
 unsigned char* dyn_smem() { return dyn_aligned; }
 
+// ---- streams: created streams may defer their work to the latest point the events allow ---------------------------
+namespace {
+std::map<cudaStream_t, std::vector<std::function<void()>>> created_streams;
+std::map<cudaEvent_t, cudaStream_t> event_stream;
+bool defer_side() { const char* e = getenv("CUEMU_DEFER_SIDE"); return e && e[0] == '1'; }
+void flush_stream(cudaStream_t st) {
+    auto it = created_streams.find(st);
+    if (it == created_streams.end()) return;
+    std::vector<std::function<void()>> q;
+    q.swap(it->second);
+    for (auto& w : q) w();
+}
+}  // namespace
+void submit(cudaStream_t st, std::function<void()> work) {
+    auto it = created_streams.find(st);
+    if (it != created_streams.end() && defer_side()) it->second.push_back(std::move(work));
+    else work();
+}
+
 void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn) {
     {   // CUEMU_SEED is read at every launch (tests flip it); the random stream restarts whenever the seed changes
         const char* e = getenv("CUEMU_SEED");
@@ -288,14 +307,16 @@ cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) { cuemu::flush_stream(st); std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) { cuemu::flush_stream(st); std::memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t st) {
+    cuemu::flush_stream(st);
     for (size_t r = 0; r < height; ++r) std::memcpy((char*)d + r * dpitch, (const char*)s + r * spitch, width);
     return cudaSuccess;
 }
-cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t) {
+cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t st) {
+    cuemu::flush_stream(st);
     const cudaPitchedPtr &S = p->srcPtr, &D = p->dstPtr;
     for (size_t z = 0; z < p->extent.depth; ++z)
         for (size_t y = 0; y < p->extent.height; ++y) {
@@ -305,7 +326,22 @@ cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t) {
         }
     return cudaSuccess;
 }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t st) { cuemu::flush_stream(st); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned) {
+    *st = (cudaStream_t)std::malloc(8);
+    cuemu::created_streams[*st];
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t st) { cuemu::flush_stream(st); cuemu::created_streams.erase(st); std::free(st); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* ev, unsigned) { *ev = (cudaEvent_t)std::malloc(8); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t ev) { cuemu::event_stream.erase(ev); std::free(ev); return cudaSuccess; }
+// an event recorded in a deferring stream completes only when that stream's queue has run: whoever waits for it runs it
+cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t st) { cuemu::event_stream[ev] = st; return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t ev, unsigned) {
+    auto it = cuemu::event_stream.find(ev);
+    if (it != cuemu::event_stream.end()) cuemu::flush_stream(it->second);
+    return cudaSuccess;
+}
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
