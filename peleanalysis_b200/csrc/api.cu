@@ -361,11 +361,14 @@ int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1, bool link
 // depends on nothing the level-0 stencil writes, and level 0 is a third or more of the cells of a hierarchy.  So one pass is
 //     caller's stream:  fill(level 0)  | stencil(level 0)            | wait | stencil(levels >= 1)
 //     side stream:      wait(fork)     | fill(levels >= 1)  record   |
-// PA_STREAM_OVERLAP=0 keeps everything on the caller's stream in the plain order fill(all) -> stencil(all).
+// Opt-in (PA_STREAM_OVERLAP=1).  Measured on B200 it does NOT pay (profiles/r01_ab_stream_overlap.txt: curvature on the
+// target hierarchy 6.90 ms with it, 6.59 ms without; grad on 16^3 boxes 0.997 vs 0.983 ms): the persistent stencil kernels
+// own the SMs, so the fill's blocks mostly wait anyway, and splitting each stencil pass in two costs a second ramp-up and
+// tail.  The default therefore keeps everything on the caller's stream in the plain order fill(all) -> stencil(all).
 bool overlap_enabled(const pa_hier* h) {
     if (h->H.nlev < 2) return false;
     const char* e = getenv("PA_STREAM_OVERLAP");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
 }
 int ensure_side(pa_hier* h) {
     if (h->side) return PA_OK;

@@ -104,28 +104,22 @@ def test_emulated_midsize_vs_oracle(emu, case, kw):
 
 @pytest.mark.parametrize("name", [n for n in CASES if n not in ("c3_threshold", "c1_options")])
 def test_emulated_side_stream_runs_late(emu, name):
-    """The ghost fill of the refined levels runs on a side stream, overlapped with the stencil of level 0
-    (api.cu: fork_side / join_side).  By default the emulator executes side-stream work at once -- the EARLIEST order the
-    events allow; here it holds it back until something waits for that stream -- the LATEST order.  Bit-exact results in
-    both say the cross-stream dependencies are all expressed as events (and PA_STREAM_OVERLAP=0, the plain single-stream
-    order, is what every other backend comparison already covers)."""
+    """PA_STREAM_OVERLAP=1 (opt-in): the ghost fill of the refined levels runs on a side stream, overlapped with the
+    stencil of level 0 (api.cu: fork_side / join_side).  The emulator executes side-stream work either at once -- the
+    EARLIEST order the events allow -- or holds it back until something waits for that stream -- the LATEST order.
+    Bit-exact results in both say the cross-stream dependencies are all expressed as events."""
     os.environ["CUEMU_SEED"] = "0"
-    os.environ["CUEMU_DEFER_SIDE"] = "1"
+    os.environ["PA_STREAM_OVERLAP"] = "1"
     try:
-        tools = CASES[name][3]
-        if "grad" in tools:
-            G.test_grad_matches_reference_golden(emu, name, "tma", "links")
-        if "curvature" in tools:
-            G.test_curvature_matches_reference_golden(emu, name, "tma", "links")
-            G.test_curvature_matches_reference_golden(emu, name, "simple", "nolinks")
+        for defer in ("0", "1"):
+            os.environ["CUEMU_DEFER_SIDE"] = defer
+            tools = CASES[name][3]
+            if "grad" in tools:
+                G.test_grad_matches_reference_golden(emu, name, "tma", "links")
+            if "curvature" in tools:
+                G.test_curvature_matches_reference_golden(emu, name, "tma", "links")
+                if defer == "1":
+                    G.test_curvature_matches_reference_golden(emu, name, "simple", "nolinks")
     finally:
         os.environ["CUEMU_DEFER_SIDE"] = "0"
-
-
-def test_emulated_single_stream_order(emu):
-    os.environ["PA_STREAM_OVERLAP"] = "0"
-    try:
-        G.test_grad_matches_reference_golden(emu, "c3_three_levels", "tma", "links")
-        G.test_curvature_matches_reference_golden(emu, "c3_three_levels", "tma", "links")
-    finally:
         os.environ.pop("PA_STREAM_OVERLAP", None)

@@ -317,3 +317,14 @@ def test_flat_field_takes_the_clamp(gpu):
     assert (want[2:5] == 0).sum() > 1000
     for c in range(5):
         assert bit_equal(out[c], want[c]), c
+
+
+@pytest.mark.parametrize("name", ["c3_three_levels", "mixed_boxes", "lshape"])
+def test_side_stream_overlap_is_bit_exact(gpu, name):
+    """PA_STREAM_OVERLAP=1 (opt-in): ghost fill of the refined levels on a side stream while level 0's stencil runs."""
+    os.environ["PA_STREAM_OVERLAP"] = "1"
+    try:
+        test_grad_matches_reference_golden(gpu, name, "tma", "links")
+        test_curvature_matches_reference_golden(gpu, name, "tma", "links")
+    finally:
+        os.environ.pop("PA_STREAM_OVERLAP", None)
