@@ -193,6 +193,10 @@ __device__ __forceinline__ void normal_pair(double ax, double bx, double gx, dou
     }
 }
 
+// CTAs per SM when the CTA carries the extra descriptor warp (PF variant): one warp more per CTA must still fit the register file
+constexpr int per_sm_pf(int cw, bool heavy) { return cw >= 16 ? 1 : cw == 8 ? 2 : cw == 4 ? 3 : (heavy ? 4 : 5); }
+constexpr int PF_LEAD = 8;                            // planes before the end of an item at which the next one is prepared
+
 template <int MODE> struct ModeTraits;
 template <> struct ModeTraits<MODE_GRAD> { static constexpr int NIN = 1, NOUT = 4; };
 template <> struct ModeTraits<MODE_GRAD3> { static constexpr int NIN = 1, NOUT = 3; };
@@ -210,6 +214,16 @@ struct TileRec {
     PaLayDev li, lo;
 };
 
+// PF variant: everything the producer's plane loop needs for one work item, prepared one item ahead by the descriptor warp
+struct ProdCtx {
+    TileRec rec;                          // rec.t.lev < 0: no more work
+    const double* own;                    // row 0 / plane 0 of the item's first input component in the box's own block
+    const double* src[4];                 // sources of the linked y-lo, z-lo, y-hi, z-hi faces (nullptr: not linked)
+    long long cs[4];                      // ... and the component strides of the slabs they live in
+    long long cs_in;                      // component stride of the box's own slab
+    const double* xsrc[2 * XG_LANES];     // x-ghost cell sources at plane 0: entry lane-1 + XG_LANES*k (nullptr: none)
+};
+
 // per-item flags (one register)
 enum : unsigned {
     F_ACTIVE = 1u, F_TWO = 2u,           // item exists; its second cell is a valid cell (not the x-hi ghost of an odd row)
@@ -222,8 +236,14 @@ enum : unsigned {
 
 // PLAIN = true: the flame normal through the plain IEEE operators (sqrt(), six divisions) instead of normal_pair() -- the
 // form the library falls back to should the device self-test of the branch-free forms ever report a differing bit
-template <int MODE, int CW, bool PLAIN>
-__global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
+// PF = true adds a DESCRIPTOR WARP: it draws the next ticket and walks the dependent descriptor loads (tile -> box, layouts,
+// neighbour links -> neighbours' layouts, peer slabs) while the producer is still streaming the current item, and hands the
+// producer a finished context through shared memory.  Without it the producer does that walk itself between two items and
+// the ring drains meanwhile (ncu, NORMAL_S: a tenth of the consumers' time is spent waiting for an item's first plane).
+template <int MODE, int CW, bool PLAIN, bool PF>
+__global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
+                                  PF ? per_sm_pf(CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S)
+                                     : Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
                                                             StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
                                                             int S /* ring depth in planes */,
                                                             unsigned long long* __restrict__ ticket, unsigned long long ticket_base) {
@@ -237,6 +257,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(16) double xg_s[MAX_STAGES][2][32];          // x ghosts of linked x faces: [stage][lo/hi][row]
     __shared__ __align__(16) TileRec rec_s[MAX_STAGES];
+    ProdCtx* ctx = nullptr;                                           // PF: the next item's producer context ...
+    uint64_t* ctx_bar = nullptr;                                      // ... [0] full (descriptor warp -> producer), [1] go (producer -> descriptor warp)
+    if constexpr (PF) {
+        __shared__ __align__(16) ProdCtx ctx_storage;
+        __shared__ __align__(8) uint64_t ctx_bar_storage[2];
+        ctx = &ctx_storage; ctx_bar = ctx_bar_storage;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long stage_stride = (long long)NIN * stage_doubles;
@@ -244,11 +271,83 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
     if (threadIdx.x == 0) {
         // a stage is full when the TMA bytes have landed (lane 0's arrive.expect_tx) and every x-ghost lane has arrived
         for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1u + XG_LANES); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        if constexpr (PF) { mbar_init(&ctx_bar[0], 1u); mbar_init(&ctx_bar[1], 1u); }
 #ifndef PA_HOST_EMULATION
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     }
     __syncthreads();
+
+    if constexpr (PF) {
+        if (warp == CONSUMER_WARPS + 1) {
+            // ===================================== descriptor warp =====================================
+            // One item ahead of the producer: ticket, tile, box / layout / link records, neighbours' layouts and slabs --
+            // three dependent round trips to L2 / HBM that would otherwise sit between two items of the ring.  The ticket is
+            // drawn only PF_LEAD planes before the producer finishes its current item, so the dynamic balance of the
+            // persistent grid stays within a fraction of an item.
+            if (lane > XG_LANES) return;
+            uint32_t gphase = 0;
+            for (int k = 0;; ++k) {
+                if (k > 0) { mbar_wait(&ctx_bar[1], gphase); gphase ^= 1u; }     // the producer took the previous context
+                unsigned long long tk = 0;
+                if (lane == 0) tk = atomicAdd(ticket, 1ULL) - ticket_base;
+                tk = __shfl_sync(0x7fffffffu, tk, 0);
+                ProdCtx& X = *ctx;
+                if (tk >= (unsigned long long)nwork) {
+                    if (lane == 0) X.rec.t.lev = -1;
+                    __syncwarp(0x7fffffffu);
+                    if (lane == 0) mbar_arrive(&ctx_bar[0]);
+                    return;
+                }
+                const int wi = (int)tk;
+                const int v = wi / ntiles;
+                const PaTile t = tiles[wi - v * ntiles];
+                const LevArgs& L = ga.L[t.lev];
+                const PaBoxDev bx = L.boxes[t.box];
+                const PaLayDev li = L.lay_in[t.box];
+                const PaNbr nb = L.nbr[t.box];
+                const int c0 = L.in_comp + (MODE == MODE_DIV ? 0 : v);
+                auto link_src = [&](int face, long long& cs) -> const double* {      // as in the producer below
+                    const PaNbrFace F = nb.f[face];
+                    cs = 0;
+                    if (F.nb < 0) return nullptr;
+                    const PaPeerSlab ps = L.peers[F.rank];
+                    const PaLayDev ln = L.lay_in[F.nb];
+                    cs = ps.cs;
+                    return ps.base + (long long)c0 * ps.cs + ln.off + (long long)(F.rel[2] + ln.ng) * ln.PS + (long long)(F.rel[1] + ln.ng) * ln.P + F.rel[0];
+                };
+                if (lane == 0) {
+                    X.rec.t = t; X.rec.v = v; X.rec.bx = bx; X.rec.li = li; X.rec.lo = L.lay_out[t.box];
+                    int lk = 0;
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) lk |= (nb.f[f].nb >= 0) ? (1 << f) : 0;
+                    X.rec.links = lk;
+                    X.own = L.in + (MODE == MODE_DIV ? 0 : (long long)v * L.cs_in) + li.off + (long long)li.ng * li.PS + (long long)li.ng * li.P;
+                    X.cs_in = L.cs_in;
+                    long long cs;
+                    X.src[0] = link_src(1, cs); X.cs[0] = cs;
+                    X.src[1] = link_src(2, cs); X.cs[1] = cs;
+                    X.src[2] = link_src(4, cs); X.cs[2] = cs;
+                    X.src[3] = link_src(5, cs); X.cs[3] = cs;
+                } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        const int idx = lane - 1 + XG_LANES * k2;
+                        const int side = idx / t.ny, xr = idx - side * t.ny;   // side 0 = x-lo, 1 = x-hi
+                        const double* src = nullptr;
+                        if (side < 2) {
+                            long long cs;
+                            const double* s0 = link_src(side ? 3 : 0, cs);
+                            if (s0) src = s0 + (long long)(t.z0 - 1) * li.PS + (long long)(t.y0 + xr) * li.P + ((side ? bx.n[0] : -1) + li.ng + li.xoff);
+                        }
+                        X.xsrc[idx] = src;
+                    }
+                }
+                __syncwarp(0x7fffffffu);
+                if (lane == 0) mbar_arrive(&ctx_bar[0]);
+            }
+        }
+    }
 
     if (warp == CONSUMER_WARPS) {
         // ===================================== producer warp =====================================
@@ -257,7 +356,84 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
         if (lane > XG_LANES) return;
         int stage = 0;
         uint32_t ephase = 1;                            // parity that lets the first pass through the ring go without waiting
-        for (;;) {
+        if constexpr (PF) {
+            // the descriptor warp has the next item's context ready in shared memory; take it, stream the item, and tell
+            // the descriptor warp to prepare the following one PF_LEAD planes before this one ends
+            uint32_t cphase = 0;
+            for (;;) {
+                mbar_wait(&ctx_bar[0], cphase); cphase ^= 1u;
+                const ProdCtx& X = *ctx;
+                const PaTile t = X.rec.t;
+                if (t.lev < 0) {
+                    mbar_wait(&empty_bar[stage], ephase);
+                    if (lane == 0) { rec_s[stage].t.lev = -1; mbar_arrive(&full_bar[stage]); }
+                    else cp_async_arrive_noinc(&full_bar[stage]);
+                    break;
+                }
+                const PaLayDev li = X.rec.li;
+                const int nyb = X.rec.bx.n[1], nzb = X.rec.bx.n[2];
+                const int rows = t.ny + 2, nplanes = t.nz + 2;
+                const uint32_t row_bytes = (uint32_t)li.P * 8u, plane_bytes = (uint32_t)rows * row_bytes;
+                long long cs_ylo = 0, cs_zlo = 0, cs_yhi = 0, cs_zhi = 0, cs_in = 0;
+                const double *own = nullptr, *s_ylo = nullptr, *s_zlo = nullptr, *s_yhi = nullptr, *s_zhi = nullptr;
+                const double* xsrc[2] = {nullptr, nullptr};
+                double* xdst[2] = {nullptr, nullptr};
+                if (lane == 0) {
+                    own = X.own; cs_in = X.cs_in;
+                    s_ylo = X.src[0]; s_zlo = X.src[1]; s_yhi = X.src[2]; s_zhi = X.src[3];
+                    cs_ylo = X.cs[0]; cs_zlo = X.cs[1]; cs_yhi = X.cs[2]; cs_zhi = X.cs[3];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int idx = lane - 1 + XG_LANES * k;
+                        const int side = idx / t.ny, xr = idx - side * t.ny;
+                        xsrc[k] = X.xsrc[idx];
+                        if (xsrc[k]) xdst[k] = &xg_s[0][side][xr];
+                    }
+                }
+                const int go_at = nplanes > PF_LEAD ? nplanes - PF_LEAD : 0;
+                for (int p = 0; p < nplanes; ++p) {
+                    mbar_wait(&empty_bar[stage], ephase);
+                    if (lane == 0) {
+                        if (p == 0) rec_s[stage] = X.rec;              // the tile record rides with the tile's first plane
+                        mbar_expect_tx(&full_bar[stage], plane_bytes * NIN);
+                        const int z = t.z0 - 1 + p;
+                        const double* zs = (z < 0) ? s_zlo : (z >= nzb ? s_zhi : nullptr);
+                        const long long zcs = (z < 0) ? cs_zlo : cs_zhi;
+#pragma unroll
+                        for (int c = 0; c < NIN; ++c) {
+                            double* dst = sm + (long long)stage * stage_stride + (long long)c * stage_doubles;
+                            if (zs) {
+                                tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
+                                continue;
+                            }
+                            int r0 = t.y0 - 1, r1 = t.y0 + t.ny;
+                            if (r0 < 0 && s_ylo) {
+                                tma_load_1d(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[stage]);
+                                r0 = 0;
+                            }
+                            if (r1 >= nyb && s_yhi) {
+                                tma_load_1d(dst + (long long)(rows - 1) * li.P, s_yhi + (long long)c * cs_yhi + (long long)z * li.PS + (long long)nyb * li.P,
+                                            row_bytes, &full_bar[stage]);
+                                r1 = nyb - 1;
+                            }
+                            tma_load_1d(dst + (long long)(r0 - (t.y0 - 1)) * li.P, own + (long long)c * cs_in + (long long)z * li.PS + (long long)r0 * li.P,
+                                        (uint32_t)(r1 - r0 + 1) * row_bytes, &full_bar[stage]);
+                        }
+                    } else {
+                        if (xsrc[0]) cp_async_8(xdst[0] + stage * 64, xsrc[0] + (long long)p * li.PS);
+                        if (xsrc[1]) cp_async_8(xdst[1] + stage * 64, xsrc[1] + (long long)p * li.PS);
+                        cp_async_arrive_noinc(&full_bar[stage]);
+                    }
+                    if (p == go_at) {                                  // every lane has read its part of the context by now
+                        __syncwarp(0x7fffffffu);
+                        if (lane == 0) mbar_arrive(&ctx_bar[1]);
+                    }
+                    if (++stage == S) { stage = 0; ephase ^= 1u; }
+                }
+            }
+        }
+        if constexpr (!PF) for (;;) {
             // next work item: the counter is never reset -- the host advances ticket_base by (nwork + grid) per launch,
             // exactly what the CTAs of one launch draw in total (every CTA overdraws once, then stops)
             unsigned long long tk = 0;
@@ -572,18 +748,21 @@ std::map<cudaStream_t, Ticket> g_tickets;
 int g_stage_cap = 0;
 size_t g_inflight_bytes = 0;
 
-template <int MODE, int CW, bool PLAIN>
+template <int MODE, int CW, bool PLAIN, bool PF>
 cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                         int nvar, cudaStream_t st) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
-    constexpr int PER_SM = Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM;
+    constexpr bool HEAVY = MODE == MODE_NORMAL || MODE == MODE_NORMAL_S;
+    constexpr int PER_SM = PF ? per_sm_pf(CW, HEAVY) : Shape<CW, HEAVY>::PER_SM;
+    constexpr int THREADS = (CW + 1 + (PF ? 1 : 0)) * 32;
     const size_t stage_bytes = (size_t)NIN * stage_doubles * sizeof(double);
     // Ring depth.  The consumers hold two planes (p-1 and p); the rest of the ring is data in flight.  Measured on B200
     // (config 2): ~40 KB in flight per SM (~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
     // ring is SLOWER (the read stream runs far ahead of the write stream and the two fight for DRAM pages / L2).
     if (g_inflight_bytes == 0) { const char* e = getenv("PA_TMA_INFLIGHT_KB"); g_inflight_bytes = (size_t)(e ? std::max(1, atoi(e)) : 20) * 1024; }
     const size_t inflight = g_inflight_bytes * 2 / PER_SM;
-    const size_t budget = (size_t)(227 * 1024) / PER_SM - STATIC_SMEM - 1024, budget1 = 227 * 1024 - STATIC_SMEM - 1024;
+    constexpr size_t STATIC = STATIC_SMEM + (PF ? sizeof(ProdCtx) + 64 : 0);
+    const size_t budget = (size_t)(227 * 1024) / PER_SM - STATIC - 1024, budget1 = 227 * 1024 - STATIC - 1024;
     int S = 2 + (int)((inflight + stage_bytes - 1) / stage_bytes), per_sm = PER_SM;
     if ((size_t)S * stage_bytes > budget) S = (int)(budget / stage_bytes);
     if (S < 3) { S = std::min(4, (int)(budget1 / stage_bytes)); per_sm = 1; }
@@ -594,7 +773,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     const size_t smem = (size_t)S * stage_bytes;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW, PLAIN, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -612,7 +791,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    PA_LAUNCH(grid, (CW + 1) * 32, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN, PF>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
@@ -638,15 +817,24 @@ int decide_normal_math(cudaStream_t st) {
     return g_normal_plain;
 }
 // PA_TMA_SMALL=0 switches the small-tile shapes (4 / 2 consumer warps) off (read at every launch: the tests flip it)
+template <int MODE, bool PLAIN, bool PF>
+cudaError_t launch_cw2(int cw, const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
+                       int nvar, cudaStream_t st) {
+    switch (cw) {
+        case 2: return launch_mode<MODE, 2, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        case 4: return launch_mode<MODE, 4, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        case 16: return launch_mode<MODE, 16, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        default: return launch_mode<MODE, 8, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    }
+}
+// PA_TMA_PREFETCH=1 selects the variant with the descriptor warp (opt-in until it has been measured on a B200; read at
+// every launch: the tests flip it)
 template <int MODE, bool PLAIN>
 cudaError_t launch_cw(int cw, const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                       int nvar, cudaStream_t st) {
-    switch (cw) {
-        case 2: return launch_mode<MODE, 2, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        case 4: return launch_mode<MODE, 4, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        case 16: return launch_mode<MODE, 16, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        default: return launch_mode<MODE, 8, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-    }
+    const char* e = getenv("PA_TMA_PREFETCH");
+    if (e && e[0] == '1') return launch_cw2<MODE, PLAIN, true>(cw, tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    return launch_cw2<MODE, PLAIN, false>(cw, tiles, ntiles, stage_doubles, ga, ex, nvar, st);
 }
 template <int MODE>
 cudaError_t launch_shape(const PaTile* tiles, int ntiles, int stage_doubles, int max_items, const GridArgs& ga, const StencilExtra& ex,

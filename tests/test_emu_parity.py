@@ -29,7 +29,7 @@ def emu():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     m.LIB_PATH = lib                     # a private module instance: the product binding itself is untouched
-    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "CUEMU_SEED")}
+    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "PA_TMA_PREFETCH", "CUEMU_SEED")}
     os.environ["PA_NORMAL_MATH"] = "fast"   # no device self-test: the emulator has no MUFU (sqrt_fast == sqrt there)
     m.init(0)
     yield m
@@ -54,7 +54,7 @@ CURV_CASES = [n for n, c in CASES.items() if "curvature" in c[3]]
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple", "tma_pf", "tma_big_pf"])
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, links):
     if schedule and (stencil == "simple" or links == "nolinks"):
@@ -63,7 +63,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple", "tma_pf", "tma_big_pf"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
     if schedule and (stencil == "simple" or links == "nolinks"):
@@ -98,6 +98,7 @@ def test_emulated_midsize_vs_oracle(emu, case, kw):
     os.environ["CUEMU_SEED"] = "7"
     try:
         G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma")
+        G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma_pf")
     finally:
         os.environ["CUEMU_SEED"] = "0"
 

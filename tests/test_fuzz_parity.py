@@ -83,16 +83,17 @@ def test_random_hierarchy_emulated_kernels_equal_oracle(emu, seed):  # noqa: F81
         OH = O.OracleHier(pf, is_per, sym)
         s = _flat(pf)
         want = OH.grad(s)
-        for stencil in ("tma", "simple"):
+        for stencil in ("tma", "simple", "tma_pf"):
             out, _, _ = G._gpu_grad(emu, pf, is_per, sym, stencil=stencil)
             for c in range(4):
                 assert bit_equal(out[c], want[c]), (seed, stencil, c, max_rel(out[c], want[c]), [l.boxes for l in pf.levels])
         if curv:
             pmin, pmax = float(s.min()), float(s.max())
             wk = OH.curvature(s, pmin, pmax)
-            out, _ = G._gpu_curv(emu, pf, is_per, sym, pmin, pmax, {})
-            for c in range(5):
-                assert bit_equal(out[c], wk[c]), (seed, "curvature", c, [l.boxes for l in pf.levels])
+            for stencil in ("tma", "tma_pf"):
+                out, _ = G._gpu_curv(emu, pf, is_per, sym, pmin, pmax, {}, stencil)
+                for c in range(5):
+                    assert bit_equal(out[c], wk[c]), (seed, "curvature", stencil, c, [l.boxes for l in pf.levels])
     finally:
         os.environ["CUEMU_SEED"] = "0"
 
