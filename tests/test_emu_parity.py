@@ -124,3 +124,11 @@ def test_emulated_side_stream_runs_late(emu, name):
     finally:
         os.environ["CUEMU_DEFER_SIDE"] = "0"
         os.environ.pop("PA_STREAM_OVERLAP", None)
+
+
+@pytest.mark.parametrize("builder", ["config1", "mixed", "config3"])
+def test_emulated_wide_ghost_inputs(emu, builder):
+    from peleanalysis_b200 import synth
+    os.environ["CUEMU_SEED"] = "0"
+    b = {"config1": lambda: synth.config1(16, 8), "mixed": synth.case_mixed, "config3": lambda: synth.config3(16, 8)}[builder]
+    G.check_wide_ghost_inputs(emu, b)

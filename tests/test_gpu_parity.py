@@ -332,6 +332,33 @@ def test_side_stream_overlap_is_bit_exact(gpu, name):
         os.environ.pop("PA_STREAM_OVERLAP", None)
 
 
+def check_wide_ghost_inputs(capi, builder):
+    """Input fields with nghost 2 or 3 (the reference allocates nGrow = 2 for curvature): general-layout route (simple
+    kernel, unfused progress pass); same bits as the oracle."""
+    pf = builder()
+    OH = O.OracleHier(pf)
+    s = OH.flatten(0)
+    want = OH.grad(s)
+    pmin, pmax = float(s.min()), float(s.max())
+    wk = OH.curvature(s, pmin, pmax)
+    _set_stencil("tma")
+    for ng in (2, 3):
+        H = capi.Hierarchy(pf.levels)
+        fin, fout = capi.Field(H, 1, ng), capi.Field(H, 4, 0)
+        fin.upload_fabs(0, [[f[0] for f in l.fabs] for l in pf.levels])
+        capi.grad(fin, 0, 1, fout, 0)
+        capi.sync()
+        for c in range(4):
+            assert bit_equal(flat_from_fabs(fout.download_fabs(c)), want[c]), (ng, c)
+        o = capi.CurvOpts()
+        o.prog_min, o.prog_max = pmin, pmax
+        out = capi.Field(H, 5, 1)
+        capi.curvature(fin, 0, 0, o, out, 0)
+        capi.sync()
+        for c in range(5):
+            assert bit_equal(flat_from_fabs(out.download_fabs(c)), wk[c]), (ng, "curvature", c)
+
+
 # Kernel variants that exist in the library but have not been run on a B200 yet (logic verified under the emulator of
 # tests/emu only): excluded from the default GPU run, enabled with PA_TEST_EXPERIMENTAL=1.
 experimental = pytest.mark.skipif(os.environ.get("PA_TEST_EXPERIMENTAL") != "1", reason="set PA_TEST_EXPERIMENTAL=1 (variants not yet run on hardware)")
@@ -358,3 +385,8 @@ def test_descriptor_prefetch_variant_full_size(gpu):
         test_full_size_properties_config2(gpu)
     finally:
         os.environ["PA_TMA_PREFETCH"] = "0"
+
+
+@experimental
+def test_wide_ghost_inputs(gpu):
+    check_wide_ghost_inputs(gpu, lambda: synth.config3(16, 8))
