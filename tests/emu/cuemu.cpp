@@ -342,6 +342,8 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t ev, unsigned) {
     if (it != cuemu::event_stream.end()) cuemu::flush_stream(it->second);
     return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+// "IPC" inside one process: the handle carries the pointer.  Lets a test stand up several ranks of a peer-linked hierarchy
+// in one address space, so the kernels' in-place reads of another rank's slab run under the emulator too.
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -1,0 +1,127 @@
+"""CPU tier: PEER LINKS under the emulator.  Two (or four) ranks of one hierarchy are stood up inside a single process --
+the emulator's "IPC handle" simply carries the slab pointer -- so the stencil producer's in-place reads of another rank's
+slab (planes, rows, x-ghost columns), the halo gather from peer-owned boxes and the slab exchange of whatever links do
+not cover all run on the CPU, for grad and for the two-pass curvature sequence of multigpu.Curvature.  Every rank's boxes
+are compared bit for bit with the oracle.  (On GPUs the same is checked by tests/dist_check.py over NVLink / NCCL.)"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES
+from oracle import oracle as O
+from peleanalysis_b200 import synth
+from test_emu_parity import emu  # noqa: F401  (fixture)
+
+
+class Ranks:
+    """nranks hierarchies of the same levels in one process, with the cross-rank steps done by hand."""
+
+    def __init__(self, capi, pf, is_per, sym, nranks, flags):
+        self.capi, self.pf, self.n = capi, pf, nranks
+        self.H = [capi.Hierarchy(pf.levels, is_per, sym, r, nranks, flags=flags) for r in range(nranks)]
+
+    def fields(self, ncomp, ng):
+        F = [self.capi.Field(h, ncomp, ng) for h in self.H]
+        if self.H[0].flags & self.capi.PEER_LINKS:
+            handles = [f.ipc_handles() for f in F]
+            for r, f in enumerate(F):
+                for q in range(self.n):
+                    if q != r:
+                        f.map_peer(q, handles[q])
+        return F
+
+    def exchange(self, F, comp, ncomp):
+        """What multigpu.SlabExchange does over NCCL: pack everywhere, move send slab segments into the peers' recv slabs."""
+        lib = self.capi.lib()
+        bufs = []
+        for f in F:
+            sp, rp = C.c_void_p(), C.c_void_p()
+            so = (C.c_int64 * (self.n + 1))()
+            ro = (C.c_int64 * (self.n + 1))()
+            self.capi.check(lib.pa_exchange_buffers(f.f, ncomp, C.byref(sp), C.byref(rp), so, ro))
+            bufs.append((sp.value, rp.value, list(so), list(ro)))
+        for f in F:
+            self.capi.check(lib.pa_exchange_pack(f.f, comp, ncomp))
+        self.capi.sync()
+        moved = 0
+        for a in range(self.n):
+            for b in range(self.n):
+                if a == b:
+                    continue
+                n = bufs[a][2][b + 1] - bufs[a][2][b]                      # a sends to b ...
+                assert n == bufs[b][3][a + 1] - bufs[b][3][a]              # ... what b expects from a
+                if n:
+                    C.memmove(bufs[b][1] + 8 * bufs[b][3][a], bufs[a][0] + 8 * bufs[a][2][b], 8 * n)
+                    moved += n
+        for f in F:
+            self.capi.check(lib.pa_exchange_mark_received(f.f, comp, ncomp))
+        return moved
+
+    def check(self, F, comps, want, tag):
+        OHu = self.OH
+        for c, w in zip(comps, want):
+            wl = OHu.unflatten(w)
+            for r, f in enumerate(F):
+                got = f.download_fabs(c)
+                for l in range(len(self.pf.levels)):
+                    for b in self.H[r].local_boxes[l]:
+                        assert np.array_equal(got[l][b].view(np.int64), wl[l][b].view(np.int64)), (tag, c, r, l, b)
+
+
+CASE_LIST = [("c1_periodic", 2), ("c1_walls", 2), ("lshape", 2), ("edge_periodic", 2), ("c3_three_levels", 2), ("mixed_boxes", 2),
+             ("uniform", 2), ("uniform", 4), ("config3", 4)]
+
+
+def _case(name):
+    if name == "uniform":
+        return synth.make_hierarchy(32, [], [], 8, ("temp",)), (1, 1, 1), (0, 0, 0)
+    if name == "config3":
+        return synth.config3(32, 8), (1, 1, 1), (0, 0, 0)
+    b, per, sym, _, _ = CASES[name]
+    return b(), per, sym
+
+
+@pytest.mark.parametrize("transport", ["peer", "slab"])
+@pytest.mark.parametrize("name,nranks", CASE_LIST)
+def test_emulated_multi_rank_in_one_process(emu, name, nranks, transport):  # noqa: F811
+    capi = emu
+    os.environ["CUEMU_SEED"] = "3"
+    os.environ["PA_STENCIL"] = "tma"
+    os.environ["PA_TMA_SMALL"] = "1"
+    os.environ["PA_TMA_PREFETCH"] = "1" if nranks == 4 else "0"
+    try:
+        pf, is_per, sym = _case(name)
+        R = Ranks(capi, pf, is_per, sym, nranks, capi.PEER_LINKS if transport == "peer" else 0)
+        R.OH = O.OracleHier(pf, is_per, sym)
+        s = R.OH.flatten(0)
+        # ---- grad
+        fin, fout = R.fields(1, 1), R.fields(4, 0)
+        for f in fin:
+            f.upload_fabs(0, [[x[0] for x in l.fabs] for l in pf.levels])
+        moved = R.exchange(fin, 0, 1)
+        if transport == "peer" and name == "uniform":
+            assert moved == 0                       # a uniform grid needs no exchange at all with peer links
+        for r in range(nranks):
+            capi.grad(fin[r], 0, 1, fout[r], 0)
+        capi.sync()
+        R.check(fout, range(4), R.OH.grad(s), "grad")
+        # ---- curvature, the sequence of multigpu.Curvature.run, twice
+        o = capi.CurvOpts()
+        o.prog_min, o.prog_max = float(s.min()), float(s.max())
+        out = R.fields(5, 1)
+        for _ in range(2):
+            R.exchange(fin, 0, 1)
+            for r in range(nranks):
+                capi.curvature_phases(fin[r], 0, 0, o, out[r], 0, 1)
+            capi.sync()
+            R.exchange(out, 2, 3)
+            for r in range(nranks):
+                capi.curvature_phases(fin[r], 0, 0, o, out[r], 0, 2)
+            capi.sync()
+        if all(x == 2 for x in R.OH.ratios):
+            R.check(out, range(5), R.OH.curvature(s, o.prog_min, o.prog_max), "curvature")
+    finally:
+        os.environ["CUEMU_SEED"] = "0"
+        os.environ["PA_TMA_PREFETCH"] = "0"
