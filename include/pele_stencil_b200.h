@@ -167,6 +167,21 @@ int pa_curvature_num_outputs(const pa_curv_opts *opts);
 int pa_curvature_phases(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out,
                         int phases);
 
+/* The same as single steps, for multi-rank callers whose options need more cross-rank steps than the two passes above
+ * (threshold_prog: the flame normal is exchanged before EVERY level's divergence, because level l reads the clipped
+ * normal of level l-1, Src/curvature.cpp:514-518 after :549-567; do_gaussCurv: the un-normalised gradient, an internal
+ * field, is exchanged too, :575-612; do_strain: the velocities, :686-717).  `steps` is a combination of PA_CURV_*; the
+ * level range applies to PA_CURV_DIV only (-1, -1 = all levels).  Before each step the caller has exchanged what it reads:
+ *   PA_CURV_PASS1  state[comp_S]          PA_CURV_DIV    out[comp_out+2 .. +4]  (with threshold_prog: one level per call)
+ *   PA_CURV_GAUSS  scratch field 0 (3)    PA_CURV_STRAIN state[comp_vel .. +2]  PA_CURV_VELN   nothing
+ * pa_curvature_phases(1) == PA_CURV_PASS1, (2) == all the other steps. */
+enum { PA_CURV_PASS1 = 1, PA_CURV_DIV = 2, PA_CURV_GAUSS = 4, PA_CURV_STRAIN = 8, PA_CURV_VELN = 16 };
+int pa_curvature_steps(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out,
+                       int steps, int lev_lo, int lev_hi);
+/* Internal field a multi-rank caller must exchange / peer-map: which = 0, the un-normalised gradient of the progress
+ * variable (3 components, nghost 1).  Owned by the hierarchy; do not free. */
+int pa_curvature_scratch(pa_hier *h, int which, pa_field **f);
+
 /* ---- multi-rank ghost exchange (one process per GPU; the transport is the caller's: NCCL send/recv) ---
  * For exchange step `step` of an operation the library packs what each peer needs into a device send slab and
  * unpacks the peer's slab after the caller moved it.  Sizes are in doubles.  Single-rank hierarchies have

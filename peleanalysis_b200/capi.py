@@ -58,6 +58,8 @@ SYMBOLS = {
     "pa_debug_selftest_math": (C.c_int64, [C.c_int64, C.c_uint64]),
     "pa_debug_normal_math": (C.c_int, []),
     "pa_curvature_phases": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i, _i]),
+    "pa_curvature_steps": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i, _i, _i, _i]),
+    "pa_curvature_scratch": (_i, [_vp, _i, C.POINTER(_vp)]),
     "pa_exchange_counts": (_i, [_vp, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "pa_exchange_buffers": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "pa_exchange_pack": (_i, [_vp, _i, _i]), "pa_exchange_mark_received": (_i, [_vp, _i, _i]),
@@ -373,6 +375,27 @@ def curvature(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, out: Fie
 
 def curvature_phases(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, out: Field, comp_out: int, phases: int) -> None:
     check(lib().pa_curvature_phases(state.f, comp_S, comp_vel, C.byref(opts), out.f, comp_out, phases))
+
+
+CURV_PASS1, CURV_DIV, CURV_GAUSS, CURV_STRAIN, CURV_VELN = 1, 2, 4, 8, 16
+
+
+def curvature_steps(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, out: Field, comp_out: int, steps: int,
+                    lev_lo: int = -1, lev_hi: int = -1) -> None:
+    check(lib().pa_curvature_steps(state.f, comp_S, comp_vel, C.byref(opts), out.f, comp_out, steps, lev_lo, lev_hi))
+
+
+class ScratchField(Field):
+    """The curvature tool's internal un-normalised gradient field (owned by the hierarchy: never freed from here)."""
+
+    def __init__(self, hier: Hierarchy, which: int = 0):
+        self.hier = hier
+        self.ncomp, self.nghost = 3, 1
+        self.f = C.c_void_p()
+        check(lib().pa_curvature_scratch(hier.h, which, C.byref(self.f)))
+
+    def free(self):
+        self.f = None
 
 
 def curvature_num_outputs(opts: CurvOpts) -> int:

@@ -849,9 +849,19 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     return pa_curvature_phases(state, comp_S, comp_vel, opts, out, comp_out, 3);
 }
 
-int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out, int phases) {
+// The curvature tool as a sequence of steps.  Single-rank callers run all of them in one call (pa_curvature); a multi-rank
+// caller runs them one at a time with its cross-rank step (slab exchange and / or a barrier) in front of each -- the
+// reference does the same through MPI inside FillBoundary / ParallelCopy (curvature.cpp:322, 487-502, 514-520, 686-717).
+//   PA_CURV_PASS1   ghost fill of S, Progress, flame normal (+ un-normalised gradient when do_gaussCurv)   needs: S exchanged
+//   PA_CURV_DIV     ghost fill of n, MeanCurvature (+ threshold clip) on levels [lev_lo, lev_hi]              needs: n exchanged
+//                   with threshold_prog the levels must be run one by one, in order: level l reads the CLIPPED n of l-1
+//   PA_CURV_GAUSS   Hessian of the progress variable, GaussianCurvature                                      needs: G (scratch 0) exchanged
+//   PA_CURV_STRAIN  velocity gradients, StrainRate, ROST                                                     needs: velocities exchanged
+//   PA_CURV_VELN    VelFlameNormal (pointwise)
+int pa_curvature_steps(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out, int steps,
+                       int lev_lo, int lev_hi) {
     if (!opts) return fail(PA_ERR_ARG, "pa_curvature: null options");
-    if (phases < 1 || phases > 3) return fail(PA_ERR_ARG, "pa_curvature_phases: phases must be 1, 2 or 3");
+    if (steps < 1 || steps > 31) return fail(PA_ERR_ARG, "pa_curvature_steps: steps must be a combination of PA_CURV_*");
     CHK(check_field(state, comp_S, 1, "pa_curvature(state)"));
     const int nout = pa_curvature_num_outputs(opts);
     CHK(check_field(out, comp_out, nout, "pa_curvature(out)"));
@@ -863,11 +873,11 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
     if (need_vel) CHK(check_field(state, comp_vel, 3, "pa_curvature(velocity)"));
     pa_hier* h = state->h;
     Hier& H = h->H;
-    if (H.nranks > 1 && (opts->do_threshold || opts->do_gauss || opts->do_strain))
-        return fail(PA_ERR_UNSUPPORTED, "pa_curvature_phases: threshold_prog / do_gaussCurv / do_strain need further cross-rank exchanges "
-                                        "(per level, of internal fields) that the multi-rank path does not sequence yet");
     CHK(ensure_device(h));
     const int nlev = H.nlev;
+    if (lev_lo < 0) lev_lo = 0;
+    if (lev_hi < 0 || lev_hi >= nlev) lev_hi = nlev - 1;
+    if (lev_lo > lev_hi) return fail(PA_ERR_ARG, "pa_curvature_steps: empty level range");
     const int cP = comp_out, cK = comp_out + 1, cN = comp_out + 2;
     int next = comp_out + 5;
     const int cKg = opts->do_gauss ? next++ : -1;
@@ -877,87 +887,94 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
     const int cVN = opts->do_velnormal ? next++ : -1;
 
     StencilExtra ex;
-    std::memset(&ex, 0, sizeof(ex));
-    if (opts->do_gauss) {
-        CHK(tmp_field(h, &h->tmpG, 3));
-        for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
-    }
     GridArgs ga;
     const double invdenom = 1.0 / (opts->prog_max - opts->prog_min);
-    const char* no_fuse = getenv("PA_CURV_UNFUSED");
-    if (!(phases & 1)) {
-        // pass 1 already ran (previous call)
-    } else if (state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
-        // 1+2 fused.  The progress pass (curvature.cpp:310-321) rides in the stencil's loader: valid cells stay S and are
-        // normalised as they are read; the few ghost cells that must be materialised (unlinked faces) are written in
-        // progress space by the ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel
-        // writes Progress and n = G/nrm; Progress never makes a separate round trip through HBM.
-        GhostXform xf{1, opts->prog_min, invdenom};
-        for (int l = 0; l < nlev; ++l) ex.cout[l] = out->slab[l] ? out->slab[l] + (long long)cP * out->cs[l] : nullptr;
-        ex.pmin = opts->prog_min; ex.inv = invdenom;
-        CHK(grid_args(state, comp_S, out, cN, ga));
-        if (overlap_enabled(h)) {
-            CHK(fill_ghosts_impl(state, comp_S, 1, 0, 0, false, xf));
-            CHK(fork_side(h, [&]() { return fill_ghosts_impl(state, comp_S, 1, 1, nlev - 1, false, xf); }));
-            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, 0, state->ng, state));
-            CHK(join_side(h));
-            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 1, nlev - 1, state->ng, state));
+
+    if (steps & PA_CURV_PASS1) {
+        std::memset(&ex, 0, sizeof(ex));
+        if (opts->do_gauss) {
+            CHK(tmp_field(h, &h->tmpG, 3));
+            for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
+        }
+        const char* no_fuse = getenv("PA_CURV_UNFUSED");
+        if (state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
+            // Progress + normal fused.  The progress pass (curvature.cpp:310-321) rides in the stencil's loader: valid cells stay S
+            // and are normalised as they are read; the few ghost cells that must be materialised (unlinked faces) are written in
+            // progress space by the ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel
+            // writes Progress and n = G/nrm; Progress never makes a separate round trip through HBM.
+            GhostXform xf{1, opts->prog_min, invdenom};
+            for (int l = 0; l < nlev; ++l) ex.cout[l] = out->slab[l] ? out->slab[l] + (long long)cP * out->cs[l] : nullptr;
+            ex.pmin = opts->prog_min; ex.inv = invdenom;
+            CHK(grid_args(state, comp_S, out, cN, ga));
+            if (overlap_enabled(h)) {
+                CHK(fill_ghosts_impl(state, comp_S, 1, 0, 0, false, xf));
+                CHK(fork_side(h, [&]() { return fill_ghosts_impl(state, comp_S, 1, 1, nlev - 1, false, xf); }));
+                CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, 0, state->ng, state));
+                CHK(join_side(h));
+                CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 1, nlev - 1, state->ng, state));
+            } else {
+                CHK(fill_ghosts_impl(state, comp_S, 1, 0, nlev - 1, false, xf));
+                CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
+            }
         } else {
-            CHK(fill_ghosts_impl(state, comp_S, 1, 0, nlev - 1, false, xf));
-            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
-        }
-    } else {
-        if (H.nranks > 1)
-            return fail(PA_ERR_UNSUPPORTED, "pa_curvature_phases: the multi-rank path needs the fused progress pass (state with nghost == 1, "
-                                            "TMA-eligible boxes); the unfused route would exchange an intermediate field");
-        // 1. progress variable on valid cells of every level (curvature.cpp:310-321)
-        for (int l = 0; l < nlev; ++l) {
-            int err = PA_OK;
-            const PaLayDev* li = dev_layout(h, l, state->ng, &err);
-            if (!li) return err;
-            const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
-            if (!lo) return err;
-            CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_S * state->cs[l],
-                               out->slab[l] + (long long)cP * out->cs[l], opts->prog_min, invdenom, t_stream));
-        }
-        // 2. ghost cells of c on all levels (coarse data = c on the next coarser level), then G -> nrm -> n
-        CHK(fill_ghosts_impl(out, cP, 1, 0, nlev - 1, false));
-        CHK(grid_args(out, cP, out, cN, ga));
-        CHK(run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, out->ng, out));
-    }
-    // 3. divergence of n.  Without the threshold clip every level's coarse data is final after step 2, so one
-    //    batched ghost fill + one stencil launch cover the hierarchy; with it, level l needs the CLIPPED n of l-1
-    //    (curvature.cpp:514-518 reads flame_normal[lev-1] after :549-567 modified it), so levels run in order.
-    if (!(phases & 2)) return PA_OK;
-    std::memset(&ex, 0, sizeof(ex));
-    ex.do_threshold = opts->do_threshold ? 1 : 0;
-    ex.threshold = opts->threshold;
-    for (int l = 0; l < nlev; ++l) ex.prog[l] = out->slab[l] + (long long)cP * out->cs[l];
-    CHK(grid_args(out, cN, out, cK, ga));
-    if (!opts->do_threshold && overlap_enabled(h)) {
-        // n of every level is final (pass 1 is complete on the caller's stream, which the fork orders the side stream after)
-        CHK(fill_ghosts_impl(out, cN, 3, 0, 0, false));
-        CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, cN, 3, 1, nlev - 1, false); }));
-        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
-        CHK(join_side(h));
-        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 1, nlev - 1, out->ng, out));
-    } else if (!opts->do_threshold) {
-        CHK(fill_ghosts_impl(out, cN, 3, 0, nlev - 1, false));
-        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, nlev - 1, out->ng, out));
-    } else {
-        for (int l = 0; l < nlev; ++l) {
-            CHK(fill_ghosts_impl(out, cN, 3, l, l, false));
-            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng, out));
-            int err = PA_OK;
-            const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
-            if (!lo) return err;
-            CU(launch_clip_normal(h->lev[l]->boxes.p, lo, lo, (int)H.lev[l].local.size(), out->slab[l] + (long long)cP * out->cs[l],
-                                  out->slab[l] + (long long)cN * out->cs[l], out->cs[l], opts->threshold, t_stream));
+            if (H.nranks > 1)
+                return fail(PA_ERR_UNSUPPORTED, "pa_curvature: the multi-rank path needs the fused progress pass (state with nghost == 1, "
+                                                "TMA-eligible boxes); the unfused route would exchange an intermediate field");
+            // progress variable on valid cells of every level (curvature.cpp:310-321), ghost cells of c on all levels (coarse
+            // data = c on the next coarser level), then G -> nrm -> n
+            for (int l = 0; l < nlev; ++l) {
+                int err = PA_OK;
+                const PaLayDev* li = dev_layout(h, l, state->ng, &err);
+                if (!li) return err;
+                const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+                if (!lo) return err;
+                CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_S * state->cs[l],
+                                   out->slab[l] + (long long)cP * out->cs[l], opts->prog_min, invdenom, t_stream));
+            }
+            CHK(fill_ghosts_impl(out, cP, 1, 0, nlev - 1, false));
+            CHK(grid_args(out, cP, out, cN, ga));
+            CHK(run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, out->ng, out));
         }
     }
-    // 4. optional branches
-    if (opts->do_gauss) {
+
+    if (steps & PA_CURV_DIV) {
+        // divergence of n.  Without the threshold clip every level's coarse data is final after pass 1, so one batched ghost
+        // fill + one stencil pass cover the level range; with it, level l needs the CLIPPED n of l-1 (curvature.cpp:514-518
+        // reads flame_normal[lev-1] after :549-567 modified it), so levels run in order.
+        if (opts->do_threshold && H.nranks > 1 && lev_lo != lev_hi)
+            return fail(PA_ERR_ARG, "pa_curvature_steps: with threshold_prog a multi-rank caller runs PA_CURV_DIV one level per call "
+                                    "(exchange the flame normal before each)");
+        std::memset(&ex, 0, sizeof(ex));
+        ex.do_threshold = opts->do_threshold ? 1 : 0;
+        ex.threshold = opts->threshold;
+        for (int l = 0; l < nlev; ++l) ex.prog[l] = out->slab[l] + (long long)cP * out->cs[l];
+        CHK(grid_args(out, cN, out, cK, ga));
+        if (!opts->do_threshold && overlap_enabled(h) && lev_lo == 0 && lev_hi > 0) {
+            // n of every level is final (pass 1 is complete on the caller's stream, which the fork orders the side stream after)
+            CHK(fill_ghosts_impl(out, cN, 3, 0, 0, false));
+            CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, cN, 3, 1, lev_hi, false); }));
+            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
+            CHK(join_side(h));
+            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 1, lev_hi, out->ng, out));
+        } else if (!opts->do_threshold) {
+            CHK(fill_ghosts_impl(out, cN, 3, lev_lo, lev_hi, false));
+            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, lev_lo, lev_hi, out->ng, out));
+        } else {
+            for (int l = lev_lo; l <= lev_hi; ++l) {
+                CHK(fill_ghosts_impl(out, cN, 3, l, l, false));
+                CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng, out));
+                int err = PA_OK;
+                const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+                if (!lo) return err;
+                CU(launch_clip_normal(h->lev[l]->boxes.p, lo, lo, (int)H.lev[l].local.size(), out->slab[l] + (long long)cP * out->cs[l],
+                                      out->slab[l] + (long long)cN * out->cs[l], out->cs[l], opts->threshold, t_stream));
+            }
+        }
+    }
+
+    if ((steps & PA_CURV_GAUSS) && opts->do_gauss) {
         // Hessian rows: grad3 of each un-normalised gradient component, ghosts by the same rules with coarse = G on l-1
+        if (!h->tmpG) return fail(PA_ERR_STATE, "pa_curvature_steps: PA_CURV_GAUSS before PA_CURV_PASS1");
         CHK(tmp_field(h, &h->tmpH, 9));
         CHK(fill_ghosts_impl(h->tmpG, 0, 3, 0, nlev - 1, false));
         StencilExtra e0;
@@ -975,7 +992,7 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
                             opts->do_threshold ? 1 : 0, opts->threshold, t_stream));
         }
     }
-    if (opts->do_strain) {
+    if ((steps & PA_CURV_STRAIN) && opts->do_strain) {
         // velocity gradients: ghosts of u_i by the same rules (curvature.cpp:686-717); needs ghost cells in `state`
         CHK(fill_ghosts_impl(state, comp_vel, 3, 0, nlev - 1, false));
         pa_field* dU = nullptr;
@@ -996,7 +1013,7 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
                              out->slab[l] + (long long)cSR * out->cs[l], t_stream));
         }
     }
-    if (opts->do_velnormal) {
+    if ((steps & PA_CURV_VELN) && opts->do_velnormal) {
         for (int l = 0; l < nlev; ++l) {
             int err = PA_OK;
             const PaLayDev* lu = dev_layout(h, l, state->ng, &err);
@@ -1008,6 +1025,29 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
                                 out->slab[l] + (long long)cVN * out->cs[l], opts->do_threshold ? 1 : 0, opts->threshold, t_stream));
         }
     }
+    return PA_OK;
+}
+
+int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out, int phases) {
+    if (!opts) return fail(PA_ERR_ARG, "pa_curvature: null options");
+    if (phases < 1 || phases > 3) return fail(PA_ERR_ARG, "pa_curvature_phases: phases must be 1, 2 or 3");
+    if (state && state->h && state->h->H.nranks > 1 && (opts->do_threshold || opts->do_gauss || opts->do_strain))
+        return fail(PA_ERR_UNSUPPORTED, "pa_curvature_phases: threshold_prog / do_gaussCurv / do_strain need further cross-rank steps "
+                                        "(per level, and of internal fields): use pa_curvature_steps");
+    int steps = 0;
+    if (phases & 1) steps |= PA_CURV_PASS1;
+    if (phases & 2) steps |= PA_CURV_DIV | PA_CURV_GAUSS | PA_CURV_STRAIN | PA_CURV_VELN;
+    return pa_curvature_steps(state, comp_S, comp_vel, opts, out, comp_out, steps, 0, -1);
+}
+
+// Internal field of the curvature tool a multi-rank caller has to exchange (and, with peer links, map): which = 0 the
+// un-normalised gradient G of the progress variable (3 components, nghost 1; exists when do_gaussCurv is set, after
+// PA_CURV_PASS1 ran once or after this call).  Owned by the hierarchy: do not free it.
+int pa_curvature_scratch(pa_hier* h, int which, pa_field** f) {
+    if (!h || !f || which != 0) return fail(PA_ERR_ARG, "pa_curvature_scratch: bad argument");
+    CHK(ensure_device(h));
+    CHK(tmp_field(h, &h->tmpG, 3));
+    *f = h->tmpG;
     return PA_OK;
 }
 

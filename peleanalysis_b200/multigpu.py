@@ -88,35 +88,68 @@ class SlabExchange:
 
 
 class Curvature:
-    """pa_curvature on a multi-rank hierarchy: the two passes with the cross-rank steps between them.
+    """The curvature tool on a multi-rank hierarchy: its steps (pa_curvature_steps) with the cross-rank step each one needs
+    in front of it.
 
-        [barrier]  exchange S  ->  pass 1 (ghost fill of S, Progress, flame normal)
-        [barrier]  exchange n  ->  pass 2 (ghost fill of n, MeanCurvature, VelFlameNormal)
+        [barrier]  exchange S            ->  PASS1   ghost fill of S, Progress, flame normal (+ un-normalised gradient G)
+        [barrier]  exchange n            ->  DIV     ghost fill of n, MeanCurvature    -- threshold_prog: once per level, in
+                                                     order, because level l reads the CLIPPED normal of level l-1
+        [barrier]  exchange G            ->  GAUSS   (do_gaussCurv)      G is an internal field of the library
+        [barrier]  exchange velocities   ->  STRAIN  (do_strain)
+                                             VELN    (do_velnormal; pointwise)
 
     The barriers (1-element all-reduce on the stream) are only needed with peer links, where a rank's kernels read the
-    other ranks' slabs in place: pass 2 must not start before every peer finished writing n, and the next step's
-    pass 1 must not overwrite n while a peer still reads it.  The reference reaches the same ordering through MPI inside
-    FillBoundary / ParallelCopy (Src/curvature.cpp:487-502, 514-520)."""
+    other ranks' slabs in place: a step must not start before every peer finished writing what it reads, and the next
+    run's PASS1 must not overwrite n while a peer still reads it.  The reference reaches the same ordering through MPI
+    inside FillBoundary / ParallelCopy (Src/curvature.cpp:322, 487-502, 514-520, 686-717)."""
 
     def __init__(self, state: capi.Field, comp_S: int, opts: capi.CurvOpts, out: capi.Field, comp_out: int = 0, comp_vel: int = 0,
                  wrap=_wrap_device):
         self.state, self.comp_S, self.opts, self.out, self.comp_out, self.comp_vel = state, comp_S, opts, out, comp_out, comp_vel
         H = state.hier
+        self.nlev = H.nlev
         self.peer = bool(H.flags & capi.PEER_LINKS) and H.nranks > 1
-        # the 3-component exchange first: the library grows its slabs to the largest request, and the tensors below
+        self.scratch = capi.ScratchField(H) if opts.do_gauss else None
+        # the 3-component exchanges first: the library grows its slabs to the largest request, and the tensors below
         # wrap raw slab pointers
         self.Xn = SlabExchange(out, 3, wrap)
+        self.Xg = SlabExchange(self.scratch, 3, wrap) if self.scratch is not None else None
+        self.Xv = SlabExchange(state, 3, wrap) if opts.do_strain else None
         self.Xs = SlabExchange(state, 1, wrap)
         if self.peer:
             map_peers(state)
             map_peers(out)
+            if self.scratch is not None:
+                map_peers(self.scratch)
+
+    def _step(self, steps: int, lo: int = -1, hi: int = -1) -> None:
+        capi.curvature_steps(self.state, self.comp_S, self.comp_vel, self.opts, self.out, self.comp_out, steps, lo, hi)
+
+    def _barrier(self) -> None:
+        if self.peer:
+            stream_barrier()
 
     def run(self) -> None:
-        if self.peer:
-            stream_barrier()
+        o, cN = self.opts, self.comp_out + 2
+        self._barrier()
         self.Xs.run(self.comp_S)
-        capi.curvature_phases(self.state, self.comp_S, self.comp_vel, self.opts, self.out, self.comp_out, 1)
-        if self.peer:
-            stream_barrier()
-        self.Xn.run(self.comp_out + 2)
-        capi.curvature_phases(self.state, self.comp_S, self.comp_vel, self.opts, self.out, self.comp_out, 2)
+        self._step(capi.CURV_PASS1)
+        if o.do_threshold:
+            for l in range(self.nlev):
+                self._barrier()
+                self.Xn.run(cN)
+                self._step(capi.CURV_DIV, l, l)
+        else:
+            self._barrier()
+            self.Xn.run(cN)
+            self._step(capi.CURV_DIV)
+        if o.do_gauss:
+            self._barrier()
+            self.Xg.run(0)
+            self._step(capi.CURV_GAUSS)
+        if o.do_strain:
+            self._barrier()
+            self.Xv.run(self.comp_vel)
+            self._step(capi.CURV_STRAIN)
+        if o.do_velnormal:
+            self._step(capi.CURV_VELN)      # reads this rank's own cells only

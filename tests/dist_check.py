@@ -96,6 +96,46 @@ def run_curv(name, pf, is_per, sym, rank, world, mode="slab", velnormal=False):
     return int(t.item())
 
 
+def run_curv_options(rank, world, mode):
+    """Every curvature option at once (threshold_prog, do_gaussCurv, do_strain + ROST, do_velnormal) through
+    multigpu.Curvature against the golden vectors of the compiled reference."""
+    from helpers import bit_equal, fabs_from_flat, load_golden, max_rel
+    pf, z = load_golden("c1_options")
+    kw = dict(x.split("=") for x in z["curv_opts"])
+    is_per, sym = tuple(int(v) for v in z["is_per"]), tuple(int(v) for v in z["sym_dir"])
+    H = capi.Hierarchy(pf.levels, is_per, sym, rank, world, flags=capi.PEER_LINKS if mode == "peer" else 0)
+    state = capi.Field(H, 4, 1)
+    for v, n in enumerate(["temp", "x_velocity", "y_velocity", "z_velocity"]):
+        state.upload_fabs(v, [[f[pf.comp(n)] for f in l.fabs] for l in pf.levels])
+    o = capi.CurvOpts()
+    o.prog_min, o.prog_max = float(z["prog_min"]), float(z["prog_max"])
+    o.do_threshold, o.threshold = int(kw["threshold_prog"]), float(kw["threshold_value"])
+    o.do_gauss, o.do_strain, o.get_strain_tensor, o.do_velnormal = 1, 1, 1, 1
+    out = capi.Field(H, capi.curvature_num_outputs(o), 1)
+    op = multigpu.Curvature(state, 0, o, out, 0, comp_vel=1)
+    capi.sync()
+    dist.barrier()
+    op.run()
+    op.run()
+    capi.sync()
+    dist.barrier()
+    order = ["Progress", "MeanCurvature_temp", "FlameNormalX_temp", "FlameNormalY_temp", "FlameNormalZ_temp", "GaussianCurvature_temp",
+             "StrainRate_temp"] + ["ROST_dU%sd%s" % (a, b) for a in "xyz" for b in "xyz"] + ["VelFlameNormal"]
+    bad = 0
+    for c, n in enumerate(order):
+        want = fabs_from_flat(pf, z["curv_" + n])
+        got = out.download_fabs(c)
+        for l in range(len(pf.levels)):
+            for b in H.local_boxes[l]:
+                ok = max_rel(got[l][b], want[l][b]) <= 1e-12 if n.startswith("Gaussian") else bit_equal(got[l][b], want[l][b])
+                bad += 0 if ok else 1
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("dist_check curvature all-options   %-4s ranks=%d mismatching boxes=%d" % (mode, world, int(t.item())), flush=True)
+    return int(t.item())
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -116,6 +156,7 @@ def main():
         bad += run_curv("config3_64", synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
         bad += run_curv("c1_walls_vn", synth.config1(32, 16, names=synth.FIELD_NAMES, corner=True), (0, 0, 0), (1, 0, 0), rank, world, mode=mode, velnormal=True)
         bad += run_curv("uniform_64", synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+        bad += run_curv_options(rank, world, mode)
     dist.destroy_process_group()
     if rank == 0:
         print("DIST_CHECK", "OK" if bad == 0 else "FAILED (%d)" % bad, flush=True)

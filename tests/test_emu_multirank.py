@@ -108,6 +108,37 @@ def _worker(rank, world, port, ok):
             else:
                 want = list(OH.curvature(s, o.prog_min, o.prog_max))
             check("curvature " + name, out, want, OH, pf, H, range(nout))
+        # every option at once through multigpu.Curvature: threshold_prog (normal exchanged per level), do_gaussCurv (the
+        # internal gradient field exchanged), do_strain + ROST (velocities exchanged), do_velnormal; golden vectors of the
+        # compiled reference
+        from helpers import bit_equal, fabs_from_flat, load_golden, max_rel
+        pf, z = load_golden("c1_options")
+        kw = dict(x.split("=") for x in z["curv_opts"])
+        is_per, sym = tuple(int(v) for v in z["is_per"]), tuple(int(v) for v in z["sym_dir"])
+        H = capi.Hierarchy(pf.levels, is_per, sym, rank, world)
+        names = ["temp", "x_velocity", "y_velocity", "z_velocity"]
+        state = capi.Field(H, 4, 1)
+        for v, n in enumerate(names):
+            state.upload_fabs(v, [[f[pf.comp(n)] for f in l.fabs] for l in pf.levels])
+        o = capi.CurvOpts()
+        o.prog_min, o.prog_max = float(z["prog_min"]), float(z["prog_max"])
+        o.do_threshold, o.threshold = int(kw["threshold_prog"]), float(kw["threshold_value"])
+        o.do_gauss, o.do_strain, o.get_strain_tensor, o.do_velnormal = 1, 1, 1, 1
+        out = capi.Field(H, capi.curvature_num_outputs(o), 1)
+        op = mg.Curvature(state, 0, o, out, 0, comp_vel=1, wrap=_wrap_host)
+        op.run()
+        op.run()
+        capi.sync()
+        order = ["Progress", "MeanCurvature_temp", "FlameNormalX_temp", "FlameNormalY_temp", "FlameNormalZ_temp", "GaussianCurvature_temp",
+                 "StrainRate_temp"] + ["ROST_dU%sd%s" % (a, b) for a in "xyz" for b in "xyz"] + ["VelFlameNormal"]
+        for c, n in enumerate(order):
+            want = fabs_from_flat(pf, z["curv_" + n])
+            got = out.download_fabs(c)
+            for l in range(len(pf.levels)):
+                for b in H.local_boxes[l]:
+                    same = max_rel(got[l][b], want[l][b]) <= 1e-12 if n.startswith("Gaussian") else bit_equal(got[l][b], want[l][b])
+                    if not same:
+                        bad.append(("options", n, l, b))
         assert not bad, bad[:10]
         assert exchanged >= 4
         ok[rank] = 1

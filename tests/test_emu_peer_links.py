@@ -125,3 +125,92 @@ def test_emulated_multi_rank_in_one_process(emu, name, nranks, transport):  # no
     finally:
         os.environ["CUEMU_SEED"] = "0"
         os.environ["PA_TMA_PREFETCH"] = "0"
+
+
+@pytest.mark.parametrize("transport", ["peer", "slab"])
+@pytest.mark.parametrize("name,nranks", [("c3_threshold", 2), ("c1_options", 2), ("c1_options", 3)])
+def test_emulated_multi_rank_curvature_options(emu, name, nranks, transport):  # noqa: F811
+    """threshold_prog (the flame normal exchanged before every level), do_gaussCurv (the internal gradient field exchanged),
+    do_strain (velocities exchanged), do_velnormal: the step sequence of multigpu.Curvature.run against the golden vectors
+    of the compiled reference."""
+    from helpers import bit_equal, load_golden, max_rel
+    capi = emu
+    os.environ["CUEMU_SEED"] = "5"
+    os.environ["PA_STENCIL"] = "tma"
+    os.environ["PA_TMA_SMALL"] = "1"
+    os.environ["PA_TMA_PREFETCH"] = "0"
+    try:
+        pf, z = load_golden(name)
+        kw = dict(s.split("=") for s in z["curv_opts"])
+        is_per, sym = tuple(int(v) for v in z["is_per"]), tuple(int(v) for v in z["sym_dir"])
+        R = Ranks(capi, pf, is_per, sym, nranks, capi.PEER_LINKS if transport == "peer" else 0)
+        o = capi.CurvOpts()
+        o.prog_min, o.prog_max = float(z["prog_min"]), float(z["prog_max"])
+        o.do_threshold = int(kw.get("threshold_prog", 0))
+        o.threshold = float(kw.get("threshold_value", 1e-4))
+        o.do_gauss, o.do_strain = int(kw.get("do_gaussCurv", 0)), int(kw.get("do_strain", 0))
+        o.get_strain_tensor, o.do_velnormal = int(kw.get("getStrainTensor", 0)), int(kw.get("do_velnormal", 0))
+        need_vel = o.do_strain or o.do_velnormal
+        names = ["temp"] + (["x_velocity", "y_velocity", "z_velocity"] if need_vel else [])
+        state = R.fields(len(names), 1)
+        for f in state:
+            for v, n in enumerate(names):
+                f.upload_fabs(v, [[x[pf.comp(n)] for x in l.fabs] for l in pf.levels])
+        nout = capi.curvature_num_outputs(o)
+        out = R.fields(nout, 1)
+        scratch = None
+        if o.do_gauss:
+            scratch = [capi.ScratchField(h) for h in R.H]
+            if transport == "peer":
+                handles = [f.ipc_handles() for f in scratch]
+                for r, f in enumerate(scratch):
+                    for q in range(nranks):
+                        if q != r:
+                            f.map_peer(q, handles[q])
+        nlev = len(pf.levels)
+
+        def step(steps, lo=-1, hi=-1):
+            for r in range(nranks):
+                capi.curvature_steps(state[r], 0, 1, o, out[r], 0, steps, lo, hi)
+            capi.sync()
+        for _ in range(2):
+            R.exchange(state, 0, 1)
+            step(capi.CURV_PASS1)
+            if o.do_threshold:
+                for l in range(nlev):
+                    R.exchange(out, 2, 3)
+                    step(capi.CURV_DIV, l, l)
+            else:
+                R.exchange(out, 2, 3)
+                step(capi.CURV_DIV)
+            if o.do_gauss:
+                R.exchange(scratch, 0, 3)
+                step(capi.CURV_GAUSS)
+            if o.do_strain:
+                R.exchange(state, 1, 3)
+                step(capi.CURV_STRAIN)
+            if o.do_velnormal:
+                step(capi.CURV_VELN)
+        # compare every rank's boxes with the reference's golden vectors
+        order = ["Progress", "MeanCurvature_temp", "FlameNormalX_temp", "FlameNormalY_temp", "FlameNormalZ_temp"]
+        if o.do_gauss:
+            order.append("GaussianCurvature_temp")
+        if o.do_strain:
+            order.append("StrainRate_temp")
+            if o.get_strain_tensor:
+                order += ["ROST_dU%sd%s" % (a, b) for a in "xyz" for b in "xyz"]
+        if o.do_velnormal:
+            order.append("VelFlameNormal")
+        from helpers import fabs_from_flat
+        for c, n in enumerate(order):
+            want = fabs_from_flat(pf, z["curv_" + n])
+            for r in range(nranks):
+                got = out[r].download_fabs(c)
+                for l in range(nlev):
+                    for b in R.H[r].local_boxes[l]:
+                        if n.startswith("Gaussian"):
+                            assert max_rel(got[l][b], want[l][b]) <= 1e-12 or np.allclose(got[l][b], want[l][b], rtol=1e-12, atol=0), (n, r, l, b)
+                        else:
+                            assert bit_equal(got[l][b], want[l][b]), (name, transport, n, r, l, b)
+    finally:
+        os.environ["CUEMU_SEED"] = "0"
