@@ -849,182 +849,225 @@ int pa_curvature(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* 
     return pa_curvature_phases(state, comp_S, comp_vel, opts, out, comp_out, 3);
 }
 
-// The curvature tool as a sequence of steps.  Single-rank callers run all of them in one call (pa_curvature); a multi-rank
-// caller runs them one at a time with its cross-rank step (slab exchange and / or a barrier) in front of each -- the
-// reference does the same through MPI inside FillBoundary / ParallelCopy (curvature.cpp:322, 487-502, 514-520, 686-717).
-//   PA_CURV_PASS1   ghost fill of S, Progress, flame normal (+ un-normalised gradient when do_gaussCurv)   needs: S exchanged
-//   PA_CURV_DIV     ghost fill of n, MeanCurvature (+ threshold clip) on levels [lev_lo, lev_hi]              needs: n exchanged
-//                   with threshold_prog the levels must be run one by one, in order: level l reads the CLIPPED n of l-1
-//   PA_CURV_GAUSS   Hessian of the progress variable, GaussianCurvature                                      needs: G (scratch 0) exchanged
-//   PA_CURV_STRAIN  velocity gradients, StrainRate, ROST                                                     needs: velocities exchanged
-//   PA_CURV_VELN    VelFlameNormal (pointwise)
+// ---- the curvature tool, step by step -----------------------------------------------------------------------------
+namespace {
+
+// what every step needs: the two fields, the options and where each output lives in `out`
+struct CurvCtx {
+    pa_field* state; int comp_S, comp_vel;
+    const pa_curv_opts* o;
+    pa_field* out;
+    pa_hier* h;
+    int nlev;
+    int cP, cK, cN, cKg, cSR, cROST, cVN;       // Progress, MeanCurvature, FlameNormalX.., optional outputs (-1: not enabled)
+    double invdenom;
+};
+
+// PASS1: progress variable (curvature.cpp:310-321), its ghost cells, G = grad c, nrm, n = G / nrm (:426-502)
+int curv_pass1(const CurvCtx& c) {
+    pa_hier* h = c.h;
+    Hier& H = h->H;
+    const int nlev = c.nlev;
+    StencilExtra ex;
+    GridArgs ga;
+    std::memset(&ex, 0, sizeof(ex));
+    if (c.o->do_gauss) {                          // the Gaussian curvature needs the un-normalised gradient later
+        CHK(tmp_field(h, &h->tmpG, 3));
+        for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
+    }
+    const char* no_fuse = getenv("PA_CURV_UNFUSED");
+    if (c.state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
+        // Progress + normal fused.  The progress pass rides in the stencil's loader: valid cells stay S and are normalised as
+        // they are read; the few ghost cells that must be materialised (unlinked faces) are written in progress space by the
+        // ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel writes Progress and
+        // n = G/nrm; Progress never makes a separate round trip through HBM.
+        GhostXform xf{1, c.o->prog_min, c.invdenom};
+        for (int l = 0; l < nlev; ++l) ex.cout[l] = c.out->slab[l] ? c.out->slab[l] + (long long)c.cP * c.out->cs[l] : nullptr;
+        ex.pmin = c.o->prog_min; ex.inv = c.invdenom;
+        CHK(grid_args(c.state, c.comp_S, c.out, c.cN, ga));
+        if (overlap_enabled(h)) {
+            CHK(fill_ghosts_impl(c.state, c.comp_S, 1, 0, 0, false, xf));
+            CHK(fork_side(h, [&]() { return fill_ghosts_impl(c.state, c.comp_S, 1, 1, nlev - 1, false, xf); }));
+            CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, 0, c.state->ng, c.state));
+            CHK(join_side(h));
+            return run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 1, nlev - 1, c.state->ng, c.state);
+        }
+        CHK(fill_ghosts_impl(c.state, c.comp_S, 1, 0, nlev - 1, false, xf));
+        return run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, c.state->ng, c.state);
+    }
+    if (H.nranks > 1)
+        return fail(PA_ERR_UNSUPPORTED, "pa_curvature: the multi-rank path needs the fused progress pass (state with nghost == 1, "
+                                        "TMA-eligible boxes); the unfused route would exchange an intermediate field");
+    // unfused: c on valid cells of every level, ghost cells of c (coarse data = c on the next coarser level), then G -> nrm -> n
+    for (int l = 0; l < nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* li = dev_layout(h, l, c.state->ng, &err);
+        if (!li) return err;
+        const PaLayDev* lo = dev_layout(h, l, c.out->ng, &err);
+        if (!lo) return err;
+        CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), c.state->slab[l] + (long long)c.comp_S * c.state->cs[l],
+                           c.out->slab[l] + (long long)c.cP * c.out->cs[l], c.o->prog_min, c.invdenom, t_stream));
+    }
+    CHK(fill_ghosts_impl(c.out, c.cP, 1, 0, nlev - 1, false));
+    CHK(grid_args(c.out, c.cP, c.out, c.cN, ga));
+    return run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, c.out->ng, c.out);
+}
+
+// DIV: ghost cells of n, K = 0.5 div n (curvature.cpp:505-547), threshold clip of K and n (:549-567) on levels [l0, l1].
+// Without the clip every level's coarse data is final after PASS1, so one batched ghost fill + one stencil pass cover the
+// range; with it, level l needs the CLIPPED n of l-1 (:514-518 reads flame_normal[lev-1] after :549-567 modified it), so
+// the levels run in order.
+int curv_div(const CurvCtx& c, int l0, int l1) {
+    pa_hier* h = c.h;
+    Hier& H = h->H;
+    pa_field* out = c.out;
+    StencilExtra ex;
+    GridArgs ga;
+    std::memset(&ex, 0, sizeof(ex));
+    ex.do_threshold = c.o->do_threshold ? 1 : 0;
+    ex.threshold = c.o->threshold;
+    for (int l = 0; l < c.nlev; ++l) ex.prog[l] = out->slab[l] + (long long)c.cP * out->cs[l];
+    CHK(grid_args(out, c.cN, out, c.cK, ga));
+    if (!c.o->do_threshold) {
+        if (overlap_enabled(h) && l0 == 0 && l1 > 0) {
+            // n of every level is final: PASS1 is complete on the caller's stream, which the fork orders the side stream after
+            CHK(fill_ghosts_impl(out, c.cN, 3, 0, 0, false));
+            CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, c.cN, 3, 1, l1, false); }));
+            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
+            CHK(join_side(h));
+            return run_stencil(h, MODE_DIV, ga, ex, 1, 1, l1, out->ng, out);
+        }
+        CHK(fill_ghosts_impl(out, c.cN, 3, l0, l1, false));
+        return run_stencil(h, MODE_DIV, ga, ex, 1, l0, l1, out->ng, out);
+    }
+    for (int l = l0; l <= l1; ++l) {
+        CHK(fill_ghosts_impl(out, c.cN, 3, l, l, false));
+        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng, out));
+        int err = PA_OK;
+        const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
+        if (!lo) return err;
+        CU(launch_clip_normal(h->lev[l]->boxes.p, lo, lo, (int)H.lev[l].local.size(), out->slab[l] + (long long)c.cP * out->cs[l],
+                              out->slab[l] + (long long)c.cN * out->cs[l], out->cs[l], c.o->threshold, t_stream));
+    }
+    return PA_OK;
+}
+
+// GAUSS: Hessian rows = grad3 of each un-normalised gradient component (ghosts by the same rules, coarse = G on l-1), then
+// the pointwise n.adj(H).n / |grad c|^4 (curvature.cpp:575-677)
+int curv_gauss(const CurvCtx& c) {
+    pa_hier* h = c.h;
+    Hier& H = h->H;
+    if (!h->tmpG) return fail(PA_ERR_STATE, "pa_curvature_steps: PA_CURV_GAUSS before PA_CURV_PASS1");
+    CHK(tmp_field(h, &h->tmpH, 9));
+    CHK(fill_ghosts_impl(h->tmpG, 0, 3, 0, c.nlev - 1, false));
+    StencilExtra e0;
+    GridArgs ga;
+    std::memset(&e0, 0, sizeof(e0));
+    for (int d = 0; d < 3; ++d) {
+        CHK(grid_args(h->tmpG, d, h->tmpH, 3 * d, ga));
+        CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, c.nlev - 1, h->tmpG->ng, h->tmpG));
+    }
+    for (int l = 0; l < c.nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* ly = dev_layout(h, l, 1, &err);
+        if (!ly) return err;
+        CU(launch_gauss(h->lev[l]->boxes.p, ly, ly, (int)H.lev[l].local.size(), h->tmpG->slab[l], h->tmpG->cs[l], h->tmpH->slab[l],
+                        h->tmpH->cs[l], c.out->slab[l] + (long long)c.cP * c.out->cs[l], c.out->slab[l] + (long long)c.cKg * c.out->cs[l],
+                        c.o->do_threshold ? 1 : 0, c.o->threshold, t_stream));
+    }
+    return PA_OK;
+}
+
+// STRAIN: velocity gradients with ghosts of u_i by the same rules (curvature.cpp:686-717), StrainRate and, on request, the
+// nine ROST components (:719-759)
+int curv_strain(const CurvCtx& c) {
+    pa_hier* h = c.h;
+    Hier& H = h->H;
+    CHK(fill_ghosts_impl(c.state, c.comp_vel, 3, 0, c.nlev - 1, false));
+    pa_field* dU = nullptr;
+    int c0 = 0;
+    if (c.cROST >= 0) { dU = c.out; c0 = c.cROST; }
+    else { CHK(tmp_field(h, &h->tmpW, 9)); dU = h->tmpW; }
+    StencilExtra e0;
+    GridArgs ga;
+    std::memset(&e0, 0, sizeof(e0));
+    for (int d = 0; d < 3; ++d) {
+        CHK(grid_args(c.state, c.comp_vel + d, dU, c0 + 3 * d, ga));
+        CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, c.nlev - 1, c.state->ng, c.state));
+    }
+    for (int l = 0; l < c.nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* ly = dev_layout(h, l, 1, &err);
+        if (!ly) return err;
+        CU(launch_strain(h->lev[l]->boxes.p, ly, (int)H.lev[l].local.size(), dU->slab[l] + (long long)c0 * dU->cs[l], dU->cs[l],
+                         c.out->slab[l] + (long long)c.cSR * c.out->cs[l], t_stream));
+    }
+    return PA_OK;
+}
+
+// VELN: u . n with the (already clipped) normal (curvature.cpp:761-789), pointwise
+int curv_veln(const CurvCtx& c) {
+    pa_hier* h = c.h;
+    Hier& H = h->H;
+    for (int l = 0; l < c.nlev; ++l) {
+        int err = PA_OK;
+        const PaLayDev* lu = dev_layout(h, l, c.state->ng, &err);
+        if (!lu) return err;
+        const PaLayDev* lo = dev_layout(h, l, 1, &err);
+        if (!lo) return err;
+        CU(launch_velnormal(h->lev[l]->boxes.p, lu, lo, lo, (int)H.lev[l].local.size(), c.state->slab[l] + (long long)c.comp_vel * c.state->cs[l],
+                            c.state->cs[l], c.out->slab[l] + (long long)c.cN * c.out->cs[l], c.out->cs[l],
+                            c.out->slab[l] + (long long)c.cP * c.out->cs[l], c.out->slab[l] + (long long)c.cVN * c.out->cs[l],
+                            c.o->do_threshold ? 1 : 0, c.o->threshold, t_stream));
+    }
+    return PA_OK;
+}
+
+}  // namespace
+
+// Single-rank callers run all steps in one call (pa_curvature); a multi-rank caller runs them one at a time with its
+// cross-rank step (slab exchange and / or a barrier) in front of each -- the reference does the same through MPI inside
+// FillBoundary / ParallelCopy (curvature.cpp:322, 487-502, 514-520, 686-717).  What each step needs exchanged:
+//   PA_CURV_PASS1  S          PA_CURV_DIV  n (with threshold_prog: one level per call, in order)
+//   PA_CURV_GAUSS  G (scratch field 0)      PA_CURV_STRAIN  the velocities      PA_CURV_VELN  nothing
 int pa_curvature_steps(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out, int steps,
                        int lev_lo, int lev_hi) {
     if (!opts) return fail(PA_ERR_ARG, "pa_curvature: null options");
     if (steps < 1 || steps > 31) return fail(PA_ERR_ARG, "pa_curvature_steps: steps must be a combination of PA_CURV_*");
     CHK(check_field(state, comp_S, 1, "pa_curvature(state)"));
-    const int nout = pa_curvature_num_outputs(opts);
-    CHK(check_field(out, comp_out, nout, "pa_curvature(out)"));
+    CHK(check_field(out, comp_out, pa_curvature_num_outputs(opts), "pa_curvature(out)"));
     if (state->h != out->h) return fail(PA_ERR_ARG, "pa_curvature: fields belong to different hierarchies");
     if (out->ng != 1) return fail(PA_ERR_ARG, "pa_curvature: the output field must have nghost == 1 (Progress and the flame normal are ghost-filled in place)");
     if (state->ng < 1) return fail(PA_ERR_ARG, "pa_curvature: state needs nghost >= 1");
     if (!(opts->prog_min < opts->prog_max)) return fail(PA_ERR_ARG, "progMin must be less than progMax");   // curvature.cpp:157-159
-    const bool need_vel = opts->do_strain || opts->do_velnormal;
-    if (need_vel) CHK(check_field(state, comp_vel, 3, "pa_curvature(velocity)"));
-    pa_hier* h = state->h;
-    Hier& H = h->H;
-    CHK(ensure_device(h));
-    const int nlev = H.nlev;
+    if (opts->do_strain || opts->do_velnormal) CHK(check_field(state, comp_vel, 3, "pa_curvature(velocity)"));
+    CurvCtx c;
+    c.state = state; c.comp_S = comp_S; c.comp_vel = comp_vel; c.o = opts; c.out = out;
+    c.h = state->h;
+    CHK(ensure_device(c.h));
+    c.nlev = c.h->H.nlev;
     if (lev_lo < 0) lev_lo = 0;
-    if (lev_hi < 0 || lev_hi >= nlev) lev_hi = nlev - 1;
+    if (lev_hi < 0 || lev_hi >= c.nlev) lev_hi = c.nlev - 1;
     if (lev_lo > lev_hi) return fail(PA_ERR_ARG, "pa_curvature_steps: empty level range");
-    const int cP = comp_out, cK = comp_out + 1, cN = comp_out + 2;
+    c.cP = comp_out; c.cK = comp_out + 1; c.cN = comp_out + 2;
     int next = comp_out + 5;
-    const int cKg = opts->do_gauss ? next++ : -1;
-    const int cSR = opts->do_strain ? next++ : -1;
-    int cROST = -1;
-    if (opts->do_strain && opts->get_strain_tensor) { cROST = next; next += 9; }
-    const int cVN = opts->do_velnormal ? next++ : -1;
+    c.cKg = opts->do_gauss ? next++ : -1;
+    c.cSR = opts->do_strain ? next++ : -1;
+    c.cROST = -1;
+    if (opts->do_strain && opts->get_strain_tensor) { c.cROST = next; next += 9; }
+    c.cVN = opts->do_velnormal ? next++ : -1;
+    c.invdenom = 1.0 / (opts->prog_max - opts->prog_min);
 
-    StencilExtra ex;
-    GridArgs ga;
-    const double invdenom = 1.0 / (opts->prog_max - opts->prog_min);
-
-    if (steps & PA_CURV_PASS1) {
-        std::memset(&ex, 0, sizeof(ex));
-        if (opts->do_gauss) {
-            CHK(tmp_field(h, &h->tmpG, 3));
-            for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
-        }
-        const char* no_fuse = getenv("PA_CURV_UNFUSED");
-        if (state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
-            // Progress + normal fused.  The progress pass (curvature.cpp:310-321) rides in the stencil's loader: valid cells stay S
-            // and are normalised as they are read; the few ghost cells that must be materialised (unlinked faces) are written in
-            // progress space by the ghost fill (coarse data = S on the next coarser level, normalised on load).  The kernel
-            // writes Progress and n = G/nrm; Progress never makes a separate round trip through HBM.
-            GhostXform xf{1, opts->prog_min, invdenom};
-            for (int l = 0; l < nlev; ++l) ex.cout[l] = out->slab[l] ? out->slab[l] + (long long)cP * out->cs[l] : nullptr;
-            ex.pmin = opts->prog_min; ex.inv = invdenom;
-            CHK(grid_args(state, comp_S, out, cN, ga));
-            if (overlap_enabled(h)) {
-                CHK(fill_ghosts_impl(state, comp_S, 1, 0, 0, false, xf));
-                CHK(fork_side(h, [&]() { return fill_ghosts_impl(state, comp_S, 1, 1, nlev - 1, false, xf); }));
-                CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, 0, state->ng, state));
-                CHK(join_side(h));
-                CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 1, nlev - 1, state->ng, state));
-            } else {
-                CHK(fill_ghosts_impl(state, comp_S, 1, 0, nlev - 1, false, xf));
-                CHK(run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 0, nlev - 1, state->ng, state));
-            }
-        } else {
-            if (H.nranks > 1)
-                return fail(PA_ERR_UNSUPPORTED, "pa_curvature: the multi-rank path needs the fused progress pass (state with nghost == 1, "
-                                                "TMA-eligible boxes); the unfused route would exchange an intermediate field");
-            // progress variable on valid cells of every level (curvature.cpp:310-321), ghost cells of c on all levels (coarse
-            // data = c on the next coarser level), then G -> nrm -> n
-            for (int l = 0; l < nlev; ++l) {
-                int err = PA_OK;
-                const PaLayDev* li = dev_layout(h, l, state->ng, &err);
-                if (!li) return err;
-                const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
-                if (!lo) return err;
-                CU(launch_progress(h->lev[l]->boxes.p, li, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_S * state->cs[l],
-                                   out->slab[l] + (long long)cP * out->cs[l], opts->prog_min, invdenom, t_stream));
-            }
-            CHK(fill_ghosts_impl(out, cP, 1, 0, nlev - 1, false));
-            CHK(grid_args(out, cP, out, cN, ga));
-            CHK(run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, out->ng, out));
-        }
-    }
-
+    if (steps & PA_CURV_PASS1) CHK(curv_pass1(c));
     if (steps & PA_CURV_DIV) {
-        // divergence of n.  Without the threshold clip every level's coarse data is final after pass 1, so one batched ghost
-        // fill + one stencil pass cover the level range; with it, level l needs the CLIPPED n of l-1 (curvature.cpp:514-518
-        // reads flame_normal[lev-1] after :549-567 modified it), so levels run in order.
-        if (opts->do_threshold && H.nranks > 1 && lev_lo != lev_hi)
+        if (opts->do_threshold && c.h->H.nranks > 1 && lev_lo != lev_hi)
             return fail(PA_ERR_ARG, "pa_curvature_steps: with threshold_prog a multi-rank caller runs PA_CURV_DIV one level per call "
                                     "(exchange the flame normal before each)");
-        std::memset(&ex, 0, sizeof(ex));
-        ex.do_threshold = opts->do_threshold ? 1 : 0;
-        ex.threshold = opts->threshold;
-        for (int l = 0; l < nlev; ++l) ex.prog[l] = out->slab[l] + (long long)cP * out->cs[l];
-        CHK(grid_args(out, cN, out, cK, ga));
-        if (!opts->do_threshold && overlap_enabled(h) && lev_lo == 0 && lev_hi > 0) {
-            // n of every level is final (pass 1 is complete on the caller's stream, which the fork orders the side stream after)
-            CHK(fill_ghosts_impl(out, cN, 3, 0, 0, false));
-            CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, cN, 3, 1, lev_hi, false); }));
-            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
-            CHK(join_side(h));
-            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 1, lev_hi, out->ng, out));
-        } else if (!opts->do_threshold) {
-            CHK(fill_ghosts_impl(out, cN, 3, lev_lo, lev_hi, false));
-            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, lev_lo, lev_hi, out->ng, out));
-        } else {
-            for (int l = lev_lo; l <= lev_hi; ++l) {
-                CHK(fill_ghosts_impl(out, cN, 3, l, l, false));
-                CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng, out));
-                int err = PA_OK;
-                const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
-                if (!lo) return err;
-                CU(launch_clip_normal(h->lev[l]->boxes.p, lo, lo, (int)H.lev[l].local.size(), out->slab[l] + (long long)cP * out->cs[l],
-                                      out->slab[l] + (long long)cN * out->cs[l], out->cs[l], opts->threshold, t_stream));
-            }
-        }
+        CHK(curv_div(c, lev_lo, lev_hi));
     }
-
-    if ((steps & PA_CURV_GAUSS) && opts->do_gauss) {
-        // Hessian rows: grad3 of each un-normalised gradient component, ghosts by the same rules with coarse = G on l-1
-        if (!h->tmpG) return fail(PA_ERR_STATE, "pa_curvature_steps: PA_CURV_GAUSS before PA_CURV_PASS1");
-        CHK(tmp_field(h, &h->tmpH, 9));
-        CHK(fill_ghosts_impl(h->tmpG, 0, 3, 0, nlev - 1, false));
-        StencilExtra e0;
-        std::memset(&e0, 0, sizeof(e0));
-        for (int d = 0; d < 3; ++d) {
-            CHK(grid_args(h->tmpG, d, h->tmpH, 3 * d, ga));
-            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, h->tmpG->ng, h->tmpG));
-        }
-        for (int l = 0; l < nlev; ++l) {
-            int err = PA_OK;
-            const PaLayDev* ly = dev_layout(h, l, 1, &err);
-            if (!ly) return err;
-            CU(launch_gauss(h->lev[l]->boxes.p, ly, ly, (int)H.lev[l].local.size(), h->tmpG->slab[l], h->tmpG->cs[l], h->tmpH->slab[l],
-                            h->tmpH->cs[l], out->slab[l] + (long long)cP * out->cs[l], out->slab[l] + (long long)cKg * out->cs[l],
-                            opts->do_threshold ? 1 : 0, opts->threshold, t_stream));
-        }
-    }
-    if ((steps & PA_CURV_STRAIN) && opts->do_strain) {
-        // velocity gradients: ghosts of u_i by the same rules (curvature.cpp:686-717); needs ghost cells in `state`
-        CHK(fill_ghosts_impl(state, comp_vel, 3, 0, nlev - 1, false));
-        pa_field* dU = nullptr;
-        int c0 = 0;
-        if (cROST >= 0) { dU = out; c0 = cROST; }
-        else { CHK(tmp_field(h, &h->tmpW, 9)); dU = h->tmpW; }
-        StencilExtra e0;
-        std::memset(&e0, 0, sizeof(e0));
-        for (int d = 0; d < 3; ++d) {
-            CHK(grid_args(state, comp_vel + d, dU, c0 + 3 * d, ga));
-            CHK(run_stencil(h, MODE_GRAD3, ga, e0, 1, 0, nlev - 1, state->ng, state));
-        }
-        for (int l = 0; l < nlev; ++l) {
-            int err = PA_OK;
-            const PaLayDev* ly = dev_layout(h, l, 1, &err);
-            if (!ly) return err;
-            CU(launch_strain(h->lev[l]->boxes.p, ly, (int)H.lev[l].local.size(), dU->slab[l] + (long long)c0 * dU->cs[l], dU->cs[l],
-                             out->slab[l] + (long long)cSR * out->cs[l], t_stream));
-        }
-    }
-    if ((steps & PA_CURV_VELN) && opts->do_velnormal) {
-        for (int l = 0; l < nlev; ++l) {
-            int err = PA_OK;
-            const PaLayDev* lu = dev_layout(h, l, state->ng, &err);
-            if (!lu) return err;
-            const PaLayDev* lo = dev_layout(h, l, 1, &err);
-            if (!lo) return err;
-            CU(launch_velnormal(h->lev[l]->boxes.p, lu, lo, lo, (int)H.lev[l].local.size(), state->slab[l] + (long long)comp_vel * state->cs[l],
-                                state->cs[l], out->slab[l] + (long long)cN * out->cs[l], out->cs[l], out->slab[l] + (long long)cP * out->cs[l],
-                                out->slab[l] + (long long)cVN * out->cs[l], opts->do_threshold ? 1 : 0, opts->threshold, t_stream));
-        }
-    }
+    if ((steps & PA_CURV_GAUSS) && opts->do_gauss) CHK(curv_gauss(c));
+    if ((steps & PA_CURV_STRAIN) && opts->do_strain) CHK(curv_strain(c));
+    if ((steps & PA_CURV_VELN) && opts->do_velnormal) CHK(curv_veln(c));
     return PA_OK;
 }
 
