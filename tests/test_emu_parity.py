@@ -49,6 +49,15 @@ def schedule(request):
     os.environ["CUEMU_SEED"] = "0"
 
 
+def _thin_out(schedule, stencil, links):
+    """Not the full cross product (the suite has to stay a few minutes): the shuffled schedule matters for the TMA pipeline
+    only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
+    if schedule and (stencil in ("simple", "tma_big_pf") or links == "nolinks"):
+        pytest.skip("combination not in the thinned-out matrix")
+    if links == "nolinks" and stencil not in ("tma", "simple"):
+        pytest.skip("combination not in the thinned-out matrix")
+
+
 GRAD_CASES = [n for n, c in CASES.items() if "grad" in c[3]]
 CURV_CASES = [n for n, c in CASES.items() if "curvature" in c[3]]
 
@@ -57,8 +66,7 @@ CURV_CASES = [n for n, c in CASES.items() if "curvature" in c[3]]
 @pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple", "tma_pf", "tma_big_pf"])
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, links):
-    if schedule and (stencil == "simple" or links == "nolinks"):
-        pytest.skip("the shuffled schedule matters for the TMA pipeline only")
+    _thin_out(schedule, stencil, links)
     G.test_grad_matches_reference_golden(emu, name, stencil, links)
 
 
@@ -66,8 +74,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 @pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple", "tma_pf", "tma_big_pf"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
-    if schedule and (stencil == "simple" or links == "nolinks"):
-        pytest.skip("the shuffled schedule matters for the TMA pipeline only")
+    _thin_out(schedule, stencil, links)
     G.test_curvature_matches_reference_golden(emu, name, stencil, links)
 
 
