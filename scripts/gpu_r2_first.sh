@@ -20,6 +20,13 @@ for ex in target_curv grad5 target_grad curvature3; do
   done
   el $ex
 done
+# rows per tile pick the CTA shape class (128-wide boxes: TY=2 -> 128 pairs -> 2 consumer warps x 5-6 CTAs/SM, TY=4 -> 4 warps x 3-4)
+for ty in 2 4; do
+  for pf in 0 1; do
+    PA_TMA_PREFETCH=$pf PA_TMA_TY=$ty timeout -s KILL 60 python bench.py --only-extra target_curv --steps 10 --warmup 3 > $O/r2a_target_curv_pf${pf}_zc32_ty$ty.log 2>&1
+  done
+done
+el shapes
 PA_TMA_PREFETCH=1 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf1.log 2>&1
 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf0.log 2>&1
 el bench
