@@ -71,7 +71,7 @@ class Ranks:
 
 
 CASE_LIST = [("c1_periodic", 2), ("c1_walls", 2), ("lshape", 2), ("edge_periodic", 2), ("c3_three_levels", 2), ("mixed_boxes", 2),
-             ("uniform", 2), ("uniform", 4), ("config3", 4)]
+             ("uniform", 2), ("uniform", 4), ("uniform", 8), ("config3", 4)]
 
 
 def _case(name):
