@@ -27,6 +27,14 @@ for ty in 2 4; do
   done
 done
 el shapes
+# DIV waits on its full barrier 39 % of the time with a 3-stage ring (3 components per stage): the 16-warp shape (mask bit 8)
+# has room for 4-5 stages
+for mask in 20 28; do
+  for kb in 20 40; do
+    PA_TMA_CW16=$mask PA_TMA_INFLIGHT_KB=$kb timeout -s KILL 60 python bench.py --only-extra target_curv --steps 10 --warmup 3 > $O/r2a_target_curv_pf0_zc32_mask${mask}_kb$kb.log 2>&1
+  done
+done
+el ring
 PA_TMA_PREFETCH=1 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf1.log 2>&1
 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf0.log 2>&1
 el bench
