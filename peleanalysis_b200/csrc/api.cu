@@ -417,7 +417,7 @@ int pa_init(int device) {
     if (p.major < 10) return fail(PA_ERR_UNSUPPORTED, "pa_init: kernels are built for sm_100a only; device is sm_" + std::to_string(p.major) + std::to_string(p.minor));
     return PA_OK;
 }
-int pa_finalize(void) { return PA_OK; }
+int pa_finalize(void) { stencil_tma_release(); return PA_OK; }
 int pa_set_stream(void* s) { t_stream = (cudaStream_t)s; return PA_OK; }
 int pa_sync(void) { CU(cudaStreamSynchronize(t_stream)); return PA_OK; }
 int pa_host_alloc(void** p, size_t bytes) { CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return PA_OK; }

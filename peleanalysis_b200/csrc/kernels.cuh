@@ -97,6 +97,7 @@ cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int ma
 // device self-test: the branch-free sqrt / reciprocal / flame-normal forms of the TMA kernel against the plain operators on
 // n pseudo-random operand sets; *bad_host = number of results that differ in any bit
 cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long long* bad_host, cudaStream_t st);
+void stencil_tma_release();      // frees the work-item ticket counters (pa_finalize)
 int stencil_tma_normal_math();   // flame-normal arithmetic in use: 0 branch-free forms, 1 plain operators, -1 not decided yet
 int stencil_tma_tile_rows();     // TY the tile table must be built with
 int stencil_tma_max_tile_rows();

@@ -923,6 +923,10 @@ cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long lo
 }
 
 int stencil_tma_normal_math() { return g_normal_plain; }
+void stencil_tma_release() {                          // pa_finalize: the per-stream ticket counters
+    for (auto& kv : g_tickets) if (kv.second.dev) cudaFree(kv.second.dev);
+    g_tickets.clear();
+}
 int stencil_tma_tile_rows() { return MAX_TILE_ROWS; }
 int stencil_tma_max_tile_rows() { return MAX_TILE_ROWS; }
 // largest staged plane ((TY+2) rows x pitch) the pipeline accepts per input component (3 stages of 3 components must fit)
