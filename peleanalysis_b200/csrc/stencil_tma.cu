@@ -266,6 +266,11 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // PF variant, MODE_DIV: "lean" staging -- only the differentiated component needs its halo, so n_x and n_z are staged
+    // without the y-halo rows and n_x, n_y without the z-halo planes (the consumers never read those cells); bit 0 of
+    // stage_doubles (a multiple of 16) switches it off for A/B runs.  Not compiled into the default kernels.
+    bool lean = false;
+    if constexpr (PF && MODE == MODE_DIV) { lean = !(stage_doubles & 1); stage_doubles &= ~15; }
     const long long stage_stride = (long long)NIN * stage_doubles;
 
     if (threadIdx.x == 0) {
@@ -396,18 +401,25 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
                     mbar_wait(&empty_bar[stage], ephase);
                     if (lane == 0) {
                         if (p == 0) rec_s[stage] = X.rec;              // the tile record rides with the tile's first plane
-                        mbar_expect_tx(&full_bar[stage], plane_bytes * NIN);
+                        const bool zhalo = (p == 0) | (p == nplanes - 1);
+                        uint32_t tx = plane_bytes * NIN;
+                        if (lean) tx = zhalo ? (uint32_t)t.ny * row_bytes : plane_bytes + 2u * (uint32_t)t.ny * row_bytes;
+                        mbar_expect_tx(&full_bar[stage], tx);
                         const int z = t.z0 - 1 + p;
                         const double* zs = (z < 0) ? s_zlo : (z >= nzb ? s_zhi : nullptr);
                         const long long zcs = (z < 0) ? cs_zlo : cs_zhi;
 #pragma unroll
                         for (int c = 0; c < NIN; ++c) {
                             double* dst = sm + (long long)stage * stage_stride + (long long)c * stage_doubles;
+                            const bool yhalo = !lean || c == 1;             // lean: only n_y is read in the rows above / below the tile
+                            if (lean && zhalo && c != 2) continue;          // ... and only n_z in the planes before / after it
                             if (zs) {
-                                tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
+                                if (yhalo) tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
+                                else tma_load_1d(dst + li.P, zs + (long long)c * zcs + (long long)z * li.PS + (long long)t.y0 * li.P, (uint32_t)t.ny * row_bytes, &full_bar[stage]);
                                 continue;
                             }
                             int r0 = t.y0 - 1, r1 = t.y0 + t.ny;
+                            if (!yhalo) { r0 = t.y0; r1 = t.y0 + t.ny - 1; }
                             if (r0 < 0 && s_ylo) {
                                 tma_load_1d(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[stage]);
                                 r0 = 0;
@@ -791,7 +803,12 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN, PF>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    int sd = stage_doubles;
+    if constexpr (PF && MODE == MODE_DIV) {               // bit 0 set: lean staging off (see the kernel)
+        const char* e = getenv("PA_DIV_LEAN");
+        if (e && e[0] == '0') sd |= 1;
+    }
+    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN, PF>)(tiles, ntiles, (int)nwork, ga, ex, sd, S, T.dev, T.base);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }

@@ -35,6 +35,9 @@ for mask in 20 28; do
   done
 done
 el ring
+# PF kernels stage DIV "lean" (no y-halo rows for n_x / n_z, no z-halo planes for n_x / n_y); PA_DIV_LEAN=0 = prefetch warp alone
+PA_TMA_PREFETCH=1 PA_DIV_LEAN=0 timeout -s KILL 60 python bench.py --only-extra target_curv --steps 10 --warmup 3 > $O/r2a_target_curv_pf1_zc32_nolean.log 2>&1
+el lean
 PA_TMA_PREFETCH=1 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf1.log 2>&1
 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf0.log 2>&1
 el bench
