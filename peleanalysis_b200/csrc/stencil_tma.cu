@@ -87,6 +87,24 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// the same on a barrier address computed once (PF kernels): the compiler otherwise rebuilds the shared-window address of
+// &bar[i] -- an S2R SR_CgaCtaId plus a LEA -- in front of every wait and every arrive of the plane loop
+typedef uint32_t bar_ref;
+__device__ __forceinline__ bar_ref bar_base(uint64_t* b) { uint32_t a = smem_u32(b); asm volatile("" : "+r"(a)); return a; }
+__device__ __forceinline__ bar_ref bar_at(bar_ref b, int i) { return b + 8u * (uint32_t)i; }
+__device__ __forceinline__ void mbar_arrive_a(bar_ref a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_wait_a(bar_ref a, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 // seeds of the IEEE sqrt / reciprocal refinements (MUFU.RSQ64H / MUFU.RCP64H on the high word)
 __device__ __forceinline__ double mufu_rsq64h(double x) { double s; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x)); return s; }
 __device__ __forceinline__ double mufu_rcp64h(double x) { double s; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x)); return s; }
@@ -98,6 +116,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { cuem
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { cuemu::tma_load_1d(smem_dst, gsrc, bytes, bar); }
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) { cuemu::cp_async_8(smem_dst, gsrc); }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) { cuemu::cp_async_arrive_noinc(bar); }
+typedef uint64_t* bar_ref;
+__device__ __forceinline__ bar_ref bar_base(uint64_t* b) { return b; }
+__device__ __forceinline__ bar_ref bar_at(bar_ref b, int i) { return b + i; }
+__device__ __forceinline__ void mbar_arrive_a(bar_ref a) { cuemu::mbar_arrive(a); }
+__device__ __forceinline__ void mbar_wait_a(bar_ref a, uint32_t parity) { cuemu::mbar_wait(a, parity); }
 #endif
 
 __device__ __forceinline__ double cdiff(double dxi, double m, double c, double p) {
@@ -556,12 +579,16 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
     // ===================================== consumer warps =====================================
     int sc = 0;                    // stage of the plane being received
     uint32_t fphase = 0;
+    bar_ref full_a = bar_ref(), empty_a = bar_ref();
+    if constexpr (PF) { full_a = bar_base(full_bar); empty_a = bar_base(empty_bar); }
+    auto wait_full = [&](int st, uint32_t ph) { if constexpr (PF) mbar_wait_a(bar_at(full_a, st), ph); else mbar_wait(&full_bar[st], ph); };
+    auto arrive_empty = [&](int st) { if constexpr (PF) mbar_arrive_a(bar_at(empty_a, st)); else mbar_arrive(&empty_bar[st]); };
     const double pmin = ex.pmin, pinv = ex.inv;
     auto prog = [&](double sv) { return (sv - pmin) * pinv; };          // curvature.cpp:316-320
 
     for (;;) {
         // ---- plane 0 of the tile (z = z0-1) and the tile record ----
-        mbar_wait(&full_bar[sc], fphase);
+        wait_full(sc, fphase);
         const TileRec& R = rec_s[sc];
         const PaTile t = R.t;
         if (t.lev < 0) break;                          // end marker
@@ -638,7 +665,7 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
         const bool xlo_link = (links & 1) != 0, xhi_link_even = (links & 8) != 0 && !(nx & 1);
 
         for (int p = 1; p < nplanes; ++p) {
-            mbar_wait(&full_bar[sc], fphase);
+            wait_full(sc, fphase);
             const double* Sp = sm + (long long)sp * stage_stride;
             const bool last_raw = zl_raw && p == nplanes - 1;
 #pragma unroll
@@ -742,13 +769,13 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
             }
             // this warp no longer needs plane p-1
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[sp]);
+            if (lane == 0) arrive_empty(sp);
             sp = sc;
             if (++sc == S) { sc = 0; fphase ^= 1u; }
         }
         // ... nor the tile's last plane
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[sp]);
+        if (lane == 0) arrive_empty(sp);
     }
 }
 
