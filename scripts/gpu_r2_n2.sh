@@ -8,3 +8,13 @@ timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 
 grep -E "dist_check|DIST_CHECK|rc=" $O/r2b_dist.log | tail -40
 timeout -s KILL 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 > $O/r2b_bench_n2.log 2>&1; echo "rc=$?" >> $O/r2b_bench_n2.log
 tail -c 700 $O/r2b_bench_n2.log
+# the plotfile tools with one process per GPU (first run over NCCL), checked against the single-GPU C++ executable with fcompare
+python - <<'PY'
+import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+from helpers import load_golden
+from peleanalysis_b200 import plotfile
+pf, z = load_golden("c3_three_levels"); plotfile.write_plotfile("gpurun_out/r2b_plt", pf, clean="remove")
+PY
+timeout -s KILL 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 -m peleanalysis_b200.mgtools grad infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_gt_n2 > $O/r2b_mgtools.log 2>&1; echo "rc=$?" >> $O/r2b_mgtools.log
+peleanalysis_b200/host/grad3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_gt_n1 >> $O/r2b_mgtools.log 2>&1
+oracle/_ref/fcompare.ref.ex gpurun_out/r2b_gt_n2 gpurun_out/r2b_gt_n1 2>&1 | tail -3 | tee -a $O/r2b_mgtools.log

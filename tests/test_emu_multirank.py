@@ -159,3 +159,122 @@ def test_emulated_slab_transport_world2():
     for p in procs:
         p.join(600)
     assert list(ok) == [1, 1], [p.exitcode for p in procs]
+
+
+def _tool_worker(rank, world, port, tmp, ok):
+    """peleanalysis_b200.mgtools (the multi-process plotfile tools) end to end: plotfile in -> one Cell_D file per rank +
+    Header / Cell_H from rank 0 -> read back and compared with the golden vectors of the compiled reference."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), CUEMU_SEED=str(1 + rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import bit_equal, load_golden, max_rel
+        from peleanalysis_b200 import mgtools, plotfile
+        capi, mg = _load_emulated()
+
+        def flat(r, n):
+            c = r.comp(n)
+            return np.concatenate([f[c].ravel() for l in r.levels for f in l.fabs])
+        for name in ("c3_three_levels", "mixed_boxes", "c1_corner_sym"):
+            pf, z = load_golden(name)
+            d = os.path.join(tmp, "plt_" + name)
+            if rank == 0:
+                plotfile.write_plotfile(d, pf)
+            dist.barrier()
+            per = " ".join(str(int(v)) for v in z["is_per"])
+            sym = " ".join(str(int(v)) for v in z["sym_dir"])
+            out = mgtools.run("grad", ["infile=" + d, "gradVar=temp", "is_per=" + per, "sym_dir=" + sym, "transport=slab",
+                                       "outfile=" + os.path.join(tmp, "gt_" + name)], capi=capi, multigpu=mg, wrap=_wrap_host, backend="gloo", device=0)
+            dist.barrier()
+            if rank == 0:
+                r = plotfile.read_plotfile(out)
+                assert r.names == ["temp", "temp_gx", "temp_gy", "temp_gz", "||gradtemp||"]
+                files = {f for l in range(len(pf.levels)) for f in os.listdir(os.path.join(out, "Level_%d" % l))}
+                assert files == {"Cell_D_00000", "Cell_D_00001", "Cell_H"}, files          # every rank wrote its own boxes
+                assert bit_equal(flat(r, "temp"), z["in_temp"])
+                for k, n in zip(["gx", "gy", "gz", "mag"], r.names[1:]):
+                    assert bit_equal(flat(r, n), z["grad_" + k]), (name, n)
+                from oracle import oracle as O
+                if O.have_ref():                                  # one file per rank: AMReX's fcompare reads it like any plotfile
+                    import subprocess
+                    ref = os.path.join(tmp, "ref_" + name)
+                    O.run_ref("grad", d, ref, gradVar="temp", is_per=list(z["is_per"]), sym_dir=list(z["sym_dir"]))
+                    q = subprocess.run([O.ref_exe("fcompare.ref.ex"), out, ref], capture_output=True, text=True)
+                    assert "PLOTFILE AGREE" in q.stdout, q.stdout[-1500:]
+        # curvature with every option, inputs file instead of key=value arguments
+        pf, z = load_golden("c1_options")
+        d = os.path.join(tmp, "plt_opts")
+        inp = os.path.join(tmp, "inputs.curv")
+        if rank == 0:
+            plotfile.write_plotfile(d, pf)
+            with open(inp, "w") as f:
+                f.write("infile = %s\noutfile = %s  # all options\nprogressName = temp\nis_per = %s\ntransport = slab\n" % (
+                    d, os.path.join(tmp, "K_opts"), " ".join(str(int(v)) for v in z["is_per"])))
+                for kv in z["curv_opts"]:
+                    f.write(str(kv).replace("=", " = ") + "\n")
+        dist.barrier()
+        out = mgtools.run("curvature", [inp], capi=capi, multigpu=mg, wrap=_wrap_host, backend="gloo", device=0)
+        dist.barrier()
+        if rank == 0:
+            r = plotfile.read_plotfile(out)
+            for key in z.files:
+                if key.startswith("curv_") and key != "curv_opts":
+                    n = key[5:]
+                    got = flat(r, n)
+                    if n.startswith("GaussianCurvature"):
+                        assert max_rel(got, z[key]) <= 1e-12
+                    else:
+                        assert bit_equal(got, z[key]), n
+            assert "SmoothedProgress" in r.names
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_emulated_plotfile_tools_world2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0, 0])
+    procs = [ctx.Process(target=_tool_worker, args=(r, 2, port, str(tmp_path), ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+    assert list(ok) == [1, 1], [p.exitcode for p in procs]
+
+
+def test_emulated_plotfile_tool_single_process(tmp_path):
+    """The same tool without torchrun (one rank), against the golden vectors."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import bit_equal, load_golden
+    from peleanalysis_b200 import mgtools, plotfile
+    capi, mg = _load_emulated()
+    old = {k: os.environ.pop(k, None) for k in ("RANK", "WORLD_SIZE")}
+    try:
+        pf, z = load_golden("c1_periodic")
+        d = str(tmp_path / "plt")
+        plotfile.write_plotfile(d, pf)
+        cwd = os.getcwd()
+        os.chdir(tmp_path)
+        try:
+            out = mgtools.run("grad", ["infile=" + d], capi=capi, device=0)
+        finally:
+            os.chdir(cwd)
+        assert out == "plt_gt"                                    # default outfile = <root>_gt in the cwd, like the reference
+        r = plotfile.read_plotfile(str(tmp_path / "plt_gt"))
+        got = np.concatenate([f[r.comp("temp_gx")].ravel() for l in r.levels for f in l.fabs])
+        assert bit_equal(got, z["grad_gx"])
+        from oracle import oracle as O
+        if O.have_ref():                                          # AMReX's own fcompare reads it and agrees with the reference tool
+            import subprocess
+            O.run_ref("grad", d, str(tmp_path / "ref_gt"), gradVar="temp")
+            p = subprocess.run([O.ref_exe("fcompare.ref.ex"), str(tmp_path / "plt_gt"), str(tmp_path / "ref_gt")], capture_output=True, text=True)
+            assert "PLOTFILE AGREE" in p.stdout, p.stdout[-1500:]
+    finally:
+        for k, v in old.items():
+            if v is not None:
+                os.environ[k] = v
