@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "kernels.cuh"
 
@@ -780,6 +781,9 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
 }
 
 int g_num_sms = 0;
+// host-side launch bookkeeping below (ticket table, per-kernel shared-memory attribute, cached device properties) is shared
+// by all host threads of the process; launches from different threads (each on its own stream) serialise on this mutex
+std::mutex g_launch_mutex;
 // work-item ticket counters, one per stream (launches on one stream are ordered, so they can share a counter that is
 // never reset; kernels on different streams may overlap and must not)
 struct Ticket { unsigned long long* dev = nullptr; unsigned long long base = 0; };
@@ -794,6 +798,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     constexpr bool HEAVY = MODE == MODE_NORMAL || MODE == MODE_NORMAL_S;
     constexpr int PER_SM = PF ? per_sm_pf(CW, HEAVY) : Shape<CW, HEAVY>::PER_SM;
     constexpr int THREADS = (CW + 1 + (PF ? 1 : 0)) * 32;
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     const size_t stage_bytes = (size_t)NIN * stage_doubles * sizeof(double);
     // Ring depth.  The consumers hold two planes (p-1 and p); the rest of the ring is data in flight.  Measured on B200
     // (config 2): ~40 KB in flight per SM (~6 MB chip-wide = bandwidth x latency) is the optimum -- a deeper
@@ -968,6 +973,7 @@ cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long lo
 
 int stencil_tma_normal_math() { return g_normal_plain; }
 void stencil_tma_release() {                          // pa_finalize: the per-stream ticket counters
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     for (auto& kv : g_tickets) if (kv.second.dev) cudaFree(kv.second.dev);
     g_tickets.clear();
 }
