@@ -142,6 +142,29 @@ void read_level_comp(const std::string& dir, const Header& h, int lev, int comp,
     if (f) std::fclose(f);
 }
 
+void read_boxes_comp(const std::string& dir, const Header& h, int lev, int comp, const std::vector<int>& box_ids, double* dst) {
+    const LevelMeta& lv = h.levels.at(lev);
+    std::string ldir = dir + "/" + lv.cell_path.substr(0, lv.cell_path.find_last_of('/'));
+    std::string open_name;
+    FILE* f = nullptr;
+    for (int b : box_ids) {
+        if (lv.fab_file.at(b) != open_name) {
+            if (f) std::fclose(f);
+            f = std::fopen((ldir + "/" + lv.fab_file[b]).c_str(), "rb");
+            if (!f) throw std::runtime_error("cannot open " + ldir + "/" + lv.fab_file[b]);
+            open_name = lv.fab_file[b];
+        }
+        std::fseek(f, lv.fab_offset[b], SEEK_SET);
+        int c;
+        while ((c = std::fgetc(f)) != EOF && c != '\n') {}      // ASCII "FAB (...)(box) ncomp" line
+        long long n = lv.boxes[b].npts();
+        std::fseek(f, (long)(8LL * n * comp), SEEK_CUR);
+        if ((long long)std::fread(dst, 8, (size_t)n, f) != n) { std::fclose(f); throw std::runtime_error("short read in " + open_name); }
+        dst += n;
+    }
+    if (f) std::fclose(f);
+}
+
 static std::string g17(double x) { char b[64]; std::snprintf(b, sizeof b, "%.17g", x); return b; }
 static std::string boxstr(const BoxI& b) {
     char s[160];
@@ -149,8 +172,7 @@ static std::string boxstr(const BoxI& b) {
     return s;
 }
 
-void write_plotfile(const std::string& dir, const Header& meta, const std::vector<std::string>& names,
-                    const std::vector<std::vector<const double*>>& data, const std::vector<int>& ref_ratio_line) {
+void create_plotfile_dirs(const std::string& dir, int nlev) {
     struct stat sb;
     if (::stat(dir.c_str(), &sb) == 0) {
         auto t = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
@@ -158,7 +180,43 @@ void write_plotfile(const std::string& dir, const Header& meta, const std::vecto
         if (std::rename(dir.c_str(), old.c_str()) != 0) throw std::runtime_error("cannot rename existing " + dir);
     }
     if (::mkdir(dir.c_str(), 0755) != 0) throw std::runtime_error("cannot create " + dir);
-    const int nlev = (int)data.size();
+    for (int l = 0; l < nlev; ++l) {
+        std::string ldir = dir + "/Level_" + std::to_string(l);
+        if (::mkdir(ldir.c_str(), 0755) != 0) throw std::runtime_error("cannot create " + ldir);
+    }
+}
+
+std::vector<FabRecord> write_fab_file(const std::string& dir, const Header& meta, int lev, const std::string& file,
+                                      const std::vector<int>& box_ids, const std::vector<const double*>& data) {
+    const LevelMeta& lv = meta.levels.at(lev);
+    const int ncomp = (int)data.size();
+    std::vector<FabRecord> recs;
+    if (box_ids.empty()) return recs;
+    FILE* f = std::fopen((dir + "/Level_" + std::to_string(lev) + "/" + file).c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot create " + file);
+    long long cell0 = 0;
+    for (int b : box_ids) {
+        FabRecord r;
+        r.lev = lev; r.box = b; r.file = file; r.offset = std::ftell(f);
+        r.mn.resize(ncomp); r.mx.resize(ncomp);
+        std::fprintf(f, "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))%s %d\n", boxstr(lv.boxes.at(b)).c_str(), ncomp);
+        const long long n = lv.boxes[b].npts();
+        for (int c = 0; c < ncomp; ++c) {
+            const double* p = data[c] + cell0;
+            std::fwrite(p, 8, (size_t)n, f);
+            double a = std::numeric_limits<double>::max(), z = std::numeric_limits<double>::lowest();
+            for (long long q = 0; q < n; ++q) { a = std::min(a, p[q]); z = std::max(z, p[q]); }
+            r.mn[c] = a; r.mx[c] = z;
+        }
+        cell0 += n;
+        recs.push_back(std::move(r));
+    }
+    std::fclose(f);
+    return recs;
+}
+
+void write_metadata(const std::string& dir, const Header& meta, const std::vector<std::string>& names, int nlev,
+                    const std::vector<FabRecord>& records, const std::vector<int>& ref_ratio_line) {
     const int ncomp = (int)names.size();
     {
         std::ofstream h(dir + "/Header");
@@ -189,42 +247,38 @@ void write_plotfile(const std::string& dir, const Header& meta, const std::vecto
     }
     for (int l = 0; l < nlev; ++l) {
         const LevelMeta& lv = meta.levels[l];
-        std::string ldir = dir + "/Level_" + std::to_string(l);
-        if (::mkdir(ldir.c_str(), 0755) != 0) throw std::runtime_error("cannot create " + ldir);
-        FILE* f = std::fopen((ldir + "/Cell_D_00000").c_str(), "wb");
-        if (!f) throw std::runtime_error("cannot create Cell_D");
-        std::vector<long long> offs;
-        std::vector<std::vector<double>> mn(lv.boxes.size(), std::vector<double>(ncomp)), mx = mn;
-        long long cell0 = 0;
-        for (size_t b = 0; b < lv.boxes.size(); ++b) {
-            offs.push_back(std::ftell(f));
-            std::fprintf(f, "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))%s %d\n", boxstr(lv.boxes[b]).c_str(), ncomp);
-            long long n = lv.boxes[b].npts();
-            for (int c = 0; c < ncomp; ++c) {
-                const double* p = data[l][c] + cell0;
-                std::fwrite(p, 8, (size_t)n, f);
-                double a = std::numeric_limits<double>::max(), z = std::numeric_limits<double>::lowest();
-                for (long long q = 0; q < n; ++q) { a = std::min(a, p[q]); z = std::max(z, p[q]); }
-                mn[b][c] = a; mx[b][c] = z;
-            }
-            cell0 += n;
-        }
-        std::fclose(f);
-        std::ofstream c(ldir + "/Cell_H");
+        std::vector<const FabRecord*> of(lv.boxes.size(), nullptr);
+        for (auto& r : records) if (r.lev == l) of.at(r.box) = &r;
+        for (auto* r : of) if (!r) throw std::runtime_error("write_metadata: a box of level " + std::to_string(l) + " was not written");
+        std::ofstream c(dir + "/Level_" + std::to_string(l) + "/Cell_H");
         c << "1\n1\n" << ncomp << "\n0\n(" << lv.boxes.size() << " 0\n";
         for (auto& b : lv.boxes) c << boxstr(b) << '\n';
         c << ")\n" << lv.boxes.size() << '\n';
-        for (auto o : offs) c << "FabOnDisk: Cell_D_00000 " << o << '\n';
+        for (auto* r : of) c << "FabOnDisk: " << r->file << ' ' << r->offset << '\n';
         c << '\n';
-        for (auto* tab : {&mn, &mx}) {
+        for (int which = 0; which < 2; ++which) {
             c << lv.boxes.size() << ',' << ncomp << '\n';
-            for (auto& row : *tab) {
-                for (double v : row) { char s[64]; std::snprintf(s, sizeof s, "%.17e,", v); c << s; }
+            for (auto* r : of) {
+                for (double v : (which ? r->mx : r->mn)) { char s[64]; std::snprintf(s, sizeof s, "%.17e,", v); c << s; }
                 c << '\n';
             }
             c << '\n';
         }
     }
+}
+
+void write_plotfile(const std::string& dir, const Header& meta, const std::vector<std::string>& names,
+                    const std::vector<std::vector<const double*>>& data, const std::vector<int>& ref_ratio_line) {
+    const int nlev = (int)data.size();
+    create_plotfile_dirs(dir, nlev);
+    std::vector<FabRecord> records;
+    for (int l = 0; l < nlev; ++l) {
+        std::vector<int> all(meta.levels[l].boxes.size());
+        for (size_t b = 0; b < all.size(); ++b) all[b] = (int)b;
+        auto r = write_fab_file(dir, meta, l, "Cell_D_00000", all, data[l]);
+        records.insert(records.end(), r.begin(), r.end());
+    }
+    write_metadata(dir, meta, names, nlev, records, ref_ratio_line);
 }
 
 }  // namespace pltio
