@@ -182,6 +182,16 @@ int pa_curvature_steps(pa_field *state, int comp_S, int comp_vel, const pa_curv_
  * variable (3 components, nghost 1).  Owned by the hierarchy; do not free. */
 int pa_curvature_scratch(pa_hier *h, int which, pa_field **f);
 
+/* ---- ranks that share ONE process (one host thread per GPU, e.g. an OpenMP-style host without MPI) -------------------
+ * The calling thread's GPU is the one its pa_init named.  pa_enable_peer_access lets that GPU address a peer GPU's memory
+ * (cudaDeviceEnablePeerAccess); pa_field_slab gives the level slab a peer thread passes to pa_field_map_peer_ptr -- the
+ * same-address-space form of pa_field_ipc_handle / pa_field_map_peer; pa_copy_async is a device-to-device copy on the
+ * calling thread's stream that may cross GPUs (it moves a peer's send slab segment into this rank's recv slab). */
+int pa_enable_peer_access(int peer_device);
+int pa_field_slab(const pa_field *f, int lev, const double **base);
+int pa_field_map_peer_ptr(pa_field *f, int lev, int peer_rank, const double *base);
+int pa_copy_async(double *dst, const double *src, int64_t n);
+
 /* ---- multi-rank ghost exchange (one process per GPU; the transport is the caller's: NCCL send/recv) ---
  * For exchange step `step` of an operation the library packs what each peer needs into a device send slab and
  * unpacks the peer's slab after the caller moved it.  Sizes are in doubles.  Single-rank hierarchies have

@@ -42,6 +42,8 @@ SYMBOLS = {
     "pa_hier_create": (_i, [C.POINTER(_vp), _i, C.POINTER(LevelDesc), C.POINTER(_i), C.POINTER(_i), _i, _i]),
     "pa_hier_create2": (_i, [C.POINTER(_vp), _i, C.POINTER(LevelDesc), C.POINTER(_i), C.POINTER(_i), _i, _i, C.c_uint]),
     "pa_field_ipc_handle": (_i, [_vp, _i, _vp]), "pa_field_map_peer": (_i, [_vp, _i, _i, _vp]),
+    "pa_enable_peer_access": (_i, [_i]), "pa_field_slab": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "pa_field_map_peer_ptr": (_i, [_vp, _i, _i, _vp]), "pa_copy_async": (_i, [_vp, _vp, _i64]),
     "pa_hier_destroy": (_i, [_vp]), "pa_hier_num_levels": (_i, [_vp]), "pa_hier_num_boxes": (_i, [_vp, _i]),
     "pa_hier_num_cells": (_i64, [_vp, _i]), "pa_hier_num_local_cells": (_i64, [_vp, _i]),
     "pa_hier_box_owner": (_i, [_vp, _i, _i]),

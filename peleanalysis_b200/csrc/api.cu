@@ -568,6 +568,15 @@ int pa_field_ipc_handle(const pa_field* f, int lev, void* handle64) {
     return PA_OK;
 }
 
+static int set_peer_base(pa_field* f, int lev, int peer_rank, const double* base) {
+    pa_hier* h = f->h;
+    f->peers_h[lev][peer_rank].base = base;
+    CU(f->peers_d[lev]->upload(f->peers_h[lev], t_stream));
+    CU(cudaStreamSynchronize(t_stream));
+    if (h->H.peer_links && f->peers_missing > 0) --f->peers_missing;
+    return PA_OK;
+}
+
 int pa_field_map_peer(pa_field* f, int lev, int peer_rank, const void* handle64) {
     if (!f || !handle64 || lev < 0 || lev >= f->h->H.nlev || peer_rank < 0 || peer_rank >= f->h->H.nranks)
         return fail(PA_ERR_ARG, "pa_field_map_peer: bad argument");
@@ -581,10 +590,35 @@ int pa_field_map_peer(pa_field* f, int lev, int peer_rank, const void* handle64)
     void* p = nullptr;
     CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
     f->ipc_mapped.push_back(p);
-    S.base = (const double*)p;
-    CU(f->peers_d[lev]->upload(f->peers_h[lev], t_stream));
-    CU(cudaStreamSynchronize(t_stream));
-    if (h->H.peer_links && f->peers_missing > 0) --f->peers_missing;
+    return set_peer_base(f, lev, peer_rank, (const double*)p);
+}
+
+// ---- the same for ranks that live in ONE process (one host thread per GPU): no IPC, the peer's pointer is valid here --
+int pa_enable_peer_access(int peer_device) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return PA_OK; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return PA_OK;
+}
+int pa_field_slab(const pa_field* f, int lev, const double** base) {
+    if (!f || !base || lev < 0 || lev >= f->h->H.nlev) return fail(PA_ERR_ARG, "pa_field_slab: bad argument");
+    *base = f->slab[lev];
+    return PA_OK;
+}
+int pa_field_map_peer_ptr(pa_field* f, int lev, int peer_rank, const double* base) {
+    if (!f || lev < 0 || lev >= f->h->H.nlev || peer_rank < 0 || peer_rank >= f->h->H.nranks)
+        return fail(PA_ERR_ARG, "pa_field_map_peer_ptr: bad argument");
+    if (peer_rank == f->h->H.rank) return PA_OK;
+    PaPeerSlab& S = f->peers_h[lev][peer_rank];
+    if (S.cs == 0) return PA_OK;                       // the peer owns no box of this level
+    if (!base) return fail(PA_ERR_ARG, "pa_field_map_peer_ptr: the peer owns boxes of this level but gave no slab");
+    if (S.base) return fail(PA_ERR_STATE, "pa_field_map_peer_ptr: this (level, rank) is already mapped");
+    return set_peer_base(f, lev, peer_rank, base);
+}
+int pa_copy_async(double* dst, const double* src, int64_t n) {
+    if (n <= 0) return PA_OK;
+    if (!dst || !src) return fail(PA_ERR_ARG, "pa_copy_async: null pointer");
+    CU(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDefault, t_stream));
     return PA_OK;
 }
 

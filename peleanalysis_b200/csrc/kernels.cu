@@ -1,13 +1,14 @@
 // kernels.cu -- hand-written sm_100a kernels of the ghost fill and the pointwise / simple stencil passes.
 // Compiled with -fmad=false: every floating-point expression below is evaluated in the reference's order with
 // separate IEEE multiplies and adds (the reference CPU build has no FMA), so results are bit-identical.
+#include <atomic>
 #include <cstdint>
 
 #include "kernels.cuh"
 
 namespace pa {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 #define PA_NAN __longlong_as_double(0x7ff8000000000000LL)
 

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "pa_types.h"
 
 // Kernel launch and dynamic shared memory, spelled as macros so that tests/emu can compile these same sources for its
@@ -66,7 +68,7 @@ struct StencilExtra {
     double pmin, inv;
 };
 
-extern long long g_launches;     // kernels launched by this library
+extern std::atomic<long long> g_launches;     // kernels launched by this library (host threads may launch concurrently)
 
 cudaError_t launch_unpack_valid(const PaBoxDev* boxes, const PaLayDev* lay, const long long* host_off, int nboxes,
                                 long long ncells, const double* staging, double* comp_base, cudaStream_t st);

@@ -787,7 +787,7 @@ std::mutex g_launch_mutex;
 // work-item ticket counters, one per stream (launches on one stream are ordered, so they can share a counter that is
 // never reset; kernels on different streams may overlap and must not)
 struct Ticket { unsigned long long* dev = nullptr; unsigned long long base = 0; };
-std::map<cudaStream_t, Ticket> g_tickets;
+std::map<std::pair<int, cudaStream_t>, Ticket> g_tickets;         // (device, stream): host threads may drive several GPUs
 int g_stage_cap = 0;
 size_t g_inflight_bytes = 0;
 
@@ -815,21 +815,21 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     if (g_stage_cap == 0) { const char* e = getenv("PA_TMA_STAGES"); g_stage_cap = e ? std::max(3, atoi(e)) : MAX_STAGES; }
     if (S > g_stage_cap) S = g_stage_cap;
     const size_t smem = (size_t)S * stage_bytes;
-    static size_t configured = 0;
-    if (smem > configured) {
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    static std::map<int, size_t> configured;                          // per device: the attribute lives in the device's context
+    if (smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW, PLAIN, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     if (g_num_sms == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
     }
     const long long nwork = (long long)ntiles * nvar;
     const int grid = (int)std::min<long long>(nwork, (long long)g_num_sms * per_sm);
-    Ticket& T = g_tickets[st];
+    Ticket& T = g_tickets[std::make_pair(dev, st)];
     if (!T.dev) {
         cudaError_t e = cudaMalloc(&T.dev, sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));

@@ -2,9 +2,11 @@
 // same output variable names; the operator block (grad.cpp:151-236) is the C ABI of libpelestencil_b200.
 //
 //   grad3d.b200.ex infile=<plotfile> [gradVar=temp] [finestLevel=N] [Aux_Variables=a b ...] [is_per=1 1 1]
-//                  [sym_dir=0 0 0] [outfile=<name>]          extension: gradVars=a b c  (several variables, one pass)
+//                  [sym_dir=0 0 0] [outfile=<name>]          extensions: gradVars=a b c  (several variables, one pass)
+//                                                                        ngpus=N  (one host thread per GPU, multi_gpu.hpp)
 #include <chrono>
 
+#include "multi_gpu.hpp"
 #include "tool_common.hpp"
 
 static void print_usage(char** argv) {
@@ -47,6 +49,21 @@ int main(int argc, char** argv) {
     for (int d = 0; d < 3; ++d) std::cout << is_per[d] << " ";
     std::cout << "\n";
 
+    int ngpus = 1;
+    pp.query("ngpus", ngpus);
+    if (ngpus > 1) {
+        GradJob J;
+        J.infile = infile; J.H = &H; J.Nlev = Nlev; J.gvars = gvars; J.aux = aux; J.is_per = is_per;
+        for (int d = 0; d < 3; ++d) J.bck[d] = sym_dir[d] ? PA_BC_REFLECT_ODD : PA_BC_NEUMANN;
+        for (auto& v : gvars) J.names.push_back(v);
+        for (auto& a : aux) J.names.push_back(a);
+        for (auto& v : gvars) { J.names.push_back(v + "_gx"); J.names.push_back(v + "_gy"); J.names.push_back(v + "_gz"); J.names.push_back("||grad" + v + "||"); }
+        J.outfile = file_root(infile) + "_gt";
+        pp.query("outfile", J.outfile);
+        std::cout << "Writing new data to " << J.outfile << std::endl;
+        run_grad_multi(ngpus, J);
+        return 0;
+    }
     auto t0 = std::chrono::steady_clock::now();
     check(pa_init(0), "pa_init");
     HierInput hi;

@@ -18,3 +18,6 @@ PY
 timeout -s KILL 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 -m peleanalysis_b200.mgtools grad infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_gt_n2 > $O/r2b_mgtools.log 2>&1; echo "rc=$?" >> $O/r2b_mgtools.log
 peleanalysis_b200/host/grad3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_gt_n1 >> $O/r2b_mgtools.log 2>&1
 oracle/_ref/fcompare.ref.ex gpurun_out/r2b_gt_n2 gpurun_out/r2b_gt_n1 2>&1 | tail -3 | tee -a $O/r2b_mgtools.log
+# the C++ executable with one host thread per GPU (first run on hardware)
+peleanalysis_b200/host/grad3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_gt_threads ngpus=2 >> $O/r2b_mgtools.log 2>&1; echo "threads rc=$?" >> $O/r2b_mgtools.log
+oracle/_ref/fcompare.ref.ex gpurun_out/r2b_gt_threads gpurun_out/r2b_gt_n1 2>&1 | tail -3 | tee -a $O/r2b_mgtools.log

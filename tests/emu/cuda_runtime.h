@@ -47,12 +47,12 @@ inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; r
 
 enum cudaError_t {
     cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorInvalidConfiguration = 9,
-    cudaErrorNotSupported = 801
+    cudaErrorPeerAccessAlreadyEnabled = 704, cudaErrorNotSupported = 801
 };
 typedef struct CUstream_st* cudaStream_t;
 typedef struct CUevent_st* cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
-enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaHostAllocDefault = 0, cudaHostRegisterDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
@@ -71,6 +71,7 @@ const char* cudaGetErrorString(cudaError_t e);
 cudaError_t cudaGetLastError();
 cudaError_t cudaGetDeviceCount(int* n);
 cudaError_t cudaSetDevice(int d);
+cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
 cudaError_t cudaGetDevice(int* d);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int d);
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int d);

@@ -15,6 +15,7 @@
 
 #include <cstdio>
 #include <map>
+#include <mutex>
 #include <sys/mman.h>
 #include <vector>
 
@@ -162,11 +163,15 @@ void run_block() {
 unsigned char* dyn_smem() { return dyn_aligned; }
 
 // ---- streams: created streams may defer their work to the latest point the events allow ---------------------------
+// The emulator itself is single-threaded (one set of fibers); host threads that drive different "GPUs" -- the one-process,
+// one-thread-per-GPU hosts -- serialise on this lock, one whole kernel launch at a time.
+static std::recursive_mutex g_emu_mutex;
 namespace {
 std::map<cudaStream_t, std::vector<std::function<void()>>> created_streams;
 std::map<cudaEvent_t, cudaStream_t> event_stream;
 bool defer_side() { const char* e = getenv("CUEMU_DEFER_SIDE"); return e && e[0] == '1'; }
 void flush_stream(cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> lock(g_emu_mutex);
     auto it = created_streams.find(st);
     if (it == created_streams.end()) return;
     std::vector<std::function<void()>> q;
@@ -175,6 +180,7 @@ void flush_stream(cudaStream_t st) {
 }
 }  // namespace
 void submit(cudaStream_t st, std::function<void()> work) {
+    std::lock_guard<std::recursive_mutex> lock(g_emu_mutex);
     auto it = created_streams.find(st);
     if (it != created_streams.end() && defer_side()) it->second.push_back(std::move(work));
     else work();
@@ -290,9 +296,11 @@ const char* cudaGetErrorString(cudaError_t e) {
     }
 }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("CUEMU_DEVICES"); *n = e ? std::max(1, atoi(e)) : 1; return cudaSuccess; }
+static thread_local int t_device = 0;                 // like CUDA: the current device is a property of the host thread
+cudaError_t cudaSetDevice(int d) { t_device = d; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = t_device; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; std::strcpy(p->name, "cuemu"); return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { const char* e = getenv("CUEMU_SMS"); *v = e ? std::max(1, atoi(e)) : 2; return cudaSuccess; }
 cudaError_t cudaMallocBytes(void** p, size_t n) {
@@ -328,16 +336,21 @@ cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t st) {
 }
 cudaError_t cudaStreamSynchronize(cudaStream_t st) { cuemu::flush_stream(st); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned) {
+    std::lock_guard<std::recursive_mutex> lock(cuemu::g_emu_mutex);
     *st = (cudaStream_t)std::malloc(8);
     cuemu::created_streams[*st];
     return cudaSuccess;
 }
-cudaError_t cudaStreamDestroy(cudaStream_t st) { cuemu::flush_stream(st); cuemu::created_streams.erase(st); std::free(st); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> lock(cuemu::g_emu_mutex);
+    cuemu::flush_stream(st); cuemu::created_streams.erase(st); std::free(st); return cudaSuccess;
+}
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* ev, unsigned) { *ev = (cudaEvent_t)std::malloc(8); return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t ev) { cuemu::event_stream.erase(ev); std::free(ev); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t ev) { std::lock_guard<std::recursive_mutex> lock(cuemu::g_emu_mutex); cuemu::event_stream.erase(ev); std::free(ev); return cudaSuccess; }
 // an event recorded in a deferring stream completes only when that stream's queue has run: whoever waits for it runs it
-cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t st) { cuemu::event_stream[ev] = st; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t st) { std::lock_guard<std::recursive_mutex> lock(cuemu::g_emu_mutex); cuemu::event_stream[ev] = st; return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t ev, unsigned) {
+    std::lock_guard<std::recursive_mutex> lock(cuemu::g_emu_mutex);
     auto it = cuemu::event_stream.find(ev);
     if (it != cuemu::event_stream.end()) cuemu::flush_stream(it->second);
     return cudaSuccess;

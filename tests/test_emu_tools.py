@@ -25,9 +25,9 @@ def emu_exes():
     for name, main in (("grad3d.emu.ex", "grad_main.cpp"), ("curvature3d.emu.ex", "curvature_main.cpp")):
         exe = os.path.join(out, name)
         srcs = [os.path.join(host, main), os.path.join(host, "plotfile.cpp")]
-        deps = srcs + [lib] + [os.path.join(host, f) for f in ("plotfile.hpp", "tool_common.hpp", "parmparse.hpp")]
+        deps = srcs + [lib] + [os.path.join(host, f) for f in ("plotfile.hpp", "tool_common.hpp", "parmparse.hpp", "multi_gpu.hpp")]
         if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-            subprocess.check_call(["g++", "-O1", "-std=c++17", *srcs, "-o", exe, "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", *srcs, "-o", exe, "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
         exes.append(exe)
     old = os.environ.get("PA_NORMAL_MATH")
     os.environ["PA_NORMAL_MATH"] = "fast"        # the emulator has no MUFU; see tests/test_emu_parity.py
@@ -50,3 +50,38 @@ def test_emulated_grad_executable_aux_and_inputs_file(emu_exes, tmp_path):
 @pytest.mark.parametrize("name", ["c1_periodic", "c3_threshold", "c1_options", "mixed_boxes"])
 def test_emulated_curvature_executable(emu_exes, tmp_path, name):
     T.test_curvature_executable(emu_exes, tmp_path, name)
+
+
+@pytest.mark.parametrize("name,ngpus", [("c1_periodic", 2), ("c3_three_levels", 2), ("mixed_boxes", 3), ("lshape", 4), ("c1_corner_sym", 2)])
+def test_emulated_grad_executable_multi_gpu(emu_exes, tmp_path, name, ngpus):
+    """grad3d ... ngpus=N: one host thread per (emulated) GPU in one process -- same-process peer links, slab copies between
+    the threads' slabs, one Cell_D file per thread; the output equals the reference's golden vectors and AMReX's fcompare
+    agrees with the reference executable's plotfile."""
+    import numpy as np
+    from helpers import bit_equal, load_golden
+    from oracle import oracle as O
+    from peleanalysis_b200 import plotfile
+    pf, z = load_golden(name)
+    d = str(tmp_path / "plt")
+    plotfile.write_plotfile(d, pf)
+    per = " ".join(str(int(v)) for v in z["is_per"])
+    sym = " ".join(str(int(v)) for v in z["sym_dir"])
+    env = dict(os.environ, CUEMU_DEVICES=str(ngpus), CUEMU_SEED="9")
+    p = subprocess.run([emu_exes[0], "infile=" + d, "gradVar=temp", "is_per=" + per, "sym_dir=" + sym, "ngpus=%d" % ngpus],
+                       capture_output=True, text=True, cwd=str(tmp_path), env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    r = plotfile.read_plotfile(str(tmp_path / "plt_gt"))
+    assert r.names == ["temp", "temp_gx", "temp_gy", "temp_gz", "||gradtemp||"]
+
+    def flat(n):
+        c = r.comp(n)
+        return np.concatenate([f[c].ravel() for l in r.levels for f in l.fabs])
+    assert bit_equal(flat("temp"), z["in_temp"])
+    for k, n in zip(["gx", "gy", "gz", "mag"], r.names[1:]):
+        assert bit_equal(flat(n), z["grad_" + k]), (name, n)
+    files = {f for l in range(len(pf.levels)) for f in os.listdir(str(tmp_path / "plt_gt" / ("Level_%d" % l)))}
+    assert len([f for f in files if f.startswith("Cell_D_")]) >= 2
+    if O.have_ref():
+        O.run_ref("grad", d, str(tmp_path / "ref_gt"), gradVar="temp", is_per=list(z["is_per"]), sym_dir=list(z["sym_dir"]))
+        q = subprocess.run([O.ref_exe("fcompare.ref.ex"), str(tmp_path / "plt_gt"), str(tmp_path / "ref_gt")], capture_output=True, text=True)
+        assert "PLOTFILE AGREE" in q.stdout, q.stdout[-1500:]
