@@ -1,9 +1,11 @@
 // curvature3d.b200.ex -- drop-in for PeleAnalysis' curvature tool (R/Src/curvature.cpp): same ParmParse keys, plotfile
 // in/out and output names; progress variable, flame normal, mean curvature and the optional Gaussian curvature /
 // strain rate / normal velocity branches run through the C ABI.  do_smooth is the one key not served (it needs a
-// multigrid solve): the shell aborts if it is set.
+// multigrid solve): the shell aborts if it is set.  Extension: ngpus=N runs on N GPUs from this one process, one host thread
+// per GPU (multi_gpu.hpp).
 #include <algorithm>
 
+#include "multi_gpu.hpp"
 #include "tool_common.hpp"
 
 int main(int argc, char** argv) {
@@ -80,17 +82,53 @@ int main(int argc, char** argv) {
     for (int d = 0; d < 3; ++d) std::cout << is_per[d] << " ";
     std::cout << "\n";
 
-    check(pa_init(0), "pa_init");
-    HierInput hi;
-    make_level_descs(H, Nlev, hi);
     int bck[3];
     for (int d = 0; d < 3; ++d) bck[d] = sym_dir[d] ? PA_BC_REFLECT_ODD : PA_BC_NEUMANN;
-    pa_hier* h = nullptr;
-    check(pa_hier_create(&h, Nlev, hi.lv.data(), is_per.data(), bck, 0, 1), "pa_hier_create");
     pa_curv_opts o{};
     o.prog_min = progMin; o.prog_max = progMax; o.do_threshold = do_threshold; o.threshold = threshold;
     o.do_gauss = do_gaussCurv; o.do_strain = do_strain; o.get_strain_tensor = getStrainTensor; o.do_velnormal = do_velnormal;
     const int nres = pa_curvature_num_outputs(&o);
+    // result component -> output slot, and the output names (curvature.cpp:794-829)
+    std::vector<int> slot{idProg, idKm, idN, idN + 1, idN + 2};
+    if (do_gaussCurv) slot.push_back(idKg);
+    if (do_strain) slot.push_back(idSR);
+    if (do_strain && getStrainTensor) for (int i = 0; i < 9; ++i) slot.push_back(idROST + i);
+    if (do_velnormal) slot.push_back(idVelNormal);
+    std::vector<std::string> names(nCompOut);
+    for (int i = 0; i < nCompIn; ++i) names[i] = inNames[i];
+    names[idProg] = "Progress"; names[idSmProg] = "SmoothedProgress"; names[idKm] = "MeanCurvature_" + progressName;
+    names[idN] = "FlameNormalX_" + progressName; names[idN + 1] = "FlameNormalY_" + progressName; names[idN + 2] = "FlameNormalZ_" + progressName;
+    names[idKg] = "GaussianCurvature_" + progressName;
+    if (do_strain) names[idSR] = "StrainRate_" + progressName;
+    if (getStrainTensor) {
+        const char* dc[3] = {"x", "y", "z"};
+        for (int i = 0; i < 9; ++i) names[idROST + i] = std::string("ROST_dU") + dc[i / 3] + "d" + dc[i % 3];
+    }
+    if (do_velnormal) names[idVelNormal] = "VelFlameNormal";
+    // SmoothedProgress (do_smooth off) and GaussianCurvature (do_gaussCurv off) are never written by the reference
+    // (uninitialised memory there); they are written as zeros here.
+    std::vector<int> zero_slots{idSmProg};
+    if (!do_gaussCurv) zero_slots.push_back(idKg);
+    if (getStrainTensor && !do_strain) for (int i = 0; i < 9; ++i) zero_slots.push_back(idROST + i);
+
+    int ngpus = 1;
+    pp.query("ngpus", ngpus);
+    if (ngpus > 1) {
+        CurvJob J;
+        J.infile = plotFileName; J.outfile = outfile; J.H = &H; J.Nlev = Nlev;
+        J.inNames = inNames; J.velNames = velNames; J.names = names; J.need_vel = need_vel; J.o = o;
+        J.slot = slot; J.zero_slots = zero_slots; J.nCompOut = nCompOut; J.is_per = is_per;
+        for (int d = 0; d < 3; ++d) J.bck[d] = bck[d];
+        std::cout << "Writing new data to " << outfile << "\n";
+        run_curv_multi(ngpus, J);
+        return 0;
+    }
+
+    check(pa_init(0), "pa_init");
+    HierInput hi;
+    make_level_descs(H, Nlev, hi);
+    pa_hier* h = nullptr;
+    check(pa_hier_create(&h, Nlev, hi.lv.data(), is_per.data(), bck, 0, 1), "pa_hier_create");
     pa_field *st = nullptr, *res = nullptr;
     check(pa_field_alloc(h, need_vel ? 4 : 1, 1, &st), "pa_field_alloc");
     check(pa_field_alloc(h, nres, 1, &res), "pa_field_alloc");
@@ -111,33 +149,12 @@ int main(int argc, char** argv) {
         }
     }
     check(pa_curvature(st, 0, 1, &o, res, 0), "pa_curvature");
-    // result component -> output slot
-    std::vector<int> slot{idProg, idKm, idN, idN + 1, idN + 2};
-    if (do_gaussCurv) slot.push_back(idKg);
-    if (do_strain) slot.push_back(idSR);
-    if (do_strain && getStrainTensor) for (int i = 0; i < 9; ++i) slot.push_back(idROST + i);
-    if (do_velnormal) slot.push_back(idVelNormal);
     for (int l = 0; l < Nlev; ++l) {
-        // SmoothedProgress (do_smooth off) and GaussianCurvature (do_gaussCurv off) are never written by the reference
-        // (uninitialised memory there); they are written as zeros here.
-        std::fill(buf[l].comp(idSmProg), buf[l].comp(idSmProg) + buf[l].ncells, 0.0);
-        if (!do_gaussCurv) std::fill(buf[l].comp(idKg), buf[l].comp(idKg) + buf[l].ncells, 0.0);
-        if (getStrainTensor && !do_strain) for (int i = 0; i < 9; ++i) std::fill(buf[l].comp(idROST + i), buf[l].comp(idROST + i) + buf[l].ncells, 0.0);
+        for (int z : zero_slots) std::fill(buf[l].comp(z), buf[l].comp(z) + buf[l].ncells, 0.0);
         for (int c = 0; c < nres; ++c) check(pa_field_download_level(res, l, c, buf[l].comp(slot[c])), "download");
     }
     check(pa_sync(), "pa_sync");
 
-    std::vector<std::string> names(nCompOut);
-    for (int i = 0; i < nCompIn; ++i) names[i] = inNames[i];
-    names[idProg] = "Progress"; names[idSmProg] = "SmoothedProgress"; names[idKm] = "MeanCurvature_" + progressName;
-    names[idN] = "FlameNormalX_" + progressName; names[idN + 1] = "FlameNormalY_" + progressName; names[idN + 2] = "FlameNormalZ_" + progressName;
-    names[idKg] = "GaussianCurvature_" + progressName;
-    if (do_strain) names[idSR] = "StrainRate_" + progressName;
-    if (getStrainTensor) {
-        const char* dc[3] = {"x", "y", "z"};
-        for (int i = 0; i < 9; ++i) names[idROST + i] = std::string("ROST_dU") + dc[i / 3] + "d" + dc[i % 3];
-    }
-    if (do_velnormal) names[idVelNormal] = "VelFlameNormal";
     std::cout << "Writing new data to " << outfile << "\n";
     std::vector<std::vector<const double*>> data(Nlev);
     for (int l = 0; l < Nlev; ++l) for (int c = 0; c < nCompOut; ++c) data[l].push_back(buf[l].comp(c));

@@ -34,12 +34,50 @@ struct MultiShared {
     int n;
     ThreadBarrier bar;
     std::mutex mu;
-    std::vector<std::vector<const double*>> slab;      // [rank][level]: input field slabs, published for the peers
+    std::vector<std::vector<const double*>> slab;      // [rank][level] (grad) / [rank][field * nlev + level]: level slabs, published for the peers
     std::vector<double*> send;                         // [rank]: send slab
     std::vector<std::vector<int64_t>> soff;            // [rank][peer .. ]: offsets into it
     std::vector<pltio::FabRecord> records;             // what every thread wrote
     long long launches = 0;
 };
+
+// every thread publishes the level slabs of its fields, then maps everyone else's (collective: all threads call it with the
+// same number of fields in the same order)
+inline void map_all_peers(int r, MultiShared& M, int nlev, const std::vector<pa_field*>& fields) {
+    M.slab[r].assign(fields.size() * nlev, nullptr);
+    for (size_t f = 0; f < fields.size(); ++f)
+        for (int l = 0; l < nlev; ++l) check(pa_field_slab(fields[f], l, &M.slab[r][f * nlev + l]), "pa_field_slab");
+    M.bar.wait();
+    for (int p = 0; p < M.n; ++p)
+        if (p != r)
+            for (size_t f = 0; f < fields.size(); ++f)
+                for (int l = 0; l < nlev; ++l) check(pa_field_map_peer_ptr(fields[f], l, p, M.slab[p][f * nlev + l]), "pa_field_map_peer_ptr");
+    M.bar.wait();
+}
+
+// The cross-rank step in front of a ghost fill (collective): what the neighbour links do not cover -- ragged same-level
+// neighbours, coarse cells of coarse-fine faces owned by another rank -- moves as packed slabs.  Its first barrier is also the
+// ordering point peer links need: every rank has finished (pa_sync) whatever wrote the data its peers are about to read.
+inline void exchange_slabs(int r, MultiShared& M, pa_field* f, int comp, int ncomp) {
+    const int n = M.n;
+    double *send = nullptr, *recv = nullptr;
+    std::vector<int64_t> so(n + 1), ro(n + 1);
+    check(pa_exchange_buffers(f, ncomp, &send, &recv, so.data(), ro.data()), "pa_exchange_buffers");
+    check(pa_exchange_pack(f, comp, ncomp), "pa_exchange_pack");
+    check(pa_sync(), "pa_sync");
+    M.send[r] = send;
+    M.soff[r] = so;
+    M.bar.wait();
+    for (int p = 0; p < n; ++p) {
+        if (p == r) continue;
+        const int64_t cnt = ro[p + 1] - ro[p];
+        if (cnt != M.soff[p][r + 1] - M.soff[p][r]) pa_abort("multi-GPU exchange plan: send / recv counts disagree");
+        if (cnt > 0) check(pa_copy_async(recv + ro[p], M.send[p] + M.soff[p][r], cnt), "pa_copy_async");
+    }
+    check(pa_exchange_mark_received(f, comp, ncomp), "pa_exchange_mark_received");
+    check(pa_sync(), "pa_sync");
+    M.bar.wait();                                      // the send slabs may be repacked from here on
+}
 
 struct GradJob {
     std::string infile, outfile;
@@ -86,27 +124,8 @@ inline void grad_rank(int r, MultiShared& M, const GradJob& J) {
     }
     check(pa_sync(), "pa_sync");
 
-    // peers: every thread publishes its slabs, then maps everyone else's
-    M.slab[r].resize(Nlev);
-    for (int l = 0; l < Nlev; ++l) check(pa_field_slab(fin, l, &M.slab[r][l]), "pa_field_slab");
-    double *send = nullptr, *recv = nullptr;
-    std::vector<int64_t> so(n + 1), ro(n + 1);
-    check(pa_exchange_buffers(fin, nv, &send, &recv, so.data(), ro.data()), "pa_exchange_buffers");
-    check(pa_exchange_pack(fin, 0, nv), "pa_exchange_pack");        // what the links do not cover: ragged neighbours, coarse cells of c-f faces
-    check(pa_sync(), "pa_sync");
-    M.send[r] = send;
-    M.soff[r] = so;
-    M.bar.wait();                                                     // every rank's inputs and send slab are complete
-    for (int p = 0; p < n; ++p)
-        if (p != r)
-            for (int l = 0; l < Nlev; ++l) check(pa_field_map_peer_ptr(fin, l, p, M.slab[p][l]), "pa_field_map_peer_ptr");
-    for (int p = 0; p < n; ++p) {
-        if (p == r) continue;
-        const int64_t cnt = ro[p + 1] - ro[p];
-        if (cnt != M.soff[p][r + 1] - M.soff[p][r]) pa_abort("multi-GPU exchange plan: send / recv counts disagree");
-        if (cnt > 0) check(pa_copy_async(recv + ro[p], M.send[p] + M.soff[p][r], cnt), "pa_copy_async");
-    }
-    check(pa_exchange_mark_received(fin, 0, nv), "pa_exchange_mark_received");
+    map_all_peers(r, M, Nlev, {fin});
+    exchange_slabs(r, M, fin, 0, nv);
 
     check(pa_grad(fin, 0, nv, fout, 0), "pa_grad");
     for (int l = 0; l < Nlev; ++l)
@@ -133,16 +152,21 @@ inline void grad_rank(int r, MultiShared& M, const GradJob& J) {
     M.bar.wait();
 }
 
+inline std::vector<std::vector<int>> sfc_owners(const pltio::Header& H, int Nlev, int ngpus) {
+    std::vector<std::vector<int>> owner(Nlev);
+    for (int l = 0; l < Nlev; ++l) {
+        std::vector<int> bx;
+        for (auto& b : H.levels[l].boxes) { for (int d = 0; d < 3; ++d) bx.push_back(b.lo[d]); for (int d = 0; d < 3; ++d) bx.push_back(b.hi[d]); }
+        owner[l].resize(H.levels[l].boxes.size());
+        check(pa_sfc_distribute((int)H.levels[l].boxes.size(), bx.data(), ngpus, owner[l].data()), "pa_sfc_distribute");
+    }
+    return owner;
+}
+
 // returns after the output plotfile is complete
 inline void run_grad_multi(int ngpus, GradJob& J) {
     const pltio::Header& H = *J.H;
-    J.owner.resize(J.Nlev);
-    for (int l = 0; l < J.Nlev; ++l) {
-        std::vector<int> bx;
-        for (auto& b : H.levels[l].boxes) { for (int d = 0; d < 3; ++d) bx.push_back(b.lo[d]); for (int d = 0; d < 3; ++d) bx.push_back(b.hi[d]); }
-        J.owner[l].resize(H.levels[l].boxes.size());
-        check(pa_sfc_distribute((int)H.levels[l].boxes.size(), bx.data(), ngpus, J.owner[l].data()), "pa_sfc_distribute");
-    }
+    J.owner = sfc_owners(H, J.Nlev, ngpus);
     try { pltio::create_plotfile_dirs(J.outfile, J.Nlev); } catch (std::exception& e) { pa_abort(e.what()); }
     MultiShared M(ngpus);
     std::vector<std::thread> th;
@@ -153,5 +177,120 @@ inline void run_grad_multi(int ngpus, GradJob& J) {
     std::vector<int> rr(std::max(J.Nlev - 1, 0), 2);              // the reference hard-codes refRatios = 2 (grad.cpp:255)
     pltio::Header meta = H;
     meta.time = 0.0;                                               // WriteMultiLevelPlotfile(..., 0.0, ...) (grad.cpp:256)
+    try { pltio::write_metadata(J.outfile, meta, J.names, J.Nlev, M.records, rr); } catch (std::exception& e) { pa_abort(e.what()); }
+}
+
+// ---- curvature: the steps of pa_curvature_steps with the cross-rank step each one needs in front of it ---------------------
+struct CurvJob {
+    std::string infile, outfile;
+    const pltio::Header* H;
+    int Nlev;
+    std::vector<std::string> inNames, velNames, names;   // pass-through inputs (progress variable first), velocities, output names
+    bool need_vel;
+    pa_curv_opts o;
+    std::vector<int> slot;                               // library result component -> output slot
+    std::vector<int> zero_slots;                         // output slots nothing writes (the reference leaves them uninitialised)
+    int nCompOut;
+    std::vector<int> is_per;
+    int bck[3];
+    std::vector<std::vector<int>> owner;
+};
+
+inline void curv_rank(int r, MultiShared& M, const CurvJob& J) {
+    const pltio::Header& H = *J.H;
+    const int n = M.n, Nlev = J.Nlev, nCompIn = (int)J.inNames.size();
+    check(pa_init(r), "pa_init");
+    for (int p = 0; p < n; ++p) if (p != r) check(pa_enable_peer_access(p), "pa_enable_peer_access");
+    HierInput hi;
+    make_level_descs(H, Nlev, hi);
+    std::vector<std::vector<int>> own(Nlev), mine(Nlev);
+    for (int l = 0; l < Nlev; ++l) {
+        own[l] = J.owner[l];
+        hi.lv[l].owner = own[l].data();
+        for (int b = 0; b < (int)own[l].size(); ++b) if (own[l][b] == r) mine[l].push_back(b);
+    }
+    pa_hier* h = nullptr;
+    check(pa_hier_create2(&h, Nlev, hi.lv.data(), J.is_per.data(), J.bck, r, n, PA_HIER_PEER_LINKS), "pa_hier_create2");
+    const int nres = pa_curvature_num_outputs(&J.o);
+    pa_field *st = nullptr, *res = nullptr, *scratch = nullptr;
+    check(pa_field_alloc(h, J.need_vel ? 4 : 1, 1, &st), "pa_field_alloc");
+    check(pa_field_alloc(h, nres, 1, &res), "pa_field_alloc");
+    if (J.o.do_gauss) check(pa_curvature_scratch(h, 0, &scratch), "pa_curvature_scratch");
+
+    std::vector<PinnedLevel> buf(Nlev), velbuf(Nlev);
+    for (int l = 0; l < Nlev; ++l) {
+        long long nc = 0;
+        for (int b : mine[l]) nc += H.levels[l].boxes[b].npts();
+        buf[l].alloc(std::max<long long>(nc, 1), J.nCompOut);
+        buf[l].ncells = nc;
+        if (J.need_vel) { velbuf[l].alloc(std::max<long long>(nc, 1), 3); velbuf[l].ncells = nc; }
+        if (mine[l].empty()) continue;
+        for (int c = 0; c < nCompIn; ++c) pltio::read_boxes_comp(J.infile, H, l, H.comp(J.inNames[c]), mine[l], buf[l].p + (long long)c * std::max<long long>(nc, 1));
+        check(pa_field_upload_level(st, l, 0, buf[l].p), "upload");
+        if (J.need_vel)
+            for (int d = 0; d < 3; ++d) {
+                double* v = velbuf[l].p + (long long)d * std::max<long long>(nc, 1);
+                pltio::read_boxes_comp(J.infile, H, l, H.comp(J.velNames[d]), mine[l], v);
+                check(pa_field_upload_level(st, l, 1 + d, v), "upload");
+            }
+    }
+    check(pa_sync(), "pa_sync");
+    std::vector<pa_field*> fields{st, res};
+    if (scratch) fields.push_back(scratch);
+    map_all_peers(r, M, Nlev, fields);
+
+    auto step = [&](int steps, int lo, int hi) { check(pa_curvature_steps(st, 0, 1, &J.o, res, 0, steps, lo, hi), "pa_curvature_steps"); };
+    exchange_slabs(r, M, st, 0, 1);
+    step(PA_CURV_PASS1, -1, -1);
+    if (J.o.do_threshold) {
+        for (int l = 0; l < Nlev; ++l) { exchange_slabs(r, M, res, 2, 3); step(PA_CURV_DIV, l, l); }
+    } else {
+        exchange_slabs(r, M, res, 2, 3);
+        step(PA_CURV_DIV, -1, -1);
+    }
+    if (J.o.do_gauss) { exchange_slabs(r, M, scratch, 0, 3); step(PA_CURV_GAUSS, -1, -1); }
+    if (J.o.do_strain) { exchange_slabs(r, M, st, 1, 3); step(PA_CURV_STRAIN, -1, -1); }
+    if (J.o.do_velnormal) step(PA_CURV_VELN, -1, -1);
+
+    for (int l = 0; l < Nlev; ++l) {
+        const long long stride = std::max<long long>(buf[l].ncells, 1);
+        for (int z : J.zero_slots) std::fill(buf[l].p + z * stride, buf[l].p + z * stride + buf[l].ncells, 0.0);
+        if (!mine[l].empty())
+            for (int c = 0; c < nres; ++c) check(pa_field_download_level(res, l, c, buf[l].p + (long long)J.slot[c] * stride), "download");
+    }
+    check(pa_sync(), "pa_sync");
+    M.bar.wait();                                                     // nobody frees a slab a peer may still be reading
+
+    char fn[32];
+    std::snprintf(fn, sizeof fn, "Cell_D_%05d", r);
+    std::vector<pltio::FabRecord> recs;
+    for (int l = 0; l < Nlev; ++l) {
+        const long long stride = std::max<long long>(buf[l].ncells, 1);
+        std::vector<const double*> data;
+        for (int c = 0; c < J.nCompOut; ++c) data.push_back(buf[l].p + (long long)c * stride);
+        auto w = pltio::write_fab_file(J.outfile, H, l, fn, mine[l], data);
+        recs.insert(recs.end(), w.begin(), w.end());
+    }
+    {
+        std::lock_guard<std::mutex> lk(M.mu);
+        M.records.insert(M.records.end(), recs.begin(), recs.end());
+    }
+    pa_field_free(st); pa_field_free(res); pa_hier_destroy(h);
+    M.bar.wait();
+}
+
+inline void run_curv_multi(int ngpus, CurvJob& J) {
+    const pltio::Header& H = *J.H;
+    J.owner = sfc_owners(H, J.Nlev, ngpus);
+    try { pltio::create_plotfile_dirs(J.outfile, J.Nlev); } catch (std::exception& e) { pa_abort(e.what()); }
+    MultiShared M(ngpus);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ngpus; ++r) th.emplace_back([&, r] {
+        try { curv_rank(r, M, J); } catch (std::exception& e) { pa_abort(e.what()); }
+    });
+    for (auto& t : th) t.join();
+    std::vector<int> rr(std::max(J.Nlev - 1, 0), 2);              // curvature.cpp:842
+    pltio::Header meta = H;
+    meta.time = 0.0;
     try { pltio::write_metadata(J.outfile, meta, J.names, J.Nlev, M.records, rr); } catch (std::exception& e) { pa_abort(e.what()); }
 }

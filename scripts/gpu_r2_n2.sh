@@ -21,3 +21,6 @@ oracle/_ref/fcompare.ref.ex gpurun_out/r2b_gt_n2 gpurun_out/r2b_gt_n1 2>&1 | tai
 # the C++ executable with one host thread per GPU (first run on hardware)
 peleanalysis_b200/host/grad3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_gt_threads ngpus=2 >> $O/r2b_mgtools.log 2>&1; echo "threads rc=$?" >> $O/r2b_mgtools.log
 oracle/_ref/fcompare.ref.ex gpurun_out/r2b_gt_threads gpurun_out/r2b_gt_n1 2>&1 | tail -3 | tee -a $O/r2b_mgtools.log
+peleanalysis_b200/host/curvature3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_K_threads ngpus=2 threshold_prog=1 threshold_value=0.01 >> $O/r2b_mgtools.log 2>&1; echo "curv threads rc=$?" >> $O/r2b_mgtools.log
+peleanalysis_b200/host/curvature3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_K_n1 threshold_prog=1 threshold_value=0.01 >> $O/r2b_mgtools.log 2>&1
+oracle/_ref/fcompare.ref.ex gpurun_out/r2b_K_threads gpurun_out/r2b_K_n1 2>&1 | tail -3 | tee -a $O/r2b_mgtools.log

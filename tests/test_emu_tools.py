@@ -85,3 +85,41 @@ def test_emulated_grad_executable_multi_gpu(emu_exes, tmp_path, name, ngpus):
         O.run_ref("grad", d, str(tmp_path / "ref_gt"), gradVar="temp", is_per=list(z["is_per"]), sym_dir=list(z["sym_dir"]))
         q = subprocess.run([O.ref_exe("fcompare.ref.ex"), str(tmp_path / "plt_gt"), str(tmp_path / "ref_gt")], capture_output=True, text=True)
         assert "PLOTFILE AGREE" in q.stdout, q.stdout[-1500:]
+
+
+@pytest.mark.parametrize("name,ngpus", [("c1_periodic", 2), ("c3_threshold", 2), ("c1_options", 3), ("mixed_boxes", 2)])
+def test_emulated_curvature_executable_multi_gpu(emu_exes, tmp_path, name, ngpus):
+    """curvature3d ... ngpus=N (one host thread per emulated GPU): every option, incl. the per-level exchange of the flame
+    normal under threshold_prog and the exchange of the internal gradient field for the Gaussian curvature."""
+    env_old = {k: os.environ.get(k) for k in ("CUEMU_DEVICES", "CUEMU_SEED")}
+    os.environ.update(CUEMU_DEVICES=str(ngpus), CUEMU_SEED="4")
+    try:
+        import numpy as np
+        from helpers import bit_equal, load_golden, max_rel
+        from peleanalysis_b200 import plotfile
+        pf, z = load_golden(name)
+        d = str(tmp_path / "plt")
+        plotfile.write_plotfile(d, pf)
+        kw = [str(s) for s in z["curv_opts"]]
+        per = " ".join(str(int(v)) for v in z["is_per"])
+        p = subprocess.run([emu_exes[1], "infile=" + d, "progressName=temp", "is_per=" + per, "outfile=" + str(tmp_path / "K"), "ngpus=%d" % ngpus, *kw],
+                           capture_output=True, text=True, cwd=str(tmp_path))
+        assert p.returncode == 0, p.stdout + p.stderr
+        r = plotfile.read_plotfile(str(tmp_path / "K"))
+        for key in z.files:
+            if not key.startswith("curv_") or key == "curv_opts":
+                continue
+            n = key[5:]
+            c = r.comp(n)
+            got = np.concatenate([f[c].ravel() for l in r.levels for f in l.fabs])
+            if n.startswith("GaussianCurvature"):
+                assert max_rel(got, z[key]) <= 1e-12
+            else:
+                assert bit_equal(got, z[key]), (name, n)
+        assert "SmoothedProgress" in r.names and "GaussianCurvature_temp" in r.names
+    finally:
+        for k, v in env_old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
