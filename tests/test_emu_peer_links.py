@@ -86,6 +86,8 @@ def _case(name):
 @pytest.mark.parametrize("transport", ["peer", "slab"])
 @pytest.mark.parametrize("name,nranks", CASE_LIST)
 def test_emulated_multi_rank_in_one_process(emu, name, nranks, transport):  # noqa: F811
+    if transport == "slab" and (name, nranks) not in (("c3_three_levels", 2), ("mixed_boxes", 2), ("config3", 4)):
+        pytest.skip("slab transport: three representative cases (tests/test_emu_multirank.py runs it over gloo as well)")
     capi = emu
     os.environ["CUEMU_SEED"] = "3"
     os.environ["PA_STENCIL"] = "tma"

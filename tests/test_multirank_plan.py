@@ -14,13 +14,22 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, case, ok, flags=0):
+def _worker(rank, world, port, cases, ok, flags=0):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        for case in cases:                      # one process group for all cases: spawning and importing torch dominate otherwise
+            _check_case(rank, world, case, flags)
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def _check_case(rank, world, case, flags):
+    if True:
         from cases import CASES
         from peleanalysis_b200 import capi
         builder, is_per, sym, _, _ = CASES[case]
@@ -78,12 +87,9 @@ def _worker(rank, world, port, case, ok, flags=0):
                 else:
                     assert np.array_equal(m == -2, remote)
                     assert np.array_equal(m[~remote], f[~remote])
-        ok[rank] = 1
-    finally:
-        dist.destroy_process_group()
 
 
-def _spawn2(case, flags):
+def _spawn2(cases, flags):
     import socket
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -91,18 +97,17 @@ def _spawn2(case, flags):
     s.close()
     ctx = mp.get_context("spawn")
     ok = ctx.Array("i", [0, 0])
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, ok, flags)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, list(cases), ok, flags)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
+        p.join(300)
     assert list(ok) == [1, 1], [p.exitcode for p in procs]
 
 
-@pytest.mark.parametrize("case", ["c1_periodic", "c3_three_levels", "edge_walls"])
-def test_exchange_plan_world2_peer_links(palib, case):
+def test_exchange_plan_world2_peer_links(palib):
     """PA_HIER_PEER_LINKS: faces linked to a peer's box leave the exchange plan; what remains is still consistent."""
-    _spawn2(case, 1)
+    _spawn2(["c1_periodic", "c3_three_levels", "edge_walls", "mixed_boxes"], 1)
 
 
 def test_uniform_grid_with_peer_links_needs_no_exchange(palib):
@@ -123,18 +128,5 @@ def test_uniform_grid_with_peer_links_needs_no_exchange(palib):
         assert sc.sum() > 0 and rc.sum() > 0
 
 
-@pytest.mark.parametrize("case", ["c1_periodic", "c3_three_levels", "lshape", "edge_walls", "ratio4"])
-def test_exchange_plan_world2(palib, case):
-    import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    ok = ctx.Array("i", [0, 0])
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, ok)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(120)
-    assert list(ok) == [1, 1], [p.exitcode for p in procs]
+def test_exchange_plan_world2(palib):
+    _spawn2(["c1_periodic", "c3_three_levels", "lshape", "edge_walls", "ratio4", "mixed_boxes"], 0)
