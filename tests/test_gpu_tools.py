@@ -94,3 +94,31 @@ def test_curvature_executable(exes, tmp_path, name):
         else:
             assert bit_equal(got, z[key]), (name, n)
     assert "SmoothedProgress" in r.names and "GaussianCurvature_temp" in r.names
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs in one box (gpurun --gpus 2)")
+@pytest.mark.parametrize("name", ["c3_three_levels", "mixed_boxes"])
+def test_executables_on_two_gpus(exes, tmp_path, name):
+    """ngpus=2: one host thread per GPU in one process (host/multi_gpu.hpp) -- peer links over NVLink by pointer, slab copies
+    between the two GPUs, one Cell_D file per GPU; same bits as the golden vectors of the compiled reference."""
+    pf, z = load_golden(name)
+    d = str(tmp_path / "plt")
+    plotfile.write_plotfile(d, pf)
+    per = " ".join(str(int(v)) for v in z["is_per"])
+    sym = " ".join(str(int(v)) for v in z["sym_dir"])
+    _run(exes[0], "infile=" + d, "gradVar=temp", "is_per=" + per, "sym_dir=" + sym, "ngpus=2", cwd=str(tmp_path))
+    r = plotfile.read_plotfile(str(tmp_path / "plt_gt"))
+    for k, n in zip(["gx", "gy", "gz", "mag"], r.names[1:]):
+        assert bit_equal(_flat(r, n), z["grad_" + k]), (name, n)
+    _run(exes[1], "infile=" + d, "progressName=temp", "is_per=" + per, "sym_dir=" + sym, "ngpus=2", "outfile=" + str(tmp_path / "K"), cwd=str(tmp_path))
+    r = plotfile.read_plotfile(str(tmp_path / "K"))
+    for n in ["Progress", "MeanCurvature_temp", "FlameNormalX_temp", "FlameNormalY_temp", "FlameNormalZ_temp"]:
+        assert bit_equal(_flat(r, n), z["curv_" + n]), (name, n)
