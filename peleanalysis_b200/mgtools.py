@@ -86,16 +86,22 @@ def read_boxes(path: str, hd, lev: int, meta, box_ids: Sequence[int], comp_ids: 
 class _Dist:
     """torch.distributed if this is a multi-process run (RANK / WORLD_SIZE from torchrun), else a single rank."""
 
-    def __init__(self, backend: str):
+    def __init__(self, backend: str, device: int):
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.dist = None
         self.own_group = False
         if self.world > 1:
+            import torch
             import torch.distributed as dist
             self.dist = dist
+            if backend == "nccl":
+                torch.cuda.set_device(device)          # torch's current device = the one the C ABI was initialised on
             if not dist.is_initialized():
-                dist.init_process_group(backend)
+                if backend == "nccl":
+                    dist.init_process_group(backend, device_id=torch.device("cuda", device))
+                else:
+                    dist.init_process_group(backend)
                 self.own_group = True
 
     def gather_objects(self, obj):
@@ -124,7 +130,8 @@ def run(tool: str, argv: Sequence[str], capi=None, multigpu=None, wrap=None, bac
     pp = parse_args(argv)
     if tool not in ("grad", "curvature") or "infile" not in pp:
         raise SystemExit(__doc__)
-    D = _Dist(backend)
+    dev = device if device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    D = _Dist(backend, dev)
     if multigpu is None and D.world > 1:
         from . import multigpu as _mg
         multigpu = _mg
@@ -149,7 +156,7 @@ def run(tool: str, argv: Sequence[str], capi=None, multigpu=None, wrap=None, bac
                              tuple((hd["prob_hi"][d] - hd["prob_lo"][d]) / (hd["domains"][l][1][d] - hd["domains"][l][0][d] + 1) for d in range(3)),
                              metas[l][1], []) for l in range(nlev)]
 
-    capi.init(device if device is not None else int(os.environ.get("LOCAL_RANK", "0")))
+    capi.init(dev)
     if D.world > 1 and backend == "nccl":
         import torch
         capi.set_stream(torch.cuda.current_stream().cuda_stream)
