@@ -186,7 +186,9 @@ int pa_curvature_scratch(pa_hier *h, int which, pa_field **f);
  * The calling thread's GPU is the one its pa_init named.  pa_enable_peer_access lets that GPU address a peer GPU's memory
  * (cudaDeviceEnablePeerAccess); pa_field_slab gives the level slab a peer thread passes to pa_field_map_peer_ptr -- the
  * same-address-space form of pa_field_ipc_handle / pa_field_map_peer; pa_copy_async is a device-to-device copy on the
- * calling thread's stream that may cross GPUs (it moves a peer's send slab segment into this rank's recv slab). */
+ * calling thread's stream that may cross GPUs (it moves a peer's send slab segment into this rank's recv slab).
+ * Together they stand where the reference has its MPI layer under FillBoundary / ParallelCopy
+ * (AX/Base/AMReX_FabArrayCommI.H:7-60 FBEP_nowait / FillBoundary_finish, AX/Base/AMReX_ParallelDescriptor.H). */
 int pa_enable_peer_access(int peer_device);
 int pa_field_slab(const pa_field *f, int lev, const double **base);
 int pa_field_map_peer_ptr(pa_field *f, int lev, int peer_rank, const double *base);
