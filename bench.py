@@ -227,6 +227,50 @@ def bench_extra(torch, capi, synth, stream, peak, kind, steps, warmup):
             "algorithmic_bytes": alg, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "hier_build_s": H.build_seconds}
 
 
+def bench_curvature_ranks(torch, dist, capi, multigpu, synth, stream, peak, kind, steps, warmup, rank, world, transport):
+    """--only-extra curvature3|target_curv under torchrun: the curvature tool (default options) with the boxes SFC-distributed
+    over the ranks -- multigpu.Curvature (peer links or slab exchange in front of each pass); max over ranks, whole-job cells."""
+    pf = synth.config3(256, 64, fill=False) if kind == "curvature3" else synth.config3(512, 128, fill=False)
+    flags = capi.PEER_LINKS if transport == "peer" else 0
+    H = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, world, flags=flags)
+    host = gen_fields(torch, pf.levels, H.local_boxes, ["temp"])
+    state = capi.Field(H, 1, 1)
+    for l in range(H.nlev):
+        if H.local_cells[l]:
+            capi.check(capi.lib().pa_field_upload_level(state.f, l, 0, host[l][0].data_ptr()))
+    capi.sync()
+    lo = torch.tensor([min([float(h[0].min()) for h in host if h[0].numel()] or [1e300])], device="cuda", dtype=torch.float64)
+    hi = torch.tensor([max([float(h[0].max()) for h in host if h[0].numel()] or [-1e300])], device="cuda", dtype=torch.float64)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    o = capi.CurvOpts()
+    o.prog_min, o.prog_max = float(lo.item()), float(hi.item())
+    out = capi.Field(H, 5, 1)
+    op = multigpu.Curvature(state, 0, o, out, 0)
+    dist.barrier()
+    for _ in range(warmup):
+        op.run()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = capi.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        op.run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    alg = H.algorithmic_bytes(5)                      # this rank's boxes
+    return {"workload": "curvature (default options), 3 levels, %d^3 base, boxes SFC-distributed over %d ranks (%s)" % (
+                256 if kind == "curvature3" else 512, world, "peer links" if flags else "slab exchange"),
+            "value": H.num_cells / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "ms_per_step": ms, "cells": H.num_cells,
+            "launches_per_step": (capi.kernel_launches() - l0) // steps, "roofline_frac_rank0": alg / (ms * 1e-3) / 1e9 / peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,6 +309,14 @@ def main():
 
     if args.only_extra:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        if world > 1:
+            if args.only_extra not in ("curvature3", "target_curv"):
+                raise SystemExit("--only-extra under torchrun: curvature3 or target_curv")
+            res = bench_curvature_ranks(torch, dist, capi, multigpu, synth, stream, peak, args.only_extra, args.steps, args.warmup, rank, world, args.transport)
+            if rank == 0:
+                print(json.dumps(res))
+            dist.destroy_process_group()
+            return
         print(json.dumps(bench_extra(torch, capi, synth, stream, peak, args.only_extra, args.steps, args.warmup)))
         return
     names = spec["names"]

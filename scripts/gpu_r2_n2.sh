@@ -24,3 +24,7 @@ oracle/_ref/fcompare.ref.ex gpurun_out/r2b_gt_threads gpurun_out/r2b_gt_n1 2>&1 
 peleanalysis_b200/host/curvature3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_K_threads ngpus=2 threshold_prog=1 threshold_value=0.01 >> $O/r2b_mgtools.log 2>&1; echo "curv threads rc=$?" >> $O/r2b_mgtools.log
 peleanalysis_b200/host/curvature3d.b200.ex infile=gpurun_out/r2b_plt outfile=gpurun_out/r2b_K_n1 threshold_prog=1 threshold_value=0.01 >> $O/r2b_mgtools.log 2>&1
 oracle/_ref/fcompare.ref.ex gpurun_out/r2b_K_threads gpurun_out/r2b_K_n1 2>&1 | tail -3 | tee -a $O/r2b_mgtools.log
+# curvature on 2 GPUs (first multi-GPU curvature timing)
+for tr in peer slab; do
+  timeout -s KILL 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --only-extra target_curv --steps 10 --warmup 3 --transport $tr > $O/r2b_curv_n2_$tr.log 2>&1; tail -c 400 $O/r2b_curv_n2_$tr.log
+done
