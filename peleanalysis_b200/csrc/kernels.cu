@@ -3,6 +3,7 @@
 // separate IEEE multiplies and adds (the reference CPU build has no FMA), so results are bit-identical.
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -234,10 +235,112 @@ __global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill(const PaFaceRec* __res
         }
     }
 }
+// ---- opt-in variant (PA_BCFILL_V2=1; emulator-verified, not yet measured on a B200) -------------------------------------------
+// Same arithmetic, different data path for the coarse values.  k_bcfill lets every ghost cell gather its (up to) nine
+// coarse neighbours itself: nine offset-table loads and nine scattered 8-byte loads per cell, the same coarse cell fetched
+// by up to nine threads (and r*r fine cells share a coarse cell): ncu shows 22-30 % DRAM utilisation at 8 useful bytes per
+// 32-byte sector.  Here the block first stages the coarse register cells its chunk can touch -- the chunk's coarse footprint
+// plus one cell all round -- in shared memory, each exactly once (row-contiguous, so coalesced for y / z faces), and the
+// nine-point formula then reads shared memory.
+constexpr int BCF_TILE = 640;        // coarse cells of a chunk's footprint incl. the one-cell rim (worst case: 128 rows of one cell, r = 2: 3 x 67)
+
+__global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill_v2(const PaFaceRec* __restrict__ recs, const int* __restrict__ rec_level,
+                                                             const PaFaceBlock* __restrict__ blocks, const unsigned short* __restrict__ flags,
+                                                             const long long* __restrict__ coff, GridArgs ga, int ncomp,
+                                                             const double* __restrict__ recv, GhostXform xf) {
+    __shared__ double cs[BCF_TILE];
+    const PaFaceBlock fb = blocks[blockIdx.x];
+    const PaFaceRec R = recs[fb.rec];
+    const int ncell = R.n1 * R.n2;
+    const int q = fb.cell0 + threadIdx.x;
+    const bool inside = q < ncell;
+    const unsigned fl = inside ? flags[R.start + q] : 0u;
+    const bool active = inside && (fl & 3u) != 0u;                 // covered cells belong to the halo copy / a neighbour link
+    const int lev = rec_level[fb.rec];
+    const LevArgs& L = ga.L[lev];
+    const PaBoxDev bx = L.boxes[R.box];
+    const PaLayDev ly = L.lay_in[R.box];
+    const int a1 = inside ? q % R.n1 : 0, a2 = inside ? q / R.n1 : 0;
+    const int d = R.face % 3;
+    const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+    const int s = (R.face < 3) ? 1 : -1;
+    int g[3];
+    g[d] = (R.face < 3) ? -1 : bx.n[d];
+    g[t1] = a1; g[t2] = a2;
+    const long long ga_ = cell_addr(ly, g[0], g[1], g[2]);
+    const long long sd = (d == 0) ? 1 : (d == 1) ? (long long)ly.P : (long long)ly.PS;
+    if (R.kind != PA_FACE_CF) {                                    // physical walls: nothing to stage (uniform per block)
+        if (!active) return;
+        for (int m = 0; m < ncomp; ++m) {
+            double* p = L.out + ga_ + m * L.cs_in;
+            const double v = xform(xf, p[s * sd]);
+            *p = (R.kind == PA_FACE_NEUMANN) ? v : -v;
+        }
+        return;
+    }
+    // coarse footprint of the chunk [fb.cell0, last] of the face plane, one coarse cell of rim all round
+    const int r = R.ratio;
+    const int last = (fb.cell0 + PA_FACE_CHUNK < ncell ? fb.cell0 + PA_FACE_CHUNK : ncell) - 1;
+    const int row0 = fb.cell0 / R.n1, row1 = last / R.n1;
+    const int c0 = (row0 == row1) ? fb.cell0 % R.n1 : 0, c1 = (row0 == row1) ? last % R.n1 : R.n1 - 1;
+    const int jc0 = fdiv_dev(bx.lo[t1] + c0, r) - 1, jc1 = fdiv_dev(bx.lo[t1] + c1, r) + 1;
+    const int kc0 = fdiv_dev(bx.lo[t2] + row0, r) - 1, kc1 = fdiv_dev(bx.lo[t2] + row1, r) + 1;
+    const int W = jc1 - jc0 + 1, Hh = kc1 - kc0 + 1;
+    const bool staged = W * Hh <= BCF_TILE;                        // always true for chunks of PA_FACE_CHUNK cells; kept as a guard
+    const LevArgs& LC = ga.L[lev - 1];
+    const int j = bx.lo[t1] + a1, k = bx.lo[t2] + a2;
+    const int jc = fdiv_dev(j, r), kc = fdiv_dev(k, r);
+    const long long e0 = R.cidx + (long long)(kc - R.rlo2) * R.rn1 + (jc - R.rlo1);
+    const int sc0 = (kc - kc0) * W + (jc - jc0);                   // this cell's coarse cell inside the staged tile
+    for (int m = 0; m < ncomp; ++m) {
+        const double* cbase = LC.in + m * LC.cs_in;
+        if (staged) {
+            __syncthreads();                                       // the previous component's readers are done with the tile
+            for (int i = threadIdx.x; i < W * Hh; i += PA_FACE_CHUNK) {
+                const int jj = jc0 + i % W, kk = kc0 + i / W;
+                double v = PA_NAN;                                 // outside the register plane: never read (the flags forbid it)
+                if (jj >= R.rlo1 && jj < R.rlo1 + R.rn1 && kk >= R.rlo2 && kk < R.rlo2 + R.rn2)
+                    v = crse_val(coff, R.cidx + (long long)(kk - R.rlo2) * R.rn1 + (jj - R.rlo1), cbase, recv, ncomp, m, xf);
+                cs[i] = v;
+            }
+            __syncthreads();
+        }
+        if (!active) continue;
+        double* p = L.out + ga_ + m * L.cs_in;
+#define CR(o1, o2) (staged ? cs[sc0 + (o2) * W + (o1)] : crse_val(coff, e0 + (long long)(o2) * R.rn1 + (o1), cbase, recv, ncomp, m, xf))
+        const double c00 = CR(0, 0);
+        int lo = PA_FLAG_NC(fl, 0) ? -1 : 0;
+        int hi = PA_FLAG_NC(fl, 1) ? 1 : 0;
+        double fac = (hi == lo + 1) ? 1.0 : 0.5;
+        const double d1 = fac * (CR(hi, 0) - CR(lo, 0));
+        const double d11 = (hi == lo + 2) ? 0.5 * (CR(1, 0) - 2. * c00 + CR(-1, 0)) : 0.;
+        lo = PA_FLAG_NC(fl, 2) ? -1 : 0;
+        hi = PA_FLAG_NC(fl, 3) ? 1 : 0;
+        fac = (hi == lo + 1) ? 1.0 : 0.5;
+        const double d2 = fac * (CR(0, hi) - CR(0, lo));
+        const double d22 = (hi == lo + 2) ? 0.5 * (CR(0, 1) - 2. * c00 + CR(0, -1)) : 0.;
+        const double d12 = (((fl >> 6) & 15u) == 15u)
+                               ? 0.25 * (CR(1, 1) - CR(-1, 1) + CR(-1, -1) - CR(1, -1)) : 0.0;
+#undef CR
+        const double x1 = -0.5 + (j - jc * r + 0.5) / r;
+        const double x2 = -0.5 + (k - kc * r + 0.5) / r;
+        const double bcval = c00 + x1 * d1 + (x1 * x1) * d11 + x2 * d2 + (x2 * x2) * d22 + x1 * x2 * d12;
+        double tmp = 0.0;
+        for (int mm = 1; mm < R.nx; ++mm) tmp += xform(xf, p[mm * s * sd]) * R.coef[mm];
+        double v = tmp;
+        v += bcval * R.coef[0];
+        *p = v;
+    }
+}
+
 cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaFaceBlock* blocks, long long blk0, long long blk1,
                           const unsigned short* flags, const long long* coff, const GridArgs& ga,
                           int ncomp, const double* recv, GhostXform xf, cudaStream_t st) {
     if (blk1 <= blk0) return cudaSuccess;
+    const char* v2 = getenv("PA_BCFILL_V2");
+    if (v2 && v2[0] == '1')
+        PA_LAUNCH((unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st, k_bcfill_v2)(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
+    else
     PA_LAUNCH((unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st, k_bcfill)(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
     ++g_launches;
     return cudaGetLastError();

@@ -38,6 +38,12 @@ el ring
 # PF kernels stage DIV "lean" (no y-halo rows for n_x / n_z, no z-halo planes for n_x / n_y); PA_DIV_LEAN=0 = prefetch warp alone
 PA_TMA_PREFETCH=1 PA_DIV_LEAN=0 timeout -s KILL 60 python bench.py --only-extra target_curv --steps 10 --warmup 3 > $O/r2a_target_curv_pf1_zc32_nolean.log 2>&1
 el lean
+# staged coarse-fine fill (coarse register cells through shared memory, each loaded once)
+for ex in grad5 target_curv curvature3 target_grad; do
+  PA_BCFILL_V2=1 timeout -s KILL 60 python bench.py --only-extra $ex --steps 10 --warmup 3 > $O/r2a_${ex}_pf0_zc32_bcfillv2.log 2>&1
+done
+PA_BCFILL_V2=1 timeout -s KILL 200 python -m pytest tests -q -m gpu -n 8 --timeout 120 -p no:cacheprovider -k "golden or ghost_cells or midsize" > $O/r2a_pytest_bcfillv2.log 2>&1; tail -n 2 $O/r2a_pytest_bcfillv2.log
+el bcfill
 PA_TMA_PREFETCH=1 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf1.log 2>&1
 timeout -s KILL 150 python bench.py --no-extras > $O/r2a_bench_pf0.log 2>&1
 el bench

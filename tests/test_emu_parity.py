@@ -139,3 +139,21 @@ def test_emulated_wide_ghost_inputs(emu, builder):
     os.environ["CUEMU_SEED"] = "0"
     b = {"config1": lambda: synth.config1(16, 8), "mixed": synth.case_mixed, "config3": lambda: synth.config3(16, 8)}[builder]
     G.check_wide_ghost_inputs(emu, b)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_staged_bcfill(emu, name):
+    """PA_BCFILL_V2=1 (opt-in): the coarse-fine / wall fill with the coarse register cells staged in shared memory -- ghost
+    cells one by one against the oracle, then both tools against the golden vectors."""
+    os.environ["CUEMU_SEED"] = "11"
+    os.environ["PA_BCFILL_V2"] = "1"
+    try:
+        G.test_ghost_cells_match_oracle(emu, name)
+        tools = CASES[name][3]
+        if "grad" in tools:
+            G.test_grad_matches_reference_golden(emu, name, "tma", "links")
+        if "curvature" in tools:
+            G.test_curvature_matches_reference_golden(emu, name, "tma", "nolinks")
+    finally:
+        os.environ["CUEMU_SEED"] = "0"
+        os.environ.pop("PA_BCFILL_V2", None)

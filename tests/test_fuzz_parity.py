@@ -79,6 +79,8 @@ def test_random_hierarchy_emulated_kernels_equal_oracle(emu, seed):  # noqa: F81
     curv = seed % 2 == 0
     pf, is_per, sym = random_case(1000 + seed, curv)
     os.environ["CUEMU_SEED"] = str(seed)
+    if seed % 3 == 0:
+        os.environ["PA_BCFILL_V2"] = "1"          # every third seed through the opt-in staged coarse-fine fill
     try:
         OH = O.OracleHier(pf, is_per, sym)
         s = _flat(pf)
@@ -96,6 +98,7 @@ def test_random_hierarchy_emulated_kernels_equal_oracle(emu, seed):  # noqa: F81
                     assert bit_equal(out[c], wk[c]), (seed, "curvature", stencil, c, [l.boxes for l in pf.levels])
     finally:
         os.environ["CUEMU_SEED"] = "0"
+        os.environ.pop("PA_BCFILL_V2", None)
 
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (python oracle/build_ref.py)")
