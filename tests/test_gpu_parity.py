@@ -390,3 +390,18 @@ def test_descriptor_prefetch_variant_full_size(gpu):
 @experimental
 def test_wide_ghost_inputs(gpu):
     check_wide_ghost_inputs(gpu, lambda: synth.config3(16, 8))
+
+
+@experimental
+@pytest.mark.parametrize("name", list(CASES))
+def test_staged_bcfill_variant(gpu, name):
+    """PA_BCFILL_V2=1: the coarse-fine fill with the coarse register cells staged in shared memory."""
+    os.environ["PA_BCFILL_V2"] = "1"
+    try:
+        test_ghost_cells_match_oracle(gpu, name)
+        if "grad" in CASES[name][3]:
+            test_grad_matches_reference_golden(gpu, name, "tma", "links")
+        if "curvature" in CASES[name][3]:
+            test_curvature_matches_reference_golden(gpu, name, "tma", "links")
+    finally:
+        os.environ.pop("PA_BCFILL_V2", None)
