@@ -257,7 +257,13 @@ const unsigned long long* warp_exchange(unsigned mask, const void* v, size_t byt
 void syncwarp(unsigned mask) { (void)warp_exchange(mask, nullptr, 0); }
 
 void mbar_init(uint64_t* bar, uint32_t count) { MBar b; b.count = count; b.pending = count; mbars[bar] = b; ++progress; }
-void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { MBar& b = mbar_of(bar); b.tx += bytes; --b.pending; mbar_check(b); }
+void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    MBar& b = mbar_of(bar);
+    b.tx += bytes;
+    if (b.tx > (1 << 20) - 1) { std::fprintf(stderr, "[cuemu] mbarrier tx-count %lld exceeds the hardware range (2^20 - 1)\n", b.tx); std::abort(); }
+    --b.pending;
+    mbar_check(b);
+}
 void mbar_arrive(uint64_t* bar) { MBar& b = mbar_of(bar); --b.pending; mbar_check(b); }
 void mbar_wait(uint64_t* bar, uint32_t parity) {
     MBar& b = mbar_of(bar);
