@@ -157,3 +157,29 @@ def test_emulated_staged_bcfill(emu, name):
     finally:
         os.environ["CUEMU_SEED"] = "0"
         os.environ.pop("PA_BCFILL_V2", None)
+
+
+@pytest.mark.parametrize("stencil", ["tma", "tma_pf"])
+def test_emulated_full_width_tiles(emu, stencil):
+    """128-cell-wide boxes: 64 x-pairs per row, 8 rows per tile -- every one of the 512 pair slots of the big CTA shapes is
+    in use (the golden cases have narrow boxes), two boxes side by side in y so that linked y rows and periodic x / z wraps
+    onto the box itself occur at full width; a refined 64-wide level on top."""
+    from oracle import oracle as O
+    from peleanalysis_b200 import synth
+    from helpers import bit_equal, flat_from_fabs
+    os.environ["CUEMU_SEED"] = "13"
+    try:
+        pf = synth.make_hierarchy((128, 32, 8), [[((64, 16, 4), (191, 47, 11))]], [2], 128, ("temp",))
+        OH = O.OracleHier(pf)
+        s = OH.flatten(0)
+        out, _, _ = G._gpu_grad(emu, pf, (1, 1, 1), (0, 0, 0), stencil=stencil)
+        want = OH.grad(s)
+        for c in range(4):
+            assert bit_equal(out[c], want[c]), c
+        pmin, pmax = float(s.min()), float(s.max())
+        outc, _ = G._gpu_curv(emu, pf, (1, 1, 1), (0, 0, 0), pmin, pmax, {}, stencil)
+        wk = OH.curvature(s, pmin, pmax)
+        for c in range(5):
+            assert bit_equal(outc[c], wk[c]), ("curvature", c)
+    finally:
+        os.environ["CUEMU_SEED"] = "0"
