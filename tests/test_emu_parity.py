@@ -183,3 +183,36 @@ def test_emulated_full_width_tiles(emu, stencil):
             assert bit_equal(outc[c], wk[c]), ("curvature", c)
     finally:
         os.environ["CUEMU_SEED"] = "0"
+
+
+@pytest.mark.parametrize("base,mgs", [((256, 8, 4), 256), ((1024, 4, 4), 1024), ((7, 5, 3), 8), ((2, 2, 2), 2), ((1, 1, 1), 1)])
+def test_emulated_extreme_box_shapes(emu, base, mgs):
+    """Very wide rows (4 and 1 row per tile), odd tiny boxes, and the one-cell periodic box that is its own neighbour six times."""
+    from oracle import oracle as O
+    from peleanalysis_b200 import synth
+    from helpers import bit_equal
+    os.environ["CUEMU_SEED"] = "17"
+    try:
+        pf = synth.make_hierarchy(base, [], [], mgs, ("temp",))
+        OH = O.OracleHier(pf)
+        s = OH.flatten(0)
+        out, _, _ = G._gpu_grad(emu, pf, (1, 1, 1), (0, 0, 0))
+        want = OH.grad(s)
+        for c in range(4):
+            assert bit_equal(out[c], want[c]), c
+        pmin, pmax = float(s.min()), float(s.max())
+        if pmin < pmax:
+            outc, _ = G._gpu_curv(emu, pf, (1, 1, 1), (0, 0, 0), pmin, pmax, {})
+            wk = OH.curvature(s, pmin, pmax)
+            for c in range(5):
+                assert bit_equal(outc[c], wk[c]), ("curvature", c)
+    finally:
+        os.environ["CUEMU_SEED"] = "0"
+
+
+def test_box_side_limit_is_an_error(emu):
+    from peleanalysis_b200 import synth
+    pf = synth.make_hierarchy((1100, 4, 4), [], [], 2048, ("temp",), fill=False)
+    with pytest.raises(emu.PaError) as e:
+        emu.Hierarchy(pf.levels)
+    assert "1024" in str(e.value)
