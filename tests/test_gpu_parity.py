@@ -405,3 +405,19 @@ def test_staged_bcfill_variant(gpu, name):
             test_curvature_matches_reference_golden(gpu, name, "tma", "links")
     finally:
         os.environ.pop("PA_BCFILL_V2", None)
+
+
+@experimental
+@pytest.mark.parametrize("base,mgs", [((256, 8, 4), 256), ((1024, 4, 4), 1024), ((7, 5, 3), 8), ((2, 2, 2), 2), ((128, 32, 8), 128)])
+def test_extreme_box_shapes(gpu, base, mgs):
+    pf = synth.make_hierarchy(base, [], [], mgs, ("temp",))
+    OH = O.OracleHier(pf)
+    s = OH.flatten(0)
+    out, _, _ = _gpu_grad(gpu, pf, (1, 1, 1), (0, 0, 0))
+    want = OH.grad(s)
+    for c in range(4):
+        assert bit_equal(out[c], want[c]), c
+    outc, _ = _gpu_curv(gpu, pf, (1, 1, 1), (0, 0, 0), float(s.min()), float(s.max()), {})
+    wk = OH.curvature(s, float(s.min()), float(s.max()))
+    for c in range(5):
+        assert bit_equal(outc[c], wk[c]), ("curvature", c)
