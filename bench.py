@@ -1,19 +1,31 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the grad stencil path (BASELINE.json metric: Gcells/s, all AMR levels).
+"""bench.py -- benchmark of the grad / curvature stencil path (BASELINE.json metric: Gcells/s over all AMR levels).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config4|config2_small] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-One "step" = one pass of the hot path (ghost fill + c-f fill + stencil) over the synthetic workload:
-  value  device-resident inputs -> device-resident outputs, CUDA-event timed, max over ranks
-  e2e    the same step through the C ABI with HOST buffers: pinned H2D of the inputs, hot path, D2H of the results
-  roofline  the stencil kernel alone (CUDA events around its launch inside the timed loop) against the measured
-            HBM copy bandwidth of MEASURED_PEAKS.json; bytes = SURVEY 8(d) algorithmic bytes
-  cpu_baseline  the compiled reference (oracle/_ref/grad3d.timed.ex, all host cores) on a bounded sample
-N > 1 (torchrun, one process per GPU): the boxes of the same workload are SFC-distributed over the ranks (strong
-scaling).  --transport peer (default): every rank maps its peers' slabs through CUDA IPC and the stencil kernel's TMA
-producer reads cross-rank neighbour planes / rows / columns in place over NVLink -- no pack, no exchange, no halo
-kernel.  --transport slab: the cross-rank ghost cells move as NCCL send/recv of packed slabs between a pack and a fill
-kernel (what an MPI code does).
+Workloads (--workload; the default, config2, is the configuration the metric is quoted on):
+  config2      grad, uniform 512^3, 64 boxes of 128^3, 5 components                         (BASELINE configs[1])
+  config4      grad, uniform 1024^3, 512 boxes of 128^3, 1 component                         (BASELINE configs[3])
+  target_grad  grad of temp, 3 levels, 512^3 base, ratio 2, 128^3 boxes                      (the north-star target hierarchy)
+  target_curv  curvature (default options) on the same hierarchy
+  curvature3   curvature, 3 levels, 256^3 base, ratio 2, 64^3 boxes                          (BASELINE configs[2])
+  grad5        grad of 12 components, 4 levels (ratios 2/4/2), 128^3 base, 16^3 boxes        (BASELINE configs[4])
+
+One "step" = one pass of the hot path (ghost fill + c-f fill + stencil kernels) over the synthetic workload:
+  value     device-resident inputs -> device-resident outputs, CUDA-event timed, max over ranks
+  e2e       the same step through the C ABI with HOST buffers: pinned H2D of the inputs, hot path, D2H of the results
+  roofline  the dominant kernel against the measured HBM copy bandwidth of MEASURED_PEAKS.json; bytes = SURVEY 8(d)
+            algorithmic bytes (inputs read once + outputs written once)
+  cpu_baseline  the compiled reference (oracle/_ref/*.timed.ex, all host cores) on a bounded sample of the workload
+  output_hash   order-independent fingerprint of every output bit (pa_field_hash, summed over the ranks): equal for any
+            number of GPUs, and compared with tests/golden/bench_hashes.json -- a mismatch makes the run fail (rc 3)
+  extras    the other workloads, measured the same way (device-resident; no e2e) and fingerprinted
+N > 1 (torchrun, one process per GPU): the boxes of the same workload are distributed over the ranks (strong scaling).
+--transport peer (default): every rank maps its peers' slabs through CUDA IPC and the stencil kernels' TMA producer reads
+cross-rank neighbour planes / rows in place over NVLink -- no pack, no exchange, no halo kernel.  --transport slab: the
+cross-rank ghost cells move as NCCL send/recv of packed slabs between a pack and a fill kernel (what an MPI code does).
+--impl reference: the unmodified reference tool (oracle/_ref) on the host cores, on the SAME workload (same grid, same
+variables), its hot-path region looped inside one process per variable.
 """
 import argparse
 import json
@@ -30,72 +42,111 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "Gcells/s (all AMR levels) for grad"
 UNIT = "Gcells/s"
+HASH_FILE = os.path.join(ROOT, "tests", "golden", "bench_hashes.json")
+
+
+def metric_name(kind):
+    return "Gcells/s (all AMR levels) for " + ("grad" if kind == "grad" else "curvature")
 
 
 def workload_spec(name):
+    """kind, hierarchy builder, differentiated variables, description.  `cells` etc. follow from the hierarchy."""
     from peleanalysis_b200 import synth
     if name == "config2":
-        return dict(n=512, mgs=128, names=list(synth.FIELD_NAMES), desc="grad, uniform 512^3, 64 boxes of 128^3, 5 components (BASELINE configs[1])")
+        return dict(name=name, kind="grad", build=lambda fill=False: synth.make_hierarchy(512, [], [], 128, list(synth.FIELD_NAMES), fill=fill),
+                    names=list(synth.FIELD_NAMES), desc="grad, uniform 512^3, 64 boxes of 128^3, 5 components (BASELINE configs[1])")
     if name == "config4":
-        return dict(n=1024, mgs=128, names=["temp"], desc="grad, uniform 1024^3, 512 boxes of 128^3, 1 component (BASELINE configs[3])")
+        return dict(name=name, kind="grad", build=lambda fill=False: synth.make_hierarchy(1024, [], [], 128, ["temp"], fill=fill),
+                    names=["temp"], desc="grad, uniform 1024^3, 512 boxes of 128^3, 1 component (BASELINE configs[3])")
     if name == "config2_small":
-        return dict(n=256, mgs=128, names=list(synth.FIELD_NAMES), desc="grad, uniform 256^3, 8 boxes of 128^3, 5 components (smoke-size)")
+        return dict(name=name, kind="grad", build=lambda fill=False: synth.make_hierarchy(256, [], [], 128, list(synth.FIELD_NAMES), fill=fill),
+                    names=list(synth.FIELD_NAMES), desc="grad, uniform 256^3, 8 boxes of 128^3, 5 components (smoke-size)")
+    if name in ("target_grad", "target_curv"):
+        kind = "grad" if name == "target_grad" else "curv"
+        return dict(name=name, kind=kind, build=lambda fill=False: synth.config3(512, 128, fill=fill), names=["temp"],
+                    desc="%s, 3 levels, 512^3 base, ratio 2, 128^3 boxes (the north-star target hierarchy)" % (
+                        "grad of temp" if kind == "grad" else "curvature (default options)"))
+    if name == "curvature3":
+        return dict(name=name, kind="curv", build=lambda fill=False: synth.config3(256, 64, fill=fill), names=["temp"],
+                    desc="curvature (default options), 3 levels, 256^3 base, ratio 2, 64^3 boxes (BASELINE configs[2])")
+    if name == "curvature3_small":
+        return dict(name=name, kind="curv", build=lambda fill=False: synth.config3(64, 32, fill=fill), names=["temp"],
+                    desc="curvature (default options), 3 levels, 64^3 base, ratio 2, 32^3 boxes (smoke-size)")
+    if name == "grad5":
+        pf0 = synth.config5(128, 16, 12, fill=False)
+        return dict(name=name, kind="grad", build=lambda fill=False: synth.config5(128, 16, 12, fill=fill), names=list(pf0.names),
+                    desc="grad of 12 components, 4 levels (ratios 2/4/2), 128^3 base, 16^3 boxes (BASELINE configs[4])")
     raise SystemExit("unknown workload " + name)
 
 
-# ---------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the compiled, unmodified reference on a bounded sample of the workload
-# ---------------------------------------------------------------------------------------------------------------
-def reference_sample(spec):
-    """Bounded sample: same structure (uniform periodic level, 128^3 boxes, differentiate `temp`), 256^3 cells."""
-    from peleanalysis_b200 import synth
-    n = min(spec["n"], 256)
-    return synth.make_hierarchy(n, [], [], spec["mgs"], ("temp",)), "grad of temp on a uniform periodic %d^3 level in %d^3 boxes (1/%d of the workload's cells, 1 of its %d variables)" % (
-        n, spec["mgs"], (spec["n"] // n) ** 3, len(spec["names"]))
+def config_of(spec, pf):
+    """The workload as both arms report it (identical objects: the driver compares them)."""
+    cells = sum(l.ncells for l in pf.levels)
+    nvar = len(spec["names"])
+    per_cell = 40 if spec["kind"] == "grad" else 48
+    return {"workload": spec["desc"], "cells": cells, "variables": nvar, "boxes": [len(l.boxes) for l in pf.levels],
+            "cache": "inputs + outputs of one step (%.1f GB) exceed the 126 MB L2; no flush needed" % (cells * nvar * per_cell / 1e9)}
 
 
-def run_reference(spec, steps, warmup):
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the compiled, unmodified reference tool on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(spec, steps, warmup, variables=None):
+    """The reference tool (oracle/_ref/{grad3d,curvature3d}.timed.ex = the unmodified sources plus timing probes around
+    grad.cpp:151-236 / curvature.cpp:283-791, FillVar's disk read subtracted) on the workload's own plotfile, one process
+    per differentiated variable, the probed region repeated warmup + steps times inside the process (PA_TIMED_REPS).
+    Returns (Gcells/s, seconds per step, cores, per-step list, variables run)."""
     from oracle import oracle as O
     from peleanalysis_b200 import plotfile
     if not O.have_ref():
         raise RuntimeError("oracle/_ref is missing (built by __graft_entry__.build() where /root/reference exists)")
-    pf, sample = reference_sample(spec)
+    names = list(variables or spec["names"])
+    pf = spec["build"](fill=True)
     cells = sum(l.ncells for l in pf.levels)
     base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     tmp = tempfile.mkdtemp(prefix="pa_ref_", dir=base)
     cores = os.cpu_count() or 1
+    per_step = np.zeros(steps)
     try:
         d = os.path.join(tmp, "plt")
         plotfile.write_plotfile(d, pf, clean="remove")
-        times = []
-        for it in range(warmup + steps):
-            _, hot = O.run_ref("grad", d, d + "_gt", threads=cores, timed=True, gradVar="temp")
-            shutil.rmtree(d + "_gt", ignore_errors=True)
-            if it >= warmup:
-                times.append(hot)
+        del pf
+        for v in names:
+            if spec["kind"] == "grad":
+                hot = O.run_ref_timed("grad", d, d + "_out", threads=cores, reps=warmup + steps, gradVar=v)
+            else:
+                hot = O.run_ref_timed("curvature", d, d + "_out", threads=cores, reps=warmup + steps, progressName=v,
+                                      progMin=300.0, progMax=1800.0)
+            shutil.rmtree(d + "_out", ignore_errors=True)
+            per_step += np.asarray(hot[warmup:warmup + steps])
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    t = float(np.mean(times))
-    return cells / t / 1e9, t, cores, sample
+    t = float(per_step.mean())
+    return cells * len(names) / t / 1e9, t, cores, per_step.tolist(), names
 
 
 def reference_arm(args, spec):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    pf = spec["build"](fill=False)
+    cfg = config_of(spec, pf)
+    del pf
     try:
-        val, t, cores, sample = run_reference(spec, args.steps, args.warmup)
+        val, t, cores, per_step, names = run_reference(spec, args.steps, args.warmup)
     except Exception as e:  # the oracle always exists; this only triggers on a broken checkout
         print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0][:200]}))
         return
+    region = "grad.cpp:151-236" if spec["kind"] == "grad" else "curvature.cpp:283-791"
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(spec["kind"]), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": spec["desc"], "timed_region": "grad.cpp:151-236 minus FillVar (hot path, host memory to host memory)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "details": {"timed_region": region + " minus FillVar (hot path, host memory to host memory), looped in-process",
+                    "step": "one pass over every differentiated variable of the workload (%s): the whole workload, no sampling" % ", ".join(names)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "the whole workload: %d cells x %d variable(s) per step" % (cfg["cells"], len(names))},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -131,13 +182,6 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.samples)}
-
-
-class DevArray:
-    """Wrap a raw device pointer as a torch tensor (via __cuda_array_interface__)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
 def gen_fields(torch, levels, local_boxes, names, prob_hi=(1.0, 1.0, 1.0)):
@@ -177,98 +221,208 @@ def gen_fields(torch, levels, local_boxes, names, prob_hi=(1.0, 1.0, 1.0)):
     return out
 
 
-def bench_extra(torch, capi, synth, stream, peak, kind, steps, warmup):
-    """Secondary measurements reported next to the headline line (same timing rules, N=1 only):
-    curvature3 : curvature tool (default options) on BASELINE configs[2] -- 3 levels, 256^3 base, ratio 2, 64^3 boxes
-    target_grad / target_curv : grad / curvature of temp on the north-star target hierarchy (3 levels, 512^3 base, 128^3 boxes)
-    grad5      : grad of 12 components on a configs[4]-like 4-level hierarchy (ratios 2/4/2, 16^3 boxes)."""
-    if kind == "curvature3":
-        pf = synth.config3(256, 64, fill=False)
-        names, desc = ["temp"], "curvature (default options), 3 levels, 256^3 base, ratio 2, 64^3 boxes (BASELINE configs[2])"
-    elif kind in ("target_grad", "target_curv"):
-        pf = synth.config3(512, 128, fill=False)
-        names = ["temp"]
-        desc = "%s, 3 levels, 512^3 base, ratio 2, 128^3 boxes (the north-star target hierarchy)" % ("grad of temp" if kind == "target_grad" else "curvature (default options)")
-    else:
-        pf = synth.config5(128, 16, 12, fill=False)
-        names, desc = list(pf.names), "grad of 12 components, 4 levels (ratios 2/4/2), 128^3 base, 16^3 boxes (BASELINE configs[4])"
-    H = capi.Hierarchy(pf.levels)
-    host = gen_fields(torch, pf.levels, H.local_boxes, names)
-    nv = len(names)
-    fin = capi.Field(H, nv, 1)
-    for l in range(H.nlev):
-        for c in range(nv):
-            capi.check(capi.lib().pa_field_upload_level(fin.f, l, c, host[l][c].data_ptr()))
-    capi.sync()
-    if kind in ("curvature3", "target_curv"):
-        o = capi.CurvOpts()
-        o.prog_min = min(float(h[0].min()) for h in host)
-        o.prog_max = max(float(h[0].max()) for h in host)
-        out = capi.Field(H, 5, 1)
-        run = lambda: capi.curvature(fin, 0, 0, o, out, 0)
-        alg, units = H.algorithmic_bytes(5), H.num_cells
-    else:
-        out = capi.Field(H, 4 * nv, 0)
-        run = lambda: capi.grad(fin, 0, nv, out, 0)
-        alg, units = H.algorithmic_bytes(4) * nv, H.num_cells * nv
-    for _ in range(warmup):
-        run()
-    torch.cuda.synchronize()
-    l0 = capi.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        run()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"workload": desc, "value": units / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "cells": H.num_cells,
-            "boxes": [len(l.boxes) for l in pf.levels], "launches_per_step": (capi.kernel_launches() - l0) // steps,
-            "algorithmic_bytes": alg, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "hier_build_s": H.build_seconds}
+class Ctx:
+    """What every measurement needs: torch, the binding, the rank layout, the stream."""
+
+    def __init__(self, torch, dist, capi, multigpu, rank, world, local_rank, stream, transport, no_links):
+        self.torch, self.dist, self.capi, self.multigpu = torch, dist, capi, multigpu
+        self.rank, self.world, self.local_rank, self.stream = rank, world, local_rank, stream
+        self.transport, self.no_links = transport, no_links
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+        try:
+            self.expected = json.load(open(HASH_FILE))
+        except Exception:
+            self.expected = {}
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_hash(self, h):
+        """wrapping 64-bit sum of the ranks' fingerprints"""
+        if self.world == 1:
+            return h & (2 ** 64 - 1)
+        t = self.torch.tensor([h - 2 ** 64 if h >= 2 ** 63 else h], device="cuda", dtype=self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item()) & (2 ** 64 - 1)
 
 
-def bench_curvature_ranks(torch, dist, capi, multigpu, synth, stream, peak, kind, steps, warmup, rank, world, transport):
-    """--only-extra curvature3|target_curv under torchrun: the curvature tool (default options) with the boxes SFC-distributed
-    over the ranks -- multigpu.Curvature (peer links or slab exchange in front of each pass); max over ranks, whole-job cells."""
-    pf = synth.config3(256, 64, fill=False) if kind == "curvature3" else synth.config3(512, 128, fill=False)
-    flags = capi.PEER_LINKS if transport == "peer" else 0
+def measure(cx, spec, steps, warmup, e2e_steps=0, sampler=None):
+    """Run one workload on the current rank layout.  Returns a dict with the device-resident timing, the dominant kernel's
+    share, the optional host-buffer (e2e) timing and the output fingerprint."""
+    torch, dist, capi, multigpu = cx.torch, cx.dist, cx.capi, cx.multigpu
+    rank, world, stream = cx.rank, cx.world, cx.stream
+    kind, names = spec["kind"], spec["names"]
+    nvar = len(names)
+    pf = spec["build"](fill=False)
+    t0 = time.perf_counter()
+    flags = capi.NO_LINKS if cx.no_links else (capi.PEER_LINKS if (world > 1 and cx.transport == "peer") else 0)
     H = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, world, flags=flags)
-    host = gen_fields(torch, pf.levels, H.local_boxes, ["temp"])
-    state = capi.Field(H, 1, 1)
-    for l in range(H.nlev):
-        if H.local_cells[l]:
-            capi.check(capi.lib().pa_field_upload_level(state.f, l, 0, host[l][0].data_ptr()))
+    hier_s = time.perf_counter() - t0
+    cells = H.num_cells
+    host_in = gen_fields(torch, pf.levels, H.local_boxes, names)
+    nout = 4 * nvar if kind == "grad" else 5
+    fin = capi.Field(H, nvar, 1)
+    fout = capi.Field(H, nout, 0 if kind == "grad" else 1)
+    peer = bool(flags & capi.PEER_LINKS)
+    if peer:
+        multigpu.map_peers(fin)
+
+    def upload(comps=range(nvar)):
+        for l in range(H.nlev):
+            if H.local_cells[l]:
+                for c in comps:
+                    capi.check(capi.lib().pa_field_upload_level(fin.f, l, c, host_in[l][c].data_ptr()))
+
+    upload()
     capi.sync()
-    lo = torch.tensor([min([float(h[0].min()) for h in host if h[0].numel()] or [1e300])], device="cuda", dtype=torch.float64)
-    hi = torch.tensor([max([float(h[0].max()) for h in host if h[0].numel()] or [-1e300])], device="cuda", dtype=torch.float64)
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    o = capi.CurvOpts()
-    o.prog_min, o.prog_max = float(lo.item()), float(hi.item())
-    out = capi.Field(H, 5, 1)
-    op = multigpu.Curvature(state, 0, o, out, 0)
-    dist.barrier()
+    if world > 1:
+        dist.barrier()                 # every rank's inputs are resident before anyone reads them in place
+
+    if kind == "grad":
+        # whatever the neighbour links do not cover moves as NCCL send/recv of packed slabs (nothing, for peer transport
+        # on a uniform grid)
+        X = multigpu.SlabExchange(fin, nvar)
+
+        def step(ev=None):
+            X.run(0)
+            capi.grad(fin, 0, nvar, fout, 0, phases=1)
+            if ev is not None:
+                ev[0].record(stream)
+            capi.grad(fin, 0, nvar, fout, 0, phases=2)
+            if ev is not None:
+                ev[1].record(stream)
+    else:
+        lo = min([float(h[0].min()) for h in host_in if h[0].numel()] or [1e300])
+        hi = max([float(h[0].max()) for h in host_in if h[0].numel()] or [-1e300])
+        if world > 1:
+            t = torch.tensor([-lo, hi], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lo, hi = -float(t[0].item()), float(t[1].item())
+        o = capi.CurvOpts()
+        o.prog_min, o.prog_max = lo, hi
+        if world > 1:
+            op = multigpu.Curvature(fin, 0, o, fout, 0)
+
+            def step(ev=None):
+                op.run()
+        else:
+            def step(ev=None):
+                capi.curvature(fin, 0, 0, o, fout, 0)
+
     for _ in range(warmup):
-        op.run()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    l0 = capi.kernel_launches()
+        step()
+    cx.barrier()
+    if sampler is not None:
+        sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)] if kind == "grad" else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0, f0 = capi.kernel_launches(), capi.curv_fused_launches()
     e0.record(stream)
-    for _ in range(steps):
-        op.run()
+    for i in range(steps):
+        step(kev[i] if kev else None)
     e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    alg = H.algorithmic_bytes(5)                      # this rank's boxes
-    return {"workload": "curvature (default options), 3 levels, %d^3 base, boxes SFC-distributed over %d ranks (%s)" % (
-                256 if kind == "curvature3" else 512, world, "peer links" if flags else "slab exchange"),
-            "value": H.num_cells / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "ms_per_step": ms, "cells": H.num_cells,
-            "launches_per_step": (capi.kernel_launches() - l0) // steps, "roofline_frac_rank0": alg / (ms * 1e-3) / 1e9 / peak}
+    cx.barrier()
+    launches = capi.kernel_launches() - l0
+    fused = capi.curv_fused_launches() - f0
+    ms_step = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    value = cells * nvar / (ms_step * 1e-3) / 1e9
+    alg_local = H.algorithmic_bytes(4) * nvar if kind == "grad" else H.algorithmic_bytes(5)      # this rank's boxes
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev])) if kev else e0.elapsed_time(e1) / steps
+    res = {"value": value, "ms_per_step": ms_step, "cells": cells, "nvar": nvar, "launches": launches, "hier_build_s": hier_s,
+           "alg_bytes_local": alg_local, "kernel_ms": kernel_ms, "local_cells": H.num_local_cells, "flags": flags,
+           "boxes": [len(l.boxes) for l in pf.levels], "fused_launches": fused,
+           "slab_cells_rank0": (X.roff[-1] // nvar) if kind == "grad" else None}
+
+    # ---- fingerprint of the outputs of the last step ----
+    res["output_hash"] = "%016x" % cx.sum_hash(fout.hash(0, nout))
+
+    # ---- e2e: host buffers through the C ABI (pinned H2D of inputs, hot path, D2H of all outputs) -------------
+    if e2e_steps > 0:
+        host_out = [[torch.empty(max(H.local_cells[l], 1), dtype=torch.float64, pin_memory=True)[:H.local_cells[l]] for _ in range(nout)]
+                    for l in range(H.nlev)]
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_end = torch.cuda.Event()
+
+        def download(comps):
+            for l in range(H.nlev):
+                if H.local_cells[l]:
+                    for c in comps:
+                        capi.check(capi.lib().pa_field_download_level(fout.f, l, c, host_out[l][c].data_ptr()))
+
+        if kind == "grad":
+            # Pipelined by variable over three streams: H2D of variable v+1 (copy engine), hot path of v (SMs) and D2H of v's
+            # four outputs (the other copy engine) overlap; PCIe is full duplex, so the step costs ~max(H2D, D2H), not the sum.
+            X1 = multigpu.SlabExchange(fin, 1) if not X.empty else None
+            ev_up = [torch.cuda.Event() for _ in range(nvar)]
+            ev_g = [torch.cuda.Event() for _ in range(nvar)]
+
+            def e2e_step():
+                s_up.wait_event(ev_end)             # the previous step's readers (this rank's and the peers') are done
+                capi.set_stream(s_up.cuda_stream)
+                for v in range(nvar):
+                    upload([v])
+                    ev_up[v].record(s_up)
+                for v in range(nvar):
+                    stream.wait_event(ev_up[v])
+                    capi.set_stream(stream.cuda_stream)
+                    if peer:
+                        multigpu.stream_barrier()   # peers' uploads of v landed before this rank's kernel reads them over NVLink
+                    if X1 is not None:
+                        X1.run(v)
+                    capi.grad(fin, v, 1, fout, 4 * v)
+                    ev_g[v].record(stream)
+                    s_dn.wait_event(ev_g[v])
+                    capi.set_stream(s_dn.cuda_stream)
+                    download(range(4 * v, 4 * v + 4))
+                capi.set_stream(stream.cuda_stream)
+                if peer:
+                    multigpu.stream_barrier()       # nobody re-uploads while a peer still reads the old data
+                ev_end.record(stream)
+        else:
+            def e2e_step():
+                upload()
+                if peer:
+                    multigpu.stream_barrier()
+                step()
+                download(range(nout))
+                if peer:
+                    multigpu.stream_barrier()
+                ev_end.record(stream)
+
+        ev_end.record(stream)
+        e2e_step()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        cx.barrier()
+        e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        res["e2e"] = {"value": cells * nvar / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": H.num_local_cells * nvar * 8,
+                      "d2h_bytes_per_step": H.num_local_cells * nout * 8, "s_per_step": e2e_s}
+        del host_out
+    del fin, fout, host_in
+    return res
+
+
+def hash_verdict(cx, name, h):
+    want = cx.expected.get(name)
+    return {"value": h, "expected": want, "ok": (want is None or want == h)}
 
 
 def main():
@@ -282,17 +436,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--transport", default="peer", choices=["peer", "slab"])
     ap.add_argument("--no-links", action="store_true", help="materialise every ghost cell (reference data flow)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary curvature / small-box measurements")
-    ap.add_argument("--only-extra", default=None, choices=["curvature3", "grad5", "target_grad", "target_curv"], help="run just one secondary measurement (profiling aid)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--only-extra", default=None, help="run just one workload device-resident and print its short record (profiling aid)")
+    ap.add_argument("--write-hashes", action="store_true", help="(N=1) record this run's fingerprints in tests/golden/bench_hashes.json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    spec = workload_spec(args.workload)
+    spec = workload_spec(args.only_extra or args.workload)
     if args.impl == "reference":
         return reference_arm(args, spec)
 
     import torch
     import torch.distributed as dist
-    from peleanalysis_b200 import build, capi, multigpu, synth
+    from peleanalysis_b200 import build, capi, multigpu
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -306,215 +461,121 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
     capi.set_stream(stream.cuda_stream)
+    cx = Ctx(torch, dist, capi, multigpu, rank, world, local_rank, stream, args.transport, args.no_links)
+
+    def short(name, r):
+        per_rank_alg = r["alg_bytes_local"]
+        return {"workload": workload_spec(name)["desc"], "value": r["value"], "unit": UNIT, "n_gpus": world, "ms_per_step": r["ms_per_step"],
+                "cells": r["cells"], "boxes": r["boxes"], "launches_per_step": r["launches"] // max(1, r["steps"]),
+                "algorithmic_bytes": per_rank_alg, "roofline_frac": per_rank_alg / (r["ms_per_step"] * 1e-3) / 1e9 / cx.peak,
+                "hier_build_s": r["hier_build_s"], "output_hash": hash_verdict(cx, name, r["output_hash"])}
 
     if args.only_extra:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        r = measure(cx, spec, args.steps, args.warmup)
+        r["steps"] = args.steps
+        if rank == 0:
+            print(json.dumps(short(args.only_extra, r)))
         if world > 1:
-            if args.only_extra not in ("curvature3", "target_curv"):
-                raise SystemExit("--only-extra under torchrun: curvature3 or target_curv")
-            res = bench_curvature_ranks(torch, dist, capi, multigpu, synth, stream, peak, args.only_extra, args.steps, args.warmup, rank, world, args.transport)
-            if rank == 0:
-                print(json.dumps(res))
             dist.destroy_process_group()
-            return
-        print(json.dumps(bench_extra(torch, capi, synth, stream, peak, args.only_extra, args.steps, args.warmup)))
         return
-    names = spec["names"]
-    nvar = len(names)
-    pf = synth.make_hierarchy(spec["n"], [], [], spec["mgs"], names, fill=False)
-    t0 = time.perf_counter()
-    flags = capi.NO_LINKS if args.no_links else (capi.PEER_LINKS if (world > 1 and args.transport == "peer") else 0)
-    H = capi.Hierarchy(pf.levels, (1, 1, 1), (0, 0, 0), rank, world, flags=flags)
-    hier_s = time.perf_counter() - t0
-    cells_global = H.num_cells
-    host_in = gen_fields(torch, pf.levels, H.local_boxes, names)
-    fin = capi.Field(H, nvar, 1)
-    fout = capi.Field(H, 4 * nvar, 0)
 
-    def upload():
-        for l in range(H.nlev):
-            if H.local_cells[l]:
-                for c in range(nvar):
-                    capi.check(capi.lib().pa_field_upload_level(fin.f, l, c, host_in[l][c].data_ptr()))
-
-    if flags & capi.PEER_LINKS:
-        multigpu.map_peers(fin)
-    upload()
-    capi.sync()
-    if world > 1:
-        dist.barrier()                 # every rank's inputs are resident before anyone reads them in place
-
-    # whatever the neighbour links do not cover moves as NCCL send/recv of packed slabs (nothing, for peer transport
-    # on a uniform grid)
-    X = multigpu.SlabExchange(fin, nvar)
-
-    def exchange():
-        X.run(0)
-
-    def step(ev=None):
-        exchange()
-        capi.grad(fin, 0, nvar, fout, 0, phases=1)
-        if ev is not None:
-            ev[0].record(stream)
-        capi.grad(fin, 0, nvar, fout, 0, phases=2)
-        if ev is not None:
-            ev[1].record(stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = capi.kernel_launches()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(kev[i])
-    e1.record(stream)
-    barrier()
-    launches = capi.kernel_launches() - l0
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = cells_global * nvar / (ms_step * 1e-3) / 1e9
-    stencil_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-
-    # ---- e2e: host buffers through the C ABI (pinned H2D of inputs, hot path, D2H of all outputs) -------------
-    host_out = [[torch.empty(max(H.local_cells[l], 1), dtype=torch.float64, pin_memory=True)[:H.local_cells[l]] for _ in range(4 * nvar)]
-                for l in range(H.nlev)]
-
-    # Pipelined by variable over three streams: H2D of variable v+1 (copy engine), hot path of v (SMs) and D2H of v's
-    # four outputs (the other copy engine) overlap; PCIe is full duplex, so the step costs ~max(H2D, D2H), not the sum.
-    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
-    X1 = multigpu.SlabExchange(fin, 1) if not X.empty else None
-    ev_up = [torch.cuda.Event() for _ in range(nvar)]
-    ev_g = [torch.cuda.Event() for _ in range(nvar)]
-    ev_end = torch.cuda.Event()
-    peer = bool(flags & capi.PEER_LINKS)
-
-    def e2e_step():
-        s_up.wait_event(ev_end)             # the previous step's readers (this rank's and the peers') are done
-        capi.set_stream(s_up.cuda_stream)
-        for v in range(nvar):
-            for l in range(H.nlev):
-                if H.local_cells[l]:
-                    capi.check(capi.lib().pa_field_upload_level(fin.f, l, v, host_in[l][v].data_ptr()))
-            ev_up[v].record(s_up)
-        for v in range(nvar):
-            stream.wait_event(ev_up[v])
-            capi.set_stream(stream.cuda_stream)
-            if peer:
-                multigpu.stream_barrier()   # peers' uploads of v landed before this rank's kernel reads them over NVLink
-            if X1 is not None:
-                X1.run(v)
-            capi.grad(fin, v, 1, fout, 4 * v)
-            ev_g[v].record(stream)
-            s_dn.wait_event(ev_g[v])
-            capi.set_stream(s_dn.cuda_stream)
-            for l in range(H.nlev):
-                if H.local_cells[l]:
-                    for c in range(4 * v, 4 * v + 4):
-                        capi.check(capi.lib().pa_field_download_level(fout.f, l, c, host_out[l][c].data_ptr()))
-        capi.set_stream(stream.cuda_stream)
-        if peer:
-            multigpu.stream_barrier()       # nobody re-uploads while a peer still reads the old data
-        ev_end.record(stream)
-
-    ev_end.record(stream)
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    r = measure(cx, spec, args.steps, args.warmup, e2e_steps=args.e2e_steps, sampler=sampler)
+    r["steps"] = args.steps
+    if sampler is not None:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-    e2e_val = cells_global * nvar / e2e_s / 1e9
-    local = H.num_local_cells
-    h2d = local * nvar * 8
-    d2h = local * 4 * nvar * 8
+    kind, nvar = spec["kind"], len(spec["names"])
+    hashes = {args.workload: r["output_hash"]}
 
-    # ---- roofline of the dominant kernel (stencil) -----------------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-    alg_bytes = H.algorithmic_bytes(4) * nvar          # this rank's boxes, all variables: one stencil launch
-    achieved = alg_bytes / (stencil_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        # ncu capture of one launch at N=1; a rank's launch covers its share of the boxes
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "stencil_traffic.json"))).get(args.workload)
-        if traffic is not None and world > 1:
-            traffic = int(traffic * H.num_local_cells / max(cells_global, 1))
-    except Exception:
-        pass
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        # every N: the strong-scaling workload BASELINE names and the north-star hierarchy (both tools); N = 1 also the rest
+        kinds = ["config4", "target_grad", "target_curv"] + (["curvature3", "grad5"] if world == 1 else [])
+        for name in kinds:
+            if name == args.workload:
+                continue
+            try:
+                x = measure(cx, workload_spec(name), max(5, args.steps // 2), 3)
+                x["steps"] = max(5, args.steps // 2)
+                extras[name] = short(name, x)
+                hashes[name] = x["output_hash"]
+            except Exception as e:
+                extras[name] = {"error": str(e).splitlines()[0][:200]}
+                if world > 1:
+                    raise                         # a rank that fails alone would hang the others at the next collective
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    extras = None
-    if world == 1 and not args.no_extras:
-        del fin, fout, host_out, host_in
-        extras = {}
-        for kind in ("curvature3", "grad5", "target_grad", "target_curv"):
-            try:
-                extras[kind] = bench_extra(torch, capi, synth, stream, peak, kind, max(5, args.steps // 2), 3)
-            except Exception as e:
-                extras[kind] = {"error": str(e).splitlines()[0][:200]}
+    if args.write_hashes and world == 1:
+        cur = dict(cx.expected)
+        cur.update(hashes)
+        with open(HASH_FILE, "w") as f:
+            json.dump(cur, f, indent=1, sort_keys=True)
+        cx.expected = cur
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            v, t, cores, sample = run_reference(spec, steps=3, warmup=1)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample, "hot_path_seconds": t}
+            one = [spec["names"][-2] if args.workload.startswith("config2") else spec["names"][0]]
+            v, t, cores, _, ran = run_reference(spec, steps=3, warmup=1, variables=one)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "hot_path_seconds": t,
+                   "sample": "%s of %s on the workload's own grid (%d cells), %d of its %d variable(s); 3 timed repetitions of the tool's hot-path region" % (
+                       "grad" if kind == "grad" else "curvature", ran[0], r["cells"], len(ran), nvar)}
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: " + str(e).splitlines()[0][:160]}
+
+    pf = spec["build"](fill=False)
+    cfg = config_of(spec, pf)
+    alg_bytes = r["alg_bytes_local"]
+    achieved = alg_bytes / (r["kernel_ms"] * 1e-3) / 1e9
+    traffic = None
+    traffic_src = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "stencil_traffic.json")))
+        ent = tj.get(args.workload)
+        if isinstance(ent, dict):
+            traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
+        if traffic is not None and world > 1:
+            traffic = int(traffic * r["local_cells"] / max(r["cells"], 1))
+    except Exception:
+        pass
+    if kind == "grad":
+        kname = "k_stencil_tma<MODE_GRAD>" if os.environ.get("PA_STENCIL", "tma") != "simple" else "k_stencil_simple<MODE_GRAD>"
+    else:
+        kname = "k_curv_fused (whole step: ghost fills + fused kernel + shell pass)" if r["fused_launches"] else "k_stencil_tma<NORMAL_S> + <DIV> (whole step)"
+    hv = hash_verdict(cx, args.workload, r["output_hash"])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": spec["desc"], "cells": cells_global, "variables": nvar, "boxes": len(pf.levels[0].boxes),
-                   "parallelism": ("1 GPU" if world == 1 else "boxes SFC-distributed over %d ranks; cross-rank ghosts: %s" % (
-                       world, "read in place over NVLink (CUDA-IPC peer links, no exchange step)" if flags & capi.PEER_LINKS
-                       else "NCCL send/recv of packed slabs (%d cells/step recv on rank 0)" % (X.roff[-1] // nvar))),
-                   "ghosts": "materialised (PA_HIER_NO_LINKS)" if args.no_links else "same-level neighbours read in place by the stencil (neighbour links)",
-                   "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % ((alg_bytes) / 1e9),
-                   "stencil": os.environ.get("PA_STENCIL", "tma"), "hier_build_s": hier_s},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "s_per_step": e2e_s},
-        "gpu_launches": int(launches),
+        "metric": metric_name(kind), "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg,
+        "details": {"parallelism": ("1 GPU" if world == 1 else "boxes distributed over %d ranks along a (z, y, x) curve; cross-rank ghosts: %s" % (
+                        world, "read in place over NVLink (CUDA-IPC peer links, no exchange step)" if r["flags"] & capi.PEER_LINKS
+                        else "NCCL send/recv of packed slabs (%s cells/step recv on rank 0)" % r["slab_cells_rank0"])),
+                    "ghosts": "materialised (PA_HIER_NO_LINKS)" if args.no_links else "same-level neighbours read in place by the stencil (neighbour links)",
+                    "stencil": os.environ.get("PA_STENCIL", "tma"), "hier_build_s": r["hier_build_s"]},
+        "e2e": r.get("e2e"),
+        "gpu_launches": int(r["launches"]),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_stencil_tma<MODE_GRAD>" if os.environ.get("PA_STENCIL", "tma") != "simple" else "k_stencil_simple<MODE_GRAD>",
-                     "kernel_ms": stencil_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                     "step_frac": value / world * (alg_bytes / max(H.num_local_cells * nvar, 1)) / peak},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "kernel": kname, "kernel_ms": r["kernel_ms"], "algorithmic_bytes": alg_bytes,
+                     "peak_source": cx.peak_src,
+                     "step_frac": alg_bytes / (r["ms_per_step"] * 1e-3) / 1e9 / cx.peak},
+        "output_hash": hv,
         "cpu_baseline": cpu,
         "extras": extras,
     }
     print(json.dumps(line))
+    bad = [n for n, x in [(args.workload, hv)] + [(n, e.get("output_hash", {})) for n, e in (extras or {}).items()] if x and x.get("ok") is False]
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        print("output fingerprint mismatch: " + ", ".join(bad), file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

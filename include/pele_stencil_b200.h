@@ -130,6 +130,11 @@ int pa_field_download(const pa_field *f, int lev, int box, int comp, double *hos
 int pa_field_upload_level(pa_field *f, int lev, int comp, const double *host_concat);
 int pa_field_download_level(const pa_field *f, int lev, int comp, double *host_concat);
 int pa_field_set_val(pa_field *f, int comp, int ncomp, double v);     /* MultiFab::setVal incl. ghost cells */
+/* Fingerprint of the valid cells of comps [comp, comp+ncomp) of this rank's boxes: sum mod 2^64 of a mix of every cell's bit
+ * pattern with (level, GLOBAL box id, component, cell index).  Adding the ranks' values (wrapping) gives a number that does
+ * not depend on the box -> rank map: equal fingerprints for 1, 2, 4, 8 ranks <=> bit-identical outputs (with overwhelming
+ * probability).  Synchronises the stream.  No reference counterpart (the nearest is MultiFab::sum, AMReX_MultiFab.H). */
+int pa_field_hash(const pa_field *f, int comp, int ncomp, uint64_t *out);
 
 /* ---- ghost cells ------------------------------------------------------------------------------------ */
 /* FabArray::FillBoundary(scomp, ncomp, periodicity, cross) (AX/Base/AMReX_FabArrayCommI.H:7-60): same-level and
@@ -152,7 +157,8 @@ int pa_grad_phases(pa_field *in, int comp_in, int nvar, pa_field *out, int comp_
 /* curvature: S = state[comp_S]; writes Progress, MeanCurvature, FlameNormalX/Y/Z into out[comp_out..+4], then
  * (if enabled, in this order) GaussianCurvature, StrainRate, 9 ROST comps, VelFlameNormal.
  * Velocities (do_strain / do_velnormal) are state[comp_vel..+2].  Replaces Src/curvature.cpp:310-326,418-791.
- * `state` needs nghost>=1; `out` may have nghost 0. */
+ * `state` needs nghost>=1 (nghost == 1 selects the fused TMA kernels); `out` must have nghost == 1 (Progress and the flame
+ * normal are ghost-filled in place). */
 int pa_curvature(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out);
 int pa_curvature_num_outputs(const pa_curv_opts *opts);
 /* The same in its two passes, so a multi-rank caller can put the cross-rank step between them (the reference does the
@@ -162,8 +168,9 @@ int pa_curvature_num_outputs(const pa_curv_opts *opts);
  *   phases bit 1: ghost fill of the normal + MeanCurvature + the optional branches;
  *                 multi-rank: the caller has exchanged out[comp_out+2 .. +4], and with peer links has ordered every
  *                 rank's pass 1 before this call (a cross-rank barrier on the stream).
- * pa_curvature == pa_curvature_phases(..., 3) and is single-rank only.  Multi-rank hierarchies support the default
- * options and do_velnormal; threshold_prog / do_gaussCurv / do_strain return PA_ERR_UNSUPPORTED there. */
+ * pa_curvature == pa_curvature_phases(..., 3) and is single-rank only.  On multi-rank hierarchies the two phases cover the
+ * default options and do_velnormal; threshold_prog / do_gaussCurv / do_strain need further cross-rank steps and return
+ * PA_ERR_UNSUPPORTED here -- use pa_curvature_steps for those (every option is supported there). */
 int pa_curvature_phases(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out,
                         int phases);
 
@@ -171,11 +178,17 @@ int pa_curvature_phases(pa_field *state, int comp_S, int comp_vel, const pa_curv
  * (threshold_prog: the flame normal is exchanged before EVERY level's divergence, because level l reads the clipped
  * normal of level l-1, Src/curvature.cpp:514-518 after :549-567; do_gaussCurv: the un-normalised gradient, an internal
  * field, is exchanged too, :575-612; do_strain: the velocities, :686-717).  `steps` is a combination of PA_CURV_*; the
- * level range applies to PA_CURV_DIV only (-1, -1 = all levels).  Before each step the caller has exchanged what it reads:
+ * level range applies to PA_CURV_DIV and PA_CURV_CLIP only (-1, -1 = all levels).  Before each step the caller has exchanged
+ * what it reads:
  *   PA_CURV_PASS1  state[comp_S]          PA_CURV_DIV    out[comp_out+2 .. +4]  (with threshold_prog: one level per call)
  *   PA_CURV_GAUSS  scratch field 0 (3)    PA_CURV_STRAIN state[comp_vel .. +2]  PA_CURV_VELN   nothing
+ *   PA_CURV_CLIP   nothing -- but it zeroes the flame normal of the level IN PLACE where the progress variable is outside
+ *                  [threshold, 1-threshold] (:549-567), and PA_CURV_DIV of the same level reads the UNCLIPPED normal of other
+ *                  boxes (on a peer-linked hierarchy: of other ranks, in place): a multi-rank caller puts a cross-rank
+ *                  barrier between DIV(l) and CLIP(l), and the exchange / barrier for level l+1 after CLIP(l).  Without
+ *                  threshold_prog the step does nothing.  Single-rank: DIV | CLIP in one call runs them level by level.
  * pa_curvature_phases(1) == PA_CURV_PASS1, (2) == all the other steps. */
-enum { PA_CURV_PASS1 = 1, PA_CURV_DIV = 2, PA_CURV_GAUSS = 4, PA_CURV_STRAIN = 8, PA_CURV_VELN = 16 };
+enum { PA_CURV_PASS1 = 1, PA_CURV_DIV = 2, PA_CURV_GAUSS = 4, PA_CURV_STRAIN = 8, PA_CURV_VELN = 16, PA_CURV_CLIP = 32 };
 int pa_curvature_steps(pa_field *state, int comp_S, int comp_vel, const pa_curv_opts *opts, pa_field *out, int comp_out,
                        int steps, int lev_lo, int lev_hi);
 /* Internal field a multi-rank caller must exchange / peer-map: which = 0, the un-normalised gradient of the progress
@@ -244,6 +257,11 @@ int64_t pa_debug_selftest_math(int64_t n, uint64_t seed);
  * forces one; otherwise the library runs the self-test above on the device and keeps the branch-free forms only if not
  * one result bit differs (both forms compute the same IEEE results; the choice affects speed only). */
 int pa_debug_normal_math(void);
+/* 1 if curvature on this hierarchy runs through the fused kernel (every local box eligible: >= 3 cells in every direction,
+ * <= 128 wide), 0 if it takes the separate flame-normal / divergence kernels, < 0 on error. */
+int pa_debug_curv_fused(pa_hier *h);
+/* kernels launched by the fused curvature path so far (fused kernel + shell pass), process-wide */
+int64_t pa_debug_curv_fused_launches(void);
 
 #ifdef __cplusplus
 }

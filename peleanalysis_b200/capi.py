@@ -53,12 +53,15 @@ SYMBOLS = {
     "pa_field_upload": (_i, [_vp, _i, _i, _i, _vp]), "pa_field_download": (_i, [_vp, _i, _i, _i, _vp]),
     "pa_field_upload_level": (_i, [_vp, _i, _i, _vp]), "pa_field_download_level": (_i, [_vp, _i, _i, _vp]),
     "pa_field_set_val": (_i, [_vp, _i, _i, _d]),
+    "pa_field_hash": (_i, [_vp, _i, _i, C.POINTER(C.c_uint64)]),
     "pa_fill_boundary": (_i, [_vp, _i, _i, _i]), "pa_fill_ghosts": (_i, [_vp, _i, _i, _i, _i]),
     "pa_grad": (_i, [_vp, _i, _i, _vp, _i]), "pa_grad_phases": (_i, [_vp, _i, _i, _vp, _i, _i]),
     "pa_curvature": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i]),
     "pa_curvature_num_outputs": (_i, [C.POINTER(CurvOpts)]),
     "pa_debug_selftest_math": (C.c_int64, [C.c_int64, C.c_uint64]),
     "pa_debug_normal_math": (C.c_int, []),
+    "pa_debug_curv_fused": (C.c_int, [_vp]),
+    "pa_debug_curv_fused_launches": (C.c_int64, []),
     "pa_curvature_phases": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i, _i]),
     "pa_curvature_steps": (_i, [_vp, _i, _i, C.POINTER(CurvOpts), _vp, _i, _i, _i, _i]),
     "pa_curvature_scratch": (_i, [_vp, _i, C.POINTER(_vp)]),
@@ -115,6 +118,10 @@ def sync() -> None:
 
 def kernel_launches() -> int:
     return int(lib().pa_kernel_launches())
+
+
+def curv_fused_launches() -> int:
+    return int(lib().pa_debug_curv_fused_launches())
 
 
 def sfc_distribute(boxes: Sequence[tuple], nranks: int) -> np.ndarray:
@@ -357,6 +364,12 @@ class Field:
     def set_val(self, v: float, comp: int = 0, ncomp: Optional[int] = None) -> None:
         check(lib().pa_field_set_val(self.f, comp, ncomp or self.ncomp - comp, v))
 
+    def hash(self, comp: int = 0, ncomp: Optional[int] = None) -> int:
+        """Order-independent fingerprint of this rank's valid cells (pa_field_hash); add the ranks' values mod 2^64."""
+        v = C.c_uint64(0)
+        check(lib().pa_field_hash(self.f, comp, ncomp or self.ncomp - comp, C.byref(v)))
+        return int(v.value)
+
     def fill_boundary(self, comp: int = 0, ncomp: int = 1, cross: bool = False) -> None:
         check(lib().pa_fill_boundary(self.f, comp, ncomp, int(cross)))
 
@@ -379,7 +392,7 @@ def curvature_phases(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, o
     check(lib().pa_curvature_phases(state.f, comp_S, comp_vel, C.byref(opts), out.f, comp_out, phases))
 
 
-CURV_PASS1, CURV_DIV, CURV_GAUSS, CURV_STRAIN, CURV_VELN = 1, 2, 4, 8, 16
+CURV_PASS1, CURV_DIV, CURV_GAUSS, CURV_STRAIN, CURV_VELN, CURV_CLIP = 1, 2, 4, 8, 16, 32
 
 
 def curvature_steps(state: Field, comp_S: int, comp_vel: int, opts: CurvOpts, out: Field, comp_out: int, steps: int,

@@ -26,6 +26,7 @@ int fail(int code, const std::string& msg) { t_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* what) {
     return fail(PA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+std::atomic<long long> g_fused_launches{0};
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
 #define CHK(call) do { int r__ = (call); if (r__ != PA_OK) return r__; } while (0)
 
@@ -56,6 +57,7 @@ struct LevelDev {
     DevBuf<PaNbr> nbr;                                 // neighbour links of the local boxes
     DevBuf<PaHaloTag> halo_cross;
     DevBuf<long long> host_off;                        // nlocal+1 prefix of valid cells (host concat order)
+    DevBuf<int> gid;                                   // global box id of every local box
     std::vector<long long> host_off_h;
 };
 
@@ -88,6 +90,12 @@ struct pa_hier {
     std::map<int, std::unique_ptr<DevBuf<long long>>> face_coff;   // coarse gather offsets per ghost width
     DevBuf<PaPackTag> pack_tags;
     TileTable tiles_simple, tiles_tma;
+    // fused curvature (curv_fused.cu): K-block work items of every level (class 0 only) and the (level, box) list of the
+    // shell pass; curv_ok = every local box is eligible (>= 3 cells in every direction, <= 128 wide, plane fits)
+    TileTable tiles_curv;
+    bool curv_ok = false;
+    DevBuf<int> shell_level, shell_box;
+    long long shell_begin[PA_MAX_LEVELS + 1] = {0};
     std::map<cudaStream_t, std::unique_ptr<DevBuf<double>>> staging;   // upload / download staging, one per stream
     DevBuf<double> send_slab, recv_slab;               // multi-rank exchange, [cell][comp]
     int slab_ncomp = 0;
@@ -180,6 +188,60 @@ void build_tiles(pa_hier* h, TileTable& T, bool tma) {
     if (tma && T.max_plane_doubles > stencil_tma_max_plane_doubles()) T.ok = false;
 }
 
+// Work items of the fused curvature kernel: the K rows [1, ny-2] and K planes [1, nz-2] of every local box cut into blocks of
+// at most (staged-row capacity - 4) rows and PA_CF_ZC planes; the kernel stages each block with a two-cell halo.  Items of one
+// box are consecutive, y fastest, so neighbouring blocks -- which share halo rows -- are in flight at the same time and the
+// re-read rows hit L2.
+void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int>& shell_box) {
+    Hier& H = h->H;
+    TileTable& T = h->tiles_curv;
+    T.h.clear();
+    T.max_plane_doubles = 0;
+    T.ok = true;
+    std::memset(T.begin, 0, sizeof(T.begin));
+    std::memset(T.plane_doubles, 0, sizeof(T.plane_doubles));
+    std::memset(T.items, 0, sizeof(T.items));
+    const char* ezc = getenv("PA_CF_ZC");
+    const int ZC0 = ezc ? std::max(1, atoi(ezc)) : 64;
+    const int cw = curv_fused_consumer_warps();
+    shell_level.clear(); shell_box.clear();
+    for (int l = 0; l < H.nlev; ++l) {
+        T.begin[0][l] = (long long)T.h.size();
+        h->shell_begin[l] = (long long)shell_level.size();
+        const Level& V = H.lev[l];
+        const Layout& Y = H.layout(l, 1);
+        for (size_t lb = 0; lb < V.local.size(); ++lb) {
+            const Box& B = V.boxes[V.local[lb]];
+            const int nx = B.len(0), ny = B.len(1), nz = B.len(2);
+            const int nq4 = (nx + 3) / 4;
+            if (nx < 3 || ny < 3 || nz < 3 || nq4 > 32) { T.ok = false; continue; }
+            int lpr = 1;
+            while (lpr < nq4) lpr *= 2;
+            const int rows_cap = std::min(cw * (32 / lpr), curv_fused_max_rows());
+            int ty = rows_cap - 4;
+            const int nky = ny - 2, nkz = nz - 2;
+            const int nty = (nky + ty - 1) / ty; ty = (nky + nty - 1) / nty;
+            const int nzc = (nkz + ZC0 - 1) / ZC0; const int zc = (nkz + nzc - 1) / nzc;
+            const int plane = (ty + 4) * Y.lay[lb].P;
+            T.max_plane_doubles = std::max(T.max_plane_doubles, plane);
+            T.plane_doubles[0][l] = std::max(T.plane_doubles[0][l], plane);
+            for (int z0 = 1; z0 < nz - 1; z0 += zc)
+                for (int y0 = 1; y0 < ny - 1; y0 += ty) {
+                    PaTile t;
+                    t.lev = l; t.box = (int)lb;
+                    t.y0 = y0; t.ny = std::min(ty, ny - 1 - y0);
+                    t.z0 = z0; t.nz = std::min(zc, nz - 1 - z0);
+                    T.h.push_back(t);
+                }
+            shell_level.push_back(l); shell_box.push_back((int)lb);
+        }
+        T.begin[0][l + 1] = (long long)T.h.size();
+        h->shell_begin[l + 1] = (long long)shell_level.size();
+    }
+    if (T.max_plane_doubles > curv_fused_max_plane_doubles()) T.ok = false;
+    h->curv_ok = T.ok;
+}
+
 int ensure_device(pa_hier* h) {
     if (h->dev_ready) return PA_OK;
     int ndev = 0;
@@ -204,6 +266,7 @@ int ensure_device(pa_hier* h) {
         CU(D->nbr.upload(V.nbr, t_stream));
         CU(D->halo_cross.upload(H.halo_cross[l].tags, t_stream));
         CU(D->host_off.upload(D->host_off_h, t_stream));
+        CU(D->gid.upload(V.local, t_stream));
         h->lev.push_back(std::move(D));
     }
     CU(h->face_recs.upload(H.faces.recs, t_stream));
@@ -215,6 +278,16 @@ int ensure_device(pa_hier* h) {
     build_tiles(h, h->tiles_tma, true);
     CU(h->tiles_simple.d.upload(h->tiles_simple.h, t_stream));
     CU(h->tiles_tma.d.upload(h->tiles_tma.h, t_stream));
+    {
+        std::vector<int> sl, sb;
+        build_curv_tiles(h, sl, sb);
+        if (h->curv_ok) {
+            CU(h->tiles_curv.d.upload(h->tiles_curv.h, t_stream));
+            CU(h->shell_level.upload(sl, t_stream));
+            CU(h->shell_box.upload(sb, t_stream));
+            CU(cudaStreamSynchronize(t_stream));   // sl / sb die at the end of this scope
+        }
+    }
     CU(cudaStreamSynchronize(t_stream));      // host vectors may be reallocated later
     h->dev_ready = true;
     return PA_OK;
@@ -739,6 +812,31 @@ int pa_field_set_val(pa_field* f, int comp, int ncomp, double v) {
     return PA_OK;
 }
 
+int pa_field_hash(const pa_field* f, int comp, int ncomp, uint64_t* out) {
+    CHK(check_field(f, comp, ncomp, "pa_field_hash"));
+    if (!out) return fail(PA_ERR_ARG, "pa_field_hash: null result");
+    pa_hier* h = f->h;
+    CHK(ensure_device(h));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), t_stream);
+    for (int l = 0; l < h->H.nlev && e == cudaSuccess; ++l) {
+        const int nb = (int)h->H.lev[l].local.size();
+        if (!nb) continue;
+        int err = PA_OK;
+        const PaLayDev* ly = dev_layout(h, l, f->ng, &err);
+        if (!ly) { cudaFree(d); return err; }
+        e = launch_field_hash(h->lev[l]->boxes.p, ly, h->lev[l]->gid.p, nb, f->slab[l] + (long long)comp * f->cs[l], f->cs[l], comp, ncomp, l, d, t_stream);
+    }
+    unsigned long long v = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, t_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t_stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "pa_field_hash");
+    *out = (uint64_t)v;
+    return PA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- ghost cells
 int pa_fill_boundary(pa_field* f, int comp, int ncomp, int cross) {
     CHK(check_field(f, comp, ncomp, "pa_fill_boundary"));
@@ -897,6 +995,17 @@ struct CurvCtx {
     double invdenom;
 };
 
+// the fused kernel serves the whole hierarchy or nothing: every local box must be eligible (build_curv_tiles).  PA_CURV_FUSED=0
+// (or PA_CURV_UNFUSED=1, or PA_STENCIL=simple) selects the separate NORMAL_S / DIV kernels -- the independent second route
+// to the same bits the tests compare against.
+bool curv_fused_path(const CurvCtx& c) {
+    const char* e = getenv("PA_CURV_FUSED");
+    const char* no_fuse = getenv("PA_CURV_UNFUSED");
+    const char* es = getenv("PA_STENCIL");
+    if ((e && e[0] == '0') || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return false;
+    return c.state->ng == 1 && c.h->curv_ok && !overlap_enabled(c.h);
+}
+
 // PASS1: progress variable (curvature.cpp:310-321), its ghost cells, G = grad c, nrm, n = G / nrm (:426-502)
 int curv_pass1(const CurvCtx& c) {
     pa_hier* h = c.h;
@@ -910,6 +1019,28 @@ int curv_pass1(const CurvCtx& c) {
         for (int l = 0; l < nlev; ++l) { ex.aux[l] = h->tmpG->slab[l]; ex.cs_aux[l] = h->tmpG->cs[l]; }
     }
     const char* no_fuse = getenv("PA_CURV_UNFUSED");
+    if (curv_fused_path(c)) {
+        // ONE kernel for Progress, the flame normal and K (curv_fused.cu): the ghost cells of S that must be materialised
+        // (unlinked faces) are written in progress space first, as for MODE_NORMAL_S; K of the outermost cell layer of every
+        // box follows in curv_div once the ghost cells of n exist.
+        GhostXform xf{1, c.o->prog_min, c.invdenom};
+        for (int l = 0; l < nlev; ++l) {
+            ex.cout[l] = c.out->slab[l] ? c.out->slab[l] + (long long)c.cP * c.out->cs[l] : nullptr;
+            ex.kout[l] = c.out->slab[l] ? c.out->slab[l] + (long long)c.cK * c.out->cs[l] : nullptr;
+        }
+        ex.pmin = c.o->prog_min; ex.inv = c.invdenom;
+        ex.do_threshold = c.o->do_threshold ? 1 : 0;
+        ex.threshold = c.o->threshold;
+        CHK(grid_args(c.state, c.comp_S, c.out, c.cN, ga));
+        if (c.state->peers_missing > 0)
+            return fail(PA_ERR_STATE, "this hierarchy uses peer links (PA_HIER_PEER_LINKS): map every rank's slab of the state field first");
+        CHK(fill_ghosts_impl(c.state, c.comp_S, 1, 0, nlev - 1, false, xf));
+        TileTable& T = h->tiles_curv;
+        const long long a = T.begin[0][0], b = T.begin[0][nlev];
+        CU(launch_curv_fused(T.d.p + a, (int)(b - a), T.max_plane_doubles, ga, ex, stencil_decide_normal_math(t_stream) != 0, t_stream));
+        ++g_fused_launches;
+        return PA_OK;
+    }
     if (c.state->ng == 1 && use_tma(h, 1) && !(no_fuse && no_fuse[0] == '1')) {
         // Progress + normal fused.  The progress pass rides in the stencil's loader: valid cells stay S and are normalised as
         // they are read; the few ghost cells that must be materialised (unlinked faces) are written in progress space by the
@@ -947,13 +1078,14 @@ int curv_pass1(const CurvCtx& c) {
     return run_stencil(h, MODE_NORMAL, ga, ex, 1, 0, nlev - 1, c.out->ng, c.out);
 }
 
-// DIV: ghost cells of n, K = 0.5 div n (curvature.cpp:505-547), threshold clip of K and n (:549-567) on levels [l0, l1].
-// Without the clip every level's coarse data is final after PASS1, so one batched ghost fill + one stencil pass cover the
-// range; with it, level l needs the CLIPPED n of l-1 (:514-518 reads flame_normal[lev-1] after :549-567 modified it), so
-// the levels run in order.
+// DIV: ghost cells of n, K = 0.5 div n (curvature.cpp:505-547) with the threshold clip of K (:549-567) on levels [l0, l1].
+// After the fused PASS1 only the outermost cell layer of every box is left to do (k_div_shell).  The clip of n itself is a
+// separate step (curv_clip): K of a level reads the UNCLIPPED n of that level (its own and, through neighbour links, other
+// boxes' -- on a peer-linked hierarchy other ranks'), so n may only be clipped once every rank has finished DIV of the level.
+// With the clip, level l needs the CLIPPED n of l-1 for its coarse-fine ghost cells (:514-518 reads flame_normal[lev-1]
+// after :549-567 modified it), so the caller runs DIV(l), CLIP(l) level by level.
 int curv_div(const CurvCtx& c, int l0, int l1) {
     pa_hier* h = c.h;
-    Hier& H = h->H;
     pa_field* out = c.out;
     StencilExtra ex;
     GridArgs ga;
@@ -962,24 +1094,39 @@ int curv_div(const CurvCtx& c, int l0, int l1) {
     ex.threshold = c.o->threshold;
     for (int l = 0; l < c.nlev; ++l) ex.prog[l] = out->slab[l] + (long long)c.cP * out->cs[l];
     CHK(grid_args(out, c.cN, out, c.cK, ga));
-    if (!c.o->do_threshold) {
-        if (overlap_enabled(h) && l0 == 0 && l1 > 0) {
-            // n of every level is final: PASS1 is complete on the caller's stream, which the fork orders the side stream after
-            CHK(fill_ghosts_impl(out, c.cN, 3, 0, 0, false));
-            CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, c.cN, 3, 1, l1, false); }));
-            CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
-            CHK(join_side(h));
-            return run_stencil(h, MODE_DIV, ga, ex, 1, 1, l1, out->ng, out);
-        }
+    if (curv_fused_path(c)) {
+        if (out->peers_missing > 0)
+            return fail(PA_ERR_STATE, "this hierarchy uses peer links (PA_HIER_PEER_LINKS): map every rank's slab of the output field first");
         CHK(fill_ghosts_impl(out, c.cN, 3, l0, l1, false));
-        return run_stencil(h, MODE_DIV, ga, ex, 1, l0, l1, out->ng, out);
+        const long long a = h->shell_begin[l0], b = h->shell_begin[l1 + 1];
+        for (long long k = a; k < b; k += 65535) {
+            const int n = (int)std::min<long long>(65535, b - k);
+            CU(launch_div_shell(h->shell_level.p + k, h->shell_box.p + k, n, 24, ga, ex, t_stream));
+            ++g_fused_launches;
+        }
+        return PA_OK;
     }
+    if (overlap_enabled(h) && l0 == 0 && l1 > 0 && !c.o->do_threshold) {
+        // n of every level is final: PASS1 is complete on the caller's stream, which the fork orders the side stream after
+        CHK(fill_ghosts_impl(out, c.cN, 3, 0, 0, false));
+        CHK(fork_side(h, [&]() { return fill_ghosts_impl(out, c.cN, 3, 1, l1, false); }));
+        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, 0, 0, out->ng, out));
+        CHK(join_side(h));
+        return run_stencil(h, MODE_DIV, ga, ex, 1, 1, l1, out->ng, out);
+    }
+    CHK(fill_ghosts_impl(out, c.cN, 3, l0, l1, false));
+    return run_stencil(h, MODE_DIV, ga, ex, 1, l0, l1, out->ng, out);
+}
+
+// CLIP: n = 0 where the progress variable is outside [threshold, 1 - threshold] (curvature.cpp:549-567), levels [l0, l1]
+int curv_clip(const CurvCtx& c, int l0, int l1) {
+    pa_hier* h = c.h;
+    Hier& H = h->H;
+    pa_field* out = c.out;
     for (int l = l0; l <= l1; ++l) {
-        CHK(fill_ghosts_impl(out, c.cN, 3, l, l, false));
-        CHK(run_stencil(h, MODE_DIV, ga, ex, 1, l, l, out->ng, out));
         int err = PA_OK;
         const PaLayDev* lo = dev_layout(h, l, out->ng, &err);
-        if (!lo) return err;
+        if (!lo) { if (H.lev[l].local.empty()) continue; return err; }
         CU(launch_clip_normal(h->lev[l]->boxes.p, lo, lo, (int)H.lev[l].local.size(), out->slab[l] + (long long)c.cP * out->cs[l],
                               out->slab[l] + (long long)c.cN * out->cs[l], out->cs[l], c.o->threshold, t_stream));
     }
@@ -1067,7 +1214,7 @@ int curv_veln(const CurvCtx& c) {
 int pa_curvature_steps(pa_field* state, int comp_S, int comp_vel, const pa_curv_opts* opts, pa_field* out, int comp_out, int steps,
                        int lev_lo, int lev_hi) {
     if (!opts) return fail(PA_ERR_ARG, "pa_curvature: null options");
-    if (steps < 1 || steps > 31) return fail(PA_ERR_ARG, "pa_curvature_steps: steps must be a combination of PA_CURV_*");
+    if (steps < 1 || steps > 63) return fail(PA_ERR_ARG, "pa_curvature_steps: steps must be a combination of PA_CURV_*");
     CHK(check_field(state, comp_S, 1, "pa_curvature(state)"));
     CHK(check_field(out, comp_out, pa_curvature_num_outputs(opts), "pa_curvature(out)"));
     if (state->h != out->h) return fail(PA_ERR_ARG, "pa_curvature: fields belong to different hierarchies");
@@ -1093,10 +1240,17 @@ int pa_curvature_steps(pa_field* state, int comp_S, int comp_vel, const pa_curv_
     c.invdenom = 1.0 / (opts->prog_max - opts->prog_min);
 
     if (steps & PA_CURV_PASS1) CHK(curv_pass1(c));
-    if (steps & PA_CURV_DIV) {
-        if (opts->do_threshold && c.h->H.nranks > 1 && lev_lo != lev_hi)
-            return fail(PA_ERR_ARG, "pa_curvature_steps: with threshold_prog a multi-rank caller runs PA_CURV_DIV one level per call "
-                                    "(exchange the flame normal before each)");
+    if ((steps & (PA_CURV_DIV | PA_CURV_CLIP)) && opts->do_threshold) {
+        if (c.h->H.nranks > 1 && (lev_lo != lev_hi || (steps & (PA_CURV_DIV | PA_CURV_CLIP)) == (PA_CURV_DIV | PA_CURV_CLIP)))
+            return fail(PA_ERR_ARG, "pa_curvature_steps: with threshold_prog a multi-rank caller runs PA_CURV_DIV and PA_CURV_CLIP one level "
+                                    "per call, each in a call of its own (exchange the flame normal before DIV; every rank must have "
+                                    "finished DIV of the level before any rank clips it)");
+        // level by level: K of level l reads the unclipped n of l and the clipped n of l-1
+        for (int l = lev_lo; l <= lev_hi; ++l) {
+            if (steps & PA_CURV_DIV) CHK(curv_div(c, l, l));
+            if (steps & PA_CURV_CLIP) CHK(curv_clip(c, l, l));
+        }
+    } else if (steps & PA_CURV_DIV) {
         CHK(curv_div(c, lev_lo, lev_hi));
     }
     if ((steps & PA_CURV_GAUSS) && opts->do_gauss) CHK(curv_gauss(c));
@@ -1113,7 +1267,7 @@ int pa_curvature_phases(pa_field* state, int comp_S, int comp_vel, const pa_curv
                                         "(per level, and of internal fields): use pa_curvature_steps");
     int steps = 0;
     if (phases & 1) steps |= PA_CURV_PASS1;
-    if (phases & 2) steps |= PA_CURV_DIV | PA_CURV_GAUSS | PA_CURV_STRAIN | PA_CURV_VELN;
+    if (phases & 2) steps |= PA_CURV_DIV | PA_CURV_CLIP | PA_CURV_GAUSS | PA_CURV_STRAIN | PA_CURV_VELN;
     return pa_curvature_steps(state, comp_S, comp_vel, opts, out, comp_out, steps, 0, -1);
 }
 
@@ -1214,6 +1368,12 @@ int64_t pa_debug_selftest_math(int64_t n, uint64_t seed) {
 }
 
 int pa_debug_normal_math(void) { return stencil_tma_normal_math(); }
+int pa_debug_curv_fused(pa_hier* h) {
+    if (!h) return -1;
+    if (ensure_device(h) != PA_OK) return -1;
+    return h->curv_ok ? 1 : 0;
+}
+int64_t pa_debug_curv_fused_launches(void) { return g_fused_launches; }
 
 int64_t pa_debug_exchange_ids(pa_hier* h, int which, int64_t* out, int64_t out_len) {
     if (!h) return 0;

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace pa {
@@ -683,15 +684,23 @@ std::vector<long long> Hier::crse_offsets(int ng) {
     return out;
 }
 
-// Morton-order the boxes by their low corner and cut the curve into nranks chunks of ~equal cell volume
-// (the idea of DistributionMapping::SFCProcessorMap, AMReX_DistributionMapping.cpp:1262-1320).
+// Order the boxes along a curve through their low corners and cut the curve into nranks chunks of ~equal cell volume
+// (the idea of DistributionMapping::SFCProcessorMap, AMReX_DistributionMapping.cpp:1262-1320; any box -> rank map is valid).
+// Default curve: lexicographic in (z, y, x) -- x fastest.  A chunk is then a run of whole x-rows of boxes (z-slabs, cut in y
+// where a slab holds more than one rank), so a rank boundary is a y or z face wherever the level has at least one x-row of
+// boxes per rank: cross-rank ghost data then moves as whole contiguous rows / planes (one TMA bulk copy over NVLink each),
+// never as the per-row 8-byte column loads an x face costs (round 1: the Morton curve cut x at 8 ranks and the
+// efficiency fell from 0.95 to 0.81 there).  PA_DISTRIBUTE=morton selects the Morton curve (x in the lowest bit).
 void sfc_distribute(int nboxes, const int* boxes, int nranks, int* owner_out) {
     std::vector<std::pair<uint64_t, int>> keys(nboxes);
     int mn[3] = {1 << 30, 1 << 30, 1 << 30};
     for (int b = 0; b < nboxes; ++b)
         for (int d = 0; d < 3; ++d) mn[d] = std::min(mn[d], boxes[6 * b + d]);
-    auto spread = [](uint64_t v) {
+    const char* ecurve = getenv("PA_DISTRIBUTE");
+    const bool morton = ecurve && !strcmp(ecurve, "morton");
+    auto spread = [morton](uint64_t v) {
         uint64_t x = v & 0x1fffff;
+        if (!morton) return x;
         x = (x | x << 32) & 0x1f00000000ffffULL;
         x = (x | x << 16) & 0x1f0000ff0000ffULL;
         x = (x | x << 8) & 0x100f00f00f00f00fULL;
@@ -702,7 +711,7 @@ void sfc_distribute(int nboxes, const int* boxes, int nranks, int* owner_out) {
     double total = 0;
     for (int b = 0; b < nboxes; ++b) {
         uint64_t k = 0;
-        for (int d = 0; d < 3; ++d) k |= spread((uint64_t)(boxes[6 * b + d] - mn[d])) << d;
+        for (int d = 0; d < 3; ++d) k |= spread((uint64_t)(boxes[6 * b + d] - mn[d])) << (morton ? d : 21 * d);
         keys[b] = {k, b};
         double v = 1;
         for (int d = 0; d < 3; ++d) v *= boxes[6 * b + 3 + d] - boxes[6 * b + d] + 1;

@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill(const PaFaceRec* __res
         }
     }
 }
-// ---- opt-in variant (PA_BCFILL_V2=1; emulator-verified, not yet measured on a B200) -------------------------------------------
+// ---- the default since round 2 (PA_BCFILL_V2=0 selects k_bcfill above, kept as the independent second route the tests compare;
+// measured on a B200, profiles/r02_ab_variants.txt: grad on 16^3 boxes 0.983 -> 0.961 ms, curvature on 64^3 boxes 1.064 -> 1.036 ms,
+// 128^3 boxes unchanged) ----
 // Same arithmetic, different data path for the coarse values.  k_bcfill lets every ghost cell gather its (up to) nine
 // coarse neighbours itself: nine offset-table loads and nine scattered 8-byte loads per cell, the same coarse cell fetched
 // by up to nine threads (and r*r fine cells share a coarse cell): ncu shows 22-30 % DRAM utilisation at 8 useful bytes per
@@ -338,7 +340,7 @@ cudaError_t launch_bcfill(const PaFaceRec* recs, const int* rec_level, const PaF
                           int ncomp, const double* recv, GhostXform xf, cudaStream_t st) {
     if (blk1 <= blk0) return cudaSuccess;
     const char* v2 = getenv("PA_BCFILL_V2");
-    if (v2 && v2[0] == '1')
+    if (!(v2 && v2[0] == '0'))
         PA_LAUNCH((unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st, k_bcfill_v2)(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
     else
     PA_LAUNCH((unsigned)(blk1 - blk0), PA_FACE_CHUNK, 0, st, k_bcfill)(recs, rec_level, blocks + blk0, flags, coff, ga, ncomp, recv, xf);
@@ -478,6 +480,59 @@ cudaError_t launch_stencil_simple(int mode, const PaTile* tiles, int ntiles, con
     return cudaGetLastError();
 }
 
+// K = 0.5 div n on the OUTERMOST cell layer of each box: the cells whose stencil leaves the box, which the fused curvature
+// kernel (curv_fused.cu) does not compute.  Arithmetic and ghost rules are MODE_DIV's: a ghost cell of a linked face is the
+// neighbour's valid cell read in place, any other one is this box's materialised ghost cell (halo / coarse-fine / wall fill
+// of n, curvature.cpp:505-547).  blockIdx.y = entry of the (level, box) list, threads stride over the box's shell cells:
+// the two z faces as whole planes, then the y faces of the remaining planes as whole rows, then the x faces cell by cell.
+// Boxes are at least 3 cells wide in every direction (the fused path's eligibility rule).
+__global__ void __launch_bounds__(256) k_div_shell(const int* __restrict__ box_level, const int* __restrict__ box_index, GridArgs ga, StencilExtra ex) {
+    const int lev = box_level[blockIdx.y], box = box_index[blockIdx.y];
+    const LevArgs& L = ga.L[lev];
+    const PaBoxDev bx = L.boxes[box];
+    const PaLayDev li = L.lay_in[box];
+    const PaLayDev lo = L.lay_out[box];
+    const int nx = bx.n[0], ny = bx.n[1], nz = bx.n[2];
+    const long long nA = (long long)nx * ny, nC = (long long)nx * (nz - 2), nE = (long long)(ny - 2) * (nz - 2);
+    const long long total = 2 * nA + 2 * nC + 2 * nE;
+    const double dxi = L.dxi[0], dyi = L.dxi[1], dzi = L.dxi[2];
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        long long r = c;
+        if (r < 2 * nA) {
+            k = (r < nA) ? 0 : nz - 1;
+            if (r >= nA) r -= nA;
+            i = (int)(r % nx); j = (int)(r / nx);
+        } else if ((r -= 2 * nA) < 2 * nC) {
+            j = (r < nC) ? 0 : ny - 1;
+            if (r >= nC) r -= nC;
+            i = (int)(r % nx); k = 1 + (int)(r / nx);
+        } else {
+            r -= 2 * nC;
+            i = (r < nE) ? 0 : nx - 1;
+            if (r >= nE) r -= nE;
+            j = 1 + (int)(r % (ny - 2)); k = 1 + (int)(r / (ny - 2));
+        }
+        const double cx = *in_ptr(L, box, li, bx, 0, i, j, k), xm = *in_ptr(L, box, li, bx, 0, i - 1, j, k), xp = *in_ptr(L, box, li, bx, 0, i + 1, j, k);
+        const double cy = *in_ptr(L, box, li, bx, 1, i, j, k), ym = *in_ptr(L, box, li, bx, 1, i, j - 1, k), yp = *in_ptr(L, box, li, bx, 1, i, j + 1, k);
+        const double cz = *in_ptr(L, box, li, bx, 2, i, j, k), zm = *in_ptr(L, box, li, bx, 2, i, j, k - 1), zp = *in_ptr(L, box, li, bx, 2, i, j, k + 1);
+        const double dx = cdiff(dxi, xm, cx, xp), dy = cdiff(dyi, ym, cy, yp), dz = cdiff(dzi, zm, cz, zp);
+        double kk = 0.5 * (((0.0 + dx) + dy) + dz);
+        if (ex.do_threshold) {
+            const double pc = ex.prog[lev][cell_addr(li, i, j, k)];
+            if (pc < ex.threshold || pc > 1.0 - ex.threshold) kk = 0.0;
+        }
+        L.out[cell_addr(lo, i, j, k)] = kk;
+    }
+}
+cudaError_t launch_div_shell(const int* box_level, const int* box_index, int nboxes, int blocks_per_box, const GridArgs& ga,
+                             const StencilExtra& ex, cudaStream_t st) {
+    if (nboxes <= 0) return cudaSuccess;
+    PA_LAUNCH(dim3(blocks_per_box, nboxes), 256, 0, st, k_div_shell)(box_level, box_index, ga, ex);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // pointwise passes of the curvature tool
 // ------------------------------------------------------------------------------------------------------------
@@ -490,6 +545,48 @@ __device__ __forceinline__ void for_valid_cells(const PaBoxDev& b, F&& f) {
         long long r = c / b.n[0];
         f(i, (int)(r % b.n[1]), (int)(r / b.n[1]));
     }
+}
+
+// Order-independent 64-bit fingerprint of the VALID cells of a level: sum (mod 2^64) over components, boxes and cells of
+// mix(bit pattern ^ mix(level, GLOBAL box id, component, cell)).  Each rank sums its own boxes; the wrapped sum of the
+// ranks' values is the same for any box -> rank map exactly when every output bit is the same (bench.py: output_hash).
+__device__ __forceinline__ unsigned long long hmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ULL; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_field_hash(const PaBoxDev* __restrict__ boxes, const PaLayDev* __restrict__ lay, const int* __restrict__ gid,
+                                                    const double* __restrict__ base, long long cs, int comp0, int ncomp, int lev,
+                                                    unsigned long long* __restrict__ out) {
+    const PaBoxDev b = boxes[blockIdx.y];
+    const PaLayDev y = lay[blockIdx.y];
+    const unsigned long long g = (unsigned long long)gid[blockIdx.y];
+    unsigned long long acc = 0;
+    for (int m = 0; m < ncomp; ++m) {
+        const unsigned long long key = hmix64(((unsigned long long)lev << 56) ^ (g << 16) ^ (unsigned long long)(comp0 + m));
+        const double* p = base + (long long)m * cs;
+        for_valid_cells(b, [&](int i, int j, int k) {
+            const unsigned long long cell = ((unsigned long long)k * b.n[1] + j) * b.n[0] + i;
+            acc += hmix64((unsigned long long)__double_as_longlong(p[cell_addr(y, i, j, k)]) ^ hmix64(key + cell));
+        });
+    }
+    // block sum, then one atomic per block
+    __shared__ unsigned long long part[256];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, part[0]);
+}
+cudaError_t launch_field_hash(const PaBoxDev* boxes, const PaLayDev* lay, const int* gid, int nboxes, const double* base, long long cs,
+                              int comp0, int ncomp, int lev, unsigned long long* out, cudaStream_t st) {
+    for (int b0 = 0; b0 < nboxes; b0 += 65535) {
+        const int n = nboxes - b0 < 65535 ? nboxes - b0 : 65535;
+        PA_LAUNCH(dim3(16, n), 256, 0, st, k_field_hash)(boxes + b0, lay + b0, gid + b0, base, cs, comp0, ncomp, lev, out);
+        ++g_launches;
+    }
+    return cudaGetLastError();
 }
 
 // Progress variable c = (S - progMin) * invdenom on valid cells (curvature.cpp:310-321)

@@ -63,9 +63,11 @@ struct StencilExtra {
     const double* prog[PA_MAX_LEVELS];
     int do_threshold;
     double threshold;
-    // MODE_NORMAL_S: Progress output (one component, same layout as `out`) and the normalisation
+    // MODE_NORMAL_S / fused curvature: Progress output (one component, same layout as `out`) and the normalisation
     double* cout[PA_MAX_LEVELS];
     double pmin, inv;
+    // fused curvature: MeanCurvature output (one component, same layout as `out`)
+    double* kout[PA_MAX_LEVELS];
 };
 
 extern std::atomic<long long> g_launches;     // kernels launched by this library (host threads may launch concurrently)
@@ -99,12 +101,31 @@ cudaError_t launch_stencil_tma(int mode, const PaTile* tiles, int ntiles, int ma
 // device self-test: the branch-free sqrt / reciprocal / flame-normal forms of the TMA kernel against the plain operators on
 // n pseudo-random operand sets; *bad_host = number of results that differ in any bit
 cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long long* bad_host, cudaStream_t st);
+// Fused curvature (curv_fused.cu): S -> Progress, flame normal, and K on every cell whose K stencil stays inside its box.
+// tiles: K rows / planes (subsets of [1, n-2]) of boxes at least 3 cells wide in every direction and at most
+// curv_fused_max_nx() wide in x; GridArgs: in = S (nghost 1 layout), out = first flame-normal component; ex.cout / ex.kout /
+// ex.aux / threshold as for the separate modes.
+cudaError_t launch_curv_fused(const PaTile* tiles, int ntiles, int max_plane_doubles, const GridArgs& ga, const StencilExtra& ex,
+                              bool plain_math, cudaStream_t st);
+int curv_fused_consumer_warps();
+int curv_fused_max_rows();           // staged rows per item (K rows + 4)
+int curv_fused_max_plane_doubles();
+// K on the outermost cell layer of the boxes (the cells the fused kernel leaves out), from the ghost-filled flame normal:
+// MODE_DIV's arithmetic, one thread per cell.  GridArgs: in = n (3 comps), out = K.
+cudaError_t launch_div_shell(const int* box_level, const int* box_index, int nboxes, int blocks_per_box, const GridArgs& ga,
+                             const StencilExtra& ex, cudaStream_t st);
+// launch bookkeeping shared by the persistent kernels (stencil_tma.cu)
+cudaError_t stencil_ticket(cudaStream_t st, unsigned long long nwork, int grid, unsigned long long** dev_out, unsigned long long* base_out);
+int stencil_num_sms(cudaError_t* err);
+int stencil_decide_normal_math(cudaStream_t st);   // 0 branch-free forms, 1 plain operators (runs the device self-test once)
 void stencil_tma_release();      // frees the work-item ticket counters (pa_finalize)
 int stencil_tma_normal_math();   // flame-normal arithmetic in use: 0 branch-free forms, 1 plain operators, -1 not decided yet
 int stencil_tma_tile_rows();     // TY the tile table must be built with
 int stencil_tma_max_tile_rows();
 int stencil_tma_max_plane_doubles();
 
+cudaError_t launch_field_hash(const PaBoxDev* boxes, const PaLayDev* lay, const int* gid, int nboxes, const double* base, long long cs,
+                              int comp0, int ncomp, int lev, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_progress(const PaBoxDev* boxes, const PaLayDev* lay_in, const PaLayDev* lay_out, int nboxes,
                             const double* S, double* C, double pmin, double invdenom, cudaStream_t st);
 cudaError_t launch_clip_normal(const PaBoxDev* boxes, const PaLayDev* lay_c, const PaLayDev* lay_n, int nboxes,

@@ -25,6 +25,7 @@
 #include <mutex>
 
 #include "kernels.cuh"
+#include "stencil_dev.cuh"
 
 namespace pa {
 
@@ -50,176 +51,6 @@ constexpr int MAX_TILE_ROWS = 30;                     // rows per tile: as many 
 constexpr int XG_LANES = 30;                          // producer lanes 1 .. 30 fetch the x ghosts: (side, row) cells lane-1 and lane-1+30
 constexpr int STATIC_SMEM = 10 * 1024 + 256;          // upper bound of the static shared memory below (10112 bytes)
 
-#ifndef PA_HOST_EMULATION
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// 8-byte asynchronous global -> shared copy (SASS LDGSTS) and its completion hooked to an mbarrier arrival
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// the same on a barrier address computed once (PF kernels): the compiler otherwise rebuilds the shared-window address of
-// &bar[i] -- an S2R SR_CgaCtaId plus a LEA -- in front of every wait and every arrive of the plane loop
-typedef uint32_t bar_ref;
-__device__ __forceinline__ bar_ref bar_base(uint64_t* b) { uint32_t a = smem_u32(b); asm volatile("" : "+r"(a)); return a; }
-__device__ __forceinline__ bar_ref bar_at(bar_ref b, int i) { return b + 8u * (uint32_t)i; }
-__device__ __forceinline__ void mbar_arrive_a(bar_ref a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
-__device__ __forceinline__ void mbar_wait_a(bar_ref a, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// seeds of the IEEE sqrt / reciprocal refinements (MUFU.RSQ64H / MUFU.RCP64H on the high word)
-__device__ __forceinline__ double mufu_rsq64h(double x) { double s; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x)); return s; }
-__device__ __forceinline__ double mufu_rcp64h(double x) { double s; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x)); return s; }
-#else   // tests/emu: the emulator's mbarrier / async-copy model instead of PTX (see tests/emu/cuda_runtime.h)
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { cuemu::mbar_init(bar, count); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { cuemu::mbar_expect_tx(bar, bytes); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { cuemu::mbar_arrive(bar); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { cuemu::mbar_wait(bar, parity); }
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { cuemu::tma_load_1d(smem_dst, gsrc, bytes, bar); }
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) { cuemu::cp_async_8(smem_dst, gsrc); }
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) { cuemu::cp_async_arrive_noinc(bar); }
-typedef uint64_t* bar_ref;
-__device__ __forceinline__ bar_ref bar_base(uint64_t* b) { return b; }
-__device__ __forceinline__ bar_ref bar_at(bar_ref b, int i) { return b + i; }
-__device__ __forceinline__ void mbar_arrive_a(bar_ref a) { cuemu::mbar_arrive(a); }
-__device__ __forceinline__ void mbar_wait_a(bar_ref a, uint32_t parity) { cuemu::mbar_wait(a, parity); }
-#endif
-
-__device__ __forceinline__ double cdiff(double dxi, double m, double c, double p) {
-    // the reference's sequence, sign of zero included: faces f = dxinv*(s(i)-s(i-1)) are multiplied by 1/b = -1
-    // (MLCellABecLap::getFluxes), averaged (average_face_to_cellcenter), and multiplied by -1 again (grad.cpp:219).  When the
-    // two face differences cancel exactly the result is -0, which 0.5*(fl+fh) would turn into +0.
-    const double fl = dxi * (c - m), fh = dxi * (p - c);
-    return -(0.5 * ((-fl) + (-fh)));
-}
-__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
-
-// Three quotients by one divisor, bit-identical to the IEEE divisions a/n the reference performs (curvature.cpp:498-502,
-// MultiFab::Divide): y = RN(1/n) once, then per numerator q0 = RN(a*y), r = a - n*q0 (exact in an FMA), q = RN(q0 + r*y).
-// With a correctly rounded reciprocal the corrected quotient is the correctly rounded a/n (Markstein, "Computation of
-// elementary functions on the IBM RISC System/6000 processor", 1990, Thm 8.8); checked here against a/n on 5e10 random and
-// adversarial operand pairs without a mismatch (tests/golden/README: divtest).  The remainder must not underflow, so
-// tiny non-zero numerators take the plain division; zeros and NaN/Inf fall out right (+-0 keeps the sign rule of a/n).
-// The reference divides valid cells by a norm that is >= |a| (or by -1e-14), so quotients never overflow.
-__device__ __forceinline__ double div_by(double a, double y, double n) {
-    const double q0 = a * y;
-    const double r = fma(-n, q0, a);
-    return fma(r, y, q0);
-}
-// non-zero and below 2^-830 (~1.4e-250): the remainder a - n*q0 (~2^-53 |a|) could underflow
-__device__ __forceinline__ bool tiny_nonzero(double a) {
-    const unsigned h = (unsigned)__double2hiint(a) & 0x7fffffffu;
-    return (h < 0x0C100000u) & ((h | (unsigned)__double2loint(a)) != 0u);
-}
-
-// ---- branch-free IEEE sqrt / reciprocal -------------------------------------------------------------------------
-// The two cells of a pair (and the two pairs of a thread) carry independent sqrt -> reciprocal -> quotient chains; the
-// compiler only overlaps them inside one basic block, and CUDA's sqrt() / __drcp_rn() each end in a branch to a slow
-// path.  These are the FAST paths of exactly those two routines -- the instruction sequences nvcc 12.9 emits for
-// sm_100a, transcribed operation by operation (MUFU seed incl. its low word, the FMA refinements, the final
-// correction) -- without the branch; the caller checks the operand range once for all chains and sends the rare
-// out-of-range case to the plain operators.  pa_debug_selftest_math compares them bit for bit with sqrt() and
-// __drcp_rn() on the device over every exponent of their range (tests/test_gpu_parity.py::test_fast_math_selftest).
-__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
-// valid for hi32(x) in [0x03500000, 0x7ff00000): 2^-970 <= x < inf
-__device__ __forceinline__ double sqrt_fast(double x) {
-#ifdef PA_HOST_EMULATION
-    return sqrt(x);                                                     // the emulator has no MUFU: the value the fast path must equal
-#else
-    const double seed = mufu_rsq64h(x);
-    const double y = __hiloint2double(hi32(seed), hi32(x) - 0x03500000);
-    const double e = fma(x, -(y * y), 1.0);
-    const double h = fma(e, 0.375, 0.5);
-    const double y1 = fma(h, y * e, y);                                 // refined 1/sqrt(x)
-    const double g = x * y1;
-    const double d = fma(g, -g, x);
-    const double hy = __hiloint2double(hi32(y1) - 0x00100000, __double2loint(y1));   // y1 / 2
-    return fma(d, hy, g);
-#endif
-}
-__device__ __forceinline__ bool sqrt_fast_ok(double x) { return (unsigned)(hi32(x) - 0x03500000) < 0x7ca00000u; }
-// valid while |float(hi32(n) + 0x300402)| >= 2^-127, i.e. for every n whose exponent is neither tiny nor huge; the
-// callers' divisors lie in [1e-14, 2^513]
-__device__ __forceinline__ double rcp_fast(double n) {
-#ifdef PA_HOST_EMULATION
-    return 1.0 / n;
-#else
-    const double seed = mufu_rcp64h(n);
-    const double y = __hiloint2double(hi32(seed), hi32(n) + 0x300402);
-    const double e = fma(-n, y, 1.0);
-    const double y1 = fma(y, fma(e, e, e), y);
-    return fma(y1, fma(-n, y1, 1.0), y1);
-#endif
-}
-__device__ __forceinline__ bool rcp_fast_ok(double n) { return fabsf(__int_as_float(hi32(n) + 0x300402)) >= 5.8789094863358348022e-39f; }
-
-// Flame normal of the two cells of a pair (curvature.cpp:467-502): nrm = -max(1e-14, sqrt(G.G)), n = G / nrm, IEEE
-// results.  Both chains run branch-free side by side; one joint predicate covers everything the fast forms exclude.
-//  * G.G below 2^-970 (exact zeros -- flat regions -- included): sqrt <= 2^-485 < 1e-14, the clamp decides, nrm = -1e-14
-//    whatever the exact root (a NaN with the sign bit set lands here too: std::max(1e-14, NaN) = 1e-14, same result)
-//  * G.G = inf / NaN, or a tiny non-zero numerator (remainder underflow in div_by): plain operators, out of line of
-//    the hot path
-__device__ __forceinline__ void normal_pair(double ax, double bx, double gx, double ay, double by, double gy, double* __restrict__ r0,
-                                            double* __restrict__ r1) {
-    const double s0 = ax * ax + bx * bx + gx * gx, s1 = ay * ay + by * by + gy * gy;
-    double n0 = -fmax(1e-14, sqrt_fast(s0)), n1 = -fmax(1e-14, sqrt_fast(s1));
-    if (hi32(s0) < 0x03500000) n0 = -1e-14;
-    if (hi32(s1) < 0x03500000) n1 = -1e-14;
-    const bool cold = (hi32(s0) >= 0x7ff00000) | (hi32(s1) >= 0x7ff00000) | tiny_nonzero(ax) | tiny_nonzero(bx) | tiny_nonzero(gx) |
-                      tiny_nonzero(ay) | tiny_nonzero(by) | tiny_nonzero(gy);
-    const double y0 = rcp_fast(n0), y1 = rcp_fast(n1);
-    r0[0] = div_by(ax, y0, n0); r0[1] = div_by(bx, y0, n0); r0[2] = div_by(gx, y0, n0);
-    r1[0] = div_by(ay, y1, n1); r1[1] = div_by(by, y1, n1); r1[2] = div_by(gy, y1, n1);
-    if (__builtin_expect(cold, 0)) {
-        n0 = -fmax(1e-14, sqrt(s0)); n1 = -fmax(1e-14, sqrt(s1));
-        r0[0] = ax / n0; r0[1] = bx / n0; r0[2] = gx / n0;
-        r1[0] = ay / n1; r1[1] = by / n1; r1[2] = gy / n1;
-    }
-}
-
-// CTAs per SM when the CTA carries the extra descriptor warp (PF variant): one warp more per CTA must still fit the register file
-constexpr int per_sm_pf(int cw, bool heavy) { return cw >= 16 ? 1 : cw == 8 ? 2 : cw == 4 ? 3 : (heavy ? 4 : 5); }
-constexpr int PF_LEAD = 8;                            // planes before the end of an item at which the next one is prepared
 
 template <int MODE> struct ModeTraits;
 template <> struct ModeTraits<MODE_GRAD> { static constexpr int NIN = 1, NOUT = 4; };
@@ -238,16 +69,6 @@ struct TileRec {
     PaLayDev li, lo;
 };
 
-// PF variant: everything the producer's plane loop needs for one work item, prepared one item ahead by the descriptor warp
-struct ProdCtx {
-    TileRec rec;                          // rec.t.lev < 0: no more work
-    const double* own;                    // row 0 / plane 0 of the item's first input component in the box's own block
-    const double* src[4];                 // sources of the linked y-lo, z-lo, y-hi, z-hi faces (nullptr: not linked)
-    long long cs[4];                      // ... and the component strides of the slabs they live in
-    long long cs_in;                      // component stride of the box's own slab
-    const double* xsrc[2 * XG_LANES];     // x-ghost cell sources at plane 0: entry lane-1 + XG_LANES*k (nullptr: none)
-};
-
 // per-item flags (one register)
 enum : unsigned {
     F_ACTIVE = 1u, F_TWO = 2u,           // item exists; its second cell is a valid cell (not the x-hi ghost of an odd row)
@@ -260,14 +81,8 @@ enum : unsigned {
 
 // PLAIN = true: the flame normal through the plain IEEE operators (sqrt(), six divisions) instead of normal_pair() -- the
 // form the library falls back to should the device self-test of the branch-free forms ever report a differing bit
-// PF = true adds a DESCRIPTOR WARP: it draws the next ticket and walks the dependent descriptor loads (tile -> box, layouts,
-// neighbour links -> neighbours' layouts, peer slabs) while the producer is still streaming the current item, and hands the
-// producer a finished context through shared memory.  Without it the producer does that walk itself between two items and
-// the ring drains meanwhile (ncu, NORMAL_S: a tenth of the consumers' time is spent waiting for an item's first plane).
-template <int MODE, int CW, bool PLAIN, bool PF>
-__global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
-                                  PF ? per_sm_pf(CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S)
-                                     : Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
+template <int MODE, int CW, bool PLAIN>
+__global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
                                                             StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
                                                             int S /* ring depth in planes */,
                                                             unsigned long long* __restrict__ ticket, unsigned long long ticket_base) {
@@ -281,102 +96,18 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(16) double xg_s[MAX_STAGES][2][32];          // x ghosts of linked x faces: [stage][lo/hi][row]
     __shared__ __align__(16) TileRec rec_s[MAX_STAGES];
-    ProdCtx* ctx = nullptr;                                           // PF: the next item's producer context ...
-    uint64_t* ctx_bar = nullptr;                                      // ... [0] full (descriptor warp -> producer), [1] go (producer -> descriptor warp)
-    if constexpr (PF) {
-        __shared__ __align__(16) ProdCtx ctx_storage;
-        __shared__ __align__(8) uint64_t ctx_bar_storage[2];
-        ctx = &ctx_storage; ctx_bar = ctx_bar_storage;
-    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // PF variant, MODE_DIV: "lean" staging -- only the differentiated component needs its halo, so n_x and n_z are staged
-    // without the y-halo rows and n_x, n_y without the z-halo planes (the consumers never read those cells); bit 0 of
-    // stage_doubles (a multiple of 16) switches it off for A/B runs.  Not compiled into the default kernels.
-    bool lean = false;
-    if constexpr (PF && MODE == MODE_DIV) { lean = !(stage_doubles & 1); stage_doubles &= ~15; }
     const long long stage_stride = (long long)NIN * stage_doubles;
 
     if (threadIdx.x == 0) {
         // a stage is full when the TMA bytes have landed (lane 0's arrive.expect_tx) and every x-ghost lane has arrived
         for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1u + XG_LANES); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
-        if constexpr (PF) { mbar_init(&ctx_bar[0], 1u); mbar_init(&ctx_bar[1], 1u); }
 #ifndef PA_HOST_EMULATION
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     }
     __syncthreads();
-
-    if constexpr (PF) {
-        if (warp == CONSUMER_WARPS + 1) {
-            // ===================================== descriptor warp =====================================
-            // One item ahead of the producer: ticket, tile, box / layout / link records, neighbours' layouts and slabs --
-            // three dependent round trips to L2 / HBM that would otherwise sit between two items of the ring.  The ticket is
-            // drawn only PF_LEAD planes before the producer finishes its current item, so the dynamic balance of the
-            // persistent grid stays within a fraction of an item.
-            if (lane > XG_LANES) return;
-            uint32_t gphase = 0;
-            for (int k = 0;; ++k) {
-                if (k > 0) { mbar_wait(&ctx_bar[1], gphase); gphase ^= 1u; }     // the producer took the previous context
-                unsigned long long tk = 0;
-                if (lane == 0) tk = atomicAdd(ticket, 1ULL) - ticket_base;
-                tk = __shfl_sync(0x7fffffffu, tk, 0);
-                ProdCtx& X = *ctx;
-                if (tk >= (unsigned long long)nwork) {
-                    if (lane == 0) X.rec.t.lev = -1;
-                    __syncwarp(0x7fffffffu);
-                    if (lane == 0) mbar_arrive(&ctx_bar[0]);
-                    return;
-                }
-                const int wi = (int)tk;
-                const int v = wi / ntiles;
-                const PaTile t = tiles[wi - v * ntiles];
-                const LevArgs& L = ga.L[t.lev];
-                const PaBoxDev bx = L.boxes[t.box];
-                const PaLayDev li = L.lay_in[t.box];
-                const PaNbr nb = L.nbr[t.box];
-                const int c0 = L.in_comp + (MODE == MODE_DIV ? 0 : v);
-                auto link_src = [&](int face, long long& cs) -> const double* {      // as in the producer below
-                    const PaNbrFace F = nb.f[face];
-                    cs = 0;
-                    if (F.nb < 0) return nullptr;
-                    const PaPeerSlab ps = L.peers[F.rank];
-                    const PaLayDev ln = L.lay_in[F.nb];
-                    cs = ps.cs;
-                    return ps.base + (long long)c0 * ps.cs + ln.off + (long long)(F.rel[2] + ln.ng) * ln.PS + (long long)(F.rel[1] + ln.ng) * ln.P + F.rel[0];
-                };
-                if (lane == 0) {
-                    X.rec.t = t; X.rec.v = v; X.rec.bx = bx; X.rec.li = li; X.rec.lo = L.lay_out[t.box];
-                    int lk = 0;
-#pragma unroll
-                    for (int f = 0; f < 6; ++f) lk |= (nb.f[f].nb >= 0) ? (1 << f) : 0;
-                    X.rec.links = lk;
-                    X.own = L.in + (MODE == MODE_DIV ? 0 : (long long)v * L.cs_in) + li.off + (long long)li.ng * li.PS + (long long)li.ng * li.P;
-                    X.cs_in = L.cs_in;
-                    long long cs;
-                    X.src[0] = link_src(1, cs); X.cs[0] = cs;
-                    X.src[1] = link_src(2, cs); X.cs[1] = cs;
-                    X.src[2] = link_src(4, cs); X.cs[2] = cs;
-                    X.src[3] = link_src(5, cs); X.cs[3] = cs;
-                } else {
-#pragma unroll
-                    for (int k2 = 0; k2 < 2; ++k2) {
-                        const int idx = lane - 1 + XG_LANES * k2;
-                        const int side = idx / t.ny, xr = idx - side * t.ny;   // side 0 = x-lo, 1 = x-hi
-                        const double* src = nullptr;
-                        if (side < 2) {
-                            long long cs;
-                            const double* s0 = link_src(side ? 3 : 0, cs);
-                            if (s0) src = s0 + (long long)(t.z0 - 1) * li.PS + (long long)(t.y0 + xr) * li.P + ((side ? bx.n[0] : -1) + li.ng + li.xoff);
-                        }
-                        X.xsrc[idx] = src;
-                    }
-                }
-                __syncwarp(0x7fffffffu);
-                if (lane == 0) mbar_arrive(&ctx_bar[0]);
-            }
-        }
-    }
 
     if (warp == CONSUMER_WARPS) {
         // ===================================== producer warp =====================================
@@ -385,91 +116,7 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
         if (lane > XG_LANES) return;
         int stage = 0;
         uint32_t ephase = 1;                            // parity that lets the first pass through the ring go without waiting
-        if constexpr (PF) {
-            // the descriptor warp has the next item's context ready in shared memory; take it, stream the item, and tell
-            // the descriptor warp to prepare the following one PF_LEAD planes before this one ends
-            uint32_t cphase = 0;
-            for (;;) {
-                mbar_wait(&ctx_bar[0], cphase); cphase ^= 1u;
-                const ProdCtx& X = *ctx;
-                const PaTile t = X.rec.t;
-                if (t.lev < 0) {
-                    mbar_wait(&empty_bar[stage], ephase);
-                    if (lane == 0) { rec_s[stage].t.lev = -1; mbar_arrive(&full_bar[stage]); }
-                    else cp_async_arrive_noinc(&full_bar[stage]);
-                    break;
-                }
-                const PaLayDev li = X.rec.li;
-                const int nyb = X.rec.bx.n[1], nzb = X.rec.bx.n[2];
-                const int rows = t.ny + 2, nplanes = t.nz + 2;
-                const uint32_t row_bytes = (uint32_t)li.P * 8u, plane_bytes = (uint32_t)rows * row_bytes;
-                long long cs_ylo = 0, cs_zlo = 0, cs_yhi = 0, cs_zhi = 0, cs_in = 0;
-                const double *own = nullptr, *s_ylo = nullptr, *s_zlo = nullptr, *s_yhi = nullptr, *s_zhi = nullptr;
-                const double* xsrc[2] = {nullptr, nullptr};
-                double* xdst[2] = {nullptr, nullptr};
-                if (lane == 0) {
-                    own = X.own; cs_in = X.cs_in;
-                    s_ylo = X.src[0]; s_zlo = X.src[1]; s_yhi = X.src[2]; s_zhi = X.src[3];
-                    cs_ylo = X.cs[0]; cs_zlo = X.cs[1]; cs_yhi = X.cs[2]; cs_zhi = X.cs[3];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int idx = lane - 1 + XG_LANES * k;
-                        const int side = idx / t.ny, xr = idx - side * t.ny;
-                        xsrc[k] = X.xsrc[idx];
-                        if (xsrc[k]) xdst[k] = &xg_s[0][side][xr];
-                    }
-                }
-                const int go_at = nplanes > PF_LEAD ? nplanes - PF_LEAD : 0;
-                for (int p = 0; p < nplanes; ++p) {
-                    mbar_wait(&empty_bar[stage], ephase);
-                    if (lane == 0) {
-                        if (p == 0) rec_s[stage] = X.rec;              // the tile record rides with the tile's first plane
-                        const bool zhalo = (p == 0) | (p == nplanes - 1);
-                        uint32_t tx = plane_bytes * NIN;
-                        if (lean) tx = zhalo ? (uint32_t)t.ny * row_bytes : plane_bytes + 2u * (uint32_t)t.ny * row_bytes;
-                        mbar_expect_tx(&full_bar[stage], tx);
-                        const int z = t.z0 - 1 + p;
-                        const double* zs = (z < 0) ? s_zlo : (z >= nzb ? s_zhi : nullptr);
-                        const long long zcs = (z < 0) ? cs_zlo : cs_zhi;
-#pragma unroll
-                        for (int c = 0; c < NIN; ++c) {
-                            double* dst = sm + (long long)stage * stage_stride + (long long)c * stage_doubles;
-                            const bool yhalo = !lean || c == 1;             // lean: only n_y is read in the rows above / below the tile
-                            if (lean && zhalo && c != 2) continue;          // ... and only n_z in the planes before / after it
-                            if (zs) {
-                                if (yhalo) tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
-                                else tma_load_1d(dst + li.P, zs + (long long)c * zcs + (long long)z * li.PS + (long long)t.y0 * li.P, (uint32_t)t.ny * row_bytes, &full_bar[stage]);
-                                continue;
-                            }
-                            int r0 = t.y0 - 1, r1 = t.y0 + t.ny;
-                            if (!yhalo) { r0 = t.y0; r1 = t.y0 + t.ny - 1; }
-                            if (r0 < 0 && s_ylo) {
-                                tma_load_1d(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[stage]);
-                                r0 = 0;
-                            }
-                            if (r1 >= nyb && s_yhi) {
-                                tma_load_1d(dst + (long long)(rows - 1) * li.P, s_yhi + (long long)c * cs_yhi + (long long)z * li.PS + (long long)nyb * li.P,
-                                            row_bytes, &full_bar[stage]);
-                                r1 = nyb - 1;
-                            }
-                            tma_load_1d(dst + (long long)(r0 - (t.y0 - 1)) * li.P, own + (long long)c * cs_in + (long long)z * li.PS + (long long)r0 * li.P,
-                                        (uint32_t)(r1 - r0 + 1) * row_bytes, &full_bar[stage]);
-                        }
-                    } else {
-                        if (xsrc[0]) cp_async_8(xdst[0] + stage * 64, xsrc[0] + (long long)p * li.PS);
-                        if (xsrc[1]) cp_async_8(xdst[1] + stage * 64, xsrc[1] + (long long)p * li.PS);
-                        cp_async_arrive_noinc(&full_bar[stage]);
-                    }
-                    if (p == go_at) {                                  // every lane has read its part of the context by now
-                        __syncwarp(0x7fffffffu);
-                        if (lane == 0) mbar_arrive(&ctx_bar[1]);
-                    }
-                    if (++stage == S) { stage = 0; ephase ^= 1u; }
-                }
-            }
-        }
-        if constexpr (!PF) for (;;) {
+        for (;;) {
             // next work item: the counter is never reset -- the host advances ticket_base by (nwork + grid) per launch,
             // exactly what the CTAs of one launch draw in total (every CTA overdraws once, then stops)
             unsigned long long tk = 0;
@@ -580,10 +227,8 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
     // ===================================== consumer warps =====================================
     int sc = 0;                    // stage of the plane being received
     uint32_t fphase = 0;
-    bar_ref full_a = bar_ref(), empty_a = bar_ref();
-    if constexpr (PF) { full_a = bar_base(full_bar); empty_a = bar_base(empty_bar); }
-    auto wait_full = [&](int st, uint32_t ph) { if constexpr (PF) mbar_wait_a(bar_at(full_a, st), ph); else mbar_wait(&full_bar[st], ph); };
-    auto arrive_empty = [&](int st) { if constexpr (PF) mbar_arrive_a(bar_at(empty_a, st)); else mbar_arrive(&empty_bar[st]); };
+    auto wait_full = [&](int st, uint32_t ph) { mbar_wait(&full_bar[st], ph); };
+    auto arrive_empty = [&](int st) { mbar_arrive(&empty_bar[st]); };
     const double pmin = ex.pmin, pinv = ex.inv;
     auto prog = [&](double sv) { return (sv - pmin) * pinv; };          // curvature.cpp:316-320
 
@@ -780,7 +425,6 @@ __global__ void __launch_bounds__((CW + 1 + (PF ? 1 : 0)) * 32,
     }
 }
 
-int g_num_sms = 0;
 // host-side launch bookkeeping below (ticket table, per-kernel shared-memory attribute, cached device properties) is shared
 // by all host threads of the process; launches from different threads (each on its own stream) serialise on this mutex
 std::mutex g_launch_mutex;
@@ -791,13 +435,13 @@ std::map<std::pair<int, cudaStream_t>, Ticket> g_tickets;         // (device, st
 int g_stage_cap = 0;
 size_t g_inflight_bytes = 0;
 
-template <int MODE, int CW, bool PLAIN, bool PF>
+template <int MODE, int CW, bool PLAIN>
 cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
                         int nvar, cudaStream_t st) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
     constexpr bool HEAVY = MODE == MODE_NORMAL || MODE == MODE_NORMAL_S;
-    constexpr int PER_SM = PF ? per_sm_pf(CW, HEAVY) : Shape<CW, HEAVY>::PER_SM;
-    constexpr int THREADS = (CW + 1 + (PF ? 1 : 0)) * 32;
+    constexpr int PER_SM = Shape<CW, HEAVY>::PER_SM;
+    constexpr int THREADS = (CW + 1) * 32;
     std::lock_guard<std::mutex> lock(g_launch_mutex);
     const size_t stage_bytes = (size_t)NIN * stage_doubles * sizeof(double);
     // Ring depth.  The consumers hold two planes (p-1 and p); the rest of the ring is data in flight.  Measured on B200
@@ -805,7 +449,7 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     // ring is SLOWER (the read stream runs far ahead of the write stream and the two fight for DRAM pages / L2).
     if (g_inflight_bytes == 0) { const char* e = getenv("PA_TMA_INFLIGHT_KB"); g_inflight_bytes = (size_t)(e ? std::max(1, atoi(e)) : 20) * 1024; }
     const size_t inflight = g_inflight_bytes * 2 / PER_SM;
-    constexpr size_t STATIC = STATIC_SMEM + (PF ? sizeof(ProdCtx) + 64 : 0);
+    constexpr size_t STATIC = STATIC_SMEM;
     const size_t budget = (size_t)(227 * 1024) / PER_SM - STATIC - 1024, budget1 = 227 * 1024 - STATIC - 1024;
     int S = 2 + (int)((inflight + stage_bytes - 1) / stage_bytes), per_sm = PER_SM;
     if ((size_t)S * stage_bytes > budget) S = (int)(budget / stage_bytes);
@@ -819,28 +463,22 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
     static std::map<int, size_t> configured;                          // per device: the attribute lives in the device's context
     if (smem > configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW, PLAIN, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_stencil_tma<MODE, CW, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured[dev] = smem;
     }
-    if (g_num_sms == 0) {
-        cudaError_t e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
+    cudaError_t esm = cudaSuccess;
+    const int num_sms = stencil_num_sms(&esm);
+    if (esm != cudaSuccess) return esm;
     const long long nwork = (long long)ntiles * nvar;
-    const int grid = (int)std::min<long long>(nwork, (long long)g_num_sms * per_sm);
+    const int grid = (int)std::min<long long>(nwork, (long long)num_sms * per_sm);
     Ticket& T = g_tickets[std::make_pair(dev, st)];
     if (!T.dev) {
         cudaError_t e = cudaMalloc(&T.dev, sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    int sd = stage_doubles;
-    if constexpr (PF && MODE == MODE_DIV) {               // bit 0 set: lean staging off (see the kernel)
-        const char* e = getenv("PA_DIV_LEAN");
-        if (e && e[0] == '0') sd |= 1;
-    }
-    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN, PF>)(tiles, ntiles, (int)nwork, ga, ex, sd, S, T.dev, T.base);
+    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
@@ -852,7 +490,9 @@ int g_cw16_mask = -1;
 // self-test once (2^20 operand sets, well under a millisecond) and the branch-free forms are used only if not one result
 // bit differs from sqrt() / division on THIS device and driver -- the transcribed sequences depend on the MUFU seeds.
 int g_normal_plain = -1;
+std::mutex g_cfg_mutex;                               // guards the lazily decided settings (host threads may launch concurrently)
 int decide_normal_math(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
     if (g_normal_plain >= 0) return g_normal_plain;
     const char* e = getenv("PA_NORMAL_MATH");
     if (e && !strcmp(e, "plain")) return g_normal_plain = 1;
@@ -866,31 +506,27 @@ int decide_normal_math(cudaStream_t st) {
     return g_normal_plain;
 }
 // PA_TMA_SMALL=0 switches the small-tile shapes (4 / 2 consumer warps) off (read at every launch: the tests flip it)
-template <int MODE, bool PLAIN, bool PF>
-cudaError_t launch_cw2(int cw, const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
-                       int nvar, cudaStream_t st) {
-    switch (cw) {
-        case 2: return launch_mode<MODE, 2, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        case 4: return launch_mode<MODE, 4, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        case 16: return launch_mode<MODE, 16, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-        default: return launch_mode<MODE, 8, PLAIN, PF>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-    }
-}
-// PA_TMA_PREFETCH=1 selects the variant with the descriptor warp (opt-in until it has been measured on a B200; read at
-// every launch: the tests flip it)
 template <int MODE, bool PLAIN>
 cudaError_t launch_cw(int cw, const PaTile* tiles, int ntiles, int stage_doubles, const GridArgs& ga, const StencilExtra& ex,
-                      int nvar, cudaStream_t st) {
-    const char* e = getenv("PA_TMA_PREFETCH");
-    if (e && e[0] == '1') return launch_cw2<MODE, PLAIN, true>(cw, tiles, ntiles, stage_doubles, ga, ex, nvar, st);
-    return launch_cw2<MODE, PLAIN, false>(cw, tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+                       int nvar, cudaStream_t st) {
+    switch (cw) {
+        case 2: return launch_mode<MODE, 2, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        case 4: return launch_mode<MODE, 4, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        case 16: return launch_mode<MODE, 16, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+        default: return launch_mode<MODE, 8, PLAIN>(tiles, ntiles, stage_doubles, ga, ex, nvar, st);
+    }
 }
 template <int MODE>
 cudaError_t launch_shape(const PaTile* tiles, int ntiles, int stage_doubles, int max_items, const GridArgs& ga, const StencilExtra& ex,
                          int nvar, cudaStream_t st) {
-    if (g_cw16_mask < 0) { const char* e = getenv("PA_TMA_CW16"); g_cw16_mask = e ? atoi(e) : ((1 << MODE_NORMAL) | (1 << MODE_NORMAL_S)); }
+    int mask16;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        if (g_cw16_mask < 0) { const char* e = getenv("PA_TMA_CW16"); g_cw16_mask = e ? atoi(e) : ((1 << MODE_NORMAL) | (1 << MODE_NORMAL_S)); }
+        mask16 = g_cw16_mask;
+    }
     const char* es = getenv("PA_TMA_SMALL");
-    int cw = (g_cw16_mask & (1 << MODE)) ? 16 : 8;
+    int cw = (mask16 & (1 << MODE)) ? 16 : 8;
     if (!(es && es[0] == '0') && max_items > 0) {
         if (max_items <= Shape<2, false>::CAP) cw = 2;
         else if (max_items <= Shape<4, false>::CAP) cw = 4;
@@ -964,14 +600,50 @@ cudaError_t selftest_math(long long n, unsigned long long seed, unsigned long lo
     cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), st);
-    if (e == cudaSuccess) { PA_LAUNCH(148 * 8, 256, 0, st, k_selftest_math)(n, seed, d); ++g_launches; e = cudaGetLastError(); }
+    int nsm = 0;
+    if (e == cudaSuccess) nsm = stencil_num_sms(&e);
+    if (e == cudaSuccess) { PA_LAUNCH(nsm * 8, 256, 0, st, k_selftest_math)(n, seed, d); ++g_launches; e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(bad_host, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     return e;
 }
 
-int stencil_tma_normal_math() { return g_normal_plain; }
+int stencil_tma_normal_math() { std::lock_guard<std::mutex> lock(g_cfg_mutex); return g_normal_plain; }
+int stencil_decide_normal_math(cudaStream_t st) { return decide_normal_math(st); }
+// SM count of the current device (cached per device)
+int stencil_num_sms(cudaError_t* err) {
+    static std::map<int, int> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    *err = cudaGetDevice(&dev);
+    if (*err != cudaSuccess) return 0;
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    *err = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (*err != cudaSuccess) return 0;
+    cache[dev] = n;
+    return n;
+}
+// the stream's work-item ticket counter for a persistent launch that draws `nwork` items with `grid` CTAs (every CTA
+// overdraws once): returns the counter and the base the kernel subtracts, and advances the base
+cudaError_t stencil_ticket(cudaStream_t st, unsigned long long nwork, int grid, unsigned long long** dev_out, unsigned long long* base_out) {
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    Ticket& T = g_tickets[std::make_pair(dev, st)];
+    if (!T.dev) {
+        e = cudaMalloc(&T.dev, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+    }
+    *dev_out = T.dev; *base_out = T.base;
+    T.base += nwork + (unsigned long long)grid;
+    return cudaSuccess;
+}
 void stencil_tma_release() {                          // pa_finalize: the per-stream ticket counters
     std::lock_guard<std::mutex> lock(g_launch_mutex);
     for (auto& kv : g_tickets) if (kv.second.dev) cudaFree(kv.second.dev);

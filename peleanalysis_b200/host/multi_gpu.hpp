@@ -243,7 +243,15 @@ inline void curv_rank(int r, MultiShared& M, const CurvJob& J) {
     exchange_slabs(r, M, st, 0, 1);
     step(PA_CURV_PASS1, -1, -1);
     if (J.o.do_threshold) {
-        for (int l = 0; l < Nlev; ++l) { exchange_slabs(r, M, res, 2, 3); step(PA_CURV_DIV, l, l); }
+        for (int l = 0; l < Nlev; ++l) {
+            exchange_slabs(r, M, res, 2, 3);
+            step(PA_CURV_DIV, l, l);
+            // the clip zeroes n(l) in place; every rank's DIV(l) reads its peers' UNCLIPPED n(l) over the links first
+            // (curvature.cpp:487-567: FillBoundary of n precedes the clip)
+            check(pa_sync(), "pa_sync");
+            M.bar.wait();
+            step(PA_CURV_CLIP, l, l);
+        }
     } else {
         exchange_slabs(r, M, res, 2, 3);
         step(PA_CURV_DIV, -1, -1);

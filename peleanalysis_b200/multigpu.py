@@ -94,6 +94,8 @@ class Curvature:
         [barrier]  exchange S            ->  PASS1   ghost fill of S, Progress, flame normal (+ un-normalised gradient G)
         [barrier]  exchange n            ->  DIV     ghost fill of n, MeanCurvature    -- threshold_prog: once per level, in
                                                      order, because level l reads the CLIPPED normal of level l-1
+        [barrier]                        ->  CLIP    (threshold_prog, per level) zeroes n in place: only after every rank's
+                                                     DIV of the level, which reads the unclipped normal of its peers
         [barrier]  exchange G            ->  GAUSS   (do_gaussCurv)      G is an internal field of the library
         [barrier]  exchange velocities   ->  STRAIN  (do_strain)
                                              VELN    (do_velnormal; pointwise)
@@ -139,6 +141,8 @@ class Curvature:
                 self._barrier()
                 self.Xn.run(cN)
                 self._step(capi.CURV_DIV, l, l)
+                self._barrier()             # every rank's DIV(l) has read its peers' UNCLIPPED n(l) (curvature.cpp:487-567)
+                self._step(capi.CURV_CLIP, l, l)
         else:
             self._barrier()
             self.Xn.run(cN)

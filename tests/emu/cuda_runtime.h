@@ -113,6 +113,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
 void submit(cudaStream_t st, std::function<void()> work);
 void syncthreads();
 void syncwarp(unsigned mask);
+void named_bar(int id, int count);                          // bar.sync id, count
 // every participating lane publishes `bytes` bytes; returns a pointer to the 32 published slots (8 bytes each)
 const unsigned long long* warp_exchange(unsigned mask, const void* v, size_t bytes);
 // mbarrier / asynchronous copies (addresses are plain host pointers)

@@ -62,6 +62,8 @@ Fiber* cur = nullptr;
 int n_threads = 0, live = 0;
 unsigned long long progress = 0, tick = 0;
 int sync_gen = 0, sync_arrived = 0;
+struct NamedBar { int gen = 0, arrived = 0; };
+std::map<int, NamedBar> named_bars;
 std::vector<WarpState> warps;
 std::map<const void*, MBar> mbars;
 std::vector<Async> asyncq;
@@ -213,6 +215,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
                 sync_gen = 0; sync_arrived = 0;
                 warps.assign((n_threads + 31) / 32, WarpState());
                 mbars.clear();
+                named_bars.clear();
                 asyncq.clear();
                 for (int t = 0; t < n_threads; ++t) {
                     Fiber& f = fibers[t];
@@ -236,6 +239,15 @@ void syncthreads() {
         if (sync_arrived >= live) { ++sync_gen; sync_arrived = 0; ++progress; break; }
         yield("__syncthreads", nullptr);
     }
+}
+
+// bar.sync id, count: the first `count` arrivals of a generation release together (threads name the same count)
+void named_bar(int id, int count) {
+    NamedBar& B = named_bars[id];
+    const int gen = B.gen;
+    ++B.arrived; ++progress;
+    if (B.arrived >= count) { B.arrived = 0; ++B.gen; ++progress; return; }
+    while (B.gen == gen) yield("bar.sync (named barrier)", &B);
 }
 
 static int popc(unsigned m) { return __builtin_popcount(m); }

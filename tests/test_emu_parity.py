@@ -29,7 +29,7 @@ def emu():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     m.LIB_PATH = lib                     # a private module instance: the product binding itself is untouched
-    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "PA_TMA_PREFETCH", "CUEMU_SEED")}
+    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "PA_CURV_FUSED", "CUEMU_SEED")}
     os.environ["PA_NORMAL_MATH"] = "fast"   # no device self-test: the emulator has no MUFU (sqrt_fast == sqrt there)
     m.init(0)
     yield m
@@ -52,9 +52,9 @@ def schedule(request):
 def _thin_out(schedule, stencil, links):
     """Not the full cross product (the suite has to stay a few minutes): the shuffled schedule matters for the TMA pipeline
     only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
-    if schedule and (stencil in ("simple", "tma_big_pf") or links == "nolinks"):
+    if schedule and (stencil == "simple" or links == "nolinks"):
         pytest.skip("combination not in the thinned-out matrix")
-    if links == "nolinks" and stencil not in ("tma", "simple"):
+    if links == "nolinks" and stencil not in ("tma", "tma_unfused", "simple"):
         pytest.skip("combination not in the thinned-out matrix")
 
 
@@ -63,7 +63,7 @@ CURV_CASES = [n for n, c in CASES.items() if "curvature" in c[3]]
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple", "tma_pf", "tma_big_pf"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, links):
     _thin_out(schedule, stencil, links)
@@ -71,7 +71,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple", "tma_pf", "tma_big_pf"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_unfused", "tma_big", "simple"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
     _thin_out(schedule, stencil, links)
@@ -105,7 +105,7 @@ def test_emulated_midsize_vs_oracle(emu, case, kw):
     os.environ["CUEMU_SEED"] = "7"
     try:
         G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma")
-        G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma_pf")
+        G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma_unfused")
     finally:
         os.environ["CUEMU_SEED"] = "0"
 
@@ -142,11 +142,11 @@ def test_emulated_wide_ghost_inputs(emu, builder):
 
 
 @pytest.mark.parametrize("name", list(CASES))
-def test_emulated_staged_bcfill(emu, name):
-    """PA_BCFILL_V2=1 (opt-in): the coarse-fine / wall fill with the coarse register cells staged in shared memory -- ghost
-    cells one by one against the oracle, then both tools against the golden vectors."""
+def test_emulated_unstaged_bcfill(emu, name):
+    """PA_BCFILL_V2=0: the coarse-fine / wall fill in which every ghost cell gathers its coarse cells itself (the default
+    stages them in shared memory) -- ghost cells one by one against the oracle, then both tools against the golden vectors."""
     os.environ["CUEMU_SEED"] = "11"
-    os.environ["PA_BCFILL_V2"] = "1"
+    os.environ["PA_BCFILL_V2"] = "0"
     try:
         G.test_ghost_cells_match_oracle(emu, name)
         tools = CASES[name][3]
@@ -159,7 +159,7 @@ def test_emulated_staged_bcfill(emu, name):
         os.environ.pop("PA_BCFILL_V2", None)
 
 
-@pytest.mark.parametrize("stencil", ["tma", "tma_pf"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_unfused"])
 def test_emulated_full_width_tiles(emu, stencil):
     """128-cell-wide boxes: 64 x-pairs per row, 8 rows per tile -- every one of the 512 pair slots of the big CTA shapes is
     in use (the golden cases have narrow boxes), two boxes side by side in y so that linked y rows and periodic x / z wraps

@@ -80,19 +80,19 @@ def test_random_hierarchy_emulated_kernels_equal_oracle(emu, seed):  # noqa: F81
     pf, is_per, sym = random_case(1000 + seed, curv)
     os.environ["CUEMU_SEED"] = str(seed)
     if seed % 3 == 0:
-        os.environ["PA_BCFILL_V2"] = "1"          # every third seed through the opt-in staged coarse-fine fill
+        os.environ["PA_BCFILL_V2"] = "0"          # every third seed through the unstaged coarse-fine fill
     try:
         OH = O.OracleHier(pf, is_per, sym)
         s = _flat(pf)
         want = OH.grad(s)
-        for stencil in ("tma", "simple", "tma_pf"):
+        for stencil in ("tma", "simple", "tma_big"):
             out, _, _ = G._gpu_grad(emu, pf, is_per, sym, stencil=stencil)
             for c in range(4):
                 assert bit_equal(out[c], want[c]), (seed, stencil, c, max_rel(out[c], want[c]), [l.boxes for l in pf.levels])
         if curv:
             pmin, pmax = float(s.min()), float(s.max())
             wk = OH.curvature(s, pmin, pmax)
-            for stencil in ("tma", "tma_pf"):
+            for stencil in ("tma", "tma_unfused"):
                 out, _ = G._gpu_curv(emu, pf, is_per, sym, pmin, pmax, {}, stencil)
                 for c in range(5):
                     assert bit_equal(out[c], wk[c]), (seed, "curvature", stencil, c, [l.boxes for l in pf.levels])

@@ -22,12 +22,12 @@ def _flat(pf, name):
 
 
 def _set_stencil(stencil):
-    """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps); tma_big: TMA pipeline in the
-    8 / 16-warp shapes whatever the tile size; simple: the plain-load kernel; *_pf: the TMA pipeline variant with the
-    descriptor-prefetch warp (PA_TMA_PREFETCH=1, opt-in)."""
+    """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps), curvature through the fused kernel
+    where the hierarchy is eligible; tma_big: TMA pipeline in the 8 / 16-warp shapes whatever the tile size; tma_unfused:
+    curvature through the separate NORMAL_S / DIV kernels (PA_CURV_FUSED=0); simple: the plain-load kernels."""
     os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
-    os.environ["PA_TMA_PREFETCH"] = "1" if stencil.endswith("_pf") else "0"
+    os.environ["PA_CURV_FUSED"] = "0" if stencil in ("tma_unfused", "tma_big") else "1"
 
 
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
@@ -83,7 +83,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_unfused", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -359,44 +359,15 @@ def check_wide_ghost_inputs(capi, builder):
             assert bit_equal(flat_from_fabs(out.download_fabs(c)), wk[c]), (ng, "curvature", c)
 
 
-# Kernel variants that exist in the library but have not been run on a B200 yet (logic verified under the emulator of
-# tests/emu only): excluded from the default GPU run, enabled with PA_TEST_EXPERIMENTAL=1.
-experimental = pytest.mark.skipif(os.environ.get("PA_TEST_EXPERIMENTAL") != "1", reason="set PA_TEST_EXPERIMENTAL=1 (variants not yet run on hardware)")
-
-
-@experimental
-@pytest.mark.parametrize("stencil", ["tma_pf", "tma_big_pf"])
-@pytest.mark.parametrize("name", list(CASES))
-def test_descriptor_prefetch_variant_golden(gpu, name, stencil):
-    """PA_TMA_PREFETCH=1: the TMA pipeline with the descriptor warp (one work item of descriptor loads ahead of the producer)."""
-    try:
-        if "grad" in CASES[name][3]:
-            test_grad_matches_reference_golden(gpu, name, stencil, "links")
-        if "curvature" in CASES[name][3]:
-            test_curvature_matches_reference_golden(gpu, name, stencil, "links")
-    finally:
-        os.environ["PA_TMA_PREFETCH"] = "0"
-
-
-@experimental
-def test_descriptor_prefetch_variant_full_size(gpu):
-    os.environ["PA_TMA_PREFETCH"] = "1"
-    try:
-        test_full_size_properties_config2(gpu)
-    finally:
-        os.environ["PA_TMA_PREFETCH"] = "0"
-
-
-@experimental
 def test_wide_ghost_inputs(gpu):
     check_wide_ghost_inputs(gpu, lambda: synth.config3(16, 8))
 
 
-@experimental
 @pytest.mark.parametrize("name", list(CASES))
-def test_staged_bcfill_variant(gpu, name):
-    """PA_BCFILL_V2=1: the coarse-fine fill with the coarse register cells staged in shared memory."""
-    os.environ["PA_BCFILL_V2"] = "1"
+def test_unstaged_bcfill_variant(gpu, name):
+    """PA_BCFILL_V2=0: the coarse-fine fill in which every ghost cell gathers its coarse cells itself (the default stages them
+    in shared memory) -- the second route to the same bits."""
+    os.environ["PA_BCFILL_V2"] = "0"
     try:
         test_ghost_cells_match_oracle(gpu, name)
         if "grad" in CASES[name][3]:
@@ -407,7 +378,6 @@ def test_staged_bcfill_variant(gpu, name):
         os.environ.pop("PA_BCFILL_V2", None)
 
 
-@experimental
 @pytest.mark.parametrize("base,mgs", [((256, 8, 4), 256), ((1024, 4, 4), 1024), ((7, 5, 3), 8), ((2, 2, 2), 2), ((128, 32, 8), 128)])
 def test_extreme_box_shapes(gpu, base, mgs):
     pf = synth.make_hierarchy(base, [], [], mgs, ("temp",))
