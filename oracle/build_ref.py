@@ -99,15 +99,21 @@ def compile_one(args):
     return src, p.returncode, p.stderr[-2000:]
 
 
-def patch_timed(src_path, dst_path, begin_after, end_before, skip_regex, tag):
+def patch_timed(src_path, dst_path, begin_after, end_before, skip_regex, tag, cleanup=""):
     """Insert amrex::second() probes into a temporary copy of a reference tool (in oracle/_ref/src,
     never committed).  `begin_after` / `end_before` are regexes matching unique anchor lines;
-    every line matching skip_regex (the FillVar disk read) is bracketed and its time subtracted."""
+    every line matching skip_regex (the FillVar disk read) is bracketed and its time subtracted.
+    The probed region is repeated PA_TIMED_REPS times inside the process (a backward goto: the objects the
+    region declares are destroyed and rebuilt each time, exactly as in a fresh run; `cleanup` frees what the
+    region allocates with new) and prints one hot_path_seconds line per repetition, so a benchmark can time
+    K steps of the full-size workload without K process start-ups and plotfile opens."""
     out = []
     began = ended = False
     for line in open(src_path):
         if not began and re.search(begin_after, line):
             out.append(line)
+            out.append("    int pa_rep__ = 0; const int pa_reps__ = std::getenv(\"PA_TIMED_REPS\") ? std::atoi(std::getenv(\"PA_TIMED_REPS\")) : 1;\n")
+            out.append("  pa_again__: ;\n")
             out.append("    double pa_t0__ = amrex::second(); double pa_skip__ = 0.0;\n")
             began = True
             continue
@@ -115,6 +121,7 @@ def patch_timed(src_path, dst_path, begin_after, end_before, skip_regex, tag):
             out.append('    { double pa_t1__ = amrex::second(); amrex::Print() << "' + tag +
                        ' hot_path_seconds " << std::setprecision(9) << (pa_t1__-pa_t0__-pa_skip__)'
                        ' << " skipped_io_seconds " << pa_skip__ << "\\n"; }\n')
+            out.append("    if (++pa_rep__ < pa_reps__) { " + cleanup + " goto pa_again__; }\n")
             ended = True
         if began and not ended and re.search(skip_regex, line):
             out.append("    { double pa_s0__ = amrex::second();\n")
@@ -125,7 +132,30 @@ def patch_timed(src_path, dst_path, begin_after, end_before, skip_regex, tag):
     if not (began and ended):
         raise RuntimeError(f"anchors not found in {src_path}")
     os.makedirs(os.path.dirname(dst_path), exist_ok=True)
-    _write_if_changed(dst_path, "#include <iomanip>\n" + "".join(out))
+    _write_if_changed(dst_path, "#include <iomanip>\n#include <cstdlib>\n" + "".join(out))
+
+
+def patch_splice(src_path, dst_path, begin_regex, end_regex, block_include):
+    """A temporary copy of a reference tool (oracle/_ref/src, never committed) whose operator block -- the lines from the
+    one matching begin_regex up to, not including, the one matching end_regex -- is replaced by `#include "<block>"`: the
+    source-level integration INTEGRATION.md describes (AMReX keeps plotfile I/O, BoxArray / Geometry metadata and, for
+    do_smooth, its own MLMG solve on the host; the stencil path goes through libpelestencil_b200's C ABI)."""
+    out, state = ['#include "pa_amrex_glue.H"\n'], 0
+    for line in open(src_path):
+        if state == 0 and re.search(begin_regex, line):
+            out.append('#include "%s"\n' % block_include)
+            state = 1
+            continue
+        if state == 1:
+            if re.search(end_regex, line):
+                state = 2
+            else:
+                continue
+        out.append(line)
+    if state != 2:
+        raise RuntimeError(f"splice anchors not found in {src_path}")
+    os.makedirs(os.path.dirname(dst_path), exist_ok=True)
+    _write_if_changed(dst_path, "".join(out))
 
 
 def main():
@@ -170,20 +200,41 @@ def main():
     patch_timed(os.path.join(REF, "Src/grad.cpp"), os.path.join(srcdir, "grad_timed.cpp"),
                 r"const int nGrow = 1;", r"Write the results", r"amrData\.FillVar\(", "[grad]")
     patch_timed(os.path.join(REF, "Src/curvature.cpp"), os.path.join(srcdir, "curvature_timed.cpp"),
-                r"const int nGrow = 2 ;", r"Set-up the output", r"amrData\.FillVar\(", "[curvature]")
+                r"const int nGrow = 2 ;", r"Set-up the output", r"amrData\.FillVar\(", "[curvature]",
+                cleanup="for (int pa_l__ = 0; pa_l__ < Nlev; ++pa_l__) { delete state[pa_l__]; delete flame_normal[pa_l__]; "
+                        "delete cell_normal[pa_l__]; delete geoms[pa_l__]; }")
+    # source-level drop-in: the reference tools with their operator blocks replaced by the C-ABI calls, linked against the
+    # host-only AMReX built above and the product library (skipped when the library has not been built yet)
+    repo = os.path.dirname(HERE)
+    glue = os.path.join(repo, "peleanalysis_b200", "host", "amrex_glue")
+    palib = os.path.join(repo, "peleanalysis_b200", "lib", "libpelestencil_b200.so")
+    shells = []
+    if os.path.exists(palib) and os.path.isdir(glue):
+        patch_splice(os.path.join(REF, "Src/grad.cpp"), os.path.join(srcdir, "grad_b200amrex.cpp"),
+                     r"Get face-centered gradients from MLMG", r"Write the results", "grad_block.inc")
+        patch_splice(os.path.join(REF, "Src/curvature.cpp"), os.path.join(srcdir, "curvature_b200amrex.cpp"),
+                     r"Compute curvature using LinearOperators", r"Set-up the output", "curvature_block.inc")
+        shells = [(os.path.join(srcdir, "grad_b200amrex.cpp"), "grad3d.b200amrex.ex"),
+                  (os.path.join(srcdir, "curvature_b200amrex.cpp"), "curvature3d.b200amrex.ex")]
+    shell_flags = ["-I" + glue, "-I" + os.path.join(repo, "include")]
+    shell_libs = ["-L" + os.path.dirname(palib), "-lpelestencil_b200", "-Wl,-rpath," + os.path.dirname(palib),
+                  "-Wl,-rpath,$ORIGIN/../../peleanalysis_b200/lib"]
     tools = [(os.path.join(REF, "Src/grad.cpp"), "grad3d.ref.ex"),
              (os.path.join(REF, "Src/curvature.cpp"), "curvature3d.ref.ex"),
              (os.path.join(srcdir, "grad_timed.cpp"), "grad3d.timed.ex"),
              (os.path.join(srcdir, "curvature_timed.cpp"), "curvature3d.timed.ex")]
     if not a.no_fcompare:
         tools.append((os.path.join(AMREX, "Tools/Plotfile/fcompare.cpp"), "fcompare.ref.ex"))
+    tools += shells
 
     def link(t):
         src, exe = t
         exe = os.path.join(OUT, exe)
         if os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(lib)):
             return exe, 0, ""
-        p = subprocess.run(["g++", *flags, src, "-o", exe, lib, "-lgomp", "-lpthread"],
+        extra_f = shell_flags if t in shells else []
+        extra_l = shell_libs if t in shells else []
+        p = subprocess.run(["g++", *flags, *extra_f, src, "-o", exe, lib, "-lgomp", "-lpthread", *extra_l],
                            capture_output=True, text=True)
         return exe, p.returncode, p.stderr[-3000:]
     rc_all = 0

@@ -184,3 +184,21 @@ def run_ref(tool: str, infile: str, outfile: str, threads: Optional[int] = None,
         raise RuntimeError("reference %s failed (%d):\n%s\n%s" % (tool, p.returncode, p.stdout[-2000:], p.stderr[-2000:]))
     m = re.search(r"hot_path_seconds\s+([0-9.eE+-]+)", p.stdout)
     return p.stdout, (float(m.group(1)) if m else None)
+
+
+def run_ref_timed(tool: str, infile: str, outfile: str, threads: Optional[int] = None, reps: int = 1, **kv):
+    """The reference tool's timed build with its hot-path region repeated `reps` times inside ONE process (PA_TIMED_REPS,
+    see build_ref.patch_timed).  Returns the list of hot-path seconds, one per repetition."""
+    old = os.environ.get("PA_TIMED_REPS")
+    os.environ["PA_TIMED_REPS"] = str(int(reps))
+    try:
+        out, _ = run_ref(tool, infile, outfile, threads=threads, timed=True, **kv)
+    finally:
+        if old is None:
+            os.environ.pop("PA_TIMED_REPS", None)
+        else:
+            os.environ["PA_TIMED_REPS"] = old
+    hot = [float(x) for x in re.findall(r"hot_path_seconds\s+([0-9.eE+-]+)", out)]
+    if len(hot) != int(reps):
+        raise RuntimeError("reference %s: expected %d timed repetitions, saw %d" % (tool, reps, len(hot)))
+    return hot

@@ -217,7 +217,8 @@ void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int
             if (nx < 3 || ny < 3 || nz < 3 || nq4 > 32) { T.ok = false; continue; }
             int lpr = 1;
             while (lpr < nq4) lpr *= 2;
-            const int rows_cap = std::min(cw * (32 / lpr), curv_fused_max_rows());
+            // one n-row per LPR lanes of a consumer warp; the two halo rows of the staged block ride with the outermost n-rows
+            const int rows_cap = std::min(cw * (32 / lpr) + 2, curv_fused_max_rows());
             int ty = rows_cap - 4;
             const int nky = ny - 2, nkz = nz - 2;
             const int nty = (nky + ty - 1) / ty; ty = (nky + nty - 1) / nty;

@@ -85,7 +85,8 @@ template <int MODE, int CW, bool PLAIN>
 __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL || MODE == MODE_NORMAL_S>::PER_SM) k_stencil_tma(const PaTile* __restrict__ tiles, int ntiles, int nwork, GridArgs ga,
                                                             StencilExtra ex, int stage_doubles /* per input component, multiple of 16 */,
                                                             int S /* ring depth in planes */,
-                                                            unsigned long long* __restrict__ ticket, unsigned long long ticket_base) {
+                                                            unsigned long long* __restrict__ ticket, unsigned long long ticket_base,
+                                                            int psleep /* ns between the producer's polls of an empty barrier; 0 = spin */) {
     constexpr int NIN = ModeTraits<MODE>::NIN;
     constexpr int NOUT = ModeTraits<MODE>::NOUT;
     constexpr bool XS = (MODE == MODE_NORMAL_S);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
             tk = __shfl_sync(0x7fffffffu, tk, 0);
             if (tk >= (unsigned long long)nwork) {
                 // end marker for the consumers: an empty record in one more ring slot
-                mbar_wait(&empty_bar[stage], ephase);
+                if (psleep) mbar_wait_sleep(&empty_bar[stage], ephase, (unsigned)psleep); else mbar_wait(&empty_bar[stage], ephase);
                 if (lane == 0) { rec_s[stage].t.lev = -1; mbar_arrive(&full_bar[stage]); }
                 else cp_async_arrive_noinc(&full_bar[stage]);
                 break;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
             }
             const int nyb = bx.n[1], nzb = bx.n[2];
             for (int p = 0; p < nplanes; ++p) {
-                mbar_wait(&empty_bar[stage], ephase);
+                if (psleep) mbar_wait_sleep(&empty_bar[stage], ephase, (unsigned)psleep); else mbar_wait(&empty_bar[stage], ephase);
                 if (lane == 0) {
                     if (p == 0) {                                  // the tile record rides with the tile's first plane
                         TileRec& R = rec_s[stage];
@@ -478,7 +479,9 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e == cudaSuccess) e = cudaMemset(T.dev, 0, sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
     }
-    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base);
+    const char* eps = getenv("PA_TMA_PSLEEP");
+    const int psleep = eps ? std::max(0, atoi(eps)) : 0;
+    PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base, psleep);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();
 }
@@ -582,6 +585,18 @@ __global__ void k_selftest_math(long long n, unsigned long long seed, unsigned l
         }
         double q0[3], q1[3];
         normal_pair(g[0], g[1], g[2], g[3], g[4], g[5], q0, q1);
+        {   // the quad form of the fused curvature kernel on the same operands (cells 0 / 1 as they are, 2 / 3 permuted)
+            const double qx[4] = {g[0], g[3], g[1], g[5]}, qy[4] = {g[1], g[4], g[2], g[3]}, qz[4] = {g[2], g[5], g[0], g[4]};
+            double m0[4], m1[4], m2[4];
+            normal_quad(qx, qy, qz, m0, m1, m2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double nn = -fmax(1e-14, sqrt(qx[j] * qx[j] + qy[j] * qy[j] + qz[j] * qz[j]));
+                if (!same_bits(m0[j], qx[j] / nn)) ++local;
+                if (!same_bits(m1[j], qy[j] / nn)) ++local;
+                if (!same_bits(m2[j], qz[j] / nn)) ++local;
+            }
+        }
         const double n0 = -fmax(1e-14, sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]));
         const double n1 = -fmax(1e-14, sqrt(g[3] * g[3] + g[4] * g[4] + g[5] * g[5]));
 #pragma unroll

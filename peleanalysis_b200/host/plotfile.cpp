@@ -119,27 +119,70 @@ Header read_header(const std::string& dir) {
     return h;
 }
 
-void read_level_comp(const std::string& dir, const Header& h, int lev, int comp, double* dst) {
-    const LevelMeta& lv = h.levels.at(lev);
-    std::string ldir = dir + "/" + lv.cell_path.substr(0, lv.cell_path.find_last_of('/'));
-    std::string open_name;
-    FILE* f = nullptr;
-    for (size_t b = 0; b < lv.boxes.size(); ++b) {
-        if (lv.fab_file[b] != open_name) {
-            if (f) std::fclose(f);
-            f = std::fopen((ldir + "/" + lv.fab_file[b]).c_str(), "rb");
-            if (!f) throw std::runtime_error("cannot open " + ldir + "/" + lv.fab_file[b]);
-            open_name = lv.fab_file[b];
-        }
-        std::fseek(f, lv.fab_offset[b], SEEK_SET);
-        int c;
-        while ((c = std::fgetc(f)) != EOF && c != '\n') {}      // ASCII "FAB (...)(box) ncomp" line
-        long long n = lv.boxes[b].npts();
-        std::fseek(f, (long)(8LL * n * comp), SEEK_CUR);
-        if ((long long)std::fread(dst, 8, (size_t)n, f) != n) { std::fclose(f); throw std::runtime_error("short read in " + open_name); }
-        dst += n;
+// One FAB on disk (AMReX_FArrayBox.cpp: FABio_binary / AMReX_FabConv.cpp): an ASCII line
+//     FAB ((nfmt, (bits expbits mantbits ...)),(nord, (byte order))) ((lo) (hi) (type)) ncomp
+// followed by ncomp * box.npts() reals in that RealDescriptor's format.  The descriptor may be IEEE double or IEEE single
+// (fab.format = NATIVE_32 / IEEE32), little- or big-endian, and the FAB's own box may be the valid box grown by the
+// MultiFab's ghost width (Cell_H ngrow > 0).  What AmrData does through RealDescriptor::convertToNativeFormat is done here
+// for these four IEEE layouts (single -> double widening is exact); anything else is an error -- never a silent misread.
+struct FabOnDisk { int bytes = 8; bool big_endian = false; BoxI box; int ncomp = 0; };
+
+static FabOnDisk parse_fab_header(FILE* f, const std::string& where) {
+    std::string line;
+    int c;
+    while ((c = std::fgetc(f)) != EOF && c != '\n') line.push_back((char)c);
+    if (line.compare(0, 3, "FAB") != 0) throw std::runtime_error("not a FAB header in " + where + ": " + line.substr(0, 60));
+    // the descriptor ends where the box begins: the first "((" after the leading one
+    const size_t box_at = line.find("((", 5);
+    if (box_at == std::string::npos) throw std::runtime_error("malformed FAB header in " + where);
+    const std::vector<int> d = ints_of(line.substr(0, box_at)), b = ints_of(line.substr(box_at));
+    // d = nfmt, fmt[nfmt], nord, ord[nord];  b = lo[3], hi[3], type[3], ncomp
+    if (d.size() < 2 || (int)d.size() < 2 + d[0] || (int)d.size() != 2 + d[0] + d[1 + d[0]] || b.size() != 10)
+        throw std::runtime_error("malformed FAB header in " + where + ": " + line);
+    const std::vector<int> fmt(d.begin() + 1, d.begin() + 1 + d[0]), ord(d.begin() + 2 + d[0], d.end());
+    FabOnDisk F;
+    const std::vector<int> f64{64, 11, 52, 0, 1, 12, 0, 1023}, f32{32, 8, 23, 0, 1, 9, 0, 127};
+    if (fmt == f64) F.bytes = 8; else if (fmt == f32) F.bytes = 4;
+    else throw std::runtime_error("unsupported real format in " + where + " (only IEEE double / single): " + line.substr(0, box_at));
+    if ((int)ord.size() != F.bytes) throw std::runtime_error("malformed byte order in " + where);
+    bool le = true, be = true;
+    for (int i = 0; i < F.bytes; ++i) { le &= ord[i] == F.bytes - i; be &= ord[i] == i + 1; }
+    if (!le && !be) throw std::runtime_error("unsupported byte order in " + where + ": " + line.substr(0, box_at));
+    F.big_endian = be && !le;
+    for (int k = 0; k < 3; ++k) { F.box.lo[k] = b[k]; F.box.hi[k] = b[3 + k]; if (b[6 + k] != 0) throw std::runtime_error("not a cell-centred FAB in " + where); }
+    F.ncomp = b[9];
+    return F;
+}
+
+// component `comp` of the VALID box `vb` of the FAB at `offset` -> dst (FArrayBox order, doubles)
+static void read_fab_comp(FILE* f, long offset, const BoxI& vb, int comp, double* dst, const std::string& where) {
+    std::fseek(f, offset, SEEK_SET);
+    const FabOnDisk F = parse_fab_header(f, where);
+    if (comp < 0 || comp >= F.ncomp) throw std::runtime_error("component out of range in " + where);
+    for (int d = 0; d < 3; ++d)
+        if (F.box.lo[d] > vb.lo[d] || F.box.hi[d] < vb.hi[d]) throw std::runtime_error("FAB box does not contain the valid box in " + where);
+    const long long nf = F.box.npts(), n = vb.npts();
+    const bool same = nf == n;
+    std::fseek(f, (long)((long long)F.bytes * nf * comp), SEEK_CUR);
+    if (same && F.bytes == 8 && !F.big_endian) {                      // the common case: straight into the destination
+        if ((long long)std::fread(dst, 8, (size_t)n, f) != n) throw std::runtime_error("short read in " + where);
+        return;
     }
-    if (f) std::fclose(f);
+    std::vector<unsigned char> raw((size_t)nf * F.bytes);
+    if ((long long)std::fread(raw.data(), F.bytes, (size_t)nf, f) != nf) throw std::runtime_error("short read in " + where);
+    auto value = [&](long long i) -> double {
+        unsigned char t[8];
+        const unsigned char* p = raw.data() + (size_t)i * F.bytes;
+        for (int k = 0; k < F.bytes; ++k) t[k] = F.big_endian ? p[F.bytes - 1 - k] : p[k];
+        if (F.bytes == 8) { double v; std::memcpy(&v, t, 8); return v; }
+        float v; std::memcpy(&v, t, 4); return (double)v;
+    };
+    const long long fx = F.box.hi[0] - F.box.lo[0] + 1, fy = F.box.hi[1] - F.box.lo[1] + 1;
+    const int nx = vb.hi[0] - vb.lo[0] + 1, ny = vb.hi[1] - vb.lo[1] + 1, nz = vb.hi[2] - vb.lo[2] + 1;
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i)
+                *dst++ = value(((long long)(k + vb.lo[2] - F.box.lo[2]) * fy + (j + vb.lo[1] - F.box.lo[1])) * fx + (i + vb.lo[0] - F.box.lo[0]));
 }
 
 void read_boxes_comp(const std::string& dir, const Header& h, int lev, int comp, const std::vector<int>& box_ids, double* dst) {
@@ -147,22 +190,28 @@ void read_boxes_comp(const std::string& dir, const Header& h, int lev, int comp,
     std::string ldir = dir + "/" + lv.cell_path.substr(0, lv.cell_path.find_last_of('/'));
     std::string open_name;
     FILE* f = nullptr;
-    for (int b : box_ids) {
-        if (lv.fab_file.at(b) != open_name) {
-            if (f) std::fclose(f);
-            f = std::fopen((ldir + "/" + lv.fab_file[b]).c_str(), "rb");
-            if (!f) throw std::runtime_error("cannot open " + ldir + "/" + lv.fab_file[b]);
-            open_name = lv.fab_file[b];
+    try {
+        for (int b : box_ids) {
+            if (lv.fab_file.at(b) != open_name) {
+                if (f) std::fclose(f);
+                f = std::fopen((ldir + "/" + lv.fab_file[b]).c_str(), "rb");
+                if (!f) throw std::runtime_error("cannot open " + ldir + "/" + lv.fab_file[b]);
+                open_name = lv.fab_file[b];
+            }
+            read_fab_comp(f, lv.fab_offset[b], lv.boxes[b], comp, dst, ldir + "/" + open_name);
+            dst += lv.boxes[b].npts();
         }
-        std::fseek(f, lv.fab_offset[b], SEEK_SET);
-        int c;
-        while ((c = std::fgetc(f)) != EOF && c != '\n') {}      // ASCII "FAB (...)(box) ncomp" line
-        long long n = lv.boxes[b].npts();
-        std::fseek(f, (long)(8LL * n * comp), SEEK_CUR);
-        if ((long long)std::fread(dst, 8, (size_t)n, f) != n) { std::fclose(f); throw std::runtime_error("short read in " + open_name); }
-        dst += n;
+    } catch (...) {
+        if (f) std::fclose(f);
+        throw;
     }
     if (f) std::fclose(f);
+}
+
+void read_level_comp(const std::string& dir, const Header& h, int lev, int comp, double* dst) {
+    std::vector<int> all(h.levels.at(lev).boxes.size());
+    for (size_t b = 0; b < all.size(); ++b) all[b] = (int)b;
+    read_boxes_comp(dir, h, lev, comp, all, dst);
 }
 
 static std::string g17(double x) { char b[64]; std::snprintf(b, sizeof b, "%.17g", x); return b; }

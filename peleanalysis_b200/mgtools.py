@@ -74,11 +74,17 @@ def read_boxes(path: str, hd, lev: int, meta, box_ids: Sequence[int], comp_ids: 
         fn, off = fod[b]
         with open(os.path.join(ldir, fn), "rb") as f:
             f.seek(off)
-            f.readline()
+            dt, flo, fhi, fnc = plotfile.parse_fab_header(f.readline().decode("ascii", "replace"), fn)
             base = f.tell()
+            lo, hi = boxes[b]
+            m = [fhi[d] - flo[d] + 1 for d in range(3)]
+            if any(flo[d] > lo[d] or fhi[d] < hi[d] for d in range(3)) or max(comp_ids) >= fnc:
+                raise ValueError("FAB in %s does not cover box %s / component %d" % (fn, boxes[b], max(comp_ids)))
+            sl = tuple(slice(lo[d] - flo[d], hi[d] - flo[d] + 1) for d in (2, 1, 0))
+            nf = m[0] * m[1] * m[2]
             for k, c in enumerate(comp_ids):
-                f.seek(base + 8 * n * c)
-                out[k, o:o + n] = np.fromfile(f, "<f8", n)
+                f.seek(base + np.dtype(dt).itemsize * nf * c)
+                out[k, o:o + n] = np.fromfile(f, dt, nf).reshape(m[2], m[1], m[0])[sl].ravel()
         o += n
     return out
 

@@ -208,6 +208,34 @@ def read_cell_h(path: str, relpath: str):
     return ncomp, boxes, fod, mins, maxs
 
 
+def parse_fab_header(line: str, where: str = "?"):
+    """`FAB ((n, (fmt...)),(m, (byte order...))) ((lo) (hi) (type)) ncomp` -> (numpy dtype, lo, hi, ncomp).  IEEE double or
+    single, little- or big-endian (what AmrData converts through RealDescriptor, AMReX_FabConv.cpp); the FAB's own box may be
+    the valid box grown by ghost cells.  Anything else raises -- a plotfile is never silently misread."""
+    import re
+    if not line.startswith("FAB"):
+        raise ValueError("not a FAB header in %s: %r" % (where, line[:60]))
+    box_at = line.find("((", 5)
+    d = [int(x) for x in re.findall(r"-?\d+", line[:box_at])]
+    b = [int(x) for x in re.findall(r"-?\d+", line[box_at:])]
+    if box_at < 0 or len(b) != 10 or len(d) < 2 or len(d) != 2 + d[0] + d[1 + d[0]]:
+        raise ValueError("malformed FAB header in %s: %r" % (where, line))
+    fmt, order = d[1:1 + d[0]], d[2 + d[0]:]
+    kinds = {(64, 11, 52, 0, 1, 12, 0, 1023): 8, (32, 8, 23, 0, 1, 9, 0, 127): 4}
+    nbytes = kinds.get(tuple(fmt))
+    if nbytes is None or len(order) != nbytes:
+        raise ValueError("unsupported real format in %s (only IEEE double / single): %r" % (where, line[:box_at]))
+    if order == list(range(nbytes, 0, -1)):
+        dt = "<f%d" % nbytes
+    elif order == list(range(1, nbytes + 1)):
+        dt = ">f%d" % nbytes
+    else:
+        raise ValueError("unsupported byte order in %s: %r" % (where, line[:box_at]))
+    if b[6:9] != [0, 0, 0]:
+        raise ValueError("not a cell-centred FAB in %s" % where)
+    return dt, tuple(b[0:3]), tuple(b[3:6]), b[9]
+
+
 def read_plotfile(path: str, comps: Sequence[str] | None = None, finest_level: int | None = None,
                   load_data: bool = True) -> Plotfile:
     """Read a plotfile.  comps=None reads every component; otherwise only the named ones, in that order."""
@@ -225,16 +253,20 @@ def read_plotfile(path: str, comps: Sequence[str] | None = None, finest_level: i
                 n = [hi[d] - lo[d] + 1 for d in range(3)]
                 with open(os.path.join(ldir, fn), "rb") as f:
                     f.seek(off)
-                    f.readline()
+                    dt, flo, fhi, fnc = parse_fab_header(f.readline().decode("ascii", "replace"), fn)
                     base = f.tell()
-                    npts = n[0] * n[1] * n[2]
+                    m = [fhi[d] - flo[d] + 1 for d in range(3)]
+                    if any(flo[d] > lo[d] or fhi[d] < hi[d] for d in range(3)) or fnc < ncomp:
+                        raise ValueError("FAB in %s does not cover box %s with %d components" % (fn, (lo, hi), ncomp))
+                    npts = m[0] * m[1] * m[2]
+                    sl = tuple(slice(lo[d] - flo[d], lo[d] - flo[d] + n[d]) for d in (2, 1, 0))
                     if len(idx) == ncomp and idx == list(range(ncomp)):
-                        a = np.fromfile(f, "<f8", npts * ncomp).reshape(ncomp, n[2], n[1], n[0])
+                        a = np.fromfile(f, dt, npts * ncomp).reshape(ncomp, m[2], m[1], m[0])[(slice(None),) + sl].astype("<f8")
                     else:
                         a = np.empty((len(idx), n[2], n[1], n[0]))
                         for o, c in enumerate(idx):
-                            f.seek(base + 8 * npts * c)
-                            a[o] = np.fromfile(f, "<f8", npts).reshape(n[2], n[1], n[0])
+                            f.seek(base + np.dtype(dt).itemsize * npts * c)
+                            a[o] = np.fromfile(f, dt, npts).reshape(m[2], m[1], m[0])[sl]
                 fabs.append(a)
         dlo, dhi = hd["domains"][lev]
         levels.append(Level(dlo, dhi, hd["dx"][lev], boxes, fabs))

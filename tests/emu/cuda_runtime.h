@@ -123,6 +123,9 @@ void mbar_arrive(uint64_t* bar);
 void mbar_wait(uint64_t* bar, uint32_t parity);
 void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
 void cp_async_8(void* dst, const void* src);
+void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes);   // cp.async.bulk.global.shared::cta.bulk_group
+void bulk_commit();                                               // cp.async.bulk.commit_group
+void bulk_wait_read(int n);                                       // cp.async.bulk.wait_group.read n
 void cp_async_arrive_noinc(uint64_t* bar);
 
 template <class... KA>

@@ -37,6 +37,10 @@ struct Fiber {
     const char* waiting = "";       // what the fiber is blocked on (deadlock report)
     const void* wait_obj = nullptr;
     unsigned long long async_due = 0;   // latest completion tick of this thread's outstanding cp.async copies
+    // bulk-store groups (cp.async.bulk shared -> global): ops still reading shared memory per committed group, oldest first;
+    // the last entry is the open (uncommitted) group
+    std::vector<int> store_groups = std::vector<int>(1, 0);
+    int groups_retired = 0;             // committed groups already dropped from the front of store_groups
 };
 
 struct WarpState {
@@ -51,9 +55,10 @@ struct MBar {
 };
 
 struct Async {
-    int kind;                       // 0: bulk copy + complete_tx, 1: plain copy, 2: arrive
+    int kind;                       // 0: bulk copy + complete_tx, 1: plain copy, 2: arrive, 3: bulk store (shared -> global)
     void* dst; const void* src; size_t bytes; uint64_t* bar;
     unsigned long long due;
+    int fiber = -1, group = -1;     // kind 3: issuing thread and its (absolute) bulk-store group
 };
 
 std::vector<Fiber> fibers;          // grows to the largest block seen; stacks are reused
@@ -72,6 +77,7 @@ std::vector<unsigned char> dyn;
 unsigned char* dyn_aligned = nullptr;
 unsigned long long rng_state = 0;
 long long seed = -1;
+int starve = 0;
 
 unsigned long long rnd() {          // splitmix64
     unsigned long long z = (rng_state += 0x9E3779B97F4A7C15ULL);
@@ -109,7 +115,12 @@ void run_async(bool all) {
     for (size_t i = 0; i < asyncq.size(); ++i) {
         Async& a = asyncq[i];
         if (all || a.due <= tick) {
-            if (a.kind != 2) std::memcpy(a.dst, a.src, a.bytes);
+            if (a.kind != 2) std::memcpy(a.dst, a.src, a.bytes);       // kind 3 reads shared memory only NOW: reuse before the wait shows
+            if (a.kind == 3) {
+                Fiber& f = fibers[a.fiber];
+                const int rel = a.group - f.groups_retired;
+                if (rel >= 0 && rel < (int)f.store_groups.size()) --f.store_groups[rel];
+            }
             if (a.kind == 0) { MBar& b = mbar_of(a.bar); b.tx -= (long long)a.bytes; mbar_check(b); }
             if (a.kind == 2) { MBar& b = mbar_of(a.bar); --b.pending; mbar_check(b); }
             ++progress;
@@ -140,10 +151,20 @@ void run_block() {
         const unsigned long long before = progress;
         if (seed > 0)
             for (int t = n_threads - 1; t > 0; --t) std::swap(order[t], order[rnd() % (unsigned long long)(t + 1)]);
+        // CUEMU_STARVE=p (1..9): every scheduler round each WARP is left out with probability p/10 -- warps then drift apart by
+        // many instructions, as they do on an SM whose schedulers favour other warps.  Protocols that only hold while all warps
+        // advance at the same pace (a phase bit that aliases when one side runs two steps ahead) fail here, not on the GPU.
+        std::vector<char> skip_warp;
+        bool skipped_any = false;
+        if (starve > 0) {
+            skip_warp.assign((n_threads + 31) / 32, 0);
+            for (auto& x : skip_warp) { x = (char)((int)(rnd() % 10ULL) < starve); }
+        }
         for (int k = 0; k < n_threads; ++k) {
             Fiber& f = fibers[order[k]];
             if (f.done) continue;
             const int t = order[k];
+            if (starve > 0 && skip_warp[t / 32]) { skipped_any = true; continue; }
             g_threadIdx.x = (unsigned)t % g_blockDim.x;
             g_threadIdx.y = ((unsigned)t / g_blockDim.x) % g_blockDim.y;
             g_threadIdx.z = (unsigned)t / (g_blockDim.x * g_blockDim.y);
@@ -152,6 +173,7 @@ void run_block() {
         }
         ++tick;
         run_async(false);
+        if (progress == before && skipped_any) continue;
         if (progress == before) {
             if (!asyncq.empty()) { tick = asyncq.front().due; for (auto& a : asyncq) tick = std::max(tick, a.due); run_async(true); }
             else deadlock();
@@ -193,6 +215,8 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
         const char* e = getenv("CUEMU_SEED");
         const long long sd = e ? atoll(e) : 0;
         if (sd != seed) { seed = sd; rng_state = (unsigned long long)seed * 0x2545F4914F6CDD1DULL + 1; }
+        const char* es = getenv("CUEMU_STARVE");
+        starve = es ? std::min(9, std::max(0, atoi(es))) : 0;
     }
     if (cur != nullptr) { std::fprintf(stderr, "[cuemu] nested kernel launch\n"); std::abort(); }
     n_threads = (int)(block.x * block.y * block.z);
@@ -220,6 +244,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
                 for (int t = 0; t < n_threads; ++t) {
                     Fiber& f = fibers[t];
                     f.done = false; f.waiting = ""; f.async_due = 0;
+                    f.store_groups.assign(1, 0); f.groups_retired = 0;
                     getcontext(&f.ctx);
                     f.ctx.uc_stack.ss_sp = f.stack;
                     f.ctx.uc_stack.ss_size = STACK_BYTES;
@@ -295,6 +320,34 @@ void cp_async_8(void* dst, const void* src) {
     cur->async_due = std::max(cur->async_due, due);
     asyncq.push_back(Async{1, dst, src, 8, nullptr, due});
     ++progress;
+}
+// cp.async.bulk.global.shared::cta (TMA store) + bulk_group commit / wait_group.read
+void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    if ((bytes & 15u) || ((uintptr_t)gdst & 15u) || ((uintptr_t)ssrc & 15u)) {
+        std::fprintf(stderr, "[cuemu] cp.async.bulk store needs 16-byte aligned addresses and size: dst %p src %p bytes %u\n", gdst, ssrc, bytes);
+        std::abort();
+    }
+    Async a{3, gdst, ssrc, bytes, nullptr, tick + 1 + delay()};
+    a.fiber = (int)(cur - &fibers[0]);
+    a.group = cur->groups_retired + (int)cur->store_groups.size() - 1;
+    ++cur->store_groups.back();
+    asyncq.push_back(a);
+    ++progress;
+}
+void bulk_commit() { cur->store_groups.push_back(0); ++progress; }
+void bulk_wait_read(int n) {
+    // all committed groups except the n most recent have finished reading shared memory
+    for (;;) {
+        const int committed = (int)cur->store_groups.size() - 1;
+        bool pending = false;
+        for (int g = 0; g < committed - n; ++g) pending |= cur->store_groups[g] > 0;
+        if (!pending) break;
+        yield("cp.async.bulk.wait_group.read", cur);
+    }
+    while (cur->store_groups.size() > 1 && cur->store_groups.front() == 0 && (int)cur->store_groups.size() - 1 > n) {
+        cur->store_groups.erase(cur->store_groups.begin());
+        ++cur->groups_retired;
+    }
 }
 void cp_async_arrive_noinc(uint64_t* bar) {
     asyncq.push_back(Async{2, nullptr, nullptr, 0, bar, std::max(cur->async_due, tick)});

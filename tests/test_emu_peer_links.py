@@ -217,3 +217,54 @@ def test_emulated_multi_rank_curvature_options(emu, name, nranks, transport):  #
                             assert bit_equal(got[l][b], want[l][b]), (name, transport, n, r, l, b)
     finally:
         os.environ["CUEMU_SEED"] = "0"
+
+
+@pytest.mark.parametrize("transport", ["peer", "slab"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport):  # noqa: F811
+    """threshold_prog on a field that is NOT mirror-symmetric about the rank boundaries (the golden `temp` is: the cells either
+    side of every cross-rank face hold equal progress values, so a clip of the flame normal that runs too early -- before a
+    peer's divergence has read the unclipped values, curvature.cpp:487-567 -- could not be seen).  Ranks run one after the
+    other in both orders; every order must reproduce the single-rank oracle bit for bit."""
+    from oracle import oracle as O
+    from peleanalysis_b200 import synth
+    capi = emu
+    os.environ["CUEMU_SEED"] = "5"
+    os.environ["PA_STENCIL"] = "tma"
+    os.environ["PA_TMA_SMALL"] = "1"
+    try:
+        pf = synth.config3(16, 8)
+        for lv in pf.levels:                                    # off-centre blob + a z-dependent ripple
+            for (lo, hi), f in zip(lv.boxes, lv.fabs):
+                ax = [(np.arange(lo[d], hi[d] + 1) - lv.domain_lo[d] + 0.5) * lv.dx[d] for d in range(3)]
+                X, Y, Z = ax[0][None, None, :], ax[1][None, :, None], ax[2][:, None, None]
+                rr = np.sqrt((X - 0.5) ** 2 + (Y - 0.47) ** 2 + (Z - 0.41) ** 2)
+                f[0] = 300.0 + 750.0 * (1.0 + np.tanh((0.27 - rr) / 0.09)) + 9.0 * np.sin(2 * np.pi * (Z + 0.13)) * np.cos(2 * np.pi * X)
+        is_per, sym = (1, 1, 1), (0, 0, 0)
+        OH = O.OracleHier(pf, is_per, sym)
+        s = OH.flatten(0)
+        o = capi.CurvOpts()
+        o.prog_min, o.prog_max = float(s.min()), float(s.max())
+        o.do_threshold, o.threshold = 1, 0.2
+        want = OH.curvature(s, o.prog_min, o.prog_max, do_threshold=True, threshold=0.2)
+        assert np.count_nonzero(want[1] == 0.0) > 100 and np.count_nonzero(want[1]) > 100   # the clip is active, and not everywhere
+        for order in (list(range(nranks)), list(reversed(range(nranks)))):
+            R = Ranks(capi, pf, is_per, sym, nranks, capi.PEER_LINKS if transport == "peer" else 0)
+            R.OH = OH
+            state, out = R.fields(1, 1), R.fields(5, 1)
+            for f in state:
+                f.upload_fabs(0, [[x[0] for x in l.fabs] for l in pf.levels])
+
+            def step(steps, lo=-1, hi=-1):
+                for r in order:
+                    capi.curvature_steps(state[r], 0, 0, o, out[r], 0, steps, lo, hi)
+                capi.sync()
+            R.exchange(state, 0, 1)
+            step(capi.CURV_PASS1)
+            for l in range(len(pf.levels)):
+                R.exchange(out, 2, 3)
+                step(capi.CURV_DIV, l, l)
+                step(capi.CURV_CLIP, l, l)
+            R.check(out, range(5), want, "curvature, threshold_prog, rank order %s" % order)
+    finally:
+        os.environ["CUEMU_SEED"] = "0"

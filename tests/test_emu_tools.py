@@ -123,3 +123,44 @@ def test_emulated_curvature_executable_multi_gpu(emu_exes, tmp_path, name, ngpus
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+# ---- source-level drop-in: the reference tools with their operator block replaced by the C-ABI calls,
+#      here linked against host AMReX (oracle/_ref/libamrex_ref.a) and the EMULATED library -------------------------------
+@pytest.fixture(scope="module")
+def emu_amrex_exes(emu_exes):
+    from oracle import oracle as O
+    ref = os.path.dirname(O.ref_exe("x"))
+    srcdir, lib_a, inc = os.path.join(ref, "src"), os.path.join(ref, "libamrex_ref.a"), os.path.join(ref, "include")
+    amrex = "/root/reference/Submodules/PelePhysics/Submodules/amrex"
+    srcs = [os.path.join(srcdir, "grad_b200amrex.cpp"), os.path.join(srcdir, "curvature_b200amrex.cpp")]
+    if not (os.path.isdir(amrex) and os.path.exists(lib_a) and all(os.path.exists(s) for s in srcs)):
+        pytest.skip("needs /root/reference and oracle/_ref (python oracle/build_ref.py)")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    import build_emu
+    out = os.path.dirname(build_emu.build())
+    glue = os.path.join(ROOT, "peleanalysis_b200", "host", "amrex_glue")
+    flags = build_ref.cxx_flags(inc) + ["-O1", "-I" + glue, "-I" + os.path.join(ROOT, "include")]
+    exes = []
+    for src, name in zip(srcs, ("grad3d.emuamrex.ex", "curvature3d.emuamrex.ex")):
+        exe = os.path.join(out, name)
+        deps = [src, lib_a, os.path.join(out, "libpelestencil_emu.so")] + [os.path.join(glue, f) for f in os.listdir(glue)]
+        if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+            subprocess.check_call(["g++", *flags, src, "-o", exe, lib_a, "-lgomp", "-lpthread", "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
+        exes.append(exe)
+    return tuple(exes)
+
+
+@pytest.mark.parametrize("name", ["c1_periodic", "c3_three_levels"])
+def test_emulated_amrex_linked_grad(emu_amrex_exes, tmp_path, name):
+    T.test_grad_executable(emu_amrex_exes, tmp_path, name)
+
+
+@pytest.mark.parametrize("name", ["c1_periodic", "c1_options"])
+def test_emulated_amrex_linked_curvature(emu_amrex_exes, tmp_path, name):
+    T.check_curvature_executable(emu_amrex_exes, tmp_path, name)
+
+
+def test_emulated_amrex_linked_curvature_do_smooth(emu_amrex_exes, tmp_path):
+    T.test_amrex_linked_curvature_do_smooth(emu_amrex_exes, tmp_path)

@@ -391,3 +391,34 @@ def test_extreme_box_shapes(gpu, base, mgs):
     wk = OH.curvature(s, float(s.min()), float(s.max()))
     for c in range(5):
         assert bit_equal(outc[c], wk[c]), ("curvature", c)
+
+
+def _hmix64(z):
+    z = (z + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return z ^ (z >> np.uint64(31))
+
+
+def test_field_hash_matches_its_definition(gpu):
+    """pa_field_hash: sum mod 2^64 of mix(bits ^ mix(mix(level, GLOBAL box id, component) + cell)) over the valid cells --
+    recomputed here in numpy.  Ghost cells do not enter, the box -> rank map does not enter (global ids)."""
+    pf = synth.config1(16, 8, names=("temp", "Y_CH4"))
+    H = gpu.Hierarchy(pf.levels)
+    f = gpu.Field(H, 2, 1)
+    f.set_val(-1.5)
+    for c in range(2):
+        f.upload_fabs(c, [[x[c] for x in l.fabs] for l in pf.levels])
+    want = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for l, lv in enumerate(pf.levels):
+            for g, fab in enumerate(lv.fabs):
+                for c in range(2):
+                    key = _hmix64(np.array([(l << 56) ^ (g << 16) ^ c], dtype=np.uint64))[0]
+                    cells = np.arange(fab[c].size, dtype=np.uint64)
+                    bits = np.ascontiguousarray(fab[c]).view(np.uint64).ravel()
+                    want = want + _hmix64(bits ^ _hmix64(key + cells)).sum(dtype=np.uint64)
+    assert f.hash(0, 2) == int(want)
+    assert f.hash(1, 1) != f.hash(0, 1)
+    f.fill_ghosts(0, 1)                                    # ghost cells change, the fingerprint does not
+    assert f.hash(0, 2) == int(want)
