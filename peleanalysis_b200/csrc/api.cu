@@ -996,14 +996,15 @@ struct CurvCtx {
     double invdenom;
 };
 
-// the fused kernel serves the whole hierarchy or nothing: every local box must be eligible (build_curv_tiles).  PA_CURV_FUSED=0
-// (or PA_CURV_UNFUSED=1, or PA_STENCIL=simple) selects the separate NORMAL_S / DIV kernels -- the independent second route
-// to the same bits the tests compare against.
+// The fused kernel (curv_fused.cu) serves the whole hierarchy or nothing: every local box must be eligible (build_curv_tiles).
+// It is OPT-IN (PA_CURV_FUSED=1): measured on a B200 it moves a third less data than the separate NORMAL_S / DIV kernels
+// (21.7 GB against 32.5 GB per step on the target hierarchy) but is bound by FP64 latency and per-SM store drain, not by HBM,
+// and ends up slower (7.1 ms against 6.5 ms; DESIGN.md section 6 has the ablation).  The separate kernels are the default.
 bool curv_fused_path(const CurvCtx& c) {
     const char* e = getenv("PA_CURV_FUSED");
     const char* no_fuse = getenv("PA_CURV_UNFUSED");
     const char* es = getenv("PA_STENCIL");
-    if ((e && e[0] == '0') || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return false;
+    if (!(e && e[0] == '1') || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return false;
     return c.state->ng == 1 && c.h->curv_ok && !overlap_enabled(c.h);
 }
 

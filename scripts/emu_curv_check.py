@@ -22,7 +22,7 @@ from cases import CASES  # noqa: E402
 names = sys.argv[1:] or [n for n, c in CASES.items() if "curvature" in c[3]]
 bad = 0
 for name in names:
-    for st in ("tma", "tma_unfused"):
+    for st in ("tma", "tma_fused"):
         for links in ("links", "nolinks"):
             f0 = m.curv_fused_launches()
             try:

@@ -136,6 +136,49 @@ def run_curv_options(rank, world, mode):
     return int(t.item())
 
 
+def run_curv_threshold_off_centre(rank, world, mode):
+    """threshold_prog on a field that is NOT mirror-symmetric about the rank boundaries (tests/test_emu_peer_links.py has the
+    reasoning): an early clip of the flame normal -- before every rank's divergence has read the unclipped values of its
+    peers -- shows up as a mismatch against the single-rank oracle here."""
+    pf = synth.config3(64, 16)
+    for lv in pf.levels:
+        for (lo, hi), f in zip(lv.boxes, lv.fabs):
+            ax = [(np.arange(lo[d], hi[d] + 1) - lv.domain_lo[d] + 0.5) * lv.dx[d] for d in range(3)]
+            X, Y, Z = ax[0][None, None, :], ax[1][None, :, None], ax[2][:, None, None]
+            rr = np.sqrt((X - 0.5) ** 2 + (Y - 0.47) ** 2 + (Z - 0.41) ** 2)
+            f[0] = 300.0 + 750.0 * (1.0 + np.tanh((0.27 - rr) / 0.09)) + 9.0 * np.sin(2 * np.pi * (Z + 0.13)) * np.cos(2 * np.pi * X)
+    is_per, sym = (1, 1, 1), (0, 0, 0)
+    H = capi.Hierarchy(pf.levels, is_per, sym, rank, world, flags=capi.PEER_LINKS if mode == "peer" else 0)
+    state = capi.Field(H, 1, 1)
+    state.upload_fabs(0, [[f[0] for f in l.fabs] for l in pf.levels])
+    OH = O.OracleHier(pf, is_per, sym)
+    s = OH.flatten(0)
+    o = capi.CurvOpts()
+    o.prog_min, o.prog_max = float(s.min()), float(s.max())
+    o.do_threshold, o.threshold = 1, 0.2
+    out = capi.Field(H, 5, 1)
+    op = multigpu.Curvature(state, 0, o, out, 0)
+    capi.sync()
+    dist.barrier()
+    op.run()
+    op.run()
+    capi.sync()
+    dist.barrier()
+    want = OH.curvature(s, o.prog_min, o.prog_max, do_threshold=True, threshold=0.2)
+    bad = 0
+    for c in range(5):
+        w = OH.unflatten(want[c])
+        got = out.download_fabs(c)
+        for l in range(len(pf.levels)):
+            for b in H.local_boxes[l]:
+                bad += 0 if np.array_equal(got[l][b], w[l][b]) else 1
+    t = torch.tensor([bad], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("dist_check curvature threshold, off-centre field %-4s ranks=%d mismatching boxes=%d" % (mode, world, int(t.item())), flush=True)
+    return int(t.item())
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -152,11 +195,16 @@ def main():
         bad += run_case("config1_5vars", synth.config1(32, 16, names=synth.FIELD_NAMES), (1, 1, 1), (0, 0, 0), rank, world, nvar=5, mode=mode)
         bad += run_case("config5_small", synth.config5(base=32, mgs=8, ncomp=2), (1, 1, 1), (0, 0, 0), rank, world, nvar=2, mode=mode)
         bad += run_case("uniform_64", synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
-        bad += run_curv("config1", synth.config1(32, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
-        bad += run_curv("config3_64", synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
-        bad += run_curv("c1_walls_vn", synth.config1(32, 16, names=synth.FIELD_NAMES, corner=True), (0, 0, 0), (1, 0, 0), rank, world, mode=mode, velnormal=True)
-        bad += run_curv("uniform_64", synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
-        bad += run_curv_options(rank, world, mode)
+        for fused in ("0", "1"):                   # the separate NORMAL_S / DIV kernels (default), then the fused kernel + shell pass
+            os.environ["PA_CURV_FUSED"] = fused
+            tag = "+fused" if fused == "1" else ""
+            bad += run_curv("config1" + tag, synth.config1(32, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+            bad += run_curv("config3_64" + tag, synth.config3(64, 16), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+            bad += run_curv("c1_walls_vn" + tag, synth.config1(32, 16, names=synth.FIELD_NAMES, corner=True), (0, 0, 0), (1, 0, 0), rank, world, mode=mode, velnormal=True)
+            bad += run_curv("uniform_64" + tag, synth.make_hierarchy(64, [], [], 16, ("temp",)), (1, 1, 1), (0, 0, 0), rank, world, mode=mode)
+            bad += run_curv_options(rank, world, mode)
+            bad += run_curv_threshold_off_centre(rank, world, mode)
+        os.environ["PA_CURV_FUSED"] = "0"
     dist.destroy_process_group()
     if rank == 0:
         print("DIST_CHECK", "OK" if bad == 0 else "FAILED (%d)" % bad, flush=True)

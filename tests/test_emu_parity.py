@@ -58,9 +58,9 @@ def _thin_out(schedule, stencil, links):
     only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
     if schedule and (stencil == "simple" or links == "nolinks"):
         pytest.skip("combination not in the thinned-out matrix")
-    if schedule < 0 and stencil not in ("tma", "tma_unfused"):
+    if schedule < 0 and stencil not in ("tma", "tma_fused"):
         pytest.skip("combination not in the thinned-out matrix")
-    if links == "nolinks" and stencil not in ("tma", "tma_unfused", "simple"):
+    if links == "nolinks" and stencil not in ("tma", "tma_fused", "simple"):
         pytest.skip("combination not in the thinned-out matrix")
 
 
@@ -77,7 +77,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_unfused", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_big", "simple"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
     _thin_out(schedule, stencil, links)
@@ -116,7 +116,7 @@ def test_emulated_midsize_vs_oracle(emu, case, kw):
     os.environ["CUEMU_SEED"] = "7"
     try:
         G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma")
-        G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma_unfused")
+        G.test_midsize_grad_and_curvature_vs_oracle(emu, case, kw, "tma_fused")
     finally:
         os.environ["CUEMU_SEED"] = "0"
 
@@ -170,7 +170,7 @@ def test_emulated_unstaged_bcfill(emu, name):
         os.environ.pop("PA_BCFILL_V2", None)
 
 
-@pytest.mark.parametrize("stencil", ["tma", "tma_unfused"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused"])
 def test_emulated_full_width_tiles(emu, stencil):
     """128-cell-wide boxes: 64 x-pairs per row, 8 rows per tile -- every one of the 512 pair slots of the big CTA shapes is
     in use (the golden cases have narrow boxes), two boxes side by side in y so that linked y rows and periodic x / z wraps

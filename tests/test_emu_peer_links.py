@@ -219,9 +219,10 @@ def test_emulated_multi_rank_curvature_options(emu, name, nranks, transport):  #
         os.environ["CUEMU_SEED"] = "0"
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("transport", ["peer", "slab"])
 @pytest.mark.parametrize("nranks", [2, 3])
-def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport):  # noqa: F811
+def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport, fused):  # noqa: F811
     """threshold_prog on a field that is NOT mirror-symmetric about the rank boundaries (the golden `temp` is: the cells either
     side of every cross-rank face hold equal progress values, so a clip of the flame normal that runs too early -- before a
     peer's divergence has read the unclipped values, curvature.cpp:487-567 -- could not be seen).  Ranks run one after the
@@ -232,6 +233,7 @@ def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport):
     os.environ["CUEMU_SEED"] = "5"
     os.environ["PA_STENCIL"] = "tma"
     os.environ["PA_TMA_SMALL"] = "1"
+    os.environ["PA_CURV_FUSED"] = fused                        # "1": the fused kernel + shell pass on every rank
     try:
         pf = synth.config3(16, 8)
         for lv in pf.levels:                                    # off-centre blob + a z-dependent ripple
@@ -268,3 +270,4 @@ def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport):
             R.check(out, range(5), want, "curvature, threshold_prog, rank order %s" % order)
     finally:
         os.environ["CUEMU_SEED"] = "0"
+        os.environ["PA_CURV_FUSED"] = "0"

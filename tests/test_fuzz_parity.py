@@ -92,7 +92,7 @@ def test_random_hierarchy_emulated_kernels_equal_oracle(emu, seed):  # noqa: F81
         if curv:
             pmin, pmax = float(s.min()), float(s.max())
             wk = OH.curvature(s, pmin, pmax)
-            for stencil in ("tma", "tma_unfused"):
+            for stencil in ("tma", "tma_fused"):
                 out, _ = G._gpu_curv(emu, pf, is_per, sym, pmin, pmax, {}, stencil)
                 for c in range(5):
                     assert bit_equal(out[c], wk[c]), (seed, "curvature", stencil, c, [l.boxes for l in pf.levels])

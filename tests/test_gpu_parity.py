@@ -22,12 +22,12 @@ def _flat(pf, name):
 
 
 def _set_stencil(stencil):
-    """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps), curvature through the fused kernel
-    where the hierarchy is eligible; tma_big: TMA pipeline in the 8 / 16-warp shapes whatever the tile size; tma_unfused:
-    curvature through the separate NORMAL_S / DIV kernels (PA_CURV_FUSED=0); simple: the plain-load kernels."""
+    """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps); tma_big: TMA pipeline in the 8 /
+    16-warp shapes whatever the tile size; tma_fused: curvature through the fused kernel + shell pass where the hierarchy is
+    eligible (PA_CURV_FUSED=1, opt-in); simple: the plain-load kernels."""
     os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
-    os.environ["PA_CURV_FUSED"] = "0" if stencil in ("tma_unfused", "tma_big") else "1"
+    os.environ["PA_CURV_FUSED"] = "1" if stencil == "tma_fused" else "0"
 
 
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
@@ -83,7 +83,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_unfused", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
