@@ -92,11 +92,12 @@ def config_of(spec, pf):
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the compiled, unmodified reference tool on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def run_reference(spec, steps, warmup, variables=None):
+def run_reference(spec, steps, warmup, variables=None, variants=("timed",)):
     """The reference tool (oracle/_ref/{grad3d,curvature3d}.timed.ex = the unmodified sources plus timing probes around
     grad.cpp:151-236 / curvature.cpp:283-791, FillVar's disk read subtracted) on the workload's own plotfile, one process
     per differentiated variable, the probed region repeated warmup + steps times inside the process (PA_TIMED_REPS).
-    Returns (Gcells/s, seconds per step, cores, per-step list, variables run)."""
+    variants: "timed" = the CPU/OpenMP build on all host cores; "cuda.timed" = the reference's own generic CUDA build
+    (oracle/build_ref_cuda.py) on this box's GPU.  Returns {variant: (Gcells/s, seconds per step, cores, per-step list)}, names."""
     from oracle import oracle as O
     from peleanalysis_b200 import plotfile
     if not O.have_ref():
@@ -107,23 +108,36 @@ def run_reference(spec, steps, warmup, variables=None):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     tmp = tempfile.mkdtemp(prefix="pa_ref_", dir=base)
     cores = os.cpu_count() or 1
-    per_step = np.zeros(steps)
+    res = {}
     try:
         d = os.path.join(tmp, "plt")
         plotfile.write_plotfile(d, pf, clean="remove")
         del pf
-        for v in names:
-            if spec["kind"] == "grad":
-                hot = O.run_ref_timed("grad", d, d + "_out", threads=cores, reps=warmup + steps, gradVar=v)
-            else:
-                hot = O.run_ref_timed("curvature", d, d + "_out", threads=cores, reps=warmup + steps, progressName=v,
-                                      progMin=300.0, progMax=1800.0)
-            shutil.rmtree(d + "_out", ignore_errors=True)
-            per_step += np.asarray(hot[warmup:warmup + steps])
+        for variant in variants:
+            if not os.path.exists(O.ref_exe("%s3d.%s.ex" % ("grad" if spec["kind"] == "grad" else "curvature", variant))):
+                res[variant] = None
+                continue
+            per_step = np.zeros(steps)
+            thr = cores if variant == "timed" else 1
+            try:
+                for v in names:
+                    if spec["kind"] == "grad":
+                        hot = O.run_ref_timed("grad", d, d + "_out", threads=thr, reps=warmup + steps, variant=variant, gradVar=v)
+                    else:
+                        hot = O.run_ref_timed("curvature", d, d + "_out", threads=thr, reps=warmup + steps, variant=variant, progressName=v,
+                                              progMin=300.0, progMax=1800.0)
+                    shutil.rmtree(d + "_out", ignore_errors=True)
+                    per_step += np.asarray(hot[warmup:warmup + steps])
+            except Exception:
+                if variant == "timed":
+                    raise
+                res[variant] = None                  # the secondary (GPU) baseline is optional: no GPU here, or it failed
+                continue
+            t = float(per_step.mean())
+            res[variant] = (cells * len(names) / t / 1e9, t, thr, per_step.tolist())
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    t = float(per_step.mean())
-    return cells * len(names) / t / 1e9, t, cores, per_step.tolist(), names
+    return res, names
 
 
 def reference_arm(args, spec):
@@ -134,7 +148,8 @@ def reference_arm(args, spec):
     cfg = config_of(spec, pf)
     del pf
     try:
-        val, t, cores, per_step, names = run_reference(spec, args.steps, args.warmup)
+        res, names = run_reference(spec, args.steps, args.warmup)
+        val, t, cores, per_step = res["timed"]
     except Exception as e:  # the oracle always exists; this only triggers on a broken checkout
         print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0][:200]}))
         return
@@ -519,13 +534,19 @@ def main():
         cx.expected = cur
 
     cpu = None
+    ref_gpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
             one = [spec["names"][-2] if args.workload.startswith("config2") else spec["names"][0]]
-            v, t, cores, _, ran = run_reference(spec, steps=3, warmup=1, variables=one)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "hot_path_seconds": t,
-                   "sample": "%s of %s on the workload's own grid (%d cells), %d of its %d variable(s); 3 timed repetitions of the tool's hot-path region" % (
-                       "grad" if kind == "grad" else "curvature", ran[0], r["cells"], len(ran), nvar)}
+            res, ran = run_reference(spec, steps=3, warmup=1, variables=one, variants=("timed", "cuda.timed"))
+            v, t, cores, _ = res["timed"]
+            sample = "%s of %s on the workload's own grid (%d cells), %d of its %d variable(s); 3 timed repetitions of the tool's hot-path region" % (
+                "grad" if kind == "grad" else "curvature", ran[0], r["cells"], len(ran), nvar)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "hot_path_seconds": t, "sample": sample}
+            if res.get("cuda.timed"):
+                gv, gt, _, _ = res["cuda.timed"]
+                ref_gpu = {"value": gv, "unit": UNIT, "kind": "the reference's own CUDA build (AMReX ParallelFor backend, USE_CUDA=TRUE CUDA_ARCH=100, "
+                           "oracle/build_ref_cuda.py) on this GPU, same probes as cpu_baseline", "hot_path_seconds": gt, "sample": sample}
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: " + str(e).splitlines()[0][:160]}
 
@@ -567,6 +588,7 @@ def main():
                      "step_frac": alg_bytes / (r["ms_per_step"] * 1e-3) / 1e9 / cx.peak},
         "output_hash": hv,
         "cpu_baseline": cpu,
+        "ref_gpu_baseline": ref_gpu,
         "extras": extras,
     }
     print(json.dumps(line))

@@ -167,12 +167,18 @@ def have_ref() -> bool:
     return os.path.exists(ref_exe("grad3d.ref.ex")) and os.path.exists(ref_exe("curvature3d.ref.ex"))
 
 
-def run_ref(tool: str, infile: str, outfile: str, threads: Optional[int] = None, timed: bool = False, **kv):
-    """Run the reference `grad` or `curvature` executable.  Returns (stdout, hot_path_seconds or None)."""
-    exe = ref_exe("%s3d.%s.ex" % (tool, "timed" if timed else "ref"))
+def run_ref(tool: str, infile: str, outfile: str, threads: Optional[int] = None, timed: bool = False, variant: Optional[str] = None, **kv):
+    """Run the reference `grad` or `curvature` executable.  Returns (stdout, hot_path_seconds or None).
+    variant: "ref" (unmodified), "timed" (probes around the hot path), "cuda.timed" (the reference's own CUDA build, see
+    build_ref_cuda.py)."""
+    exe = ref_exe("%s3d.%s.ex" % (tool, variant or ("timed" if timed else "ref")))
     if os.path.lexists(outfile):
         shutil.rmtree(outfile)
     args = [exe, "infile=" + infile, "outfile=" + outfile]
+    if (variant or "").startswith("cuda"):
+        # the tools fill their MultiFabs from host code (AmrData::FillVar): on a GPU build that needs AMReX's managed arena
+        # (a runtime ParmParse switch of AMReX, not a source change)
+        args.append("amrex.the_arena_is_managed=1")
     for k, v in kv.items():
         if isinstance(v, (list, tuple)):
             v = " ".join(str(x) for x in v)
@@ -186,13 +192,13 @@ def run_ref(tool: str, infile: str, outfile: str, threads: Optional[int] = None,
     return p.stdout, (float(m.group(1)) if m else None)
 
 
-def run_ref_timed(tool: str, infile: str, outfile: str, threads: Optional[int] = None, reps: int = 1, **kv):
+def run_ref_timed(tool: str, infile: str, outfile: str, threads: Optional[int] = None, reps: int = 1, variant: str = "timed", **kv):
     """The reference tool's timed build with its hot-path region repeated `reps` times inside ONE process (PA_TIMED_REPS,
     see build_ref.patch_timed).  Returns the list of hot-path seconds, one per repetition."""
     old = os.environ.get("PA_TIMED_REPS")
     os.environ["PA_TIMED_REPS"] = str(int(reps))
     try:
-        out, _ = run_ref(tool, infile, outfile, threads=threads, timed=True, **kv)
+        out, _ = run_ref(tool, infile, outfile, threads=threads, variant=variant, **kv)
     finally:
         if old is None:
             os.environ.pop("PA_TIMED_REPS", None)

@@ -403,7 +403,8 @@ int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1, bool link
             return fail(PA_ERR_STATE, "multi-rank ghost fill: exchange this component range first (pa_exchange_pack -> transport -> pa_exchange_mark_received)");
         recv = h->recv_slab.p;
     }
-    if (linked_too && f->peers_missing > 0)
+    // with peer links the coarse cells of coarse-fine faces owned by other ranks are read in place, as linked faces are
+    if ((linked_too || (H.peer_links && H.nranks > 1 && H.nlev > 1)) && f->peers_missing > 0)
         return fail(PA_ERR_STATE, "peer links: map every rank's slab of this field first (pa_field_map_peer)");
     GridArgs ga;
     CHK(grid_args_inplace(f, comp, ga));

@@ -154,6 +154,7 @@ const Layout& Hier::layout(int l, int ng) {
         all[gb] = e;
     }
     for (int gb : V.ext) Y.lay.push_back(all[gb]);
+    Y.all = all;
     Y.comp_stride = Y.rank_comp_stride[rank];
     return layouts_.emplace(key, std::move(Y)).first->second;
 }
@@ -364,7 +365,9 @@ void Hier::build_exchange() {
                     crse_needs(*this, l, gb, face, cn);
                     for (auto& n : cn) {
                         int sowner = C.owner[n.cbox];
-                        if (sowner == downer) continue;
+                        // with peer links the coarse cells of another rank are read in place through the peer mapping
+                        // (coarse gather index entries <= -3), like linked neighbour faces: nothing to exchange
+                        if (sowner == downer || peer_links) continue;
                         long long c = n.reg.npts();
                         if (downer == rank) recv_lvl[l][sowner] += c;
                         if (sowner == rank) {
@@ -461,7 +464,7 @@ void Hier::build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remo
                 for (int face = 0; face < 6; ++face) {
                     if (face_is_physical(*this, l, gb, face) || !face_has_uncovered(*this, l, gb, face)) continue;
                     cn.clear(); crse_needs(*this, l, gb, face, cn);
-                    for (auto& n : cn) if (lev[l - 1].owner[n.cbox] != rank) rcur[lev[l - 1].owner[n.cbox]] += n.reg.npts();
+                    for (auto& n : cn) if (!peer_links && lev[l - 1].owner[n.cbox] != rank) rcur[lev[l - 1].owner[n.cbox]] += n.reg.npts();
                 }
             // linked faces: materialised only on request, straight from the neighbour (local or peer-mapped)
             hn.clear();
@@ -621,8 +624,9 @@ std::string Hier::build_faces() {
                     for (auto& n : cn) {
                         const Box& cb = C.boxes[n.cbox];
                         bool local = (C.owner[n.cbox] == rank);
+                        const bool in_place = !local && peer_links;     // a peer's coarse box, read through the peer mapping
                         long long rbase = 0;
-                        if (!local) { rbase = rcur[C.owner[n.cbox]]; rcur[C.owner[n.cbox]] += n.reg.npts(); }
+                        if (!local && !in_place) { rbase = rcur[C.owner[n.cbox]]; rcur[C.owner[n.cbox]] += n.reg.npts(); }
                         long long q = 0;
                         for (int k = n.reg.lo[2]; k <= n.reg.hi[2]; ++k)
                             for (int j = n.reg.lo[1]; j <= n.reg.hi[1]; ++j)
@@ -630,8 +634,8 @@ std::string Hier::build_faces() {
                                     int c[3] = {i, j, k};
                                     size_t e = (size_t)R.cidx + (size_t)(c[t2] - R.rlo2) * R.rn1 + (size_t)(c[t1] - R.rlo1);
                                     PaCrseIdx& X = faces.cidx[e];
-                                    if (local) {
-                                        X.box = C.g2l[n.cbox];
+                                    if (local || in_place) {
+                                        X.box = local ? C.g2l[n.cbox] : -3 - n.cbox;        // <= -3: GLOBAL id of a peer-owned box
                                         X.rel = (unsigned)(i + n.shift[0] - cb.lo[0]) | ((unsigned)(j + n.shift[1] - cb.lo[1]) << 10) |
                                                 ((unsigned)(k + n.shift[2] - cb.lo[2]) << 20);
                                     } else {
@@ -676,8 +680,15 @@ std::vector<long long> Hier::crse_offsets(int ng) {
                 out[(size_t)e] = y.off + (long long)(k + y.ng) * y.PS + (long long)(j + y.ng) * y.P + (i + y.ng + y.xoff);
             } else if (X.box == -1) {
                 out[(size_t)e] = -1;
-            } else {
+            } else if (X.box == -2) {
                 out[(size_t)e] = -2 - (long long)X.rel;
+            } else {
+                // peer-owned coarse box: (owner rank, element offset inside that rank's slab), PA_CRSE_PEER_* in pa_types.h
+                const int gid = -3 - X.box;
+                const PaLayDev& y = Y.all[(size_t)gid];
+                const int i = (int)(X.rel & 1023u), j = (int)((X.rel >> 10) & 1023u), k = (int)(X.rel >> 20);
+                const long long off = y.off + (long long)(k + y.ng) * y.PS + (long long)(j + y.ng) * y.P + (i + y.ng + y.xoff);
+                out[(size_t)e] = -(PA_CRSE_PEER_BASE + ((long long)lev[faces.rec_level[r] - 1].owner[gid] << PA_CRSE_PEER_SHIFT) + off);
             }
         }
     }

@@ -92,6 +92,7 @@ struct Level {
 struct Layout {
     int ng = 0;
     std::vector<PaLayDev> lay;        // per box of the extended index (peer boxes: offsets inside THEIR rank's slab)
+    std::vector<PaLayDev> all;        // per GLOBAL box id: the box's place inside its owner's slab
     long long comp_stride = 0;        // elements per component of this rank's level slab (multiple of 16)
     std::vector<long long> rank_comp_stride;   // the same for every rank
 };

@@ -165,12 +165,18 @@ cudaError_t launch_exchange_pack(const PaPackTag* tags, long long tag0, long lon
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double xform(const GhostXform& xf, double v) { return xf.on ? (v - xf.pmin) * xf.inv : v; }
 
+// value of a coarse register cell (pa_types.h: coarse gather offset table); `peers` / `pcomp` = the coarse level's peer slabs
+// and the component's index inside the field (peer slabs are addressed from component 0)
 __device__ __forceinline__ double crse_val(const long long* __restrict__ coff, long long e, const double* __restrict__ cbase,
-                                           const double* __restrict__ recv, int ncomp, int comp, const GhostXform& xf) {
+                                           const double* __restrict__ recv, int ncomp, int comp, const GhostXform& xf,
+                                           const PaPeerSlab* __restrict__ peers, int pcomp) {
     const long long a = coff[e];
     if (a >= 0) return xform(xf, cbase[a]);
     if (a == -1) return PA_NAN;
-    return xform(xf, recv[(-2 - a) * ncomp + comp]);
+    if (a > -PA_CRSE_PEER_BASE) return xform(xf, recv[(-2 - a) * ncomp + comp]);
+    const long long v = -a - PA_CRSE_PEER_BASE;
+    const PaPeerSlab ps = peers[v >> PA_CRSE_PEER_SHIFT];
+    return xform(xf, ps.base[(long long)pcomp * ps.cs + (v & ((1LL << PA_CRSE_PEER_SHIFT) - 1))]);
 }
 
 __global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill(const PaFaceRec* __restrict__ recs, const int* __restrict__ rec_level,
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill(const PaFaceRec* __res
             const int j = bx.lo[t1] + a1, k = bx.lo[t2] + a2;
             const int jc = fdiv_dev(j, r), kc = fdiv_dev(k, r);
             const long long e0 = R.cidx + (long long)(kc - R.rlo2) * R.rn1 + (jc - R.rlo1);
-#define CR(o1, o2) crse_val(coff, e0 + (long long)(o2) * R.rn1 + (o1), cbase, recv, ncomp, m, xf)
+#define CR(o1, o2) crse_val(coff, e0 + (long long)(o2) * R.rn1 + (o1), cbase, recv, ncomp, m, xf, LC.peers, LC.in_comp + m)
             const double c00 = CR(0, 0);
             int lo = PA_FLAG_NC(fl, 0) ? -1 : 0;
             int hi = PA_FLAG_NC(fl, 1) ? 1 : 0;
@@ -302,14 +308,14 @@ __global__ void __launch_bounds__(PA_FACE_CHUNK) k_bcfill_v2(const PaFaceRec* __
                 const int jj = jc0 + i % W, kk = kc0 + i / W;
                 double v = PA_NAN;                                 // outside the register plane: never read (the flags forbid it)
                 if (jj >= R.rlo1 && jj < R.rlo1 + R.rn1 && kk >= R.rlo2 && kk < R.rlo2 + R.rn2)
-                    v = crse_val(coff, R.cidx + (long long)(kk - R.rlo2) * R.rn1 + (jj - R.rlo1), cbase, recv, ncomp, m, xf);
+                    v = crse_val(coff, R.cidx + (long long)(kk - R.rlo2) * R.rn1 + (jj - R.rlo1), cbase, recv, ncomp, m, xf, LC.peers, LC.in_comp + m);
                 cs[i] = v;
             }
             __syncthreads();
         }
         if (!active) continue;
         double* p = L.out + ga_ + m * L.cs_in;
-#define CR(o1, o2) (staged ? cs[sc0 + (o2) * W + (o1)] : crse_val(coff, e0 + (long long)(o2) * R.rn1 + (o1), cbase, recv, ncomp, m, xf))
+#define CR(o1, o2) (staged ? cs[sc0 + (o2) * W + (o1)] : crse_val(coff, e0 + (long long)(o2) * R.rn1 + (o1), cbase, recv, ncomp, m, xf, LC.peers, LC.in_comp + m))
         const double c00 = CR(0, 0);
         int lo = PA_FLAG_NC(fl, 0) ? -1 : 0;
         int hi = PA_FLAG_NC(fl, 1) ? 1 : 0;
@@ -583,7 +589,7 @@ cudaError_t launch_field_hash(const PaBoxDev* boxes, const PaLayDev* lay, const 
                               int comp0, int ncomp, int lev, unsigned long long* out, cudaStream_t st) {
     for (int b0 = 0; b0 < nboxes; b0 += 65535) {
         const int n = nboxes - b0 < 65535 ? nboxes - b0 : 65535;
-        PA_LAUNCH(dim3(16, n), 256, 0, st, k_field_hash)(boxes + b0, lay + b0, gid + b0, base, cs, comp0, ncomp, lev, out);
+        PA_LAUNCH(dim3(96, n), 256, 0, st, k_field_hash)(boxes + b0, lay + b0, gid + b0, base, cs, comp0, ncomp, lev, out);
         ++g_launches;
     }
     return cudaGetLastError();

@@ -92,6 +92,15 @@ struct PaCrseIdx {
     unsigned rel;     // i | j<<10 | k<<20 relative to the coarse box's low corner (or remote slot offset)
 };
 
+// coarse gather OFFSET table (Hier::crse_offsets), one entry per register cell:
+//   >= 0                       element offset inside this rank's coarse slab (one component)
+//   -1                         nothing copied there (the reference leaves NaN)
+//   -2 - slot                  slot of the recv slab (coarse cell of another rank, moved by the slab exchange)
+//   -(PA_CRSE_PEER_BASE + (rank << PA_CRSE_PEER_SHIFT) + offset)   coarse cell of another rank, read in place through the
+//                              peer mapping of that rank's slab (PA_HIER_PEER_LINKS)
+#define PA_CRSE_PEER_BASE (1LL << 60)
+#define PA_CRSE_PEER_SHIFT 44
+
 // BC-fill work item: up to PA_FACE_CHUNK consecutive plane cells of one face record (one thread block each), so the
 // kernel never searches for "which record does this cell belong to"
 #define PA_FACE_CHUNK 128

@@ -110,11 +110,15 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
     }
     __syncthreads();
 
+    const bool hint_ld = (psleep & (1 << 30)) != 0, hint_st = (psleep & (1 << 29)) != 0;   // PA_TMA_L2HINT bits 0 / 1 (launch_mode)
+    psleep &= 0xffff;
+#define TMA_LOAD(d_, s_, n_, b_) do { if (hint_ld) tma_load_1d_hint(d_, s_, n_, b_, l2pol); else tma_load_1d(d_, s_, n_, b_); } while (0)
     if (warp == CONSUMER_WARPS) {
         // ===================================== producer warp =====================================
         // lane 0 drives the TMA ring; lanes 1 .. 2*ny each own one x-ghost cell (side, row) per plane of a linked x face;
         // lanes without such a cell just arrive, so the full barrier's arrival count is the same for every tile.
         if (lane > XG_LANES) return;
+        const uint64_t l2pol = hint_ld ? l2_policy_evict_last() : 0;
         int stage = 0;
         uint32_t ephase = 1;                            // parity that lets the first pass through the ring go without waiting
         for (;;) {
@@ -198,20 +202,20 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
                     for (int c = 0; c < NIN; ++c) {
                         double* dst = sm + (long long)stage * stage_stride + (long long)c * stage_doubles;
                         if (zs) {
-                            tma_load_1d(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
+                            TMA_LOAD(dst, zs + (long long)c * zcs + (long long)z * li.PS + (long long)(t.y0 - 1) * li.P, plane_bytes, &full_bar[stage]);
                             continue;
                         }
                         int r0 = t.y0 - 1, r1 = t.y0 + t.ny;             // first / last staged row (box-relative)
                         if (r0 < 0 && s_ylo) {
-                            tma_load_1d(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[stage]);
+                            TMA_LOAD(dst, s_ylo + (long long)c * cs_ylo + (long long)z * li.PS - li.P, row_bytes, &full_bar[stage]);
                             r0 = 0;
                         }
                         if (r1 >= nyb && s_yhi) {
-                            tma_load_1d(dst + (long long)(rows - 1) * li.P, s_yhi + (long long)c * cs_yhi + (long long)z * li.PS + (long long)nyb * li.P,
+                            TMA_LOAD(dst + (long long)(rows - 1) * li.P, s_yhi + (long long)c * cs_yhi + (long long)z * li.PS + (long long)nyb * li.P,
                                         row_bytes, &full_bar[stage]);
                             r1 = nyb - 1;
                         }
-                        tma_load_1d(dst + (long long)(r0 - (t.y0 - 1)) * li.P, own + (long long)c * L.cs_in + (long long)z * li.PS + (long long)r0 * li.P,
+                        TMA_LOAD(dst + (long long)(r0 - (t.y0 - 1)) * li.P, own + (long long)c * L.cs_in + (long long)z * li.PS + (long long)r0 * li.P,
                                     (uint32_t)(r1 - r0 + 1) * row_bytes, &full_bar[stage]);
                     }
                 } else {
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
                     if (act) {
                         if (XS) {                                            // Progress of plane p-1 (curvature.cpp:310-321)
                             double* pc = cout_base + o;
-                            if (two) stg2(pc, c.x, c.y); else pc[0] = c.x;
+                            if (two) { if (hint_st) stg2_cs(pc, c.x, c.y); else stg2(pc, c.x, c.y); } else pc[0] = c.x;
                         }
                         if ((MODE == MODE_NORMAL || MODE == MODE_NORMAL_S) && aux_base) {
                             double* g = aux_base + o;
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, Shape<CW, MODE == MODE_NORMAL |
                         double* po = out0 + o;
 #pragma unroll
                         for (int m = 0; m < NOUT; ++m) {
-                            if (two) stg2(po, r0[m], r1[m]); else po[0] = r0[m];
+                            if (two) { if (hint_st) stg2_cs(po, r0[m], r1[m]); else stg2(po, r0[m], r1[m]); } else po[0] = r0[m];
                             po += cs_out;
                         }
                     }
@@ -480,7 +484,13 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
         if (e != cudaSuccess) return e;
     }
     const char* eps = getenv("PA_TMA_PSLEEP");
-    const int psleep = eps ? std::max(0, atoi(eps)) : 0;
+    // L2 eviction hints (bit 0: evict_last on the staged loads, bit 1: streaming stores).  Measured on a B200
+    // (profiles/r02_ab_l2_hints.txt): the bandwidth-bound gradient modes gain 2.5 % with both (config 2: 92.4 -> 95.0 % of the
+    // roofline, DRAM reads 7.04 -> 6.48 GB for 5.6 GB of input: fewer halo rows shared by neighbouring tiles are fetched twice); the FP64-bound
+    // flame-normal pass and the divergence do not (curvature 6.58 -> 6.65 ms), so they keep the default policy.
+    const char* eh = getenv("PA_TMA_L2HINT");
+    const int hints = eh ? atoi(eh) : ((MODE == MODE_GRAD || MODE == MODE_GRAD3) ? 3 : 0);
+    const int psleep = (eps ? std::min(std::max(0, atoi(eps)), 0xffff) : 0) | ((hints & 1) << 30) | (((hints >> 1) & 1) << 29);
     PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base, psleep);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
     return cudaGetLastError();

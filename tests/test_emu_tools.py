@@ -22,13 +22,17 @@ def emu_exes():
     out = os.path.dirname(lib)
     host = os.path.join(ROOT, "peleanalysis_b200", "host")
     exes = []
-    for name, main in (("grad3d.emu.ex", "grad_main.cpp"), ("curvature3d.emu.ex", "curvature_main.cpp")):
-        exe = os.path.join(out, name)
-        srcs = [os.path.join(host, main), os.path.join(host, "plotfile.cpp")]
-        deps = srcs + [lib] + [os.path.join(host, f) for f in ("plotfile.hpp", "tool_common.hpp", "parmparse.hpp", "multi_gpu.hpp")]
-        if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-            subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", *srcs, "-o", exe, "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
-        exes.append(exe)
+    import fcntl
+    with open(os.path.join(out, ".exe_build.lock"), "w") as lk:      # one build at a time (pytest-xdist workers share the directory)
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        for name, main in (("grad3d.emu.ex", "grad_main.cpp"), ("curvature3d.emu.ex", "curvature_main.cpp")):
+            exe = os.path.join(out, name)
+            srcs = [os.path.join(host, main), os.path.join(host, "plotfile.cpp")]
+            deps = srcs + [lib] + [os.path.join(host, f) for f in ("plotfile.hpp", "tool_common.hpp", "parmparse.hpp", "multi_gpu.hpp")]
+            if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+                subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", *srcs, "-o", exe + ".tmp", "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
+                os.replace(exe + ".tmp", exe)
+            exes.append(exe)
     old = os.environ.get("PA_NORMAL_MATH")
     os.environ["PA_NORMAL_MATH"] = "fast"        # the emulator has no MUFU; see tests/test_emu_parity.py
     yield tuple(exes)
@@ -143,12 +147,16 @@ def emu_amrex_exes(emu_exes):
     glue = os.path.join(ROOT, "peleanalysis_b200", "host", "amrex_glue")
     flags = build_ref.cxx_flags(inc) + ["-O1", "-I" + glue, "-I" + os.path.join(ROOT, "include")]
     exes = []
-    for src, name in zip(srcs, ("grad3d.emuamrex.ex", "curvature3d.emuamrex.ex")):
-        exe = os.path.join(out, name)
-        deps = [src, lib_a, os.path.join(out, "libpelestencil_emu.so")] + [os.path.join(glue, f) for f in os.listdir(glue)]
-        if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-            subprocess.check_call(["g++", *flags, src, "-o", exe, lib_a, "-lgomp", "-lpthread", "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
-        exes.append(exe)
+    import fcntl
+    with open(os.path.join(out, ".exe_build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        for src, name in zip(srcs, ("grad3d.emuamrex.ex", "curvature3d.emuamrex.ex")):
+            exe = os.path.join(out, name)
+            deps = [src, lib_a, os.path.join(out, "libpelestencil_emu.so")] + [os.path.join(glue, f) for f in os.listdir(glue)]
+            if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+                subprocess.check_call(["g++", *flags, src, "-o", exe + ".tmp", lib_a, "-lgomp", "-lpthread", "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
+                os.replace(exe + ".tmp", exe)
+            exes.append(exe)
     return tuple(exes)
 
 

@@ -98,8 +98,12 @@ def test_other_on_disk_formats(tmp_path, dtype, grow):
     host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "peleanalysis_b200", "host")
     exe = os.path.join(out, "grad3d.fmt.ex")
     srcs = [os.path.join(host, "grad_main.cpp"), os.path.join(host, "plotfile.cpp")]
-    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs + [lib]):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", *srcs, "-o", exe, "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
+    import fcntl
+    with open(os.path.join(out, ".exe_build.lock"), "w") as lk:      # one build at a time (pytest-xdist workers share the directory)
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs + [lib]):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", *srcs, "-o", exe + ".tmp", "-L", out, "-lpelestencil_emu", "-Wl,-rpath," + out])
+            os.replace(exe + ".tmp", exe)
     env = dict(os.environ, PA_NORMAL_MATH="fast", CUEMU_SEED="0")
     p = subprocess.run([exe, "infile=" + d, "gradVar=temp", "outfile=" + str(tmp_path / "g")], capture_output=True, text=True, env=env, cwd=str(tmp_path))
     assert p.returncode == 0, p.stdout + p.stderr
