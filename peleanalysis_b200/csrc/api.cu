@@ -90,6 +90,9 @@ struct pa_hier {
     std::map<int, std::unique_ptr<DevBuf<long long>>> face_coff;   // coarse gather offsets per ghost width
     DevBuf<PaPackTag> pack_tags;
     TileTable tiles_simple, tiles_tma;
+    // the same boxes cut into shallower work items (half / a quarter of the planes per item): picked at launch when the deepest
+    // table would leave the persistent grid with only a handful of items per CTA (strong scaling: few boxes per rank)
+    TileTable tiles_tma_fine[2];
     // fused curvature (curv_fused.cu): K-block work items of every level (class 0 only) and the (level, box) list of the
     // shell pass; curv_ok = every local box is eligible (>= 3 cells in every direction, <= 128 wide, plane fits)
     TileTable tiles_curv;
@@ -137,7 +140,7 @@ const PaLayDev* dev_layout(pa_hier* h, int l, int ng, int* err) {
     return p;
 }
 
-void build_tiles(pa_hier* h, TileTable& T, bool tma) {
+void build_tiles(pa_hier* h, TileTable& T, bool tma, int zdiv = 1) {
     Hier& H = h->H;
     T.h.clear();
     T.max_plane_doubles = 0;
@@ -148,7 +151,7 @@ void build_tiles(pa_hier* h, TileTable& T, bool tma) {
     const char* ety = getenv("PA_TMA_TY");
     const char* ezc = getenv("PA_TMA_ZC");
     const int TY0 = ety ? std::min(std::max(1, atoi(ety)), stencil_tma_max_tile_rows()) : stencil_tma_tile_rows();
-    const int ZC0 = ezc ? std::max(1, atoi(ezc)) : 32;
+    const int ZC0 = std::max(4, (ezc ? std::max(1, atoi(ezc)) : 32) / zdiv);
     for (int c = 0; c < (tma ? N_TILE_CLASSES : 1); ++c)
         for (int l = 0; l < H.nlev; ++l) {
             T.begin[c][l] = (long long)T.h.size();
@@ -279,6 +282,10 @@ int ensure_device(pa_hier* h) {
     build_tiles(h, h->tiles_tma, true);
     CU(h->tiles_simple.d.upload(h->tiles_simple.h, t_stream));
     CU(h->tiles_tma.d.upload(h->tiles_tma.h, t_stream));
+    for (int k = 0; k < 2; ++k) {
+        build_tiles(h, h->tiles_tma_fine[k], true, 2 << k);
+        CU(h->tiles_tma_fine[k].d.upload(h->tiles_tma_fine[k].h, t_stream));
+    }
     {
         std::vector<int> sl, sb;
         build_curv_tiles(h, sl, sb);
@@ -366,7 +373,23 @@ int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex
                                   "(pa_field_ipc_handle -> exchange -> pa_field_map_peer)");
     // the TMA tile table is sized for the nghost == 1 layout (row pitch nx+4)
     if (in_ng == 1 && use_tma(h, nin)) {
-        TileTable& T = h->tiles_tma;
+        // Work items per launch: (tiles of the level range) x variables, drawn dynamically by 148 x 2 (or so) persistent CTAs.
+        // With fewer than ~8 items per CTA the last round of items leaves most SMs idle (strong scaling at 8 ranks: 5 items
+        // per CTA, 13 % tail): take the table with half / a quarter of the planes per item then.  PA_TMA_ZDIV=0|1|2 forces one.
+        TileTable* Tp = &h->tiles_tma;
+        {
+            cudaError_t esm = cudaSuccess;
+            const long long slots = 2LL * std::max(1, stencil_num_sms(&esm));
+            const char* ez = getenv("PA_TMA_ZDIV");
+            int pick = 0;
+            if (ez) pick = std::min(2, std::max(0, atoi(ez)));
+            else {
+                auto items = [&](const TileTable& X) { long long n = 0; for (int c = 0; c < N_TILE_CLASSES; ++c) n += X.begin[c][l1 + 1] - X.begin[c][l0]; return n * nvar; };
+                while (pick < 2 && items(pick == 0 ? h->tiles_tma : h->tiles_tma_fine[pick - 1]) < 8 * slots) ++pick;
+            }
+            if (pick > 0 && h->tiles_tma_fine[pick - 1].ok) Tp = &h->tiles_tma_fine[pick - 1];
+        }
+        TileTable& T = *Tp;
         for (int c = 0; c < N_TILE_CLASSES; ++c) {
             const long long a = T.begin[c][l0], b = T.begin[c][l1 + 1];
             if (b <= a) continue;
