@@ -22,6 +22,9 @@ Products (oracle/_ref/):
                                          curvature.cpp:283-791, FillVar excluded); the patched
                                          temporaries live only in oracle/_ref/src/
   fcompare.ref.ex                        AMReX's plotfile differ (Tools/Plotfile/fcompare.cpp)
+  filterPlt3d.ref.ex, filterPlt3d.timed.ex  the neighbouring stencil tool (Src/filterPlt.cpp) with PelePhysics' Filter and
+                                         PltFileManager and AMReX's FillPatchUtil; the timed variant probes
+                                         filterPlt.cpp:166-221 (ghost-cell fill + filter, no plotfile I/O)
 """
 import argparse
 import concurrent.futures as cf
@@ -227,14 +230,37 @@ def main():
         tools.append((os.path.join(AMREX, "Tools/Plotfile/fcompare.cpp"), "fcompare.ref.ex"))
     tools += shells
 
+    # filterPlt: three more objects (AMReX's FillPatchUtil is excluded from the library above because neither grad nor
+    # curvature references it; Filter and PltFileManager live in PelePhysics)
+    pp = os.path.join(REF, "Submodules/PelePhysics/Source/Utility")
+    filt_flags = ["-I" + os.path.join(pp, "Filter"), "-I" + os.path.join(pp, "PltFileManager")]
+    filt_objs = []
+    filt_jobs = [(os.path.join(AMREX, "Src/AmrCore/AMReX_FillPatchUtil.cpp"), os.path.join(objdir, "AMReX_FillPatchUtil.o"), flags),
+                 (os.path.join(pp, "Filter/Filter.cpp"), os.path.join(objdir, "PP_Filter.o"), flags + filt_flags),
+                 (os.path.join(pp, "PltFileManager/PltFileManager.cpp"), os.path.join(objdir, "PP_PltFileManager.o"), flags + filt_flags)]
+    if all(os.path.exists(j[0]) for j in filt_jobs):
+        with cf.ThreadPoolExecutor(a.j) as ex:
+            for src, rc, err in ex.map(compile_one, filt_jobs):
+                if rc != 0:
+                    print(f"[build_ref] FAILED {src}\n{err}", file=sys.stderr)
+        filt_objs = [j[1] for j in filt_jobs if os.path.exists(j[1])]
+    filt_tools = []
+    if len(filt_objs) == len(filt_jobs):
+        patch_timed(os.path.join(REF, "Src/filterPlt.cpp"), os.path.join(srcdir, "filterPlt_timed.cpp"),
+                    r"fillPatchFromPlt doesn.t fill ghost cells", r"Saving filtered data", r"PA_NEVER_MATCHES", "[filterPlt]")
+        filt_tools = [(os.path.join(REF, "Src/filterPlt.cpp"), "filterPlt3d.ref.ex"),
+                      (os.path.join(srcdir, "filterPlt_timed.cpp"), "filterPlt3d.timed.ex")]
+        tools += filt_tools
+
     def link(t):
         src, exe = t
         exe = os.path.join(OUT, exe)
         if os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(lib)):
             return exe, 0, ""
-        extra_f = shell_flags if t in shells else []
+        extra_f = shell_flags if t in shells else (filt_flags if t in filt_tools else [])
         extra_l = shell_libs if t in shells else []
-        p = subprocess.run(["g++", *flags, *extra_f, src, "-o", exe, lib, "-lgomp", "-lpthread", *extra_l],
+        extra_o = filt_objs if t in filt_tools else []
+        p = subprocess.run(["g++", *flags, *extra_f, src, *extra_o, "-o", exe, lib, "-lgomp", "-lpthread", *extra_l],
                            capture_output=True, text=True)
         return exe, p.returncode, p.stderr[-3000:]
     rc_all = 0

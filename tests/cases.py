@@ -31,3 +31,18 @@ CASES = {
 
 GRAD_OUT = ["gx", "gy", "gz", "mag"]
 CURV_OUT = ["Progress", "MeanCurvature", "FlameNormalX", "FlameNormalY", "FlameNormalZ"]
+
+# filterPlt cases: (builder, tool options).  The tool's geometry is always non-periodic; ghost widths follow from
+# base_fgr x refinement ratios (1, 2, 4 cells on three ratio-2 levels with the default base_fgr = 2).
+FILTER_CASES = {
+    "filter_c1": (lambda: synth.config1(16, 8), {}),
+    "filter_c1_corner_gauss": (lambda: synth.config1(16, 8, corner=True), dict(filter_type=2, base_fgr=4, max_grid_size=8)),
+    "filter_c3": (lambda: synth.config3(16, 8, names=("temp", "x_velocity")), dict(max_grid_size=8)),
+    "filter_c3_pc_samefgr": (lambda: synth.config3(16, 8), dict(interp_type=0, same_fgr_all_levels=1, base_fgr=4, filter_type=2)),
+    "filter_c3_subset": (lambda: synth.config3(16, 8, names=("temp", "x_velocity", "Y_CH4")), dict(variables="Y_CH4 temp", max_filter_level=1, max_grid_size=12)),
+    "filter_lshape": (lambda: synth.case_lshape(16, 8), dict(max_grid_size=8)),
+    "filter_ratio4": (lambda: synth.case_ratio4(8, 16), {}),
+    "filter_np2": (_np2_small, dict(filter_type=4, base_fgr=3)),
+}
+# every filter type at an even and an odd filter-to-grid ratio on one small file (level 0 and 1, same ratio on both)
+FILTER_TYPE_SWEEP = ("filter_types", lambda: synth.config1(16, 8), [(t, f) for t in range(0, 11) for f in (3, 4) if not (t in (1, 2) and f % 2)] + [(6, 12), (9, 11)])
