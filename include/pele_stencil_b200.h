@@ -195,6 +195,30 @@ int pa_curvature_steps(pa_field *state, int comp_S, int comp_vel, const pa_curv_
  * variable (3 components, nghost 1).  Owned by the hierarchy; do not free. */
 int pa_curvature_scratch(pa_hier *h, int which, pa_field **f);
 
+/* ---- filterPlt: the neighbouring stencil tool (Src/filterPlt.cpp:100-222) -------------------------
+ * PP/ = Submodules/PelePhysics/Source.  The tool re-chops the plotfile's grids to max_grid_size, fills nGrow = fgr/2 ghost
+ * layers of every level by FillPatch rules on a NON-periodic geometry (PP/Utility/PltFileManager/PltFileManager.cpp:118-120)
+ * and applies PelePhysics' Filter box by box.  Create the hierarchy with is_per = {0,0,0} on the re-chopped grids, allocate the
+ * input field with nghost >= the widest level's nGrow and upload the plotfile's valid data; then per level
+ * pa_fill_patch + pa_filter.  Results are bit-identical to the reference tool's.  Single-rank. */
+/* Filter::Filter(type, fgr) (PP/Utility/Filter/Filter.H:56-111 + Filter.cpp:3-404): ghost width and the 2*ngrow+1 weights of
+ * filter_types 0..10 (1 box, 2 Gaussian, 3-10 the Sagaut & Grohens approximations).  Returns the number of weights
+ * (weights may be NULL to query) or a negative pa_status. */
+int pa_filter_weights(int filter_type, int fgr, int *ngrow, double *weights, int cap);
+/* BoxArray::maxSize(max_grid_size) (AX/Base/AMReX_BoxArray.cpp:549-564 -> AMReX_BoxList.cpp:765-815) on nboxes x 6 ints:
+ * every box replaced, in place, by its chunks.  Returns the new box count (out_boxes may be NULL to query). */
+int pa_boxes_max_size(int nboxes, const int *boxes, int max_grid_size, int *out_boxes, int cap);
+/* Ghost cells of level `lev`, `nghost` layers, as Src/filterPlt.cpp:170-203 fills them: FillPatchSingleLevel on level 0,
+ * FillPatchTwoLevels above (AX/AmrCore/AMReX_FillPatchUtil_I.H) -- same-level valid data where a box of the level covers the
+ * cell; else interpolation from the VALID cells of level lev-1 (interp_type 1: MFCellConsLinInterp with the monotonised-central
+ * slope, AX/AmrCore/AMReX_MFInterp_3D_C.H:178-260; 0: MFPCInterp); first-order extrapolation outside the domain
+ * (AX/Base/AMReX_PhysBCFunct.H:406-640, AMReX_FilCC_3D_C.H), on the coarse patch as well.  Levels are independent of each
+ * other (only valid coarse data is read).  PA_ERR_ARG if the coarse level does not cover a needed coarse patch. */
+int pa_fill_patch(pa_field *f, int comp, int ncomp, int lev, int nghost, int interp_type);
+/* Filter::apply_filter on every box of level `lev` (PP/Utility/Filter/Filter.H:28-50, Filter.cpp:462-491):
+ * out = sum over (n, m, l) of w[l]*w[m]*w[n] * in(i+l, j+m, k+n), the reference's summation order.  `in` must hold ngrow
+ * filled ghost layers (pa_fill_patch); out's ghost cells are not written. */
+int pa_filter(pa_field *in, int comp_in, pa_field *out, int comp_out, int ncomp, int lev, int filter_type, int fgr);
 /* ---- ranks that share ONE process (one host thread per GPU, e.g. an OpenMP-style host without MPI) -------------------
  * The calling thread's GPU is the one its pa_init named.  pa_enable_peer_access lets that GPU address a peer GPU's memory
  * (cudaDeviceEnablePeerAccess); pa_field_slab gives the level slab a peer thread passes to pa_field_map_peer_ptr -- the

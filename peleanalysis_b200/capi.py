@@ -76,6 +76,10 @@ SYMBOLS = {
     "pa_debug_exchange_ids": (_i64, [_vp, _i, _vp, _i64]),
     "pa_debug_links": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "pa_debug_face_coef": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d)]),
+    "pa_filter_weights": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_d), _i]),
+    "pa_boxes_max_size": (_i, [_i, C.POINTER(_i), _i, C.POINTER(_i), _i]),
+    "pa_fill_patch": (_i, [_vp, _i, _i, _i, _i, _i]),
+    "pa_filter": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i]),
 }
 
 _lib = None
@@ -411,6 +415,42 @@ class ScratchField(Field):
 
     def free(self):
         self.f = None
+
+
+# ---- filterPlt path (Src/filterPlt.cpp): one Python call per C entry point
+def filter_weights(filter_type: int, fgr: int):
+    """(ngrow, weights) of Filter(filter_type, fgr)."""
+    n = lib().pa_filter_weights(filter_type, fgr, None, None, 0)
+    if n < 0:
+        check(n)
+    w = np.zeros(n)
+    ng = C.c_int(0)
+    n2 = lib().pa_filter_weights(filter_type, fgr, C.byref(ng), w.ctypes.data_as(C.POINTER(C.c_double)), n)
+    if n2 < 0:
+        check(n2)
+    return int(ng.value), w
+
+
+def boxes_max_size(boxes: Sequence[tuple], max_grid_size: int) -> List[tuple]:
+    """BoxArray::maxSize on [(lo, hi), ...]."""
+    bx = np.array([list(lo) + list(hi) for lo, hi in boxes], dtype=np.int32).reshape(-1, 6)
+    p = bx.ctypes.data_as(C.POINTER(C.c_int))
+    n = lib().pa_boxes_max_size(len(boxes), p, max_grid_size, None, 0)
+    if n < 0:
+        check(n)
+    out = np.zeros((n, 6), dtype=np.int32)
+    n2 = lib().pa_boxes_max_size(len(boxes), p, max_grid_size, out.ctypes.data_as(C.POINTER(C.c_int)), n)
+    if n2 < 0:
+        check(n2)
+    return [(tuple(int(v) for v in b[:3]), tuple(int(v) for v in b[3:])) for b in out]
+
+
+def fill_patch(f: Field, comp: int, ncomp: int, lev: int, nghost: int, interp_type: int = 1) -> None:
+    check(lib().pa_fill_patch(f.f, comp, ncomp, lev, nghost, interp_type))
+
+
+def filter_level(inp: Field, comp_in: int, out: Field, comp_out: int, ncomp: int, lev: int, filter_type: int, fgr: int) -> None:
+    check(lib().pa_filter(inp.f, comp_in, out.f, comp_out, ncomp, lev, filter_type, fgr))
 
 
 def curvature_num_outputs(opts: CurvOpts) -> int:

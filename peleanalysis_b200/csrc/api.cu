@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -105,6 +107,13 @@ struct pa_hier {
     // side stream on which the ghost fill of the refined levels overlaps the stencil of level 0 (created on demand)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // filterPlt path: FillPatch tables per (level, ghost width, interpolater stencil), coarse-patch scratch, filter work prefix
+    struct FpDev { DevBuf<PaFpPiece> pieces; DevBuf<PaFpCopy> copies; DevBuf<PaFpClamp> clamps; };
+    std::map<std::array<int, 3>, std::unique_ptr<FpDev>> fp;
+    DevBuf<double> fp_scratch;
+    std::map<int, std::unique_ptr<DevBuf<long long>>> filter_prefix;   // per level
+    std::map<int, long long> filter_nwork;
+    DevBuf<double> filter_w3;
     // curvature temporaries (allocated on demand)
     pa_field* tmpG = nullptr;
     pa_field* tmpH = nullptr;
@@ -603,7 +612,7 @@ int64_t pa_algorithmic_bytes(const pa_hier* h, int nout) {
 
 // ---------------------------------------------------------------------------------------------- fields
 int pa_field_alloc(pa_hier* h, int ncomp, int nghost, pa_field** out) {
-    if (!h || !out || ncomp < 1 || nghost < 0 || nghost > 4) return fail(PA_ERR_ARG, "pa_field_alloc: bad argument");
+    if (!h || !out || ncomp < 1 || nghost < 0 || nghost > 32) return fail(PA_ERR_ARG, "pa_field_alloc: bad argument (ncomp >= 1, 0 <= nghost <= 32)");
     CHK(ensure_device(h));
     auto f = std::make_unique<pa_field>();
     f->h = h; f->ncomp = ncomp; f->ng = nghost;
@@ -1406,6 +1415,199 @@ int64_t pa_debug_exchange_ids(pa_hier* h, int which, int64_t* out, int64_t out_l
     const std::vector<long long>& v = which ? h->H.xplan.recv_ids : h->H.xplan.send_ids;
     if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < out_len; ++i) out[i] = v[i];
     return (int64_t)v.size();
+}
+
+// ------------------------------------------------------------------------------------------------ filterPlt path
+// Filter::Filter(type, fgr) + set_*_weights (PelePhysics Source/Utility/Filter/Filter.H:56-111, Filter.cpp:3-404): ghost width
+// and the 1-D weights.  The formulas and the Sagaut & Grohens (1999) ratio tables are data of the method; the arithmetic
+// follows the reference expression by expression so that the weights agree to the last bit (same libm).
+static int filter_weights_host(int type, int fgr, std::vector<double>& w) {
+    auto box = [&](void) { const int ng = fgr / 2, n = 2 * ng + 1; w.assign(n, 1.0 / fgr); if (fgr > 1) { w[0] = 0.5 * w[0]; w[n - 1] = w[0]; } return ng; };
+    auto box3 = [&](void) { w.assign(3, 0.0); w[0] = fgr * fgr / 24.0; w[1] = (12.0 - fgr * fgr) / 12.0; w[2] = w[0]; return 1; };
+    auto gauss5 = [&](void) { const int f2 = fgr * fgr, f4 = f2 * f2; w.assign(5, 0.0); w[0] = (f4 - 4.0 * f2) / 1152.0; w[1] = (16.0 * f2 - f4) / 288.0;
+                              w[2] = (f4 - 20.0 * f2 + 192.0) / 192.0; w[3] = w[1]; w[4] = w[0]; return 2; };
+    static const double o3b[10] = {0.079, 0.274, 1.377, -2.375, -1.000, -0.779, -0.680, -0.627, -0.596, -0.575};
+    static const double o3g[10] = {0.0763, 0.2527, 1.1160, -3.144, -1.102, -0.809, -0.696, -0.638, -0.604, -0.581};
+    static const double o5b[10][2] = {{0.0886, -0.0169}, {0.3178, -0.0130}, {1.0237, 0.0368}, {2.4414, 0.5559}, {0.2949, 0.7096},
+                                      {-0.5276, 0.4437}, {-0.6708, 0.3302}, {-0.7003, 0.2767}, {-0.7077, 0.2532}, {-0.6996, 0.2222}};
+    static const double o5g[10][2] = {{0.0871, -0.0175}, {0.2596, -0.0021}, {0.4740, 0.0785}, {0.1036, 0.2611}, {-0.4252, 0.3007},
+                                      {-0.6134, 0.2696}, {-0.6679, 0.2419}, {-0.6836, 0.2231}, {-0.6873, 0.2103}, {-0.6870, 0.2014}};
+    switch (type) {
+    case 1: return box();
+    case 2: {
+        const int ng = fgr / 2, n = 2 * ng + 1;
+        w.assign(n, 0.0);
+        const double gamma = 6.0, sigma = std::sqrt(1.0 / (2.0 * gamma)) * fgr;
+        for (int i = 0; i < n; ++i) w[i] = 1.0 / (std::sqrt(2.0 * 3.1415926535897932384626433832795029) * sigma) * std::exp((-(i - ng) * (i - ng)) / (2 * sigma * sigma));
+        double sum = 0.0;
+        for (int i = 0; i < n; ++i) sum += w[i];
+        for (int i = 0; i < n; ++i) w[i] /= sum;
+        return ng;
+    }
+    case 3: case 7: return box3();
+    case 4: {
+        const int f2 = fgr * fgr, f4 = f2 * f2;
+        w.assign(5, 0.0);
+        w[0] = (3.0 * f4 - 20.0 * f2) / 5760.0; w[1] = (80.0 * f2 - 3.0 * f4) / 1440.0; w[2] = (3.0 * f4 - 100.0 * f2 + 960.0) / 960.0; w[3] = w[1]; w[4] = w[0];
+        return 2;
+    }
+    case 5: case 9: {
+        if (fgr < 1 || fgr > 10) return type == 5 ? box() : box3();
+        const double ratio = (type == 5 ? o3b : o3g)[fgr - 1];
+        w.assign(3, 0.0);
+        w[0] = ratio / (1 + 2.0 * ratio); w[1] = 1.0 - 2.0 * w[0]; w[2] = w[0];
+        return 1;
+    }
+    case 6: case 10: {
+        if (fgr < 1 || fgr > 10) return type == 6 ? box() : gauss5();
+        const double r1 = (type == 6 ? o5b : o5g)[fgr - 1][0], r2 = (type == 6 ? o5b : o5g)[fgr - 1][1];
+        w.assign(5, 0.0);
+        w[0] = r2 / (1 + 2.0 * r1 + 2.0 * r2); w[1] = r1 / r2 * w[0]; w[2] = 1.0 - 2.0 * w[0] - 2.0 * w[1]; w[3] = w[1]; w[4] = w[0];
+        return 2;
+    }
+    case 8: return gauss5();
+    default: w.assign(1, 1.0); return 0;
+    }
+}
+
+int pa_filter_weights(int filter_type, int fgr, int* ngrow, double* weights, int cap) {
+    if (fgr < 1) return fail(PA_ERR_ARG, "pa_filter_weights: filter-to-grid ratio must be >= 1");
+    if ((filter_type == 1 || filter_type == 2) && fgr != 1 && fgr % 2) return fail(PA_ERR_ARG, "pa_filter_weights: the box / Gaussian filters need an even filter-to-grid ratio");
+    std::vector<double> w;
+    const int ng = filter_weights_host(filter_type, fgr, w);
+    if (ngrow) *ngrow = ng;
+    if (weights) {
+        if ((int)w.size() > cap) return fail(PA_ERR_ARG, "pa_filter_weights: weight buffer too small");
+        for (size_t i = 0; i < w.size(); ++i) weights[i] = w[i];
+    }
+    return (int)w.size();
+}
+
+int pa_boxes_max_size(int nboxes, const int* boxes, int max_grid_size, int* out_boxes, int cap) {
+    if (nboxes < 0 || (nboxes && !boxes) || max_grid_size < 1) { fail(PA_ERR_ARG, "pa_boxes_max_size: bad arguments"); return PA_ERR_ARG; }
+    std::vector<Box> out;
+    box_max_size(nboxes, boxes, max_grid_size, out);
+    if (out_boxes) {
+        if ((int)out.size() > cap) { fail(PA_ERR_ARG, "pa_boxes_max_size: output buffer too small"); return PA_ERR_ARG; }
+        for (size_t b = 0; b < out.size(); ++b)
+            for (int d = 0; d < 3; ++d) { out_boxes[6 * b + d] = out[b].lo[d]; out_boxes[6 * b + 3 + d] = out[b].hi[d]; }
+    }
+    return (int)out.size();
+}
+
+int pa_fill_patch(pa_field* f, int comp, int ncomp, int lev, int nghost, int interp_type) {
+    CHK(check_field(f, comp, ncomp, "pa_fill_patch"));
+    pa_hier* h = f->h;
+    Hier& H = h->H;
+    if (lev < 0 || lev >= H.nlev) return fail(PA_ERR_ARG, "pa_fill_patch: level out of range");
+    if (nghost < 0 || nghost > f->ng) return fail(PA_ERR_ARG, "pa_fill_patch: the field has fewer ghost layers than asked for");
+    if (H.nranks > 1) return fail(PA_ERR_UNSUPPORTED, "pa_fill_patch is single-rank (shard whole plotfiles / variables over ranks instead)");
+    if (H.is_per[0] || H.is_per[1] || H.is_per[2])
+        return fail(PA_ERR_UNSUPPORTED, "pa_fill_patch: periodic directions are not served -- the reference tool's PltFileManager geometry is never periodic");
+    CHK(ensure_device(h));
+    if (nghost == 0) return PA_OK;
+    int err = PA_OK;
+    const PaLayDev* lay = dev_layout(h, lev, f->ng, &err);
+    if (!lay) return err;
+    double* base = f->slab[lev] + (long long)comp * f->cs[lev];
+    const Level& V = H.lev[lev];
+    // 1. same-level valid data into every ghost cell another box of the level covers (all layers, edges and corners)
+    {
+        auto key = std::make_pair(lev, f->ng);
+        const HaloTable& T = H.halo_full(lev, f->ng);
+        auto it = h->halo_full.find(key);
+        if (it == h->halo_full.end()) {
+            auto buf = std::make_unique<DevBuf<PaHaloTag>>();
+            CU(buf->upload(T.tags, t_stream));
+            it = h->halo_full.emplace(key, std::move(buf)).first;
+        }
+        CU(launch_halo(it->second->p, 0, (int)T.tags.size(), 0, T.ncells, h->lev[lev]->boxes.p, lay, base, f->cs[lev], ncomp, nullptr,
+                       nullptr, comp, H.rank, GhostXform{0, 0.0, 1.0}, t_stream));
+    }
+    // 2. the rest of the in-domain ghost cells from the next coarser level, 3. the out-of-domain ones by extrapolation
+    const int cgrow = interp_type == 1 ? 1 : 0;
+    const FillPatchTable& T = H.fill_patch(lev, nghost, cgrow);
+    if (!T.err.empty()) return fail(PA_ERR_ARG, "pa_fill_patch: " + T.err);
+    std::array<int, 3> key{lev, nghost, cgrow};
+    auto it = h->fp.find(key);
+    if (it == h->fp.end()) {
+        auto d = std::make_unique<pa_hier::FpDev>();
+        CU(d->pieces.upload(T.pieces, t_stream));
+        CU(d->copies.upload(T.copies, t_stream));
+        CU(d->clamps.upload(T.clamps, t_stream));
+        it = h->fp.emplace(key, std::move(d)).first;
+    }
+    if (T.nfine > 0) {
+        const Level& Cv = H.lev[lev - 1];
+        const PaLayDev* clay = dev_layout(h, lev - 1, f->ng, &err);
+        if (!clay) return err;
+        const size_t need = (size_t)T.ncrse * ncomp;
+        if (h->fp_scratch.n < need) {
+            CU(cudaStreamSynchronize(t_stream));          // an earlier fill may still read the buffer this replaces
+            CU(h->fp_scratch.reserve(need));
+        }
+        const double* cbase = f->slab[lev - 1] + (long long)comp * f->cs[lev - 1];
+        CU(launch_fp_gather(it->second->copies.p, (int)T.copies.size(), T.ncopy, it->second->pieces.p, h->lev[lev - 1]->boxes.p, clay, cbase,
+                            f->cs[lev - 1], ncomp, h->fp_scratch.p, T.ncrse, t_stream));
+        CU(launch_fp_interp(interp_type == 1, it->second->pieces.p, (int)T.pieces.size(), T.nfine, h->fp_scratch.p, T.ncrse, Cv.dom.lo, Cv.dom.hi,
+                            V.ratio, h->lev[lev]->boxes.p, lay, base, f->cs[lev], ncomp, t_stream));
+    }
+    CU(launch_fp_clamp(it->second->clamps.p, (int)T.clamps.size(), T.nclamp, V.dom.lo, V.dom.hi, nghost, h->lev[lev]->boxes.p, lay, base,
+                       f->cs[lev], ncomp, t_stream));
+    return PA_OK;
+}
+
+int pa_filter(pa_field* in, int comp_in, pa_field* out, int comp_out, int ncomp, int lev, int filter_type, int fgr) {
+    CHK(check_field(in, comp_in, ncomp, "pa_filter (in)"));
+    CHK(check_field(out, comp_out, ncomp, "pa_filter (out)"));
+    if (in->h != out->h) return fail(PA_ERR_ARG, "pa_filter: fields of different hierarchies");
+    if (in == out) return fail(PA_ERR_ARG, "pa_filter: in and out must be different fields");
+    pa_hier* h = in->h;
+    Hier& H = h->H;
+    if (lev < 0 || lev >= H.nlev) return fail(PA_ERR_ARG, "pa_filter: level out of range");
+    std::vector<double> w;
+    {
+        const int rc = pa_filter_weights(filter_type, fgr, nullptr, nullptr, 0);
+        if (rc < 0) return rc;
+    }
+    const int g = filter_weights_host(filter_type, fgr, w);
+    if (g > in->ng) return fail(PA_ERR_ARG, "pa_filter: the input field has fewer ghost layers than the filter needs");
+    CHK(ensure_device(h));
+    const Level& V = H.lev[lev];
+    const int nb = (int)V.local.size();
+    if (nb == 0) return PA_OK;
+    int err = PA_OK;
+    const PaLayDev* lin = dev_layout(h, lev, in->ng, &err);
+    if (!lin) return err;
+    const PaLayDev* lout = dev_layout(h, lev, out->ng, &err);
+    if (!lout) return err;
+    auto pit = h->filter_prefix.find(lev);
+    if (pit == h->filter_prefix.end()) {
+        std::vector<long long> pre(nb + 1, 0);
+        for (int b = 0; b < nb; ++b) {
+            const Box& B = V.boxes[V.local[b]];
+            pre[b + 1] = pre[b] + (long long)((B.len(0) + 3) / 4) * B.len(1) * B.len(2);
+        }
+        auto buf = std::make_unique<DevBuf<long long>>();
+        CU(buf->upload(pre, t_stream));
+        h->filter_nwork[lev] = pre[nb];
+        pit = h->filter_prefix.emplace(lev, std::move(buf)).first;
+    }
+    // weight products in the reference's order: ((w[l] * w[m]) * w[n]), n slowest
+    const int W = 2 * g + 1;
+    std::vector<double> w3((size_t)W * W * W);
+    for (int n = 0; n < W; ++n)
+        for (int m = 0; m < W; ++m)
+            for (int l = 0; l < W; ++l) w3[((size_t)n * W + m) * W + l] = (w[l] * w[m]) * w[n];
+    if (h->filter_w3.n < w3.size()) {
+        CU(cudaStreamSynchronize(t_stream));
+        CU(h->filter_w3.reserve(std::max<size_t>(w3.size(), 729)));
+    }
+    // pageable source: the runtime stages the bytes before returning, so w3 may go out of scope
+    CU(cudaMemcpyAsync(h->filter_w3.p, w3.data(), w3.size() * sizeof(double), cudaMemcpyHostToDevice, t_stream));
+    CU(launch_filter(g, h->lev[lev]->boxes.p, lin, lout, nb, pit->second->p, h->filter_nwork[lev], in->slab[lev] + (long long)comp_in * in->cs[lev],
+                     in->cs[lev], out->slab[lev] + (long long)comp_out * out->cs[lev], out->cs[lev], ncomp, h->filter_w3.p, t_stream));
+    return PA_OK;
 }
 
 }  // extern "C"

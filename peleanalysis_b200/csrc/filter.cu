@@ -1,0 +1,281 @@
+// filter.cu -- device side of the filterPlt path (R/Src/filterPlt.cpp:166-221): ghost cells of a level by FillPatch rules,
+// then PelePhysics' Filter on every box.  R = /root/reference, AX = its vendored amrex/Src, PP = PelePhysics/Source.
+//
+//   k_fp_gather   coarse VALID cells -> coarse patches of the pieces (FillPatchSingleLevel into mf_crse_patch,
+//                 AX/AmrCore/AMReX_FillPatchUtil_I.H), one thread per coarse cell over the copy-tag table
+//   k_fp_interp   pieces <- coarse patches: MFCellConsLinInterp with the monotonised-central slope
+//                 (AX/AmrCore/AMReX_MFInterp_3D_C.H:178-260) or MFPCInterp; coarse reads clamp their index into the coarse
+//                 domain, which IS the first-order extrapolation the reference applies to the patch (AMReX_FilCC_3D_C.H)
+//   k_fp_clamp    ghost cells outside the domain <- the cell at the clamped index of the same FAB (faces, edges, corners:
+//                 AX/Base/AMReX_PhysBCFunct.H:406-640 ends in exactly that)
+//   k_filter      qh = 0; for n, m, l: qh += ((w[l] * w[m]) * w[n]) * q(i+l, j+m, k+n)   (PP/Utility/Filter/Filter.H:28-50)
+//
+// All arithmetic keeps the reference's operation order with separate IEEE multiplies and adds (-fmad=false): results are
+// bit-identical to the reference's CPU build.  The same-level copies of the fill are the library's FillBoundary table
+// (k_halo, all ghost layers).  These are gather kernels over precomputed descriptor tables (hier.cpp: Hier::fill_patch);
+// the filter is a dense (2g+1)^3 weighted sum whose bound is the FP64 pipe for g >= 2 and HBM for g = 1.
+#include <algorithm>
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace pa {
+
+namespace {
+
+__device__ __forceinline__ long long lay_addr(const PaLayDev& y, int i, int j, int k) {
+    return y.off + (long long)(k + y.ng) * y.PS + (long long)(j + y.ng) * y.P + (i + y.ng + y.xoff);
+}
+// last index in [0, n) whose start is <= c
+template <class T, class F>
+__device__ __forceinline__ int last_le(const T* a, int n, long long c, F start) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (start(a[mid]) <= c) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+static inline int blocks_for(long long n, int block, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(g, cap));
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+#ifdef PA_HOST_EMULATION
+__device__ __forceinline__ double ldro(const double* p) { return *p; }
+#else
+__device__ __forceinline__ double ldro(const double* p) { return __ldg(p); }      // read-only path, L1-cached
+#endif
+
+__global__ void k_fp_gather(const PaFpCopy* __restrict__ copies, int ncopies, long long ncells, const PaFpPiece* __restrict__ pieces,
+                            const PaBoxDev* __restrict__ cboxes, const PaLayDev* __restrict__ clay, const double* __restrict__ cbase,
+                            long long ccs, int ncomp, double* __restrict__ scratch, long long ncrse) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+        const PaFpCopy t = copies[last_le(copies, ncopies, c, [](const PaFpCopy& x) { return x.start; })];
+        const long long q = c - t.start;
+        const int i = (int)(q % t.n[0]);
+        const long long r = q / t.n[0];
+        const int j = (int)(r % t.n[1]), k = (int)(r / t.n[1]);
+        const int ci = t.lo[0] + i, cj = t.lo[1] + j, ck = t.lo[2] + k;
+        const PaFpPiece P = pieces[t.piece];
+        const long long dst = P.cstart + ((long long)(ck - P.clo[2]) * P.cn[1] + (cj - P.clo[1])) * P.cn[0] + (ci - P.clo[0]);
+        const PaBoxDev sb = cboxes[t.sbox];
+        const long long sa = lay_addr(clay[t.sbox], ci - sb.lo[0], cj - sb.lo[1], ck - sb.lo[2]);
+        for (int m = 0; m < ncomp; ++m) scratch[dst + m * ncrse] = cbase[sa + m * ccs];
+    }
+}
+
+struct Dom { int lo[3], hi[3]; };
+
+// the reference's monotonised-central slope of one direction (AMReX_MFInterp_3D_C.H:190-196); amrex::min is std::min
+__device__ __forceinline__ double mc_slope(double um, double u0, double up) {
+    const double dc = 0.5 * (up - um);
+    const double df = 2.0 * (up - u0);
+    const double db = 2.0 * (u0 - um);
+    const double adf = fabs(df), adb = fabs(db), adc = fabs(dc);
+    double s = (df * db >= 0.0) ? (adb < adf ? adb : adf) : 0.0;
+    return copysign(1.0, dc) * (adc < s ? adc : s);
+}
+
+template <bool CONS>
+__global__ void k_fp_interp(const PaFpPiece* __restrict__ pieces, int npieces, long long ncells, const double* __restrict__ scratch,
+                            long long ncrse, Dom cdom, int ratio, const PaBoxDev* __restrict__ fboxes, const PaLayDev* __restrict__ flay,
+                            double* __restrict__ fbase, long long fcs, int ncomp) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+        const PaFpPiece P = pieces[last_le(pieces, npieces, c, [](const PaFpPiece& x) { return x.fstart; })];
+        const long long q = c - P.fstart;
+        const int i = P.lo[0] + (int)(q % P.n[0]);
+        const long long rr = q / P.n[0];
+        const int j = P.lo[1] + (int)(rr % P.n[1]), k = P.lo[2] + (int)(rr / P.n[1]);
+        const int ic = (i < 0) ? -((-i + ratio - 1) / ratio) : i / ratio;
+        const int jc = (j < 0) ? -((-j + ratio - 1) / ratio) : j / ratio;
+        const int kc = (k < 0) ? -((-k + ratio - 1) / ratio) : k / ratio;
+        const PaBoxDev fb = fboxes[P.box];
+        const long long da = lay_addr(flay[P.box], i - fb.lo[0], j - fb.lo[1], k - fb.lo[2]);
+        // coarse patch element, index clamped into the coarse domain (first-order extrapolation of the patch)
+        auto U = [&](int a, int b, int d) -> long long {
+            a = clampi(a, cdom.lo[0], cdom.hi[0]); b = clampi(b, cdom.lo[1], cdom.hi[1]); d = clampi(d, cdom.lo[2], cdom.hi[2]);
+            return P.cstart + ((long long)(d - P.clo[2]) * P.cn[1] + (b - P.clo[1])) * P.cn[0] + (a - P.clo[0]);
+        };
+        for (int m = 0; m < ncomp; ++m) {
+            const double* u = scratch + m * ncrse;
+            const double u0 = u[U(ic, jc, kc)];
+            if (!CONS) { fbase[da + m * fcs] = u0; continue; }                       // MFPCInterp
+            const double sx = mc_slope(u[U(ic - 1, jc, kc)], u0, u[U(ic + 1, jc, kc)]);
+            const double sy = mc_slope(u[U(ic, jc - 1, kc)], u0, u[U(ic, jc + 1, kc)]);
+            const double sz = mc_slope(u[U(ic, jc, kc - 1)], u0, u[U(ic, jc, kc + 1)]);
+            double alpha = 1.0;
+            if (sx != 0.0 || sy != 0.0 || sz != 0.0) {                               // :216-238
+                const double rm1 = (double)(ratio - 1), r2 = (double)(2 * ratio);
+                const double dumax = (fabs(sx) * rm1) / r2 + (fabs(sy) * rm1) / r2 + (fabs(sz) * rm1) / r2;
+                double umax = u0, umin = u0;
+                for (int kk = -1; kk <= 1; ++kk)
+                    for (int jj = -1; jj <= 1; ++jj)
+                        for (int ii = -1; ii <= 1; ++ii) {
+                            const double v = u[U(ic + ii, jc + jj, kc + kk)];
+                            umin = (v < umin) ? v : umin;
+                            umax = (umax < v) ? v : umax;
+                        }
+                if (dumax * alpha > (umax - u0)) alpha = (umax - u0) / dumax;
+                if (dumax * alpha > (u0 - umin)) alpha = (u0 - umin) / dumax;
+            }
+            const double slx = sx * alpha, sly = sy * alpha, slz = sz * alpha;
+            const double xoff = ((double)(i - ic * ratio) + 0.5) / (double)ratio - 0.5;      // :253-259
+            const double yoff = ((double)(j - jc * ratio) + 0.5) / (double)ratio - 0.5;
+            const double zoff = ((double)(k - kc * ratio) + 0.5) / (double)ratio - 0.5;
+            fbase[da + m * fcs] = ((u0 + xoff * slx) + yoff * sly) + zoff * slz;
+        }
+    }
+}
+
+__global__ void k_fp_clamp(const PaFpClamp* __restrict__ clamps, int nclamps, long long ncells, Dom dom, int g,
+                           const PaBoxDev* __restrict__ boxes, const PaLayDev* __restrict__ lay, double* __restrict__ base,
+                           long long cs, int ncomp) {
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+        const PaFpClamp t = clamps[last_le(clamps, nclamps, c, [](const PaFpClamp& x) { return x.start; })];
+        const PaBoxDev b = boxes[t.box];
+        const int gx = b.n[0] + 2 * g, gy = b.n[1] + 2 * g;
+        const long long q = c - t.start;
+        const int i = b.lo[0] - g + (int)(q % gx);
+        const long long r = q / gx;
+        const int j = b.lo[1] - g + (int)(r % gy), k = b.lo[2] - g + (int)(r / gy);
+        const int ci = clampi(i, dom.lo[0], dom.hi[0]), cj = clampi(j, dom.lo[1], dom.hi[1]), ck = clampi(k, dom.lo[2], dom.hi[2]);
+        if (ci == i && cj == j && ck == k) continue;                                  // inside the domain
+        const long long da = lay_addr(lay[t.box], i - b.lo[0], j - b.lo[1], k - b.lo[2]);
+        const long long sa = lay_addr(lay[t.box], ci - b.lo[0], cj - b.lo[1], ck - b.lo[2]);
+        for (int m = 0; m < ncomp; ++m) base[da + m * cs] = base[sa + m * cs];
+    }
+}
+
+// ---- the filter -------------------------------------------------------------------------------------------------------
+// One thread = four consecutive x cells of one (box, component, k, j): four independent accumulation chains, and the
+// 4 + 2g row values of every (n, m) offset are loaded once and reused by the 2g + 1 terms of each chain.  The weight
+// products ((w[l] * w[m]) * w[n]) are formed once on the host in that order (they are the leading factors of the reference's
+// left-to-right product) and sit in shared memory.  G > 0: ghost width known at compile time (loops unrolled, row values in
+// registers); G == 0: any width, values re-read from L1.
+constexpr int FILTER_THREADS = 128;
+constexpr int FILTER_MAX_W3 = 17 * 17 * 17;           // ghost width <= 8 in shared memory; wider filters read w3 from global memory
+
+template <int G>
+__global__ void __launch_bounds__(FILTER_THREADS) k_filter(const PaBoxDev* __restrict__ boxes, const PaLayDev* __restrict__ lin,
+                                                            const PaLayDev* __restrict__ lout, int nboxes,
+                                                            const long long* __restrict__ work_prefix /* nboxes+1, quads */,
+                                                            const double* __restrict__ in, long long cs_in, double* __restrict__ out,
+                                                            long long cs_out, int ncomp, const double* __restrict__ w3g, int g_rt) {
+    const int g = G > 0 ? G : g_rt;
+    const int W = 2 * g + 1;
+    PA_DYN_SMEM(smem_raw);
+    double* w3s = reinterpret_cast<double*>(smem_raw);
+    const bool w_in_smem = W * W * W <= FILTER_MAX_W3;
+    if (w_in_smem) {
+        for (int t = threadIdx.x; t < W * W * W; t += blockDim.x) w3s[t] = w3g[t];
+        __syncthreads();
+    }
+    const double* __restrict__ w3 = w_in_smem ? w3s : w3g;
+    const long long nwork = work_prefix[nboxes] * ncomp;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nwork; c += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(c / work_prefix[nboxes]);                 // component-major: a component's boxes are contiguous work
+        const long long cw = c - (long long)m * work_prefix[nboxes];
+        int lo = 0, hi = nboxes - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (work_prefix[mid] <= cw) lo = mid; else hi = mid - 1; }
+        const PaBoxDev b = boxes[lo];
+        const int nq = (b.n[0] + 3) >> 2;
+        const long long q = cw - work_prefix[lo];
+        const int xq = (int)(q % nq);
+        const long long r = q / nq;
+        const int j = (int)(r % b.n[1]), k = (int)(r / b.n[1]);
+        const int x0 = 4 * xq;
+        const int nv = b.n[0] - x0 >= 4 ? 4 : b.n[0] - x0;
+        const PaLayDev yi = lin[lo];
+        const double* __restrict__ src = in + (long long)m * cs_in + lay_addr(yi, x0 - g, j - g, k - g);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (G > 0 && nv == 4) {
+#pragma unroll 1
+            for (int n = 0; n < W; ++n) {
+#pragma unroll 1
+                for (int mm = 0; mm < W; ++mm) {
+                    const double* __restrict__ row = src + (long long)n * yi.PS + (long long)mm * yi.P;
+                    const double* __restrict__ wr = w3 + (n * W + mm) * W;
+                    double v[4 + 2 * (G > 0 ? G : 1)];
+#pragma unroll
+                    for (int t = 0; t < 4 + 2 * G; ++t) v[t] = ldro(row + t);
+#pragma unroll
+                    for (int l = 0; l < 2 * G + 1; ++l) {
+                        const double w = wr[l];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) acc[t] = acc[t] + w * v[t + l];
+                    }
+                }
+            }
+        } else {
+            for (int n = 0; n < W; ++n)
+                for (int mm = 0; mm < W; ++mm) {
+                    const double* __restrict__ row = src + (long long)n * yi.PS + (long long)mm * yi.P;
+                    const double* __restrict__ wr = w3 + (n * W + mm) * W;
+                    for (int l = 0; l < W; ++l) {
+                        const double w = wr[l];
+                        for (int t = 0; t < nv; ++t) acc[t] = acc[t] + w * ldro(row + t + l);
+                    }
+                }
+        }
+        double* dst = out + (long long)m * cs_out + lay_addr(lout[lo], x0, j, k);
+        for (int t = 0; t < nv; ++t) dst[t] = acc[t];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_fp_gather(const PaFpCopy* copies, int ncopies, long long ncells, const PaFpPiece* pieces, const PaBoxDev* cboxes,
+                             const PaLayDev* clay, const double* cbase, long long ccs, int ncomp, double* scratch, long long ncrse,
+                             cudaStream_t st) {
+    if (ncells <= 0 || ncopies <= 0) return cudaSuccess;
+    PA_LAUNCH(blocks_for(ncells, 256), 256, 0, st, k_fp_gather)(copies, ncopies, ncells, pieces, cboxes, clay, cbase, ccs, ncomp, scratch, ncrse);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp_interp(bool conservative, const PaFpPiece* pieces, int npieces, long long ncells, const double* scratch,
+                             long long ncrse, const int cdom_lo[3], const int cdom_hi[3], int ratio, const PaBoxDev* fboxes,
+                             const PaLayDev* flay, double* fbase, long long fcs, int ncomp, cudaStream_t st) {
+    if (ncells <= 0 || npieces <= 0) return cudaSuccess;
+    Dom d;
+    for (int a = 0; a < 3; ++a) { d.lo[a] = cdom_lo[a]; d.hi[a] = cdom_hi[a]; }
+    if (conservative)
+        PA_LAUNCH(blocks_for(ncells, 128), 128, 0, st, k_fp_interp<true>)(pieces, npieces, ncells, scratch, ncrse, d, ratio, fboxes, flay, fbase, fcs, ncomp);
+    else
+        PA_LAUNCH(blocks_for(ncells, 128), 128, 0, st, k_fp_interp<false>)(pieces, npieces, ncells, scratch, ncrse, d, ratio, fboxes, flay, fbase, fcs, ncomp);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp_clamp(const PaFpClamp* clamps, int nclamps, long long ncells, const int dom_lo[3], const int dom_hi[3], int g,
+                            const PaBoxDev* boxes, const PaLayDev* lay, double* base, long long cs, int ncomp, cudaStream_t st) {
+    if (ncells <= 0 || nclamps <= 0) return cudaSuccess;
+    Dom d;
+    for (int a = 0; a < 3; ++a) { d.lo[a] = dom_lo[a]; d.hi[a] = dom_hi[a]; }
+    PA_LAUNCH(blocks_for(ncells, 256), 256, 0, st, k_fp_clamp)(clamps, nclamps, ncells, d, g, boxes, lay, base, cs, ncomp);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter(int g, const PaBoxDev* boxes, const PaLayDev* lin, const PaLayDev* lout, int nboxes, const long long* work_prefix,
+                          long long nwork_per_comp, const double* in, long long cs_in, double* out, long long cs_out, int ncomp,
+                          const double* w3_dev, cudaStream_t st) {
+    if (nboxes <= 0 || nwork_per_comp <= 0 || ncomp <= 0) return cudaSuccess;
+    const int W = 2 * g + 1;
+    const size_t smem = (size_t)(W * W * W <= FILTER_MAX_W3 ? W * W * W : 0) * sizeof(double);
+    const int grid = blocks_for(nwork_per_comp * ncomp, FILTER_THREADS, 148 * 64);
+#define PA_FILTER_GO(GG) PA_LAUNCH(grid, FILTER_THREADS, smem, st, k_filter<GG>)(boxes, lin, lout, nboxes, work_prefix, in, cs_in, out, cs_out, ncomp, w3_dev, g)
+    switch (g) {
+    case 1: PA_FILTER_GO(1); break;
+    case 2: PA_FILTER_GO(2); break;
+    case 3: PA_FILTER_GO(3); break;
+    case 4: PA_FILTER_GO(4); break;
+    default: PA_FILTER_GO(0); break;
+    }
+#undef PA_FILTER_GO
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace pa

@@ -535,6 +535,107 @@ const HaloTable& Hier::halo_full(int l, int ng) {
     return halo_full_.emplace(key, std::move(T)).first->second;
 }
 
+// ---- filterPlt path: grids and FillPatch tables -------------------------------------------------------------------
+// BoxList::maxSize (AMReX_BoxList.cpp:765-815): per direction the length and the chunk are divided by their common powers
+// of two, the coarsened length is cut into ceil(nlen / bs) blocks whose sizes differ by at most one (the larger ones
+// first), and the blocks are scaled back; the chunks of a box replace it in place, x fastest.
+void box_max_size(int nboxes, const int* boxes, int max_grid_size, std::vector<Box>& out) {
+    out.clear();
+    for (int b = 0; b < nboxes; ++b) {
+        Box bx;
+        for (int d = 0; d < 3; ++d) { bx.lo[d] = boxes[6 * b + d]; bx.hi[d] = boxes[6 * b + 3 + d]; }
+        int ratio[3] = {1, 1, 1}, numblk[3] = {1, 1, 1}, extra[3] = {0, 0, 0}, sz[3];
+        for (int d = 0; d < 3; ++d) {
+            sz[d] = bx.len(d);
+            if (bx.len(d) > max_grid_size) {
+                int bs = max_grid_size, nlen = bx.len(d);
+                while (bs % 2 == 0 && nlen % 2 == 0) { ratio[d] *= 2; bs /= 2; nlen /= 2; }
+                numblk[d] = (nlen + bs - 1) / bs;
+                sz[d] = nlen / numblk[d];
+                extra[d] = nlen - sz[d] * numblk[d];
+            }
+        }
+        auto cut = [&](int d, int a, int& l0, int& h0) {
+            if (a < extra[d]) { l0 = a * (sz[d] + 1) * ratio[d]; h0 = l0 + (sz[d] + 1) * ratio[d] - 1; }
+            else { l0 = (a * sz[d] + extra[d]) * ratio[d]; h0 = l0 + sz[d] * ratio[d] - 1; }
+            l0 += bx.lo[d]; h0 += bx.lo[d];
+        };
+        if (numblk[0] == 1 && numblk[1] == 1 && numblk[2] == 1) { out.push_back(bx); continue; }
+        for (int k = 0; k < numblk[2]; ++k)
+            for (int j = 0; j < numblk[1]; ++j)
+                for (int i = 0; i < numblk[0]; ++i) {
+                    Box c;
+                    cut(0, i, c.lo[0], c.hi[0]); cut(1, j, c.lo[1], c.hi[1]); cut(2, k, c.lo[2], c.hi[2]);
+                    out.push_back(c);
+                }
+    }
+}
+
+// FillPatchTwoLevels as filterPlt calls it (filterPlt.cpp:170-203; FabArrayBase::FPinfo): for every local box the part of
+// its grown region that lies inside the domain and that no box of the level covers is cut into boxes ("pieces",
+// BoxArray::complementIn); each piece is interpolated from a coarse patch that is gathered from the coarse level's valid
+// cells.  Ghost cells outside the (non-periodic) domain are first-order extrapolated afterwards: `clamps`.
+const FillPatchTable& Hier::fill_patch(int l, int ng, int cgrow) {
+    std::array<int, 3> key{l, ng, cgrow};
+    auto it = fill_patch_.find(key);
+    if (it != fill_patch_.end()) return it->second;
+    FillPatchTable T;
+    const Level& V = lev[l];
+    for (size_t lb = 0; lb < V.local.size(); ++lb) {
+        const Box g = V.boxes[V.local[lb]].grown(ng);
+        bool out = false;
+        for (int d = 0; d < 3; ++d) out |= g.lo[d] < V.dom.lo[d] || g.hi[d] > V.dom.hi[d];
+        if (out) {
+            PaFpClamp c;
+            c.box = (int)lb; c.pad = 0; c.start = T.nclamp;
+            T.nclamp += g.npts();
+            T.clamps.push_back(c);
+        }
+    }
+    if (l > 0) {
+        const Level& Cv = lev[l - 1];
+        const int r = V.ratio;
+        std::vector<Box> cur, nxt;
+        for (size_t lb = 0; lb < V.local.size(); ++lb) {
+            const Box region = V.boxes[V.local[lb]].grown(ng).isect(V.dom);
+            cur.assign(1, region);
+            V.hash.query(region, [&](int idx, const Box&) {
+                nxt.clear();
+                for (const Box& b : cur) box_diff(b, V.boxes[idx], nxt);
+                cur.swap(nxt);
+            });
+            for (const Box& pc : cur) {
+                PaFpPiece P;
+                P.box = (int)lb;
+                Box cp;
+                for (int d = 0; d < 3; ++d) {
+                    P.lo[d] = pc.lo[d]; P.n[d] = pc.len(d);
+                    cp.lo[d] = coarsen(pc.lo[d], r) - cgrow; cp.hi[d] = coarsen(pc.hi[d], r) + cgrow;
+                    P.clo[d] = cp.lo[d]; P.cn[d] = cp.len(d);
+                }
+                P.cstart = T.ncrse; P.fstart = T.nfine;
+                const Box cpd = cp.isect(Cv.dom);
+                long long got = 0;
+                const int piece = (int)T.pieces.size();
+                Cv.hash.query(cpd, [&](int idx, const Box& is) {
+                    PaFpCopy c;
+                    c.piece = piece; c.sbox = Cv.g2l[idx];
+                    for (int d = 0; d < 3; ++d) { c.lo[d] = is.lo[d]; c.n[d] = is.len(d); }
+                    c.start = T.ncopy;
+                    T.ncopy += is.npts(); got += is.npts();
+                    T.copies.push_back(c);
+                });
+                if (got != cpd.npts() && T.err.empty())
+                    T.err = "level " + std::to_string(l) + ": ghost cells of box " + std::to_string(V.local[lb]) +
+                            " need coarse cells that level " + std::to_string(l - 1) + " does not cover (grids not properly nested for this ghost width)";
+                T.ncrse += cp.npts(); T.nfine += pc.npts();
+                T.pieces.push_back(P);
+            }
+        }
+    }
+    return fill_patch_.emplace(key, std::move(T)).first->second;
+}
+
 // poly_interp_coeff (AMReX_LOUtil_K.H:24-37), same loop so the last bits match
 static void poly_interp_coeff(double xInt, const double* x, int N, double* c) {
     for (int j = 0; j < N; ++j) {

@@ -134,6 +134,21 @@ struct ExchangePlan {
     std::vector<long long> recv_ids, send_ids;
 };
 
+// Ghost-cell fill of the filterPlt path for one (level, ghost width, interpolater stencil width): see PaFpPiece.
+struct FillPatchTable {
+    std::vector<PaFpPiece> pieces;
+    std::vector<PaFpCopy> copies;
+    std::vector<PaFpClamp> clamps;
+    long long nfine = 0;              // fine cells to interpolate
+    long long ncrse = 0;              // scratch cells (per component)
+    long long ncopy = 0;              // coarse cells gathered
+    long long nclamp = 0;             // cells of the grown boxes in `clamps`
+    std::string err;                  // non-empty: the coarse level does not cover a coarse patch (improper nesting)
+};
+
+// BoxList::maxSize: every box replaced, in place, by its chunks no longer than max_grid_size (AMReX_BoxList.cpp:765-815)
+void box_max_size(int nboxes, const int* boxes, int max_grid_size, std::vector<Box>& out);
+
 class Hier {
 public:
     int nlev = 0;
@@ -160,12 +175,16 @@ public:
     std::vector<long long> crse_offsets(int ng);
     // full FillBoundary table (all ng layers incl. edges/corners) -- debug / pa_fill_boundary(cross=0); local sources only
     const HaloTable& halo_full(int l, int ng);
+    // FillPatchTwoLevels / FillPatchSingleLevel tables of level l for ng ghost layers; cgrow = coarse cells the
+    // interpolater reads around the coarsened piece.  Single-rank, non-periodic hierarchies only.
+    const FillPatchTable& fill_patch(int l, int ng, int cgrow);
 
     void periodic_shifts(const Box& dom, int ng, std::vector<std::array<int, 3>>& out) const;
 
 private:
     std::map<std::pair<int, int>, Layout> layouts_;
     std::map<std::pair<int, int>, HaloTable> halo_full_;
+    std::map<std::array<int, 3>, FillPatchTable> fill_patch_;
     void build_links();
     void build_halo(int l, int ng, bool cross, HaloTable& out, bool allow_remote);
     std::string build_faces();

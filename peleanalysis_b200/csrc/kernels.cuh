@@ -140,5 +140,22 @@ cudaError_t launch_velnormal(const PaBoxDev* boxes, const PaLayDev* lay_u, const
                              int nboxes, const double* U, long long cs_u, const double* N, long long cs_n,
                              const double* C, double* out, int do_thr, double thr, cudaStream_t st);
 
+
+// ---- filterPlt path (filter.cu) ----------------------------------------------------------------------------------------
+// coarse valid cells -> coarse patches (scratch, component stride ncrse); pieces <- coarse patches (conservative linear with
+// the mcslope limiter, or piecewise constant); ghost cells outside the domain <- clamped index; the filter itself
+cudaError_t launch_fp_gather(const PaFpCopy* copies, int ncopies, long long ncells, const PaFpPiece* pieces, const PaBoxDev* cboxes,
+                             const PaLayDev* clay, const double* cbase, long long ccs, int ncomp, double* scratch, long long ncrse,
+                             cudaStream_t st);
+cudaError_t launch_fp_interp(bool conservative, const PaFpPiece* pieces, int npieces, long long ncells, const double* scratch,
+                             long long ncrse, const int cdom_lo[3], const int cdom_hi[3], int ratio, const PaBoxDev* fboxes,
+                             const PaLayDev* flay, double* fbase, long long fcs, int ncomp, cudaStream_t st);
+cudaError_t launch_fp_clamp(const PaFpClamp* clamps, int nclamps, long long ncells, const int dom_lo[3], const int dom_hi[3], int g,
+                            const PaBoxDev* boxes, const PaLayDev* lay, double* base, long long cs, int ncomp, cudaStream_t st);
+// work_prefix: per box the prefix of (x-quads * ny * nz), nboxes + 1 entries; w3_dev: (2g+1)^3 weight products, n slowest
+cudaError_t launch_filter(int g, const PaBoxDev* boxes, const PaLayDev* lin, const PaLayDev* lout, int nboxes, const long long* work_prefix,
+                          long long nwork_per_comp, const double* in, long long cs_in, double* out, long long cs_out, int ncomp,
+                          const double* w3_dev, cudaStream_t st);
+
 }  // namespace pa
 #endif

@@ -117,6 +117,33 @@ struct PaTile {
     int z0, nz;
 };
 
+// ---- FillPatchTwoLevels bookkeeping of the filterPlt path (FabArrayBase::FPinfo, AMReX_FabArrayBase.cpp) --------------
+// A "piece" is a box of ghost cells of one fine box that lie inside the domain and that no fine box covers: they are
+// interpolated from the next coarser level.  Its coarse patch = coarsen(piece, ratio) grown by the interpolater's stencil
+// (1 cell for the conservative linear one, 0 for piecewise constant) lives in a scratch buffer, gathered from the coarse
+// level's VALID cells; coarse patch cells outside the domain are never stored -- readers clamp the index (first-order
+// extrapolation, AMReX_FilCC_3D_C.H).
+struct PaFpPiece {
+    int box;            // local fine box the ghost cells belong to
+    int lo[3], n[3];    // the piece (fine index space)
+    int clo[3], cn[3];  // coarse patch box (coarse index space), may stick out of the coarse domain
+    long long cstart;   // first cell of the coarse patch in the scratch buffer (per component)
+    long long fstart;   // prefix over the fine cells of all pieces (the interpolation kernel's enumeration)
+};
+// coarse VALID cells [lo, lo+n) of local coarse box sbox -> coarse patch of piece `piece`
+struct PaFpCopy {
+    int piece;
+    int sbox;
+    int lo[3], n[3];
+    long long start;    // prefix over the cells of all copy tags
+};
+// a local box whose grown region leaves the domain: its ghost cells outside take the value at the clamped index
+struct PaFpClamp {
+    int box;
+    int pad;
+    long long start;    // prefix over the cells of the grown boxes in this list
+};
+
 // face flags (uint16 per face-plane cell)
 #define PA_FLAG_MASK(f)   ((f) & 3)
 #define PA_FLAG_NC(f, b)  (((f) >> (2 + (b))) & 1)   // b: 0 (-r,0) 1 (+r,0) 2 (0,-r) 3 (0,+r) 4 (-,-) 5 (+,-) 6 (-,+) 7 (+,+)
