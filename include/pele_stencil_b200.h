@@ -94,8 +94,12 @@ int pa_hier_create(pa_hier **h, int nlev, const pa_level_desc *levels, const int
  *   PA_HIER_PEER_LINKS  links may also point at boxes of OTHER ranks; their slabs are then read over NVLink through
  *                       CUDA-IPC mappings (pa_field_ipc_handle / pa_field_map_peer), replacing the MPI send/recv of
  *                       AX/Base/AMReX_FabArrayCommI.H:62-110 for those faces.
- *   PA_HIER_NO_LINKS    no links at all: every ghost cell is materialised by the halo gather (reference data flow). */
-enum { PA_HIER_PEER_LINKS = 1, PA_HIER_NO_LINKS = 2 };
+ *   PA_HIER_NO_LINKS    no links at all: every ghost cell is materialised by the halo gather (reference data flow).
+ *   PA_HIER_FILTER_ONLY grids of the filterPlt path (pa_fill_patch / pa_filter): BoxArray::maxSize may cut fine boxes at
+ *                       positions that are not multiples of the refinement ratio, which FillPatch accepts and MLMG's
+ *                       coarse-fine stencil does not.  No face masks / BC records are built; pa_grad, pa_curvature and
+ *                       pa_fill_ghosts return PA_ERR_UNSUPPORTED on such a hierarchy. */
+enum { PA_HIER_PEER_LINKS = 1, PA_HIER_NO_LINKS = 2, PA_HIER_FILTER_ONLY = 4 };
 int pa_hier_create2(pa_hier **h, int nlev, const pa_level_desc *levels, const int is_per[3],
                     const int bc_kind[3], int rank, int nranks, unsigned flags);
 int pa_hier_destroy(pa_hier *h);

@@ -381,7 +381,7 @@ class Field:
         check(lib().pa_fill_ghosts(self.f, comp, ncomp, lev_lo, lev_hi))
 
 
-PEER_LINKS, NO_LINKS = 1, 2
+PEER_LINKS, NO_LINKS, FILTER_ONLY = 1, 2, 4
 
 
 def grad(inp: Field, comp_in: int, nvar: int, out: Field, comp_out: int, phases: int = 3) -> None:

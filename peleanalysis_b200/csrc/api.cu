@@ -429,6 +429,9 @@ int fill_ghosts_impl(pa_field* f, int comp, int ncomp, int l0, int l1, bool link
     Hier& H = h->H;
     CHK(ensure_device(h));
     if (f->ng < 1) return fail(PA_ERR_ARG, "ghost fill needs a field with nghost >= 1");
+    if (H.filter_only)
+        return fail(PA_ERR_UNSUPPORTED, "this hierarchy was created with PA_HIER_FILTER_ONLY: it has no coarse-fine / wall face tables; "
+                                        "grad, curvature and pa_fill_ghosts need a hierarchy created without that flag");
     const double* recv = nullptr;
     if (H.nranks > 1 && H.xplan.recv_prefix[H.nranks] + H.xplan.send_prefix[H.nranks] > 0) {
         if (f->recv_ncomp != ncomp || f->recv_comp0 != comp)
@@ -540,7 +543,7 @@ int pa_hier_create(pa_hier** out, int nlev, const pa_level_desc* levels, const i
 
 int pa_hier_create2(pa_hier** out, int nlev, const pa_level_desc* levels, const int is_per[3], const int bc_kind[3],
                     int rank, int nranks, unsigned flags) {
-    if (flags & ~(unsigned)(PA_HIER_PEER_LINKS | PA_HIER_NO_LINKS)) return fail(PA_ERR_ARG, "pa_hier_create2: unknown flag");
+    if (flags & ~(unsigned)(PA_HIER_PEER_LINKS | PA_HIER_NO_LINKS | PA_HIER_FILTER_ONLY)) return fail(PA_ERR_ARG, "pa_hier_create2: unknown flag");
     if (!out || !levels || !is_per) return fail(PA_ERR_ARG, "pa_hier_create: null argument");
     std::vector<pa_level_desc_host> L(std::max(nlev, 0));
     for (int l = 0; l < nlev; ++l) {
@@ -1586,7 +1589,7 @@ int pa_filter(pa_field* in, int comp_in, pa_field* out, int comp_out, int ncomp,
         std::vector<long long> pre(nb + 1, 0);
         for (int b = 0; b < nb; ++b) {
             const Box& B = V.boxes[V.local[b]];
-            pre[b + 1] = pre[b] + (long long)((B.len(0) + 3) / 4) * B.len(1) * B.len(2);
+            pre[b + 1] = pre[b] + (long long)((B.len(0) + 3) / 4) * ((B.len(1) + 1) / 2) * B.len(2);   // blocks of 4 x 2 cells
         }
         auto buf = std::make_unique<DevBuf<long long>>();
         CU(buf->upload(pre, t_stream));

@@ -148,18 +148,22 @@ __global__ void k_fp_clamp(const PaFpClamp* __restrict__ clamps, int nclamps, lo
 }
 
 // ---- the filter -------------------------------------------------------------------------------------------------------
-// One thread = four consecutive x cells of one (box, component, k, j): four independent accumulation chains, and the
-// 4 + 2g row values of every (n, m) offset are loaded once and reused by the 2g + 1 terms of each chain.  The weight
-// products ((w[l] * w[m]) * w[n]) are formed once on the host in that order (they are the leading factors of the reference's
-// left-to-right product) and sit in shared memory.  G > 0: ghost width known at compile time (loops unrolled, row values in
-// registers); G == 0: any width, values re-read from L1.
+// One thread = a block of four consecutive x cells by two consecutive rows of one (box, component, k): eight independent
+// accumulation chains.  For every z offset n the thread walks the 2g + 2 input rows the block touches; a row's 4 + 2g values
+// arrive as aligned 128-bit loads and feed BOTH output rows (as y offset m for the upper one and m - 1 for the lower one), and a
+// weight row w3[n][m][*] is fetched from shared memory once and serves two consecutive input rows the same way.  Every chain
+// still sees its terms in the reference's order (n, then m, then l ascending).  The weight products ((w[l] * w[m]) * w[n]) are
+// formed once on the host in that order -- they are the leading factors of the reference's left-to-right product.
+// Measured on a B200 (profiles/r02_filter_*): the first version (one row per thread, 64-bit loads at a 32-byte lane stride) was
+// bound by L1 throughput at a third of the FP64 pipe; see DESIGN.md section 9.
+// G > 0: ghost width known at compile time; G == 0 and ragged blocks (nx not a multiple of 4, odd last row): plain loops.
 constexpr int FILTER_THREADS = 128;
 constexpr int FILTER_MAX_W3 = 17 * 17 * 17;           // ghost width <= 8 in shared memory; wider filters read w3 from global memory
 
 template <int G>
 __global__ void __launch_bounds__(FILTER_THREADS) k_filter(const PaBoxDev* __restrict__ boxes, const PaLayDev* __restrict__ lin,
                                                             const PaLayDev* __restrict__ lout, int nboxes,
-                                                            const long long* __restrict__ work_prefix /* nboxes+1, quads */,
+                                                            const long long* __restrict__ work_prefix /* nboxes+1: blocks of 4 x 2 cells */,
                                                             const double* __restrict__ in, long long cs_in, double* __restrict__ out,
                                                             long long cs_out, int ncomp, const double* __restrict__ w3g, int g_rt) {
     const int g = G > 0 ? G : g_rt;
@@ -172,54 +176,92 @@ __global__ void __launch_bounds__(FILTER_THREADS) k_filter(const PaBoxDev* __res
         __syncthreads();
     }
     const double* __restrict__ w3 = w_in_smem ? w3s : w3g;
-    const long long nwork = work_prefix[nboxes] * ncomp;
+    const long long per_comp = work_prefix[nboxes];
+    const long long nwork = per_comp * ncomp;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nwork; c += (long long)gridDim.x * blockDim.x) {
-        const int m = (int)(c / work_prefix[nboxes]);                 // component-major: a component's boxes are contiguous work
-        const long long cw = c - (long long)m * work_prefix[nboxes];
+        const int m = (int)(c / per_comp);                            // component-major: a component's boxes are contiguous work
+        const long long cw = c - (long long)m * per_comp;
         int lo = 0, hi = nboxes - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (work_prefix[mid] <= cw) lo = mid; else hi = mid - 1; }
         const PaBoxDev b = boxes[lo];
-        const int nq = (b.n[0] + 3) >> 2;
+        const int nq = (b.n[0] + 3) >> 2, nr = (b.n[1] + 1) >> 1;
         const long long q = cw - work_prefix[lo];
         const int xq = (int)(q % nq);
         const long long r = q / nq;
-        const int j = (int)(r % b.n[1]), k = (int)(r / b.n[1]);
+        const int j = 2 * (int)(r % nr), k = (int)(r / nr);
         const int x0 = 4 * xq;
         const int nv = b.n[0] - x0 >= 4 ? 4 : b.n[0] - x0;
+        const int nrow = b.n[1] - j >= 2 ? 2 : 1;
         const PaLayDev yi = lin[lo];
         const double* __restrict__ src = in + (long long)m * cs_in + lay_addr(yi, x0 - g, j - g, k - g);
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (G > 0 && nv == 4) {
+        double* dst = out + (long long)m * cs_out + lay_addr(lout[lo], x0, j, k);
+        const int Pout = lout[lo].P;
+        if (G > 0 && nv == 4 && nrow == 2) {
+            constexpr int GG = G > 0 ? G : 1;
+            constexpr int A = GG & 1;                                 // one leading element more keeps the row segment 16-byte aligned
+            constexpr int NV = 4 + 2 * GG + 2 * A;
+            constexpr int WW = 2 * GG + 1;
+            double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-            for (int n = 0; n < W; ++n) {
-#pragma unroll 1
-                for (int mm = 0; mm < W; ++mm) {
-                    const double* __restrict__ row = src + (long long)n * yi.PS + (long long)mm * yi.P;
-                    const double* __restrict__ wr = w3 + (n * W + mm) * W;
-                    double v[4 + 2 * (G > 0 ? G : 1)];
+            for (int n = 0; n < WW; ++n) {
+                const double* __restrict__ plane = src + (long long)n * yi.PS - A;
+                const double* __restrict__ wn = w3 + n * WW * WW;
+                double wprev[WW];
 #pragma unroll
-                    for (int t = 0; t < 4 + 2 * G; ++t) v[t] = ldro(row + t);
+                for (int l = 0; l < WW; ++l) wprev[l] = 0.0;
+#pragma unroll 2
+                for (int rr = 0; rr < WW + 1; ++rr) {                 // input row j - g + rr
+                    double v[NV];
+                    const double2* __restrict__ row2 = reinterpret_cast<const double2*>(plane + (long long)rr * yi.P);
 #pragma unroll
-                    for (int l = 0; l < 2 * G + 1; ++l) {
-                        const double w = wr[l];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) acc[t] = acc[t] + w * v[t + l];
+                    for (int t = 0; t < NV / 2; ++t) {
+#ifdef PA_HOST_EMULATION
+                        const double2 p2 = row2[t];
+#else
+                        const double2 p2 = __ldg(row2 + t);
+#endif
+                        v[2 * t] = p2.x; v[2 * t + 1] = p2.y;
                     }
+                    double wcur[WW];
+                    if (rr < WW) {
+#pragma unroll
+                        for (int l = 0; l < WW; ++l) wcur[l] = wn[rr * WW + l];
+#pragma unroll
+                        for (int l = 0; l < WW; ++l) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) a0[t] = a0[t] + wcur[l] * v[A + t + l];
+                        }
+                    }
+                    if (rr > 0) {
+#pragma unroll
+                        for (int l = 0; l < WW; ++l) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) a1[t] = a1[t] + wprev[l] * v[A + t + l];
+                        }
+                    }
+#pragma unroll
+                    for (int l = 0; l < WW; ++l) wprev[l] = wcur[l];
                 }
             }
+            *reinterpret_cast<double2*>(dst) = make_double2(a0[0], a0[1]);
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(a0[2], a0[3]);
+            *reinterpret_cast<double2*>(dst + Pout) = make_double2(a1[0], a1[1]);
+            *reinterpret_cast<double2*>(dst + Pout + 2) = make_double2(a1[2], a1[3]);
         } else {
-            for (int n = 0; n < W; ++n)
-                for (int mm = 0; mm < W; ++mm) {
-                    const double* __restrict__ row = src + (long long)n * yi.PS + (long long)mm * yi.P;
-                    const double* __restrict__ wr = w3 + (n * W + mm) * W;
-                    for (int l = 0; l < W; ++l) {
-                        const double w = wr[l];
-                        for (int t = 0; t < nv; ++t) acc[t] = acc[t] + w * ldro(row + t + l);
+            for (int rw = 0; rw < nrow; ++rw) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int n = 0; n < W; ++n)
+                    for (int mm = 0; mm < W; ++mm) {
+                        const double* __restrict__ row = src + (long long)n * yi.PS + (long long)(mm + rw) * yi.P;
+                        const double* __restrict__ wr = w3 + (n * W + mm) * W;
+                        for (int l = 0; l < W; ++l) {
+                            const double w = wr[l];
+                            for (int t = 0; t < nv; ++t) acc[t] = acc[t] + w * ldro(row + t + l);
+                        }
                     }
-                }
+                for (int t = 0; t < nv; ++t) dst[(long long)rw * Pout + t] = acc[t];
+            }
         }
-        double* dst = out + (long long)m * cs_out + lay_addr(lout[lo], x0, j, k);
-        for (int t = 0; t < nv; ++t) dst[t] = acc[t];
     }
 }
 
@@ -271,6 +313,7 @@ cudaError_t launch_filter(int g, const PaBoxDev* boxes, const PaLayDev* lin, con
     case 2: PA_FILTER_GO(2); break;
     case 3: PA_FILTER_GO(3); break;
     case 4: PA_FILTER_GO(4); break;
+    case 8: PA_FILTER_GO(8); break;
     default: PA_FILTER_GO(0); break;
     }
 #undef PA_FILTER_GO

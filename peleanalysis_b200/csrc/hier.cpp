@@ -72,6 +72,7 @@ std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, c
     auto t0 = std::chrono::steady_clock::now();
     peer_links = (flags & 1u) != 0;
     no_links = (flags & 2u) != 0;
+    filter_only = (flags & 4u) != 0;
     if (nlev_ < 1 || nlev_ > PA_MAX_LEVELS) return "number of levels must be in [1," + std::to_string(PA_MAX_LEVELS) + "]";
     if (nranks_ < 1 || rank_ < 0 || rank_ >= nranks_) return "bad rank / nranks";
     nlev = nlev_; rank = rank_; nranks = nranks_;
@@ -104,7 +105,7 @@ std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, c
             for (int d = 0; d < 3; ++d) {
                 if (B.lo[d] < V.dom.lo[d] || B.hi[d] > V.dom.hi[d]) return "box outside its level domain";
                 if (B.len(d) > PA_MAX_BOX_SIDE) return "box side > " + std::to_string(PA_MAX_BOX_SIDE) + " cells is not supported";
-                if (l > 0 && (coarsen(B.lo[d], V.ratio) * V.ratio != B.lo[d] || (B.hi[d] + 1) % V.ratio != 0))
+                if (l > 0 && !filter_only && (coarsen(B.lo[d], V.ratio) * V.ratio != B.lo[d] || (B.hi[d] + 1) % V.ratio != 0))
                     return "fine box is not aligned to the refinement ratio";
             }
             int o = L[l].owner ? L[l].owner[b] : 0;
@@ -123,8 +124,14 @@ std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, c
     xplan.pack_level_begin.assign(nlev + 1, 0);
     if (nranks > 1) build_exchange();          // fixes recv/send slab offsets first
     for (int l = 0; l < nlev; ++l) build_halo(l, 1, true, halo_cross[l], true);
-    std::string e = build_faces();
-    if (!e.empty()) return e;
+    if (filter_only) {                             // FillPatch needs no face masks / BC records; grids may be unaligned
+        faces = FaceTable();
+        faces.level_rec_begin.assign(nlev + 1, 0);
+        faces.level_blk_begin.assign(nlev + 1, 0);
+    } else {
+        std::string e = build_faces();
+        if (!e.empty()) return e;
+    }
     build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return "";
 }

@@ -155,6 +155,7 @@ public:
     int rank = 0, nranks = 1;
     bool peer_links = false;          // links may cross ranks (every rank's slabs are peer-mapped, PA_HIER_PEER_LINKS)
     bool no_links = false;            // PA_HIER_NO_LINKS: materialise every ghost cell (reference-style data flow)
+    bool filter_only = false;         // PA_HIER_FILTER_ONLY: grids of the filterPlt path (no ratio alignment, no face tables)
     int is_per[3] = {1, 1, 1};
     int bc_kind[3] = {0, 0, 0};
     std::vector<Level> lev;

@@ -152,7 +152,7 @@ cudaError_t launch_fp_interp(bool conservative, const PaFpPiece* pieces, int npi
                              const PaLayDev* flay, double* fbase, long long fcs, int ncomp, cudaStream_t st);
 cudaError_t launch_fp_clamp(const PaFpClamp* clamps, int nclamps, long long ncells, const int dom_lo[3], const int dom_hi[3], int g,
                             const PaBoxDev* boxes, const PaLayDev* lay, double* base, long long cs, int ncomp, cudaStream_t st);
-// work_prefix: per box the prefix of (x-quads * ny * nz), nboxes + 1 entries; w3_dev: (2g+1)^3 weight products, n slowest
+// work_prefix: per box the prefix of (x-quads * row pairs * nz) = blocks of 4 x 2 cells, nboxes + 1 entries; w3_dev: (2g+1)^3 weight products, n slowest
 cudaError_t launch_filter(int g, const PaBoxDev* boxes, const PaLayDev* lin, const PaLayDev* lout, int nboxes, const long long* work_prefix,
                           long long nwork_per_comp, const double* in, long long cs_in, double* out, long long cs_out, int ncomp,
                           const double* w3_dev, cudaStream_t st);

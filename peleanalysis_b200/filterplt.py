@@ -28,11 +28,13 @@ def rechop(P, pf: Plotfile, comps: Sequence[int], max_grid_size: int, nlev: int)
     out = []
     for lv in pf.levels[:nlev]:
         boxes, fabs = [], []
-        for (lo, hi), fab in zip(lv.boxes, lv.fabs):
+        have_data = len(lv.fabs) == len(lv.boxes)          # metadata-only levels (timing runs) carry no FABs
+        for b, (lo, hi) in enumerate(lv.boxes):
             for clo, chi in P.boxes_max_size([(lo, hi)], max_grid_size):
-                s = tuple(slice(clo[d] - lo[d], chi[d] - lo[d] + 1) for d in (2, 1, 0))
                 boxes.append((clo, chi))
-                fabs.append(np.ascontiguousarray(fab[(comps,) + s]) if len(fab) else fab)
+                if have_data:
+                    s = tuple(slice(clo[d] - lo[d], chi[d] - lo[d] + 1) for d in (2, 1, 0))
+                    fabs.append(np.ascontiguousarray(lv.fabs[b][(comps,) + s]))
         out.append(Level(lv.domain_lo, lv.domain_hi, lv.dx, boxes, fabs))
     return out
 
@@ -53,7 +55,7 @@ class FilterRun:
         self.fgr = [level_fgr(base_fgr, ratios, same_fgr_all_levels, l) for l in range(self.nlev)]
         self.ngrow = [P.filter_weights(filter_type, f)[0] for f in self.fgr]
         self.levels = rechop(P, pf, comps, max_grid_size, self.nlev)
-        self.hier = P.Hierarchy(self.levels, is_per=(0, 0, 0), sym_dir=(0, 0, 0))
+        self.hier = P.Hierarchy(self.levels, is_per=(0, 0, 0), sym_dir=(0, 0, 0), flags=P.FILTER_ONLY)
         self.ncomp = len(comps)
         self.fin = P.Field(self.hier, self.ncomp, max(self.ngrow))
         self.fout = P.Field(self.hier, self.ncomp, 0)

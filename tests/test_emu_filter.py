@@ -19,3 +19,8 @@ def test_emulated_filter_types(emu):  # noqa: F811
 @pytest.mark.parametrize("name", ["filter_c1_corner_gauss", "filter_c3", "filter_lshape", "filter_ratio4"])
 def test_emulated_filter_ghost_cells(emu, name):  # noqa: F811
     GF.check_ghost_cells(emu, name)
+
+
+@pytest.mark.parametrize("ftype,fgr,mgs", GF.MIDSIZE)
+def test_emulated_filter_midsize(emu, ftype, fgr, mgs):  # noqa: F811
+    GF.check_midsize(emu, ftype, fgr, mgs)

@@ -25,7 +25,7 @@ def emu_exes():
     import fcntl
     with open(os.path.join(out, ".exe_build.lock"), "w") as lk:      # one build at a time (pytest-xdist workers share the directory)
         fcntl.flock(lk, fcntl.LOCK_EX)
-        for name, main in (("grad3d.emu.ex", "grad_main.cpp"), ("curvature3d.emu.ex", "curvature_main.cpp")):
+        for name, main in (("grad3d.emu.ex", "grad_main.cpp"), ("curvature3d.emu.ex", "curvature_main.cpp"), ("filterPlt3d.emu.ex", "filter_main.cpp")):
             exe = os.path.join(out, name)
             srcs = [os.path.join(host, main), os.path.join(host, "plotfile.cpp")]
             deps = srcs + [lib] + [os.path.join(host, f) for f in ("plotfile.hpp", "tool_common.hpp", "parmparse.hpp", "multi_gpu.hpp")]
@@ -54,6 +54,15 @@ def test_emulated_grad_executable_aux_and_inputs_file(emu_exes, tmp_path):
 @pytest.mark.parametrize("name", ["c1_periodic", "c3_threshold", "c1_options", "mixed_boxes"])
 def test_emulated_curvature_executable(emu_exes, tmp_path, name):
     T.test_curvature_executable(emu_exes, tmp_path, name)
+
+
+@pytest.mark.parametrize("name", ["filter_c1", "filter_c1_corner_gauss", "filter_c3", "filter_c3_subset", "filter_c3_pc_samefgr", "filter_ratio4"])
+def test_emulated_filter_executable(emu_exes, tmp_path, name):
+    T.test_filter_executable(emu_exes, tmp_path, name)
+
+
+def test_emulated_filter_executable_errors(emu_exes, tmp_path):
+    T.test_filter_executable_errors(emu_exes, tmp_path)
 
 
 @pytest.mark.parametrize("name,ngpus", [("c1_periodic", 2), ("c3_three_levels", 2), ("mixed_boxes", 3), ("lshape", 4), ("c1_corner_sym", 2)])

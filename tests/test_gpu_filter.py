@@ -62,22 +62,27 @@ def test_filter_ghost_cells_match_oracle(gpu, name):
     check_ghost_cells(gpu, name)
 
 
-def check_midsize(P):
-    """a hierarchy the fixtures do not hold (64^3 base, 3 levels, two variables, 16^3 output boxes) against the restatement"""
+MIDSIZE = [  # (filter_type, base_fgr, max_grid_size): ghost widths 1/2/4, 2/4/8, 3/6/12 (generic kernel), ragged 4 x 2 blocks
+    (2, 2, 16), (2, 4, 16), (1, 6, 16), (1, 2, 10), (2, 4, 11), (4, 3, 7)]
+
+
+def check_midsize(P, ftype, fgr, mgs):
+    """hierarchies the fixtures do not hold (32^3 base, 3 levels, two variables) against the restatement"""
     from oracle import filter_oracle as FO
     pf = synth.config3(32, 16, names=("temp", "Y_CH4"))
-    kw = dict(filter_type=2, base_fgr=2, max_grid_size=16)
+    kw = dict(filter_type=ftype, base_fgr=fgr, max_grid_size=mgs)
     names, ref, _ = FO.filter_plotfile(pf, **kw)
     names2, got, _ = filterplt.filter_plotfile(P, pf, **kw)
     assert names == names2
     for (rb, rf), (gb, gf) in zip(ref, got):
         assert rb == gb
         for a, b in zip(rf, gf):
-            assert bit_equal(b, a)
+            assert bit_equal(b, a), (ftype, fgr, mgs)
 
 
-def test_filter_midsize_matches_oracle(gpu):
-    check_midsize(gpu)
+@pytest.mark.parametrize("ftype,fgr,mgs", MIDSIZE)
+def test_filter_midsize_matches_oracle(gpu, ftype, fgr, mgs):
+    check_midsize(gpu, ftype, fgr, mgs)
 
 
 def test_fill_patch_rejects_periodic_and_bad_nesting(gpu):

@@ -24,7 +24,7 @@ def exes(gpu):
     with open(os.path.join(HOST, ".build.lock"), "w") as lk:
         fcntl.flock(lk, fcntl.LOCK_EX)
         subprocess.check_call(["make", "-s", "-C", HOST])
-    return os.path.join(HOST, "grad3d.b200.ex"), os.path.join(HOST, "curvature3d.b200.ex")
+    return os.path.join(HOST, "grad3d.b200.ex"), os.path.join(HOST, "curvature3d.b200.ex"), os.path.join(HOST, "filterPlt3d.b200.ex")
 
 
 def _flat(pf, name):
@@ -220,3 +220,38 @@ def test_full_size_curvature_vs_reference_executable(exes):
         b = plotfile.read_plotfile(os.path.join(tmp, "ref"), comps=names)
         for n in names:
             assert bit_equal(_flat(a, n), _flat(b, n)), n
+
+
+@pytest.mark.parametrize("name", ["filter_c1", "filter_c1_corner_gauss", "filter_c3", "filter_c3_subset", "filter_c3_pc_samefgr", "filter_ratio4"])
+def test_filter_executable(exes, tmp_path, name):
+    """filterPlt3d.b200.ex: the reference tool's keys, output name (<root>_filtered in the working directory), re-chopped
+    output grids and variable names; data bit-identical to the reference's golden vectors; AMReX's fcompare agrees with the
+    reference executable's plotfile."""
+    pf, z = load_golden(name)
+    d = str(tmp_path / "plt")
+    plotfile.write_plotfile(d, pf)
+    opts = [str(s) for s in z["opts"]]
+    out = _run(exes[2], "infile=" + d, *opts, cwd=str(tmp_path))
+    assert "FillPatching data..." in out and "Filtering data..." in out
+    r = plotfile.read_plotfile(str(tmp_path / "plt_filtered"))
+    assert r.names == [str(n) for n in z["out_names"]]
+    want_boxes = [tuple(int(v) for v in b) for b in z["out_boxes"]]
+    assert [tuple(lo) + tuple(hi) for l in r.levels for lo, hi in l.boxes] == want_boxes
+    for n in r.names:
+        assert bit_equal(_flat(r, n), z["out_" + n]), (name, n)
+    if O.have_ref() and os.path.exists(O.ref_exe("filterPlt3d.ref.ex")):
+        os.makedirs(str(tmp_path / "ref"))
+        kv = dict(s.split("=", 1) for s in opts)
+        O.run_ref("filterPlt", d, str(tmp_path / "ref" / "plt_filtered"), **kv)
+        p = subprocess.run([O.ref_exe("fcompare.ref.ex"), str(tmp_path / "plt_filtered"), str(tmp_path / "ref" / "plt_filtered")], capture_output=True, text=True)
+        assert "PLOTFILE AGREE" in p.stdout, p.stdout[-1500:]
+
+
+def test_filter_executable_errors(exes, tmp_path):
+    pf, _ = load_golden("filter_c1")
+    d = str(tmp_path / "plt")
+    plotfile.write_plotfile(d, pf)
+    p = subprocess.run([exes[2], "infile=" + d, "variables=nope"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert p.returncode != 0 and "Variable 'nope' not found in file" in p.stderr
+    p = subprocess.run([exes[2], "infile=" + d, "base_fgr=3"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert p.returncode != 0 and "even" in p.stderr
