@@ -10,6 +10,8 @@ Workloads (--workload; the default, config2, is the configuration the metric is 
   target_curv  curvature (default options) on the same hierarchy
   curvature3   curvature, 3 levels, 256^3 base, ratio 2, 64^3 boxes                          (BASELINE configs[2])
   grad5        grad of 12 components, 4 levels (ratios 2/4/2), 128^3 base, 16^3 boxes        (BASELINE configs[4])
+  filter3      filterPlt (box filter, base_fgr 2 -> ghost widths 1/2/4, max_grid_size 32) of temp on the configs[2]
+               hierarchy: SURVEY 8(f) rank 4, the neighbouring stencil tool (extra only; FP64-pipe-bound)
 
 One "step" = one pass of the hot path (ghost fill + c-f fill + stencil kernels) over the synthetic workload:
   value     device-resident inputs -> device-resident outputs, CUDA-event timed, max over ranks
@@ -435,6 +437,94 @@ def measure(cx, spec, steps, warmup, e2e_steps=0, sampler=None):
     return res
 
 
+FILTER3_DESC = "filterPlt of temp (box filter, base_fgr 2: ghost widths 1/2/4; max_grid_size 32), 3 levels, 256^3 base, ratio 2 (SURVEY 8(f) rank 4)"
+
+
+def measure_filter(cx, steps, warmup, cpu_baseline=True):
+    """filterPlt's compute block (filterPlt.cpp:166-221: FillPatch ghost cells + Filter::apply_filter of every level),
+    device-resident, single GPU.  value = cells of all levels / step time.  The filter is a dense (2g+1)^3 weighted sum with
+    separate multiplies and adds (bit parity with the reference forbids FMA), so for g >= 2 its bound is the FP64 pipe:
+    fp64_frac = useful multiply+add operations / time / the MEASURED rate of that instruction mix on this GPU."""
+    torch, P = cx.torch, cx.capi
+    from peleanalysis_b200 import filterplt, synth
+    pf = synth.config3(256, 64, fill=False)
+    run = filterplt.FilterRun(P, pf, filter_type=1, base_fgr=2, max_grid_size=32, upload=False)
+    names = ["temp"]
+    # synthetic field values on the re-chopped grids, generated on the device
+    fields = gen_fields(torch, run.levels, run.hier.local_boxes, names)
+    for l in range(run.nlev):
+        host = fields[l][0].cpu().numpy()
+        run.fin.upload_level(l, 0, host)
+    P.sync()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        run.step()
+    cx.torch.cuda.synchronize()
+    l0 = P.kernel_launches()
+    a, b = ev(), ev()
+    a.record(cx.stream)
+    for _ in range(steps):
+        run.step()
+    b.record(cx.stream)
+    torch.cuda.synchronize()
+    launches = P.kernel_launches() - l0
+    ms = a.elapsed_time(b) / steps
+    per_level = []
+    for l in range(run.nlev):
+        x, y, z = ev(), ev(), ev()
+        x.record(cx.stream)
+        P.fill_patch(run.fin, 0, 1, l, run.ngrow[l], 1)
+        y.record(cx.stream)
+        P.filter_level(run.fin, 0, run.fout, 0, 1, l, 1, run.fgr[l])
+        z.record(cx.stream)
+        torch.cuda.synchronize()
+        per_level.append({"level": l, "ngrow": run.ngrow[l], "boxes": len(run.levels[l].boxes), "cells": run.levels[l].ncells,
+                          "fill_ms": x.elapsed_time(y), "filter_ms": y.elapsed_time(z)})
+    cells = run.cells()
+    ops = sum(2.0 * (2 * g + 1) ** 3 * lv.ncells for g, lv in zip(run.ngrow, run.levels))
+    peak = P.fp64_rate_gops()
+    filt_ms = sum(x["filter_ms"] for x in per_level)
+    rec = {"workload": FILTER3_DESC, "value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1, "ms_per_step": ms, "cells": cells,
+           "boxes": [len(lv.boxes) for lv in run.levels], "launches_per_step": launches // max(1, steps), "levels": per_level,
+           "roofline": {"bound": "fp64 pipe (separate multiply + add, no FMA)", "useful_ops": ops, "achieved": ops / (filt_ms * 1e-3) / 1e9,
+                        "peak": peak, "unit": "Gop/s", "frac": ops / (filt_ms * 1e-3) / 1e9 / peak,
+                        "peak_source": "measured on this GPU by pa_debug_fp64_rate (8 independent multiply-add chains per thread)",
+                        "hbm_frac_level0": (16.0 * run.levels[0].ncells) / (per_level[0]["filter_ms"] * 1e-3) / 1e9 / cx.peak},
+           "output_hash": hash_verdict(cx, "filter3", "%016x" % run.fout.hash(0, 1))}
+    if cpu_baseline:
+        try:
+            rec["cpu_baseline"] = filter_reference(steps=2, warmup=1)
+        except Exception as e:
+            rec["cpu_baseline"] = {"value": None, "sample": "unavailable: " + str(e).splitlines()[0][:160]}
+    return rec
+
+
+def filter_reference(steps, warmup, base=64, mgs_in=32):
+    """The reference filterPlt tool's timed build (oracle/_ref/filterPlt3d.timed.ex: probes around filterPlt.cpp:166-221) on
+    all host cores.  The filter3 hierarchy has 50 M cells and the reference needs minutes per pass on it (ghost width 4 = 729
+    terms per cell), so the baseline runs a bounded sample: the same three-level shape (equal cells per level, same ghost
+    widths, same max_grid_size) with a smaller base grid.  Gcells/s is intensive in the grid size."""
+    from oracle import oracle as O
+    from peleanalysis_b200 import plotfile, synth
+    if not os.path.exists(O.ref_exe("filterPlt3d.timed.ex")):
+        raise RuntimeError("oracle/_ref/filterPlt3d.timed.ex is missing")
+    pf = synth.config3(base, mgs_in, fill=True)
+    cells = sum(l.ncells for l in pf.levels)
+    basedir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    tmp = tempfile.mkdtemp(prefix="pa_reff_", dir=basedir)
+    cores = os.cpu_count() or 1
+    try:
+        d = os.path.join(tmp, "plt")
+        plotfile.write_plotfile(d, pf, clean="remove")
+        hot = O.run_ref_timed("filterPlt", d, os.path.join(tmp, "plt_filtered"), threads=cores, reps=warmup + steps, variables="temp")
+        t = float(np.mean(hot[warmup:]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": cells / t / 1e9, "unit": UNIT, "cores": cores, "kind": "reference", "hot_path_seconds": t,
+            "sample": "filterPlt of temp on a %d^3-base three-level hierarchy (%d cells; the workload's shape, ghost widths and max_grid_size at "
+                      "1/%d of its cells); %d timed repetitions of filterPlt.cpp:166-221" % (base, cells, (256 // base) ** 3, steps)}
+
+
 def hash_verdict(cx, name, h):
     want = cx.expected.get(name)
     return {"value": h, "expected": want, "ok": (want is None or want == h)}
@@ -456,7 +546,8 @@ def main():
     ap.add_argument("--write-hashes", action="store_true", help="(N=1) record this run's fingerprints in tests/golden/bench_hashes.json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    spec = workload_spec(args.only_extra or args.workload)
+    filter_only = args.only_extra == "filter3"
+    spec = workload_spec("config2" if filter_only else (args.only_extra or args.workload))
     if args.impl == "reference":
         return reference_arm(args, spec)
 
@@ -485,6 +576,11 @@ def main():
                 "algorithmic_bytes": per_rank_alg, "roofline_frac": per_rank_alg / (r["ms_per_step"] * 1e-3) / 1e9 / cx.peak,
                 "hier_build_s": r["hier_build_s"], "output_hash": hash_verdict(cx, name, r["output_hash"])}
 
+    if filter_only:
+        if world > 1:
+            raise SystemExit("filter3 is a single-GPU workload")
+        print(json.dumps(measure_filter(cx, args.steps, args.warmup, cpu_baseline=not args.no_cpu_baseline)))
+        return
     if args.only_extra:
         r = measure(cx, spec, args.steps, args.warmup)
         r["steps"] = args.steps
@@ -520,6 +616,13 @@ def main():
                 extras[name] = {"error": str(e).splitlines()[0][:200]}
                 if world > 1:
                     raise                         # a rank that fails alone would hang the others at the next collective
+
+    if extras is not None and world == 1:
+        try:
+            extras["filter3"] = measure_filter(cx, max(3, args.steps // 4), 2, cpu_baseline=not args.no_cpu_baseline)
+            hashes["filter3"] = extras["filter3"]["output_hash"]["value"]
+        except Exception as e:
+            extras["filter3"] = {"error": str(e).splitlines()[0][:200]}
 
     if rank != 0:
         if world > 1:

@@ -285,6 +285,9 @@ int64_t pa_debug_selftest_math(int64_t n, uint64_t seed);
  * forces one; otherwise the library runs the self-test above on the device and keeps the branch-free forms only if not
  * one result bit differs (both forms compute the same IEEE results; the choice affects speed only). */
 int pa_debug_normal_math(void);
+/* Measured FP64 rate of the device for separate multiplies and adds (no FMA: the instruction mix bit parity with the
+ * reference's CPU build imposes on pa_filter), in Gop/s: the roofline denominator of the filter for ghost widths >= 2. */
+int pa_debug_fp64_rate(double *gops);
 /* 1 if curvature on this hierarchy runs through the fused kernel (every local box eligible: >= 3 cells in every direction,
  * <= 128 wide), 0 if it takes the separate flame-normal / divergence kernels, < 0 on error. */
 int pa_debug_curv_fused(pa_hier *h);

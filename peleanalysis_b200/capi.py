@@ -76,6 +76,7 @@ SYMBOLS = {
     "pa_debug_exchange_ids": (_i64, [_vp, _i, _vp, _i64]),
     "pa_debug_links": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "pa_debug_face_coef": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d)]),
+    "pa_debug_fp64_rate": (_i, [C.POINTER(_d)]),
     "pa_filter_weights": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_d), _i]),
     "pa_boxes_max_size": (_i, [_i, C.POINTER(_i), _i, C.POINTER(_i), _i]),
     "pa_fill_patch": (_i, [_vp, _i, _i, _i, _i, _i]),
@@ -443,6 +444,13 @@ def boxes_max_size(boxes: Sequence[tuple], max_grid_size: int) -> List[tuple]:
     if n2 < 0:
         check(n2)
     return [(tuple(int(v) for v in b[:3]), tuple(int(v) for v in b[3:])) for b in out]
+
+
+def fp64_rate_gops() -> float:
+    """measured FP64 rate for separate multiplies and adds (no FMA), Gop/s"""
+    v = C.c_double(0.0)
+    check(lib().pa_debug_fp64_rate(C.byref(v)))
+    return float(v.value)
 
 
 def fill_patch(f: Field, comp: int, ncomp: int, lev: int, nghost: int, interp_type: int = 1) -> None:

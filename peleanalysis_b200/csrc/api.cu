@@ -1613,4 +1613,32 @@ int pa_filter(pa_field* in, int comp_in, pa_field* out, int comp_out, int ncomp,
     return PA_OK;
 }
 
+// Measured FP64 rate of this GPU for separate multiplies and adds (the filter's instruction mix, no FMA): Gop/s.
+int pa_debug_fp64_rate(double* gops) {
+    if (!gops) return fail(PA_ERR_ARG, "pa_debug_fp64_rate: null output");
+    cudaError_t esm = cudaSuccess;
+    const int nsm = stencil_num_sms(&esm);
+    if (esm != cudaSuccess) return cuda_fail(esm, "device query");
+    const int blocks = nsm * 8, threads = 256, iters = 4096;
+    double* buf = nullptr;
+    CU(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaError_t e = launch_fp64_rate(buf, blocks, threads, 64, t_stream);        // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, t_stream);
+        e = launch_fp64_rate(buf, blocks, threads, iters, t_stream);
+        cudaEventRecord(e1, t_stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) { cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (e != cudaSuccess) return cuda_fail(e, "pa_debug_fp64_rate");
+    *gops = (double)blocks * threads * iters * 16.0 / (best * 1e-3) / 1e9;
+    return PA_OK;
+}
+
 }  // extern "C"

@@ -265,7 +265,30 @@ __global__ void __launch_bounds__(FILTER_THREADS) k_filter(const PaBoxDev* __res
     }
 }
 
+// FP64 pipe rate with the filter's instruction mix (separate multiplies and adds, no FMA): 8 independent chains per thread.
+// The measured roofline denominator of k_filter for ghost widths >= 2 (bench.py); results are written so nothing is optimised away.
+__global__ void k_fp64_rate(double* __restrict__ out, int iters, double seed) {
+    double a[8], w = 1.0 + seed * 1e-9;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a[t] = seed + t + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) a[t] = a[t] + w * a[(t + 1) & 7];
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += a[t];
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
+
+cudaError_t launch_fp64_rate(double* out, int blocks, int threads, int iters, cudaStream_t st) {
+    PA_LAUNCH(blocks, threads, 0, st, k_fp64_rate)(out, iters, 0.5);
+    ++g_launches;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fp_gather(const PaFpCopy* copies, int ncopies, long long ncells, const PaFpPiece* pieces, const PaBoxDev* cboxes,
                              const PaLayDev* clay, const double* cbase, long long ccs, int ncomp, double* scratch, long long ncrse,

@@ -156,6 +156,8 @@ cudaError_t launch_fp_clamp(const PaFpClamp* clamps, int nclamps, long long ncel
 cudaError_t launch_filter(int g, const PaBoxDev* boxes, const PaLayDev* lin, const PaLayDev* lout, int nboxes, const long long* work_prefix,
                           long long nwork_per_comp, const double* in, long long cs_in, double* out, long long cs_out, int ncomp,
                           const double* w3_dev, cudaStream_t st);
+// microbenchmark: blocks x threads threads each doing iters x 8 (multiply, add) pairs; out has blocks * threads doubles
+cudaError_t launch_fp64_rate(double* out, int blocks, int threads, int iters, cudaStream_t st);
 
 }  // namespace pa
 #endif

@@ -85,6 +85,19 @@ def test_filter_midsize_matches_oracle(gpu, ftype, fgr, mgs):
     check_midsize(gpu, ftype, fgr, mgs)
 
 
+def test_filter_large_matches_oracle(gpu):
+    """128^3 base, 3 levels, 32^3 output boxes (the bench workload's box size and ghost widths 1/2/4; 6.3 M cells) against the
+    restatement, bit for bit"""
+    from oracle import filter_oracle as FO
+    pf = synth.config3(128, 64)
+    names, ref, _ = FO.filter_plotfile(pf, max_grid_size=32)
+    _, got, _ = filterplt.filter_plotfile(gpu, pf, max_grid_size=32)
+    for (rb, rf), (gb, gf) in zip(ref, got):
+        assert rb == gb
+        for a, b in zip(rf, gf):
+            assert bit_equal(b, a)
+
+
 def test_fill_patch_rejects_periodic_and_bad_nesting(gpu):
     P = gpu
     pf = synth.config1(16, 8)
