@@ -383,8 +383,12 @@ int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex
     // the TMA tile table is sized for the nghost == 1 layout (row pitch nx+4)
     if (in_ng == 1 && use_tma(h, nin)) {
         // Work items per launch: (tiles of the level range) x variables, drawn dynamically by 148 x 2 (or so) persistent CTAs.
-        // With fewer than ~8 items per CTA the last round of items leaves most SMs idle (strong scaling at 8 ranks: 5 items
-        // per CTA, 13 % tail): take the table with half / a quarter of the planes per item then.  PA_TMA_ZDIV=0|1|2 forces one.
+        // With few items per CTA the last round of items leaves most SMs idle (strong scaling at 8 ranks): take the table
+        // with half / a quarter of the planes per item then.  Measured on the per-rank load of configs[1] at N = 8 (8 boxes x 5
+        // variables, 8.65 items per slot): 93.1 / 95.7 / 97.0 % of the HBM roofline for 32 / 16 / 8 planes per item
+        // (profiles/r02_ab_zdiv.txt) -- the bandwidth-bound gradient modes switch below 24 items per slot.  The flame-normal
+        // and divergence modes pay more per item (first-plane wait of a deeper ring) and were 3-5 % slower with shallower
+        // items on large workloads: they switch only below 8.  PA_TMA_ZDIV=0|1|2 forces one.
         TileTable* Tp = &h->tiles_tma;
         {
             cudaError_t esm = cudaSuccess;
@@ -394,7 +398,8 @@ int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex
             if (ez) pick = std::min(2, std::max(0, atoi(ez)));
             else {
                 auto items = [&](const TileTable& X) { long long n = 0; for (int c = 0; c < N_TILE_CLASSES; ++c) n += X.begin[c][l1 + 1] - X.begin[c][l0]; return n * nvar; };
-                while (pick < 2 && items(pick == 0 ? h->tiles_tma : h->tiles_tma_fine[pick - 1]) < 8 * slots) ++pick;
+                const long long want = (mode == MODE_GRAD || mode == MODE_GRAD3) ? 24 : 8;
+                while (pick < 2 && items(pick == 0 ? h->tiles_tma : h->tiles_tma_fine[pick - 1]) < want * slots) ++pick;
             }
             if (pick > 0 && h->tiles_tma_fine[pick - 1].ok) Tp = &h->tiles_tma_fine[pick - 1];
         }
