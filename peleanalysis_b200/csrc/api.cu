@@ -103,6 +103,7 @@ struct pa_hier {
     long long shell_begin[PA_MAX_LEVELS + 1] = {0};
     std::map<cudaStream_t, std::unique_ptr<DevBuf<double>>> staging;   // upload / download staging, one per stream
     DevBuf<double> send_slab, recv_slab;               // multi-rank exchange, [cell][comp]
+    pa_field* recv_owner = nullptr;                    // the field whose exchanged data the (shared) recv slab holds right now
     int slab_ncomp = 0;
     // side stream on which the ghost fill of the refined levels overlaps the stencil of level 0 (created on demand)
     cudaStream_t side = nullptr;
@@ -657,6 +658,7 @@ int pa_field_alloc(pa_hier* h, int ncomp, int nghost, pa_field** out) {
 }
 int pa_field_free(pa_field* f) {
     if (!f) return PA_OK;
+    if (f->h && f->h->recv_owner == f) f->h->recv_owner = nullptr;
     for (void* p : f->ipc_mapped) cudaIpcCloseMemHandle(p);
     for (double* p : f->slab) if (p) cudaFree(p);
     delete f;
@@ -954,6 +956,10 @@ int pa_exchange_pack(pa_field* f, int comp, int ncomp) {
     Hier& H = h->H;
     CHK(ensure_device(h));
     f->recv_ncomp = 0;
+    // the recv slab is shared by all fields of the hierarchy: the transport that follows this pack overwrites whatever another
+    // field had received, so that field's mark must not survive (a later ghost fill on it would read this field's data)
+    if (h->recv_owner && h->recv_owner != f) h->recv_owner->recv_ncomp = 0;
+    h->recv_owner = nullptr;
     if (H.nranks <= 1) return PA_OK;
     CHK(ensure_slabs(h, std::max(ncomp, h->slab_ncomp)));
     h->slab_ncomp = std::max(ncomp, h->slab_ncomp);
@@ -969,6 +975,9 @@ int pa_exchange_pack(pa_field* f, int comp, int ncomp) {
 }
 int pa_exchange_mark_received(pa_field* f, int comp, int ncomp) {
     CHK(check_field(f, comp, ncomp, "pa_exchange_mark_received"));
+    pa_hier* h = f->h;
+    if (h->recv_owner && h->recv_owner != f) h->recv_owner->recv_ncomp = 0;
+    h->recv_owner = f;
     f->recv_ncomp = ncomp;
     f->recv_comp0 = comp;
     return PA_OK;
@@ -1621,6 +1630,9 @@ int pa_filter(pa_field* in, int comp_in, pa_field* out, int comp_out, int ncomp,
 // Measured FP64 rate of this GPU for separate multiplies and adds (the filter's instruction mix, no FMA): Gop/s.
 int pa_debug_fp64_rate(double* gops) {
     if (!gops) return fail(PA_ERR_ARG, "pa_debug_fp64_rate: null output");
+#ifdef PA_HOST_EMULATION
+    return fail(PA_ERR_UNSUPPORTED, "pa_debug_fp64_rate: a timing measurement, GPU only");
+#else
     cudaError_t esm = cudaSuccess;
     const int nsm = stencil_num_sms(&esm);
     if (esm != cudaSuccess) return cuda_fail(esm, "device query");
@@ -1644,6 +1656,7 @@ int pa_debug_fp64_rate(double* gops) {
     if (e != cudaSuccess) return cuda_fail(e, "pa_debug_fp64_rate");
     *gops = (double)blocks * threads * iters * 16.0 / (best * 1e-3) / 1e9;
     return PA_OK;
+#endif
 }
 
 }  // extern "C"

@@ -227,3 +227,26 @@ def test_box_side_limit_is_an_error(emu):
     with pytest.raises(emu.PaError) as e:
         emu.Hierarchy(pf.levels)
     assert "1024" in str(e.value)
+
+
+def test_emulated_recv_slab_has_one_owner(emu):
+    """The recv slab is shared by all fields of a hierarchy: once another field packs / receives, the first field's
+    "received" mark must be gone, or a ghost fill on it would silently read the other field's data (round-1 advisor finding)."""
+    from peleanalysis_b200 import synth
+    P = emu
+    pf = synth.config1(16, 8)
+    H = P.Hierarchy(pf.levels, is_per=(1, 1, 1), rank=0, nranks=2)
+    a, b = P.Field(H, 1, 1), P.Field(H, 1, 1)
+    L = P.lib()
+    P.check(L.pa_exchange_pack(a.f, 0, 1))
+    P.check(L.pa_exchange_mark_received(a.f, 0, 1))
+    a.fill_ghosts(0, 1)                                   # a's data is in the slab: accepted
+    P.check(L.pa_exchange_pack(b.f, 0, 1))                # b's transport will overwrite the slab
+    with pytest.raises(P.PaError) as e:
+        a.fill_ghosts(0, 1)
+    assert e.value.code == -5
+    P.check(L.pa_exchange_mark_received(b.f, 0, 1))
+    b.fill_ghosts(0, 1)
+    P.check(L.pa_exchange_mark_received(a.f, 0, 1))       # marking a again takes the slab away from b
+    with pytest.raises(P.PaError):
+        b.fill_ghosts(0, 1)
