@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this file's library; the product path never does.
  *
- * Parity is PINNED: tests/test_oracle_vs_reference.py checks this restatement bit-for-bit against
+ * Parity is PINNED: tests/test_oracle_golden.py checks this restatement bit-for-bit against
  * outputs of the compiled, unmodified reference (oracle/_ref, built by oracle/build_ref.py) on the
  * committed fixtures under tests/golden/ (the reference has no golden vectors of its own).
  *
