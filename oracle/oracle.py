@@ -24,7 +24,11 @@ def build() -> str:
     so = os.path.join(HERE, "libpa_oracle.so")
     src = os.path.join(HERE, "pa_oracle.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", HERE, "libpa_oracle.so"], stdout=subprocess.DEVNULL)
+        import fcntl
+        with open(os.path.join(HERE, ".build.lock"), "w") as lk:     # pytest-xdist workers: one make at a time
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+                subprocess.check_call(["make", "-C", HERE, "libpa_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
 

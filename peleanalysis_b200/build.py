@@ -29,24 +29,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objs = []
-    procs = []
-    for s in SOURCES:
-        o = os.path.join(LIBDIR, s.rsplit(".", 1)[0] + ".o")
-        objs.append(o)
-        cmd = [NVCC, *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    log = []
-    for s, p in procs:
-        out, _ = p.communicate()
-        log.append("== %s\n%s" % (s, out))
-        if p.returncode != 0:
-            raise RuntimeError("nvcc failed on %s:\n%s" % (s, out))
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
-    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
-        f.write("\n".join(log))
-    if verbose:
-        print("\n".join(log))
+    import fcntl
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lk:       # several processes (pytest-xdist workers, torchrun ranks) may get here at once
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        objs = []
+        procs = []
+        for s in SOURCES:
+            o = os.path.join(LIBDIR, s.rsplit(".", 1)[0] + ".o")
+            objs.append(o)
+            cmd = [NVCC, *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        log = []
+        for s, p in procs:
+            out, _ = p.communicate()
+            log.append("== %s\n%s" % (s, out))
+            if p.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s" % (s, out))
+        subprocess.check_call([NVCC, "-shared", "-o", LIB + ".tmp", *objs, "-lcudart"])
+        os.replace(LIB + ".tmp", LIB)
+        with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+            f.write("\n".join(log))
+        if verbose:
+            print("\n".join(log))
     return LIB
 
 

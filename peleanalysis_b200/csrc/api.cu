@@ -1528,10 +1528,12 @@ int pa_fill_patch(pa_field* f, int comp, int ncomp, int lev, int nghost, int int
     if (!lay) return err;
     double* base = f->slab[lev] + (long long)comp * f->cs[lev];
     const Level& V = H.lev[lev];
-    // 1. same-level valid data into every ghost cell another box of the level covers (all layers, edges and corners)
+    // 1. same-level valid data into every ghost cell another box of the level covers (`nghost` layers, edges and corners).
+    //    The tags are in index space and the layout is passed separately, so the table of the level's own width serves a
+    //    field that carries more layers (the widest level decides the field's ghost width).
     {
-        auto key = std::make_pair(lev, f->ng);
-        const HaloTable& T = H.halo_full(lev, f->ng);
+        auto key = std::make_pair(lev, nghost);
+        const HaloTable& T = H.halo_full(lev, nghost);
         auto it = h->halo_full.find(key);
         if (it == h->halo_full.end()) {
             auto buf = std::make_unique<DevBuf<PaHaloTag>>();

@@ -27,15 +27,21 @@ def build(force: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(OUT, exist_ok=True)
-    procs = []
-    for s in SOURCES:
-        o = os.path.join(OUT, os.path.basename(s).rsplit(".", 1)[0] + ".o")
-        procs.append((s, o, subprocess.Popen(["g++", *FLAGS, "-x", "c++", "-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for s, o, p in procs:
-        out, _ = p.communicate()
-        if p.returncode != 0:
-            raise RuntimeError("g++ failed on %s:\n%s" % (s, out))
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + [o for _, o, _ in procs])
+    import fcntl
+    with open(os.path.join(OUT, ".build.lock"), "w") as lk:          # pytest-xdist workers share this directory: one build at a time
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if not force and not needs_build():                          # another worker built it while this one waited
+            return LIB
+        procs = []
+        for s in SOURCES:
+            o = os.path.join(OUT, os.path.basename(s).rsplit(".", 1)[0] + ".o")
+            procs.append((s, o, subprocess.Popen(["g++", *FLAGS, "-x", "c++", "-c", s, "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for s, o, p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError("g++ failed on %s:\n%s" % (s, out))
+        subprocess.check_call(["g++", "-shared", "-o", LIB + ".tmp"] + [o for _, o, _ in procs])
+        os.replace(LIB + ".tmp", LIB)                                # a process that already mapped the old file keeps its copy
     return LIB
 
 
