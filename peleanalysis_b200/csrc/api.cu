@@ -1540,8 +1540,10 @@ int pa_fill_patch(pa_field* f, int comp, int ncomp, int lev, int nghost, int int
             CU(buf->upload(T.tags, t_stream));
             it = h->halo_full.emplace(key, std::move(buf)).first;
         }
-        CU(launch_halo(it->second->p, 0, (int)T.tags.size(), 0, T.ncells, h->lev[lev]->boxes.p, lay, base, f->cs[lev], ncomp, nullptr,
-                       nullptr, comp, H.rank, GhostXform{0, 0.0, 1.0}, t_stream));
+        // slices per tag: enough blocks for the device when the level has few, large tags (128^3 boxes: 65 k cells per face tag)
+        const long long per_tag = T.tags.empty() ? 0 : T.ncells / (long long)T.tags.size();
+        const int slices = (int)std::min<long long>(16, std::max<long long>(1, per_tag / 2048));
+        CU(launch_halo_blocks(it->second->p, (int)T.tags.size(), slices, h->lev[lev]->boxes.p, lay, base, f->cs[lev], ncomp, t_stream));
     }
     // 2. the rest of the in-domain ghost cells from the next coarser level, 3. the out-of-domain ones by extrapolation
     const int cgrow = interp_type == 1 ? 1 : 0;

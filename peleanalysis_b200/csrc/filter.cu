@@ -65,6 +65,38 @@ __global__ void k_fp_gather(const PaFpCopy* __restrict__ copies, int ncopies, lo
     }
 }
 
+// Same-level copies of the fill, one thread block per (tag, slice): the tag and the two boxes' records are read once per block
+// instead of being searched for and reloaded by every cell's thread (k_halo's general form costs a 14-step binary search over
+// ~13 k tags per ghost cell on 512 boxes with 4 ghost layers: 0.31 ms for 16 M cells).  Local sources only, no value transform:
+// what the filterPlt path needs.  Cells of a tag are walked row by row (x fastest), so loads and stores of a row are contiguous.
+__global__ void __launch_bounds__(128) k_halo_blk(const PaHaloTag* __restrict__ tags, const PaBoxDev* __restrict__ boxes,
+                                                  const PaLayDev* __restrict__ lay, double* __restrict__ base, long long cs, int ncomp) {
+    const PaHaloTag t = tags[blockIdx.x];
+    if (t.sbox < 0) return;                                           // never on a single-rank hierarchy
+    const PaBoxDev db = boxes[t.dbox], sb = boxes[t.sbox];
+    const PaLayDev dl = lay[t.dbox], sl = lay[t.sbox];
+    const int nrows = t.n[1] * t.n[2];
+    const long long d0 = lay_addr(dl, t.dlo[0] - db.lo[0], t.dlo[1] - db.lo[1], t.dlo[2] - db.lo[2]);
+    const long long s0 = lay_addr(sl, t.dlo[0] + t.shift[0] - sb.lo[0], t.dlo[1] + t.shift[1] - sb.lo[1], t.dlo[2] + t.shift[2] - sb.lo[2]);
+    if (t.n[0] >= 16) {                                               // long rows: a warp per row, lanes along x
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int r = blockIdx.y * nw + warp; r < nrows; r += gridDim.y * nw) {
+            const int j = r % t.n[1], k = r / t.n[1];
+            const long long da = d0 + (long long)k * dl.PS + (long long)j * dl.P, sa = s0 + (long long)k * sl.PS + (long long)j * sl.P;
+            for (int m = 0; m < ncomp; ++m)
+                for (int i = lane; i < t.n[0]; i += 32) base[da + i + m * cs] = base[sa + i + m * cs];
+        }
+    } else {                                                          // thin tags (x faces, edges, corners): a thread per cell
+        const int ncell = nrows * t.n[0];
+        for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < ncell; c += gridDim.y * blockDim.x) {
+            const int i = c % t.n[0], r = c / t.n[0];
+            const int j = r % t.n[1], k = r / t.n[1];
+            const long long da = d0 + (long long)k * dl.PS + (long long)j * dl.P + i, sa = s0 + (long long)k * sl.PS + (long long)j * sl.P + i;
+            for (int m = 0; m < ncomp; ++m) base[da + m * cs] = base[sa + m * cs];
+        }
+    }
+}
+
 struct Dom { int lo[3], hi[3]; };
 
 // the reference's monotonised-central slope of one direction (AMReX_MFInterp_3D_C.H:190-196); amrex::min is std::min
@@ -287,6 +319,18 @@ __global__ void k_fp64_rate(double* __restrict__ out, int iters, double seed) {
 cudaError_t launch_fp64_rate(double* out, int blocks, int threads, int iters, cudaStream_t st) {
     PA_LAUNCH(blocks, threads, 0, st, k_fp64_rate)(out, iters, 0.5);
     ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_blocks(const PaHaloTag* tags, int ntags, int slices, const PaBoxDev* boxes, const PaLayDev* lay, double* base,
+                               long long cs, int ncomp, cudaStream_t st) {
+    if (ntags <= 0) return cudaSuccess;
+    for (int t0 = 0; t0 < ntags; t0 += 65535 * 32) {                   // grid.x limit is 2^31-1; keep launches modest anyway
+        const int n = std::min(ntags - t0, 65535 * 32);
+        dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(slices, 64)));
+        PA_LAUNCH(grid, 128, 0, st, k_halo_blk)(tags + t0, boxes, lay, base, cs, ncomp);
+        ++g_launches;
+    }
     return cudaGetLastError();
 }
 

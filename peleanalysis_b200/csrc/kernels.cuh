@@ -144,6 +144,9 @@ cudaError_t launch_velnormal(const PaBoxDev* boxes, const PaLayDev* lay_u, const
 // ---- filterPlt path (filter.cu) ----------------------------------------------------------------------------------------
 // coarse valid cells -> coarse patches (scratch, component stride ncrse); pieces <- coarse patches (conservative linear with
 // the mcslope limiter, or piecewise constant); ghost cells outside the domain <- clamped index; the filter itself
+// same-level ghost copies, one thread block per (tag, slice of its rows / cells); local sources only (filterPlt path)
+cudaError_t launch_halo_blocks(const PaHaloTag* tags, int ntags, int slices, const PaBoxDev* boxes, const PaLayDev* lay, double* base,
+                               long long cs, int ncomp, cudaStream_t st);
 cudaError_t launch_fp_gather(const PaFpCopy* copies, int ncopies, long long ncells, const PaFpPiece* pieces, const PaBoxDev* cboxes,
                              const PaLayDev* clay, const double* cbase, long long ccs, int ncomp, double* scratch, long long ncrse,
                              cudaStream_t st);

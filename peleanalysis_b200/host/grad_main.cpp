@@ -65,7 +65,11 @@ int main(int argc, char** argv) {
         return 0;
     }
     auto t0 = std::chrono::steady_clock::now();
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    double t_init = 0, t_pin = 0, t_read = 0;
     check(pa_init(0), "pa_init");
+    t_init = secs(t0, tnow());
     HierInput hi;
     make_level_descs(H, Nlev, hi);
     int bck[3];
@@ -82,12 +86,15 @@ int main(int argc, char** argv) {
     std::vector<PinnedLevel> buf(Nlev);
     for (int l = 0; l < Nlev; ++l) {
         std::cout << "Reading data for level: " << l << std::endl;
+        auto ta = tnow();
         buf[l].alloc(H.levels[l].ncells(), nOut);
+        auto tb = tnow();
         for (int v = 0; v < nv; ++v) {
             pltio::read_level_comp(infile, H, l, H.comp(gvars[v]), buf[l].comp(v));
             check(pa_field_upload_level(fin, l, v, buf[l].comp(v)), "upload");
         }
         for (int a = 0; a < nAux; ++a) pltio::read_level_comp(infile, H, l, H.comp(aux[a]), buf[l].comp(nv + a));
+        t_pin += secs(ta, tb); t_read += secs(tb, tnow());
     }
     auto t1 = std::chrono::steady_clock::now();
     check(pa_grad(fin, 0, nv, fout, 0), "pa_grad");
@@ -109,9 +116,12 @@ int main(int argc, char** argv) {
     pltio::Header meta = H;
     meta.time = 0.0;                                           // WriteMultiLevelPlotfile(..., 0.0, ...) (grad.cpp:256)
     try { pltio::write_plotfile(outfile, meta, names, data, rr); } catch (std::exception& e) { pa_abort(e.what()); }
+    auto t3 = tnow();
     if (verbose) {
         auto s = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         std::cout << "[b200] read+upload " << s(t0, t1) << " s, hot path+download " << s(t1, t2) << " s, kernels " << pa_kernel_launches() << "\n";
+        std::cout << "[b200] phases: cuda init " << t_init << " s, pinned alloc " << t_pin << " s, file read + upload " << t_read
+                  << " s, hierarchy + fields " << s(t0, t1) - t_init - t_pin - t_read << " s, plotfile write " << s(t2, t3) << " s\n";
     }
     pa_field_free(fin); pa_field_free(fout); pa_hier_destroy(h);
     return 0;

@@ -5,11 +5,13 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <limits>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 namespace pltio {
 
@@ -320,12 +322,44 @@ void write_plotfile(const std::string& dir, const Header& meta, const std::vecto
                     const std::vector<std::vector<const double*>>& data, const std::vector<int>& ref_ratio_line) {
     const int nlev = (int)data.size();
     create_plotfile_dirs(dir, nlev);
-    std::vector<FabRecord> records;
+    // Every level has its own Cell_D file and the write is a CPU-bound copy plus a min / max scan: one thread per box range
+    // (up to four files per level, the layout VisMF produces with several writers), all levels at once.  Measured on the
+    // B200 box: 0.8-0.9 s for the 2 GB of a 50 M-cell grad output from one thread.
+    struct Job { int lev; std::string file; std::vector<int> boxes; std::vector<FabRecord> recs; std::string err; };
+    std::vector<Job> jobs;
     for (int l = 0; l < nlev; ++l) {
-        std::vector<int> all(meta.levels[l].boxes.size());
-        for (size_t b = 0; b < all.size(); ++b) all[b] = (int)b;
-        auto r = write_fab_file(dir, meta, l, "Cell_D_00000", all, data[l]);
-        records.insert(records.end(), r.begin(), r.end());
+        const int nb = (int)meta.levels[l].boxes.size();
+        const long long cells = meta.levels[l].ncells();
+        int nfiles = std::max(1, std::min(std::min(4, nb), (int)(cells * (long long)data[l].size() / (32LL << 20)) + 1));
+        if (const char* e = std::getenv("PA_PLT_NFILES")) nfiles = std::max(1, std::min(nb, std::atoi(e)));   // tests: force the multi-file layout
+        for (int f = 0; f < nfiles; ++f) {
+            Job j;
+            j.lev = l;
+            char nm[32];
+            std::snprintf(nm, sizeof nm, "Cell_D_%05d", f);
+            j.file = nm;
+            for (int b = (int)((long long)nb * f / nfiles); b < (int)((long long)nb * (f + 1) / nfiles); ++b) j.boxes.push_back(b);
+            jobs.push_back(std::move(j));
+        }
+    }
+    // data[l][c] is the level's boxes concatenated in box order: a job's boxes start at the prefix of the boxes before them
+    std::vector<std::thread> th;
+    for (Job& j : jobs)
+        th.emplace_back([&dir, &meta, &data, &j]() {
+            try {
+                long long cell0 = 0;
+                for (int b = 0; b < j.boxes.front(); ++b) cell0 += meta.levels[j.lev].boxes[b].npts();
+                std::vector<const double*> shifted;
+                // write_fab_file indexes data[c] from the first box it is given
+                for (const double* p : data[j.lev]) shifted.push_back(p + cell0);
+                j.recs = write_fab_file(dir, meta, j.lev, j.file, j.boxes, shifted);
+            } catch (std::exception& e) { j.err = e.what(); }
+        });
+    for (auto& t : th) t.join();
+    std::vector<FabRecord> records;
+    for (Job& j : jobs) {
+        if (!j.err.empty()) throw std::runtime_error(j.err);
+        records.insert(records.end(), j.recs.begin(), j.recs.end());
     }
     write_metadata(dir, meta, names, nlev, records, ref_ratio_line);
 }

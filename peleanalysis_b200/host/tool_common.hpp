@@ -50,17 +50,30 @@ inline void make_level_descs(const pltio::Header& h, int nlev, HierInput& out) {
     }
 }
 
-// pinned host buffer holding [comp][level cells]
+// host buffer holding [comp][level cells].  Pageable by default: measured on the B200 box (profiles/r02_tool_walltime.txt),
+// cudaHostAlloc of the tools' buffers costs 0.4 s per GB and as much again to release at exit -- more than the pinned DMA saves on
+// data that crosses PCIe once (2 GB pinned for a 50 M-cell grad run: 0.9 s to pin, against 0.2 s of slower copies).  PA_TOOL_PIN=1
+// pins them (worth it when the same buffers are reused many times).
 struct PinnedLevel {
     double* p = nullptr;
     long long ncells = 0;
     int ncomp = 0;
+    bool pinned = false;
     void alloc(long long cells, int comps) {
         ncells = cells; ncomp = comps;
-        void* q = nullptr;
-        check(pa_host_alloc(&q, (size_t)cells * comps * 8), "pa_host_alloc");
-        p = (double*)q;
+        const char* e = std::getenv("PA_TOOL_PIN");
+        pinned = e && e[0] == '1';
+        const size_t bytes = (size_t)cells * comps * 8;
+        if (pinned) {
+            void* q = nullptr;
+            check(pa_host_alloc(&q, bytes), "pa_host_alloc");
+            p = (double*)q;
+        } else {
+            void* q = nullptr;
+            if (posix_memalign(&q, 4096, bytes ? bytes : 8) != 0) pa_abort("out of host memory");
+            p = (double*)q;
+        }
     }
     double* comp(int c) { return p + (long long)c * ncells; }
-    ~PinnedLevel() { if (p) pa_host_free(p); }
+    ~PinnedLevel() { if (p) { if (pinned) pa_host_free(p); else std::free(p); } }
 };

@@ -47,6 +47,10 @@ def test_emulated_grad_executable(emu_exes, tmp_path, name):
     T.test_grad_executable(emu_exes, tmp_path, name)
 
 
+def test_emulated_grad_executable_several_files_per_level(emu_exes, tmp_path, monkeypatch):
+    T.test_grad_executable_several_files_per_level(emu_exes, tmp_path, monkeypatch)
+
+
 def test_emulated_grad_executable_aux_and_inputs_file(emu_exes, tmp_path):
     T.test_grad_executable_aux_and_inputs_file(emu_exes, tmp_path)
 

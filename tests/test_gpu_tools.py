@@ -255,3 +255,12 @@ def test_filter_executable_errors(exes, tmp_path):
     assert p.returncode != 0 and "Variable 'nope' not found in file" in p.stderr
     p = subprocess.run([exes[2], "infile=" + d, "base_fgr=3"], capture_output=True, text=True, cwd=str(tmp_path))
     assert p.returncode != 0 and "even" in p.stderr
+
+
+def test_grad_executable_several_files_per_level(exes, tmp_path, monkeypatch):
+    """the writer's multi-file layout (one writer thread per box range, as VisMF with several writers): forced here, chosen
+    automatically for large levels; AMReX's own reader (fcompare) must accept it"""
+    monkeypatch.setenv("PA_PLT_NFILES", "3")
+    test_grad_executable(exes, tmp_path, "c3_three_levels")
+    files = sorted(os.listdir(str(tmp_path / "plt_gt" / "Level_0")))
+    assert [f for f in files if f.startswith("Cell_D_")] == ["Cell_D_00000", "Cell_D_00001", "Cell_D_00002"]
