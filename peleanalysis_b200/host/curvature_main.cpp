@@ -149,9 +149,15 @@ int main(int argc, char** argv) {
         }
     }
     check(pa_curvature(st, 0, 1, &o, res, 0), "pa_curvature");
-    for (int l = 0; l < Nlev; ++l) {
-        for (int z : zero_slots) std::fill(buf[l].comp(z), buf[l].comp(z) + buf[l].ncells, 0.0);
-        for (int c = 0; c < nres; ++c) check(pa_field_download_level(res, l, c, buf[l].comp(slot[c])), "download");
+    {
+        long long mx = 0;
+        for (int l = 0; l < Nlev; ++l) mx = std::max(mx, buf[l].ncells);
+        StagedDownloader dl(mx);
+        for (int l = 0; l < Nlev; ++l) {
+            for (int z : zero_slots) std::fill(buf[l].comp(z), buf[l].comp(z) + buf[l].ncells, 0.0);
+            for (int c = 0; c < nres; ++c) dl.download(res, l, c, buf[l].comp(slot[c]), buf[l].ncells);
+        }
+        dl.flush();
     }
     check(pa_sync(), "pa_sync");
 

@@ -140,8 +140,14 @@ int main(int argc, char** argv) {
         std::cout << "on level " << l << std::endl;
         check(pa_filter(fin, 0, fout, 0, ncomp, l, filter_type, fgr[l]), "pa_filter");
     }
-    for (int l = 0; l < Nlev; ++l)
-        for (int c = 0; c < ncomp; ++c) check(pa_field_download_level(fout, l, c, buf[l].comp(c)), "download");
+    {
+        long long mx = 0;
+        for (int l = 0; l < Nlev; ++l) mx = std::max(mx, buf[l].ncells);
+        StagedDownloader dl(mx);
+        for (int l = 0; l < Nlev; ++l)
+            for (int c = 0; c < ncomp; ++c) dl.download(fout, l, c, buf[l].comp(c), buf[l].ncells);
+        dl.flush();
+    }
     check(pa_sync(), "pa_sync");
     std::cout << "Done!" << std::endl;
     auto t2 = std::chrono::steady_clock::now();

@@ -98,8 +98,14 @@ int main(int argc, char** argv) {
     }
     auto t1 = std::chrono::steady_clock::now();
     check(pa_grad(fin, 0, nv, fout, 0), "pa_grad");
-    for (int l = 0; l < Nlev; ++l)
-        for (int c = 0; c < 4 * nv; ++c) check(pa_field_download_level(fout, l, c, buf[l].comp(nIn + c)), "download");
+    {
+        long long mx = 0;
+        for (int l = 0; l < Nlev; ++l) mx = std::max(mx, H.levels[l].ncells());
+        StagedDownloader dl(mx);
+        for (int l = 0; l < Nlev; ++l)
+            for (int c = 0; c < 4 * nv; ++c) dl.download(fout, l, c, buf[l].comp(nIn + c), H.levels[l].ncells());
+        dl.flush();
+    }
     check(pa_sync(), "pa_sync");
     auto t2 = std::chrono::steady_clock::now();
 

@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -76,4 +78,41 @@ struct PinnedLevel {
     }
     double* comp(int c) { return p + (long long)c * ncells; }
     ~PinnedLevel() { if (p) { if (pinned) pa_host_free(p); else std::free(p); } }
+};
+
+// Device -> pageable host memory through a pair of pinned bounce buffers: the DMA runs at full PCIe speed into pinned memory and
+// the host-side copy of one (level, component) overlaps the transfer of the next.  Measured on the B200 box: a direct download
+// into pageable memory ran at 2.2 GB/s (1.6 GB in 0.74 s, profiles/r02_tool_walltime.txt); pinning the whole output instead
+// costs 0.4 s per GB to pin and as much to release.  The two buffers hold one component of the largest level each.
+class StagedDownloader {
+public:
+    explicit StagedDownloader(long long max_cells) : cap_(max_cells) {
+        for (int i = 0; i < 2; ++i) {
+            void* q = nullptr;
+            check(pa_host_alloc(&q, (size_t)std::max<long long>(cap_, 1) * 8), "pa_host_alloc");
+            b_[i] = (double*)q;
+        }
+    }
+    ~StagedDownloader() { flush(); for (int i = 0; i < 2; ++i) if (b_[i]) pa_host_free(b_[i]); }
+    StagedDownloader(const StagedDownloader&) = delete;
+    StagedDownloader& operator=(const StagedDownloader&) = delete;
+    // queue: component `comp` of level `lev` of `f` -> dst (ncells doubles, pageable or pinned)
+    void download(const pa_field* f, int lev, int comp, double* dst, long long ncells) {
+        if (ncells > cap_) pa_abort("StagedDownloader: level larger than the bounce buffer");
+        const int cur = n_ & 1;
+        check(pa_field_download_level(f, lev, comp, b_[cur]), "download");      // asynchronous on the library stream
+        if (pend_dst_) copy_out();                                              // host copy of the previous one overlaps this DMA
+        check(pa_sync(), "pa_sync");
+        pend_dst_ = dst; pend_src_ = b_[cur]; pend_n_ = ncells;
+        ++n_;
+    }
+    void flush() { if (pend_dst_) copy_out(); }
+private:
+    void copy_out() { std::memcpy(pend_dst_, pend_src_, (size_t)pend_n_ * 8); pend_dst_ = nullptr; }
+    long long cap_;
+    double* b_[2] = {nullptr, nullptr};
+    double* pend_dst_ = nullptr;
+    const double* pend_src_ = nullptr;
+    long long pend_n_ = 0;
+    int n_ = 0;
 };

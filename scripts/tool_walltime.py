@@ -9,6 +9,7 @@ from oracle import oracle as O
 from peleanalysis_b200 import plotfile, synth
 
 base = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else ["grad", "curvature", "filterPlt"]
 HOST = os.path.join(ROOT, "peleanalysis_b200", "host")
 subprocess.check_call(["make", "-s", "-C", HOST])
 tmp = tempfile.mkdtemp(prefix="pa_wall_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
@@ -35,6 +36,8 @@ try:
             ("grad", "grad3d.ref.ex", "grad3d.b200.ex", ["gradVar=temp"]),
             ("curvature", "curvature3d.ref.ex", "curvature3d.b200.ex", ["progressName=temp"]),
             ("filterPlt", "filterPlt3d.ref.ex", "filterPlt3d.b200.ex", ["variables=temp", "max_filter_level=1"])):
+        if tool not in only:
+            continue
         rec = {"tool": tool, "cells": cells if tool != "filterPlt" else cells * 2 // 3, "args": args, "host_cores": os.cpu_count()}
         for who, exe in (("reference_s", O.ref_exe(ref)), ("b200_s", os.path.join(HOST, mine)), ("b200_second_run_s", os.path.join(HOST, mine))):
             wd = os.path.join(tmp, who + "_" + tool)
