@@ -95,6 +95,9 @@ struct pa_hier {
     // the same boxes cut into shallower work items (half / a quarter of the planes per item): picked at launch when the deepest
     // table would leave the persistent grid with only a handful of items per CTA (strong scaling: few boxes per rank)
     TileTable tiles_tma_fine[2];
+    // ... and into deeper ones (four times the planes per item) for the flame-normal / divergence modes, which lose time at the
+    // first plane of every item (the ring drains there) and gain 1.5-2 % from fewer, longer items where enough items remain
+    TileTable tiles_tma_deep;
     // fused curvature (curv_fused.cu): K-block work items of every level (class 0 only) and the (level, box) list of the
     // shell pass; curv_ok = every local box is eligible (>= 3 cells in every direction, <= 128 wide, plane fits)
     TileTable tiles_curv;
@@ -150,7 +153,7 @@ const PaLayDev* dev_layout(pa_hier* h, int l, int ng, int* err) {
     return p;
 }
 
-void build_tiles(pa_hier* h, TileTable& T, bool tma, int zdiv = 1) {
+void build_tiles(pa_hier* h, TileTable& T, bool tma, int zdiv = 1, int zmul = 1) {
     Hier& H = h->H;
     T.h.clear();
     T.max_plane_doubles = 0;
@@ -161,7 +164,7 @@ void build_tiles(pa_hier* h, TileTable& T, bool tma, int zdiv = 1) {
     const char* ety = getenv("PA_TMA_TY");
     const char* ezc = getenv("PA_TMA_ZC");
     const int TY0 = ety ? std::min(std::max(1, atoi(ety)), stencil_tma_max_tile_rows()) : stencil_tma_tile_rows();
-    const int ZC0 = std::max(4, (ezc ? std::max(1, atoi(ezc)) : 32) / zdiv);
+    const int ZC0 = std::max(4, (ezc ? std::max(1, atoi(ezc)) : 32) * zmul / zdiv);
     for (int c = 0; c < (tma ? N_TILE_CLASSES : 1); ++c)
         for (int l = 0; l < H.nlev; ++l) {
             T.begin[c][l] = (long long)T.h.size();
@@ -296,6 +299,8 @@ int ensure_device(pa_hier* h) {
         build_tiles(h, h->tiles_tma_fine[k], true, 2 << k);
         CU(h->tiles_tma_fine[k].d.upload(h->tiles_tma_fine[k].h, t_stream));
     }
+    build_tiles(h, h->tiles_tma_deep, true, 1, 4);
+    CU(h->tiles_tma_deep.d.upload(h->tiles_tma_deep.h, t_stream));
     {
         std::vector<int> sl, sb;
         build_curv_tiles(h, sl, sb);
@@ -403,6 +408,14 @@ int run_stencil(pa_hier* h, int mode, const GridArgs& ga, const StencilExtra& ex
                 while (pick < 2 && items(pick == 0 ? h->tiles_tma : h->tiles_tma_fine[pick - 1]) < want * slots) ++pick;
             }
             if (pick > 0 && h->tiles_tma_fine[pick - 1].ok) Tp = &h->tiles_tma_fine[pick - 1];
+            // measured (profiles/r02_ab_zc_curvature.txt): 128 instead of 32 planes per item, curvature on the north-star
+            // hierarchy 6.66 -> 6.53 ms; on 64^3 boxes (5 items per slot left) 1.024 -> 1.034 ms, hence the item-count condition
+            const bool heavy = mode == MODE_NORMAL || mode == MODE_NORMAL_S || mode == MODE_DIV;
+            if (!ez && pick == 0 && heavy && h->tiles_tma_deep.ok) {
+                long long n = 0;
+                for (int c = 0; c < N_TILE_CLASSES; ++c) n += h->tiles_tma_deep.begin[c][l1 + 1] - h->tiles_tma_deep.begin[c][l0];
+                if (n * nvar >= 8 * slots) Tp = &h->tiles_tma_deep;
+            }
         }
         TileTable& T = *Tp;
         for (int c = 0; c < N_TILE_CLASSES; ++c) {
