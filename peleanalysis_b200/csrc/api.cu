@@ -101,6 +101,8 @@ struct pa_hier {
     // fused curvature (curv_fused.cu): K-block work items of every level (class 0 only) and the (level, box) list of the
     // shell pass; curv_ok = every local box is eligible (>= 3 cells in every direction, <= 128 wide, plane fits)
     TileTable tiles_curv;
+    TileTable tiles_f2;                         // work items of the second fused kernel (curv_f2.cu); f2_ok = every box eligible
+    bool f2_ok = false;
     bool curv_ok = false;
     DevBuf<int> shell_level, shell_box;
     long long shell_begin[PA_MAX_LEVELS + 1] = {0};
@@ -257,6 +259,37 @@ void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int
     }
     if (T.max_plane_doubles > curv_fused_max_plane_doubles()) T.ok = false;
     h->curv_ok = T.ok;
+    {   // second fused kernel: same K-row / K-plane items with its own row count; boxes need an even width
+        TileTable& F = h->tiles_f2;
+        F.h.clear();
+        F.ok = true;
+        std::memset(F.begin, 0, sizeof(F.begin));
+        const char* ez2 = getenv("PA_CF2_ZC");
+        const int ZC2 = ez2 ? std::max(1, atoi(ez2)) : 63;
+        const int ty2 = curv_f2_rows();
+        for (int l = 0; l < H.nlev; ++l) {
+            F.begin[0][l] = (long long)F.h.size();
+            const Level& V = H.lev[l];
+            for (size_t lb = 0; lb < V.local.size(); ++lb) {
+                const Box& B = V.boxes[V.local[lb]];
+                const int nx = B.len(0), ny = B.len(1), nz = B.len(2);
+                if (nx < 4 || (nx & 1) || nx > curv_f2_max_nx() || ny < 3 || nz < 3) { F.ok = false; continue; }
+                const int nky = ny - 2, nkz = nz - 2;
+                const int nty = (nky + ty2 - 1) / ty2, ty = (nky + nty - 1) / nty;
+                const int nzc = (nkz + ZC2 - 1) / ZC2, zc = (nkz + nzc - 1) / nzc;
+                for (int z0 = 1; z0 < nz - 1; z0 += zc)
+                    for (int y0 = 1; y0 < ny - 1; y0 += ty) {
+                        PaTile t;
+                        t.lev = l; t.box = (int)lb;
+                        t.y0 = y0; t.ny = std::min(ty, ny - 1 - y0);
+                        t.z0 = z0; t.nz = std::min(zc, nz - 1 - z0);
+                        F.h.push_back(t);
+                    }
+            }
+            F.begin[0][l + 1] = (long long)F.h.size();
+        }
+        h->f2_ok = F.ok && !F.h.empty();
+    }
 }
 
 int ensure_device(pa_hier* h) {
@@ -304,6 +337,7 @@ int ensure_device(pa_hier* h) {
     {
         std::vector<int> sl, sb;
         build_curv_tiles(h, sl, sb);
+        if (h->f2_ok) CU(h->tiles_f2.d.upload(h->tiles_f2.h, t_stream));
         if (h->curv_ok) {
             CU(h->tiles_curv.d.upload(h->tiles_curv.h, t_stream));
             CU(h->shell_level.upload(sl, t_stream));
@@ -1063,13 +1097,18 @@ struct CurvCtx {
 // It is OPT-IN (PA_CURV_FUSED=1): measured on a B200 it moves a third less data than the separate NORMAL_S / DIV kernels
 // (21.7 GB against 32.5 GB per step on the target hierarchy) but is bound by FP64 latency and per-SM store drain, not by HBM,
 // and ends up slower (7.1 ms against 6.5 ms; DESIGN.md section 6 has the ablation).  The separate kernels are the default.
-bool curv_fused_path(const CurvCtx& c) {
+// PA_CURV_FUSED=2 selects the second fused kernel (curv_f2.cu: one CTA per item, planes in shared memory) where every box is
+// eligible for it (even width); the shell pass and the ghost fills are the same.  Returns 0 (separate kernels), 1 or 2.
+int curv_fused_mode(const CurvCtx& c) {
     const char* e = getenv("PA_CURV_FUSED");
     const char* no_fuse = getenv("PA_CURV_UNFUSED");
     const char* es = getenv("PA_STENCIL");
-    if (!(e && e[0] == '1') || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return false;
-    return c.state->ng == 1 && c.h->curv_ok && !overlap_enabled(c.h);
+    if (!(e && (e[0] == '1' || e[0] == '2')) || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return 0;
+    if (!(c.state->ng == 1 && c.h->curv_ok && !overlap_enabled(c.h))) return 0;
+    if (e[0] == '2') return (c.h->f2_ok && stencil_decide_normal_math(t_stream) == 0) ? 2 : 0;
+    return 1;
 }
+bool curv_fused_path(const CurvCtx& c) { return curv_fused_mode(c) != 0; }
 
 // PASS1: progress variable (curvature.cpp:310-321), its ghost cells, G = grad c, nrm, n = G / nrm (:426-502)
 int curv_pass1(const CurvCtx& c) {
@@ -1100,6 +1139,13 @@ int curv_pass1(const CurvCtx& c) {
         if (c.state->peers_missing > 0)
             return fail(PA_ERR_STATE, "this hierarchy uses peer links (PA_HIER_PEER_LINKS): map every rank's slab of the state field first");
         CHK(fill_ghosts_impl(c.state, c.comp_S, 1, 0, nlev - 1, false, xf));
+        if (curv_fused_mode(c) == 2) {
+            TileTable& T = h->tiles_f2;
+            const long long a = T.begin[0][0], b = T.begin[0][nlev];
+            CU(launch_curv_f2(T.d.p + a, (int)(b - a), ga, ex, t_stream));
+            ++g_fused_launches;
+            return PA_OK;
+        }
         TileTable& T = h->tiles_curv;
         const long long a = T.begin[0][0], b = T.begin[0][nlev];
         CU(launch_curv_fused(T.d.p + a, (int)(b - a), T.max_plane_doubles, ga, ex, stencil_decide_normal_math(t_stream) != 0, t_stream));

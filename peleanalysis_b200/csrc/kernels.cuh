@@ -110,6 +110,11 @@ cudaError_t launch_curv_fused(const PaTile* tiles, int ntiles, int max_plane_dou
 int curv_fused_consumer_warps();
 int curv_fused_max_rows();           // staged rows per item (K rows + 4)
 int curv_fused_max_plane_doubles();
+// Second fused curvature kernel (curv_f2.cu, PA_CURV_FUSED=2): one CTA per item, progress / normal planes in shared memory.
+// tiles: K rows (at most curv_f2_rows()) x K planes of boxes with an even width <= curv_f2_max_nx(), >= 3 cells in y and z.
+cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st);
+int curv_f2_rows();
+int curv_f2_max_nx();
 // K on the outermost cell layer of the boxes (the cells the fused kernel leaves out), from the ghost-filled flame normal:
 // MODE_DIV's arithmetic, one thread per cell.  GridArgs: in = n (3 comps), out = K.
 cudaError_t launch_div_shell(const int* box_level, const int* box_index, int nboxes, int blocks_per_box, const GridArgs& ga,

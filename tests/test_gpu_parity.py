@@ -27,7 +27,7 @@ def _set_stencil(stencil):
     eligible (PA_CURV_FUSED=1, opt-in); simple: the plain-load kernels."""
     os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
-    os.environ["PA_CURV_FUSED"] = "1" if stencil == "tma_fused" else "0"
+    os.environ["PA_CURV_FUSED"] = "1" if stencil == "tma_fused" else ("2" if stencil == "tma_fused2" else "0")
 
 
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
@@ -83,7 +83,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
