@@ -103,6 +103,7 @@ struct pa_hier {
     TileTable tiles_curv;
     TileTable tiles_f2;                         // work items of the second fused kernel (curv_f2.cu); f2_ok = every box eligible
     bool f2_ok = false;
+    int f2_lnxp = -1;                           // log2(width / 2) if every box has the same power-of-two width, else -1
     bool curv_ok = false;
     DevBuf<int> shell_level, shell_box;
     long long shell_begin[PA_MAX_LEVELS + 1] = {0};
@@ -289,6 +290,14 @@ void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int
             F.begin[0][l + 1] = (long long)F.h.size();
         }
         h->f2_ok = F.ok && !F.h.empty();
+        int w = -2;
+        for (int l = 0; l < H.nlev; ++l)
+            for (size_t lb = 0; lb < H.lev[l].local.size(); ++lb) {
+                const int nx = H.lev[l].boxes[H.lev[l].local[lb]].len(0);
+                w = (w == -2 || w == nx) ? nx : -1;
+            }
+        h->f2_lnxp = -1;
+        for (int k = 3; k <= 6; ++k) if (w == (2 << k)) h->f2_lnxp = k;
     }
 }
 
@@ -1142,7 +1151,7 @@ int curv_pass1(const CurvCtx& c) {
         if (curv_fused_mode(c) == 2) {
             TileTable& T = h->tiles_f2;
             const long long a = T.begin[0][0], b = T.begin[0][nlev];
-            CU(launch_curv_f2(T.d.p + a, (int)(b - a), ga, ex, t_stream));
+            CU(launch_curv_f2(T.d.p + a, (int)(b - a), h->f2_lnxp, ga, ex, t_stream));
             ++g_fused_launches;
             return PA_OK;
         }

@@ -48,6 +48,10 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterp
 __device__ __forceinline__ double ldg1(const double* p) { return __ldg(p); }
 #endif
 
+// LNXP >= 0: every box of the launch is 2 << LNXP cells wide, so (row, pair) of a flattened index are a shift and a mask.  The
+// first version divided by the runtime pair count in every loop: ncu showed 4.0 G instructions with IMAD / ISETP / IABS / MUFU.RCP /
+// I2F at the top of the mix (integer division), FP64 pipe 27 %.  LNXP < 0 keeps the division (any even width).
+template <int LNXP>
 __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restrict__ tiles, GridArgs ga, StencilExtra ex) {
     PA_DYN_SMEM(smem_raw);
     double* const C = reinterpret_cast<double*>(smem_raw);       // [F2_RING][F2_SR][F2_PW] progress ring
@@ -61,7 +65,11 @@ __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restr
     const PaLayDev li = L.lay_in[t.box], lo = L.lay_out[t.box];
     const PaNbr nb = L.nbr[t.box];
     const int nx = bx.n[0], nyb = bx.n[1], nzb = bx.n[2];
-    const int nxp = nx >> 1;
+    const int nxp = LNXP >= 0 ? (1 << (LNXP >= 0 ? LNXP : 0)) : (nx >> 1);
+    auto split = [&](int p, int& r, int& q) {
+        if (LNXP >= 0) { r = p >> (LNXP >= 0 ? LNXP : 0); q = p & ((1 << (LNXP >= 0 ? LNXP : 0)) - 1); }
+        else { r = p / nxp; q = p - r * nxp; }
+    };
     const int KR = t.ny, NR = t.ny + 2, SR = t.ny + 4;
     const int nplanes = t.nz + 4;                                // scalar planes z0-2 .. z0+nz+1
     const int yS0 = t.y0 - 2, zS0 = t.z0 - 2;                    // first scalar row / plane (box-relative, >= -1)
@@ -109,7 +117,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restr
             const int p = tid + i * F2_THREADS;
             pre[i] = make_double2(0.0, 0.0);
             if (p < SR * nxp) {
-                const int rs = p / nxp, q = p - rs * nxp;
+                int rs, q;
+                split(p, rs, q);
                 bool raw;
                 const double* src = row_src(yS0 + rs, z, raw);
                 pre[i] = ldg2(src + 2 * q);
@@ -136,7 +145,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restr
         for (int i = 0; i < F2_LOADS; ++i) {
             const int p = tid + i * F2_THREADS;
             if (p < SR * nxp) {
-                const int rs = p / nxp, q = p - rs * nxp;
+                int rs, q;
+                split(p, rs, q);
                 double2 v = pre[i];
                 if (praw & (1u << i)) { v.x = (v.x - pmin) * pinv; v.y = (v.y - pmin) * pinv; }
                 *reinterpret_cast<double2*>(Cs + rs * F2_PW + 2 + 2 * q) = v;
@@ -181,7 +191,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restr
             const bool wplane = (zn >= wz0) & (zn <= wz1);
 #pragma unroll 2
             for (int p = tid; p < NR * nxp; p += F2_THREADS) {
-                const int rn = p / nxp, q = p - rn * nxp;
+                int rn, q;
+                split(p, rn, q);
                 const int o = (rn + 1) * F2_PW + 2 + 2 * q;
                 const double2 c = lds2(C1 + o);
                 const double xm = C1[o - 1], xp = C1[o + 2];
@@ -219,7 +230,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restr
             const int zk = zS0 + ps - 2;
 #pragma unroll 2
             for (int p = tid; p < KR * nxp; p += F2_THREADS) {
-                const int rk = p / nxp, q = p - rk * nxp;
+                int rk, q;
+                split(p, rk, q);
                 const int no = (rk + 1) * F2_NXMAX + 2 * q;
                 const double2 a = lds2(nxr + no);
                 const double am = nxr[no - 1], ap = nxr[no + 2];       // out of the row for the first / last pair: those cells are not stored
@@ -249,23 +261,34 @@ __global__ void __launch_bounds__(F2_THREADS, 1) k_curv_f2(const PaTile* __restr
 int curv_f2_rows() { return F2_KR; }
 int curv_f2_max_nx() { return F2_NXMAX; }
 
-cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st) {
+cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, int lnxp, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st) {
     if (ntiles <= 0) return cudaSuccess;
-    static std::map<int, bool> configured;
+    static std::map<std::pair<int, int>, bool> configured;
     static std::mutex mu;
     int dev = 0;
     { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(k_curv_f2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM);
-            if (e != cudaSuccess) return e;
-            configured[dev] = true;
+    auto go = [&](auto kern, int key) -> cudaError_t {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (!configured[std::make_pair(dev, key)]) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM);
+                if (e != cudaSuccess) return e;
+                configured[std::make_pair(dev, key)] = true;
+            }
         }
+        PA_LAUNCH(ntiles, F2_THREADS, F2_SMEM, st, kern)(tiles, ga, ex);
+        return cudaGetLastError();
+    };
+    cudaError_t e;
+    switch (lnxp) {
+    case 6: e = go(k_curv_f2<6>, 6); break;      // 128-wide boxes
+    case 5: e = go(k_curv_f2<5>, 5); break;      // 64
+    case 4: e = go(k_curv_f2<4>, 4); break;      // 32
+    case 3: e = go(k_curv_f2<3>, 3); break;      // 16
+    default: e = go(k_curv_f2<-1>, -1); break;
     }
-    PA_LAUNCH(ntiles, F2_THREADS, F2_SMEM, st, k_curv_f2)(tiles, ga, ex);
     ++g_launches;
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace pa

@@ -112,7 +112,8 @@ int curv_fused_max_rows();           // staged rows per item (K rows + 4)
 int curv_fused_max_plane_doubles();
 // Second fused curvature kernel (curv_f2.cu, PA_CURV_FUSED=2): one CTA per item, progress / normal planes in shared memory.
 // tiles: K rows (at most curv_f2_rows()) x K planes of boxes with an even width <= curv_f2_max_nx(), >= 3 cells in y and z.
-cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st);
+// lnxp: log2(width / 2) when every box of the launch has that (power-of-two) width, else -1
+cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, int lnxp, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st);
 int curv_f2_rows();
 int curv_f2_max_nx();
 // K on the outermost cell layer of the boxes (the cells the fused kernel leaves out), from the ghost-filled flame normal:

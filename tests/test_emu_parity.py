@@ -250,3 +250,8 @@ def test_emulated_recv_slab_has_one_owner(emu):
     P.check(L.pa_exchange_mark_received(a.f, 0, 1))       # marking a again takes the slab away from b
     with pytest.raises(P.PaError):
         b.fill_ghosts(0, 1)
+
+
+@pytest.mark.parametrize("base,mgs,walls", [(32, 16, False), (32, 16, True)])
+def test_emulated_fused2_power_of_two_widths(emu, base, mgs, walls):
+    G.test_fused2_power_of_two_widths_match_separate_kernels(emu, base, mgs, walls)

@@ -422,3 +422,19 @@ def test_field_hash_matches_its_definition(gpu):
     assert f.hash(1, 1) != f.hash(0, 1)
     f.fill_ghosts(0, 1)                                    # ghost cells change, the fingerprint does not
     assert f.hash(0, 2) == int(want)
+
+
+@pytest.mark.parametrize("base,mgs,walls", [(32, 16, False), (64, 32, True), (32, 16, True)])
+def test_fused2_power_of_two_widths_match_separate_kernels(gpu, base, mgs, walls):
+    """the second fused kernel's shift-based instantiations (all boxes 16 / 32 cells wide: row and pair of a flattened index
+    by shift and mask) against the separate kernels, bit for bit, threshold clip included; three levels, with and without walls"""
+    from peleanalysis_b200 import synth
+    pf = synth.config3(base, mgs)
+    per = (0, 0, 0) if walls else (1, 1, 1)
+    kw = dict(threshold_prog=1, threshold_value=0.02)
+    n0 = gpu.curv_fused_launches()
+    a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_fused2")
+    assert gpu.curv_fused_launches() > n0                      # the fused kernel ran (no silent fallback)
+    b, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma")
+    for c in range(a.shape[0]):
+        assert bit_equal(a[c], b[c]), c
