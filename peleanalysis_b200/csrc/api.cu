@@ -103,6 +103,8 @@ struct pa_hier {
     TileTable tiles_curv;
     TileTable tiles_f2;                         // work items of the second fused kernel (curv_f2.cu); f2_ok = every box eligible
     bool f2_ok = false;
+    TileTable tiles_f3;                         // work items of the third fused kernel (curv_f3.cu): K rows x K planes x an x strip
+    bool f3_ok = false;
     int f2_lnxp = -1;                           // log2(width / 2) if every box has the same power-of-two width, else -1
     bool curv_ok = false;
     DevBuf<int> shell_level, shell_box;
@@ -299,6 +301,42 @@ void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int
         h->f2_lnxp = -1;
         for (int k = 3; k <= 6; ++k) if (w == (2 << k)) h->f2_lnxp = k;
     }
+    {   // third fused kernel: the same K rows / K planes cut into x strips of at most curv_f3_strip_pairs() pairs as well; the
+        // strip (first pair, pairs) rides in the upper bits of PaTile::lev.  Strips of a row block are consecutive items.
+        TileTable& F = h->tiles_f3;
+        F.h.clear();
+        F.ok = true;
+        std::memset(F.begin, 0, sizeof(F.begin));
+        const char* ez3 = getenv("PA_CF3_ZC");
+        const int ZC3 = ez3 ? std::max(1, atoi(ez3)) : 63;
+        const int ty3 = curv_f3_rows(), kq3 = curv_f3_strip_pairs();
+        for (int l = 0; l < H.nlev; ++l) {
+            F.begin[0][l] = (long long)F.h.size();
+            const Level& V = H.lev[l];
+            for (size_t lb = 0; lb < V.local.size(); ++lb) {
+                const Box& B = V.boxes[V.local[lb]];
+                const int nx = B.len(0), ny = B.len(1), nz = B.len(2);
+                if (nx < 4 || (nx & 1) || nx > 256 || ny < 3 || nz < 3) { F.ok = false; continue; }
+                const int nxp = nx / 2;
+                const int nst = (nxp + kq3 - 1) / kq3, kq = (nxp + nst - 1) / nst;
+                const int nky = ny - 2, nkz = nz - 2;
+                const int nty = (nky + ty3 - 1) / ty3, ty = (nky + nty - 1) / nty;
+                const int nzc = (nkz + ZC3 - 1) / ZC3, zc = (nkz + nzc - 1) / nzc;
+                for (int z0 = 1; z0 < nz - 1; z0 += zc)
+                    for (int y0 = 1; y0 < ny - 1; y0 += ty)
+                        for (int q0 = 0; q0 < nxp; q0 += kq) {
+                            PaTile t;
+                            t.lev = l | (q0 << 8) | (std::min(kq, nxp - q0) << 16);
+                            t.box = (int)lb;
+                            t.y0 = y0; t.ny = std::min(ty, ny - 1 - y0);
+                            t.z0 = z0; t.nz = std::min(zc, nz - 1 - z0);
+                            F.h.push_back(t);
+                        }
+            }
+            F.begin[0][l + 1] = (long long)F.h.size();
+        }
+        h->f3_ok = F.ok && !F.h.empty();
+    }
 }
 
 int ensure_device(pa_hier* h) {
@@ -347,6 +385,7 @@ int ensure_device(pa_hier* h) {
         std::vector<int> sl, sb;
         build_curv_tiles(h, sl, sb);
         if (h->f2_ok) CU(h->tiles_f2.d.upload(h->tiles_f2.h, t_stream));
+        if (h->f3_ok) CU(h->tiles_f3.d.upload(h->tiles_f3.h, t_stream));
         if (h->curv_ok) {
             CU(h->tiles_curv.d.upload(h->tiles_curv.h, t_stream));
             CU(h->shell_level.upload(sl, t_stream));
@@ -1112,9 +1151,10 @@ int curv_fused_mode(const CurvCtx& c) {
     const char* e = getenv("PA_CURV_FUSED");
     const char* no_fuse = getenv("PA_CURV_UNFUSED");
     const char* es = getenv("PA_STENCIL");
-    if (!(e && (e[0] == '1' || e[0] == '2')) || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return 0;
+    if (!(e && (e[0] == '1' || e[0] == '2' || e[0] == '3')) || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return 0;
     if (!(c.state->ng == 1 && c.h->curv_ok && !overlap_enabled(c.h))) return 0;
     if (e[0] == '2') return (c.h->f2_ok && stencil_decide_normal_math(t_stream) == 0) ? 2 : 0;
+    if (e[0] == '3') return (c.h->f3_ok && stencil_decide_normal_math(t_stream) == 0) ? 3 : 0;
     return 1;
 }
 bool curv_fused_path(const CurvCtx& c) { return curv_fused_mode(c) != 0; }
@@ -1148,6 +1188,15 @@ int curv_pass1(const CurvCtx& c) {
         if (c.state->peers_missing > 0)
             return fail(PA_ERR_STATE, "this hierarchy uses peer links (PA_HIER_PEER_LINKS): map every rank's slab of the state field first");
         CHK(fill_ghosts_impl(c.state, c.comp_S, 1, 0, nlev - 1, false, xf));
+        if (curv_fused_mode(c) == 3) {
+            TileTable& T = h->tiles_f3;
+            const long long a = T.begin[0][0], b = T.begin[0][nlev];
+            int lend[PA_MAX_LEVELS];
+            for (int l = 0; l < nlev; ++l) lend[l] = (int)(T.begin[0][l + 1] - a);
+            CU(launch_curv_f3(T.d.p + a, (int)(b - a), lend, nlev, ga, ex, t_stream));
+            ++g_fused_launches;
+            return PA_OK;
+        }
         if (curv_fused_mode(c) == 2) {
             TileTable& T = h->tiles_f2;
             const long long a = T.begin[0][0], b = T.begin[0][nlev];

@@ -116,6 +116,14 @@ int curv_fused_max_plane_doubles();
 cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, int lnxp, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st);
 int curv_f2_rows();
 int curv_f2_max_nx();
+// Third fused curvature kernel (curv_f3.cu, PA_CURV_FUSED=3): 256-thread CTAs, two per SM, one block barrier per plane.
+// tiles: K rows (at most curv_f3_rows()) x K planes x an x strip; PaTile::lev = level | first K pair << 8 | K pairs << 16 with
+// at most curv_f3_strip_pairs() pairs; boxes of even width >= 4, >= 3 cells in y and z.
+// level_end[l] = number of tiles of levels 0 .. l (tiles are sorted by level; the kernel derives a CTA's level from blockIdx)
+cudaError_t launch_curv_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
+                           cudaStream_t st);
+int curv_f3_rows();
+int curv_f3_strip_pairs();
 // K on the outermost cell layer of the boxes (the cells the fused kernel leaves out), from the ghost-filled flame normal:
 // MODE_DIV's arithmetic, one thread per cell.  GridArgs: in = n (3 comps), out = K.
 cudaError_t launch_div_shell(const int* box_level, const int* box_index, int nboxes, int blocks_per_box, const GridArgs& ga,

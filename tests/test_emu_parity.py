@@ -58,9 +58,9 @@ def _thin_out(schedule, stencil, links):
     only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
     if schedule and (stencil == "simple" or links == "nolinks"):
         pytest.skip("combination not in the thinned-out matrix")
-    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2"):
+    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3"):
         pytest.skip("combination not in the thinned-out matrix")
-    if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused2", "simple"):
+    if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "simple"):
         pytest.skip("combination not in the thinned-out matrix")
 
 
@@ -77,7 +77,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_big", "simple"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
     _thin_out(schedule, stencil, links)
@@ -255,3 +255,8 @@ def test_emulated_recv_slab_has_one_owner(emu):
 @pytest.mark.parametrize("base,mgs,walls", [(32, 16, False), (32, 16, True)])
 def test_emulated_fused2_power_of_two_widths(emu, base, mgs, walls):
     G.test_fused2_power_of_two_widths_match_separate_kernels(emu, base, mgs, walls)
+
+
+@pytest.mark.parametrize("base,mgs,walls", [(32, 16, True), (96, 96, False)])
+def test_emulated_fused3_strips(emu, base, mgs, walls):
+    G.test_fused3_strips_match_separate_kernels(emu, base, mgs, walls)

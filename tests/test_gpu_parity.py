@@ -24,10 +24,10 @@ def _flat(pf, name):
 def _set_stencil(stencil):
     """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps); tma_big: TMA pipeline in the 8 /
     16-warp shapes whatever the tile size; tma_fused: curvature through the fused kernel + shell pass where the hierarchy is
-    eligible (PA_CURV_FUSED=1, opt-in); simple: the plain-load kernels."""
+    eligible (PA_CURV_FUSED=1, opt-in; tma_fused2 / tma_fused3: the later fused kernels); simple: the plain-load kernels."""
     os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
-    os.environ["PA_CURV_FUSED"] = "1" if stencil == "tma_fused" else ("2" if stencil == "tma_fused2" else "0")
+    os.environ["PA_CURV_FUSED"] = {"tma_fused": "1", "tma_fused2": "2", "tma_fused3": "3"}.get(stencil, "0")
 
 
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
@@ -83,7 +83,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -434,6 +434,22 @@ def test_fused2_power_of_two_widths_match_separate_kernels(gpu, base, mgs, walls
     kw = dict(threshold_prog=1, threshold_value=0.02)
     n0 = gpu.curv_fused_launches()
     a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_fused2")
+    assert gpu.curv_fused_launches() > n0                      # the fused kernel ran (no silent fallback)
+    b, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma")
+    for c in range(a.shape[0]):
+        assert bit_equal(a[c], b[c]), c
+
+
+@pytest.mark.parametrize("base,mgs,walls", [(32, 16, True), (96, 96, False), (128, 128, True)])
+def test_fused3_strips_match_separate_kernels(gpu, base, mgs, walls):
+    """the third fused kernel (x strips of at most 64 cells, one barrier per plane) against the separate kernels, bit for bit,
+    threshold clip included: narrow boxes (one strip), 96-wide boxes (two strips of 48) and 128-wide boxes (two of 64)"""
+    from peleanalysis_b200 import synth
+    pf = synth.config3(base, mgs, nlev=3 if base <= 32 else 2)
+    per = (0, 0, 0) if walls else (1, 1, 1)
+    kw = dict(threshold_prog=1, threshold_value=0.02)
+    n0 = gpu.curv_fused_launches()
+    a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_fused3")
     assert gpu.curv_fused_launches() > n0                      # the fused kernel ran (no silent fallback)
     b, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma")
     for c in range(a.shape[0]):
