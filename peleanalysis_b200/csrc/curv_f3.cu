@@ -29,20 +29,29 @@ namespace pa {
 namespace {
 
 constexpr int F3_THREADS = 256;
-constexpr int F3_KR = 13;                 // K rows per item at most
-constexpr int F3_NR = F3_KR + 2;          // rows of n
-constexpr int F3_SR = F3_KR + 4;          // rows of the scalar
-constexpr int F3_KQ = 32;                 // K pairs (x) per strip at most
-constexpr int F3_NQ = F3_KQ + 2;          // pairs of n per row at most (one rim pair per inner side)
-constexpr int F3_SQ = F3_NQ + 2;          // pairs of the scalar per row at most
-constexpr int F3_PW = 2 * F3_SQ;          // row pitch of a progress plane (doubles)
-constexpr int F3_NW = 2 * F3_NQ;          // row pitch of a normal-component plane
-constexpr int F3_CPL = F3_SR * F3_PW;     // doubles per progress plane
-constexpr int F3_NPL = F3_NR * F3_NW;     // doubles per normal-component plane
-constexpr int F3_SL = (F3_SR * F3_SQ + F3_THREADS - 1) / F3_THREADS;   // scalar pairs a thread stages per plane (3)
 constexpr int F3_NL = 2;                  // (row, pair) slots of n / K per thread
-constexpr int F3_RING = 4;                // progress planes: three are read by a step, the fourth is being staged
-static_assert(F3_NR * F3_NQ <= F3_NL * F3_THREADS, "n slots");
+// Tile geometry.  FK = true: the fused kernel (n with a one-cell rim around the K cells, flame-normal planes in shared memory).
+// FK = false: the same sweep without the K part -- S -> Progress and n only, no rim, whole rows of up to 128 cells, 45 KB of
+// shared memory; it stands in for MODE_NORMAL_S of the TMA pipeline in front of the separate divergence kernel (PA_NORMAL_F3).
+template <bool FK> struct F3Geo {
+    static constexpr int KR = FK ? 13 : 8;                // K rows (FK) / rows of n (!FK) per item at most
+    static constexpr int NR = FK ? KR + 2 : KR;           // rows of n
+    static constexpr int SR = NR + 2;                     // rows of the scalar
+    static constexpr int KQ = FK ? 32 : 64;               // pairs (x) per strip at most
+    static constexpr int NQ = FK ? KQ + 2 : KQ;           // pairs of n per row at most (FK: one rim pair per inner side)
+    static constexpr int SQ = NQ + 2;                     // pairs of the scalar per row at most
+    static constexpr int PW = 2 * SQ;                     // row pitch of a progress plane (doubles)
+    static constexpr int NW = 2 * NQ;                     // row pitch of a normal-component plane
+    static constexpr int CPL = SR * PW;                   // doubles per progress plane
+    static constexpr int NPL = FK ? NR * NW : 0;          // doubles per normal-component plane
+    static constexpr int SL = (SR * SQ + F3_THREADS - 1) / F3_THREADS;   // scalar pairs a thread stages per plane (3)
+    // progress planes in shared memory.  FK: three are read by a step, the fourth is being staged from registers (the plane
+    // loaded one step ahead).  !FK: the planes arrive by cp.async up to four steps ahead and are normalised in place: three
+    // read + one being normalised + four in flight.  (The register prefetch of one plane was not enough for the shorter
+    // steps of the K-less kernel: ncu showed 3.5 cycles of long-scoreboard and 5.7 of barrier stall per issued instruction.)
+    static constexpr int RING = FK ? 4 : 8;
+    static_assert(NR * NQ <= F3_NL * F3_THREADS, "n slots");
+};
 
 // Shared memory is addressed through 32-bit shared-window addresses and ld/st.shared with immediate offsets: with generic
 // pointers nvcc re-derives the window base (S2UR SR_CgaCtaId + ULEA) in every basic block and spends a LEA per access.
@@ -79,6 +88,24 @@ template <int D> __device__ __forceinline__ void sm_st2(SmA a, double x, double 
 }
 #endif
 
+// 16-byte asynchronous copy global -> shared (LDGSTS), commit / wait as in PTX
+#ifdef PA_HOST_EMULATION
+__device__ __forceinline__ void cpa16(SmA dst, const double* src) { cuemu::cp_async_16(dst.p, src); }
+__device__ __forceinline__ void cpa_commit() { cuemu::cp_async_commit(); }
+__device__ __forceinline__ void cpa_wait(int n) { cuemu::cp_async_wait(n); }
+#else
+__device__ __forceinline__ void cpa16(SmA dst, const double* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst.a), "l"(src) : "memory"); }
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpa_wait(int n) {
+    switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+#endif
+
 // tiles [0, end[0]) of the launch belong to level 0, [end[0], end[1]) to level 1, ...: the level of a CTA follows from
 // blockIdx alone, so the compiler knows it is uniform and keeps the level's pointers and constants in uniform registers
 // (a level read from the tile record made every use of them a constant-bank load with a computed index)
@@ -97,8 +124,9 @@ enum {
     IC_GZ0, IC_GZ1,               // source of cell (0, 0, z) on the box's ghost planes z = -1 / z = nz, bit 0: raw scalar
     IC_N
 };
-constexpr int F3_ITEM_DOUBLES = IC_N + 3 * F3_THREADS / 2;   // + srow[3][256] ints
-constexpr size_t F3_SMEM = (size_t)(F3_RING * F3_CPL + 7 * F3_NPL + F3_ITEM_DOUBLES) * sizeof(double);
+template <bool FK> constexpr size_t f3_smem() {
+    return (size_t)(F3Geo<FK>::RING * F3Geo<FK>::CPL + 7 * F3Geo<FK>::NPL + IC_N + F3Geo<FK>::SL * F3_THREADS / 2) * sizeof(double);   // + srow[SL][256] ints
+}
 
 #ifdef PA_HOST_EMULATION
 template <int D> __device__ __forceinline__ long long sm_ldq(SmA a) { return reinterpret_cast<const long long*>(a.p)[D]; }
@@ -132,13 +160,18 @@ __device__ __forceinline__ void stg2b(char* p, double x, double y) { asm volatil
 __device__ __forceinline__ void stg1b(char* p, double x) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory"); }
 #endif
 
-__global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restrict__ tiles, F3Levels lv, GridArgs ga, StencilExtra ex) {
+template <bool FK, int MINB>
+__global__ void __launch_bounds__(F3_THREADS, MINB) k_curv_f3(const PaTile* __restrict__ tiles, F3Levels lv, GridArgs ga, StencilExtra ex, int depth) {
+    using G = F3Geo<FK>;
+    constexpr int F3_PW = G::PW, F3_NW = G::NW, F3_CPL = G::CPL, F3_NPL = G::NPL, F3_SL = G::SL;
+    constexpr int RH = FK ? 1 : 0;                               // rim of n around the item's own rows / planes
+    constexpr int F3_RING = G::RING;
     PA_DYN_SMEM(smem_raw);
-    const SmA C = sm_base(smem_raw);                             // [F3_RING][F3_SR][F3_PW] progress ring
+    const SmA C = sm_base(smem_raw);                             // [F3_RING][SR][PW] progress ring
     const SmA NXY = C + F3_RING * F3_CPL;                        // [2]{n_x plane, n_y plane}
     const SmA NZs = NXY + 4 * F3_NPL;                            // [3] n_z ring
     const SmA IC = NZs + 3 * F3_NPL;                             // item constants
-    const SmA SROW = IC + IC_N;                                  // [F3_SL][F3_THREADS] ints: y * P + x of the pairs a thread stages
+    const SmA SROW = IC + IC_N;                                  // [SL][F3_THREADS] ints: y * P + x of the pairs a thread stages
     const int tid = threadIdx.x;
 
     int nplanes, g0, g1, mw0, mw1, PSin, PSout;                  // the plane loop's scalars
@@ -160,12 +193,12 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
         const PaNbr nb = L.nbr[t.box];
         const int nx = bx.n[0], nyb = bx.n[1], nzb = bx.n[2];
         const int nxp = nx >> 1;
-        const int nq0 = xq0 > 0 ? xq0 - 1 : 0, nq1 = xq0 + KQ + 1 < nxp ? xq0 + KQ + 1 : nxp;   // pairs of n this item computes
+        const int nq0 = (FK && xq0 > 0) ? xq0 - 1 : xq0, nq1 = (FK && xq0 + KQ + 1 <= nxp) ? xq0 + KQ + 1 : xq0 + KQ;   // pairs of n this item computes
         const int NQ = nq1 - nq0, SQ = NQ + 2;
         const int sq0 = nq0 - 1;                                 // first staged pair; pair -1 = cells (-2, -1), pair nxp = (nx, nx + 1)
-        const int KR = t.ny, NR = KR + 2, SR = KR + 4;
-        const int yS0 = t.y0 - 2, zS0 = t.z0 - 2;                // first scalar row / plane (box-relative, >= -1)
-        nplanes = t.nz + 4;                                      // scalar planes z0-2 .. z0+nz+1
+        const int KR = t.ny, NR = KR + 2 * RH, SR = NR + 2;
+        const int yS0 = t.y0 - RH - 1, zS0 = t.z0 - RH - 1;      // first scalar row / plane (box-relative, >= -1)
+        nplanes = t.nz + 2 * RH + 2;                             // scalar planes
         g0 = zS0 < 0 ? 0 : -1;                                   // plane indices of the box's z ghost planes inside the item, -1: none
         g1 = zS0 + nplanes - 1 >= nzb ? nplanes - 1 : -1;
         PSin = li.PS; PSout = lo.PS;
@@ -216,8 +249,8 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
         // ---- what this thread computes: F3_NL (row, pair) slots of n, and K of the same cells one plane behind.  Progress and n
         //      are written by the item that holds the cell as a K row / plane / strip column; the box's outermost rows / planes
         //      go with the first / last item ----
-        const int wy0 = (t.y0 == 1) ? 0 : t.y0, wy1 = (t.y0 + t.ny == nyb - 1) ? nyb - 1 : t.y0 + t.ny - 1;
-        const int wz0 = (t.z0 == 1) ? 0 : t.z0, wz1 = (t.z0 + t.nz == nzb - 1) ? nzb - 1 : t.z0 + t.nz - 1;
+        const int wy0 = (FK && t.y0 == 1) ? 0 : t.y0, wy1 = (FK && t.y0 + t.ny == nyb - 1) ? nyb - 1 : t.y0 + t.ny - 1;
+        const int wz0 = (FK && t.z0 == 1) ? 0 : t.z0, wz1 = (FK && t.z0 + t.nz == nzb - 1) ? nzb - 1 : t.z0 + t.nz - 1;
         mw0 = wz0 - zS0; mw1 = wz1 - zS0;                        // planes (item-relative) whose c / n this item writes
 #pragma unroll
         for (int j = 0; j < F3_NL; ++j) {
@@ -225,7 +258,7 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
             const bool act = p < NR * NQ;
             if (!act) p = 0;
             const int rn = p / NQ, qn = p - rn * NQ;
-            const int y = t.y0 - 1 + rn, q = nq0 + qn;
+            const int y = t.y0 - RH + rn, q = nq0 + qn;
             so[j] = (rn + 1) * F3_PW + 2 * (qn + 1);
             no[j] = rn * F3_NW + 2 * qn;
             oe[j] = (zS0 + 1) * lo.PS + y * lo.P + 2 * q;
@@ -233,7 +266,7 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
             if (act) {
                 fl |= 1u << j;
                 if (incol & (y >= wy0) & (y <= wy1)) fl |= 16u << j;
-                if (incol & (rn >= 1) & (rn <= KR)) fl |= 256u << j;
+                if (FK && (incol & (rn >= 1) & (rn <= KR))) fl |= 256u << j;
                 if (q == 0) fl |= 4096u << j;
                 if (q == nxp - 1) fl |= 65536u << j;
             }
@@ -245,7 +278,7 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
             sm_stq<IC_DZI>(IC, __double_as_longlong(L.dxi[2]));
             sm_stq<IC_PC>(IC, (long long)(ex.cout[lev] + ob));
             sm_stq<IC_PN>(IC, (long long)(L.out + ob));
-            sm_stq<IC_PK>(IC, (long long)(ex.kout[lev] + ob));
+            if (FK) sm_stq<IC_PK>(IC, (long long)(ex.kout[lev] + ob));
             sm_stq<IC_PA>(IC, ex.aux[lev] ? (long long)(ex.aux[lev] + ob) : 0ll);
             sm_stq<IC_CSN>(IC, L.cs_out * 8);
             sm_stq<IC_CSA>(IC, ex.cs_aux[lev] * 8);
@@ -260,7 +293,7 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
     const double pmin = ex.pmin, pinv = ex.inv;
     double2 pre[F3_SL];
     unsigned praw = 0;
-    auto issue_loads = [&](int ps) {                             // plane ps of the item into registers
+    auto issue_loads = [&](int ps) {                             // FK: plane ps of the item into registers
         if ((ps != g0) & (ps != g1)) {
 #pragma unroll
             for (int i = 0; i < F3_SL; ++i)
@@ -287,22 +320,59 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
                 sm_st2<0>(Cs + ssm[i], v.x, v.y);
             }
     };
+    auto issue_async = [&](int ps) {                             // !FK: plane ps of the item straight into its ring slot; one group per plane
+        if (ps < nplanes) {
+            const SmA Cs = C + (ps & (F3_RING - 1)) * F3_CPL;
+            if ((ps != g0) & (ps != g1)) {
+#pragma unroll
+                for (int i = 0; i < F3_SL; ++i)
+                    if (ssm[i] >= 0) cpa16(Cs + ssm[i], sp[i]);
+            } else {
+                const long long gz = ps == g0 ? sm_ldq<IC_GZ0>(IC) : sm_ldq<IC_GZ1>(IC);
+                const double* base = reinterpret_cast<const double*>(gz & ~1ll);
+#pragma unroll
+                for (int i = 0; i < F3_SL; ++i)
+                    if (ssm[i] >= 0) cpa16(Cs + ssm[i], base + sm_ldi(SROW, i * F3_THREADS + tid));
+            }
+#pragma unroll
+            for (int i = 0; i < F3_SL; ++i) sp[i] += PSin;
+        }
+        cpa_commit();
+    };
+    auto normalise_own = [&](int ps) {                           // !FK: the pairs this thread copied, in place (curvature.cpp:316-320)
+        unsigned raw = sraw;
+        if ((ps == g0) | (ps == g1)) raw = ((ps == g0 ? sm_ldq<IC_GZ0>(IC) : sm_ldq<IC_GZ1>(IC)) & 1) ? 7u : 0u;
+        const SmA Cs = C + (ps & (F3_RING - 1)) * F3_CPL;
+#pragma unroll
+        for (int i = 0; i < F3_SL; ++i)
+            if (ssm[i] >= 0 && (raw & (1u << i))) {
+                const double2 v = sm_ld2<0>(Cs + ssm[i]);
+                sm_st2<0>(Cs + ssm[i], (v.x - pmin) * pinv, (v.y - pmin) * pinv);
+            }
+    };
 
     const bool do_thr = ex.do_threshold != 0;
     const double thr_lo = ex.threshold, thr_hi = 1.0 - ex.threshold;
     int r3 = 1;                                                  // (plane of n) % 3 without the division
-    issue_loads(0);
+    if (FK) issue_loads(0);
+    else for (int d = 0; d < depth; ++d) issue_async(d);
     for (int ps = 0; ps <= nplanes; ++ps) {
-        if (ps < nplanes) {
-            store_loads(ps);
-            if (ps + 1 < nplanes) issue_loads(ps + 1);           // in flight across the arithmetic below
+        if (FK) {
+            if (ps < nplanes) {
+                store_loads(ps);
+                if (ps + 1 < nplanes) issue_loads(ps + 1);       // in flight across the arithmetic below
+            }
+        } else {
+            cpa_wait(depth - 1);                                 // this thread's copies of plane ps have landed
+            if (ps < nplanes) normalise_own(ps);
+            issue_async(ps + depth);
         }
         if (ps >= 3) {
             // ---- flame normal of plane m = ps - 2 from the progress planes m-1, m, m+1 staged by earlier steps ----
             const int m = ps - 2;
-            const SmA C0 = C + ((ps + 1) & 3) * F3_CPL;          // plane m - 1
-            const SmA C1 = C + ((ps + 2) & 3) * F3_CPL;
-            const SmA C2 = C + ((ps + 3) & 3) * F3_CPL;
+            const SmA C0 = C + ((ps - 3) & (F3_RING - 1)) * F3_CPL;   // plane m - 1
+            const SmA C1 = C + ((ps - 2) & (F3_RING - 1)) * F3_CPL;
+            const SmA C2 = C + ((ps - 1) & (F3_RING - 1)) * F3_CPL;
             const SmA nw = NXY + (m & 1) * (2 * F3_NPL);
             const SmA nr = NXY + ((m & 1) ^ 1) * (2 * F3_NPL);
             const int r3m1 = r3 == 0 ? 2 : r3 - 1, r3m2 = r3m1 == 0 ? 2 : r3m1 - 1;
@@ -328,7 +398,7 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
             const bool wplane = (m >= mw0) & (m <= mw1);
 #pragma unroll
             for (int j = 0; j < F3_NL; ++j) {
-                if (fl & (1u << j)) {
+                if (FK && (fl & (1u << j))) {
                     sm_st2<0>(nw + no[j], n0[2 * j], n0[2 * j + 1]);
                     sm_st2<F3_NPL>(nw + no[j], n1[2 * j], n1[2 * j + 1]);
                     sm_st2<0>(zw + no[j], n2[2 * j], n2[2 * j + 1]);
@@ -350,7 +420,7 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
                     }
                 }
             }
-            if (m >= 3) {
+            if (FK && m >= 3) {
                 // ---- K of plane m - 1: n_x / n_y of that plane (staged one step ago), n_z of m-2, m-1 (shared memory) and m (registers).
                 //      Every thread evaluates its cells; only K rows / columns are stored ----
 #pragma unroll
@@ -388,11 +458,14 @@ __global__ void __launch_bounds__(F3_THREADS, 2) k_curv_f3(const PaTile* __restr
 
 }  // namespace
 
-int curv_f3_rows() { return F3_KR; }
-int curv_f3_strip_pairs() { return F3_KQ; }
+int curv_f3_rows() { return F3Geo<true>::KR; }
+int curv_f3_strip_pairs() { return F3Geo<true>::KQ; }
+int normal_f3_rows() { return F3Geo<false>::KR; }
+int normal_f3_strip_pairs() { return F3Geo<false>::KQ; }
 
-cudaError_t launch_curv_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
-                           cudaStream_t st) {
+template <bool FK, int MINB>
+static cudaError_t launch_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
+                             int depth, cudaStream_t st) {
     if (ntiles <= 0) return cudaSuccess;
     F3Levels lv;
     for (int l = 0; l < PA_MAX_LEVELS; ++l) lv.end[l] = l < nlev ? level_end[l] : 0x7fffffff;
@@ -403,18 +476,31 @@ cudaError_t launch_curv_f3(const PaTile* tiles, int ntiles, const int* level_end
     {
         std::lock_guard<std::mutex> lock(mu);
         if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(k_curv_f3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F3_SMEM);
+            cudaError_t e = cudaFuncSetAttribute(k_curv_f3<FK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem<FK>());
             if (e != cudaSuccess) return e;
 #ifndef PA_HOST_EMULATION
-            e = cudaFuncSetAttribute(k_curv_f3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // two CTAs per SM need 188 KB
+            e = cudaFuncSetAttribute(k_curv_f3<FK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // FK: two CTAs per SM need 195 KB
             if (e != cudaSuccess) return e;
 #endif
             configured[dev] = true;
         }
     }
-    PA_LAUNCH(ntiles, F3_THREADS, F3_SMEM, st, k_curv_f3)(tiles, lv, ga, ex);
+    PA_LAUNCH(ntiles, F3_THREADS, f3_smem<FK>(), st, k_curv_f3<FK, MINB>)(tiles, lv, ga, ex, depth);
     ++g_launches;
     return cudaGetLastError();
+}
+
+cudaError_t launch_curv_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
+                           cudaStream_t st) {
+    return launch_f3<true, 2>(tiles, ntiles, level_end, nlev, ga, ex, 1, st);
+}
+cudaError_t launch_normal_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
+                             cudaStream_t st) {
+    const char* e = getenv("PA_NF3_CTAS");                      // 3: 80-register build, three CTAs per SM (spills 160 bytes)
+    const char* ed = getenv("PA_NF3_DEPTH");                    // planes in flight per CTA (1 .. 4)
+    const int depth = ed ? std::min(4, std::max(1, atoi(ed))) : 3;
+    if (e && e[0] == '3') return launch_f3<false, 3>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
+    return launch_f3<false, 2>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
 }
 
 }  // namespace pa

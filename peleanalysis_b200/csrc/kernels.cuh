@@ -124,6 +124,12 @@ cudaError_t launch_curv_f3(const PaTile* tiles, int ntiles, const int* level_end
                            cudaStream_t st);
 int curv_f3_rows();
 int curv_f3_strip_pairs();
+// The same kernel without its K part (PA_NORMAL_F3=1): S -> Progress and n, the work of MODE_NORMAL_S.  tiles: rows (at most
+// normal_f3_rows()) x planes x an x strip (at most normal_f3_strip_pairs() pairs) of whole boxes, strip encoded as above.
+cudaError_t launch_normal_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
+                             cudaStream_t st);
+int normal_f3_rows();
+int normal_f3_strip_pairs();
 // K on the outermost cell layer of the boxes (the cells the fused kernel leaves out), from the ghost-filled flame normal:
 // MODE_DIV's arithmetic, one thread per cell.  GridArgs: in = n (3 comps), out = K.
 cudaError_t launch_div_shell(const int* box_level, const int* box_index, int nboxes, int blocks_per_box, const GridArgs& ga,

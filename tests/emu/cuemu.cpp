@@ -41,6 +41,10 @@ struct Fiber {
     // the last entry is the open (uncommitted) group
     std::vector<int> store_groups = std::vector<int>(1, 0);
     int groups_retired = 0;             // committed groups already dropped from the front of store_groups
+    // cp.async (non-bulk) groups: completion tick of every committed group that may still be in flight, oldest first, and of
+    // the open group
+    std::vector<unsigned long long> cpa_groups;
+    unsigned long long cpa_open = 0;
 };
 
 struct WarpState {
@@ -244,7 +248,7 @@ void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()>
                 for (int t = 0; t < n_threads; ++t) {
                     Fiber& f = fibers[t];
                     f.done = false; f.waiting = ""; f.async_due = 0;
-                    f.store_groups.assign(1, 0); f.groups_retired = 0;
+                    f.store_groups.assign(1, 0); f.groups_retired = 0; f.cpa_groups.clear(); f.cpa_open = 0;
                     getcontext(&f.ctx);
                     f.ctx.uc_stack.ss_sp = f.stack;
                     f.ctx.uc_stack.ss_size = STACK_BYTES;
@@ -320,6 +324,26 @@ void cp_async_8(void* dst, const void* src) {
     cur->async_due = std::max(cur->async_due, due);
     asyncq.push_back(Async{1, dst, src, 8, nullptr, due});
     ++progress;
+}
+void cp_async_16(void* dst, const void* src) {
+    if (((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u)) { std::fprintf(stderr, "[cuemu] cp.async 16: misaligned\n"); std::abort(); }
+    const unsigned long long due = tick + delay();
+    cur->cpa_open = std::max(cur->cpa_open, due + 1);             // lands in run_async once tick >= due, visible from tick due + 1
+    asyncq.push_back(Async{1, dst, src, 16, nullptr, due});
+    ++progress;
+}
+void cp_async_commit() { cur->cpa_groups.push_back(cur->cpa_open); cur->cpa_open = 0; ++progress; }
+void cp_async_wait(int n) {
+    // all committed groups of this thread except the n most recent are complete
+    for (;;) {
+        const int must = (int)cur->cpa_groups.size() - n;
+        bool pending = false;
+        for (int g = 0; g < must; ++g) pending |= cur->cpa_groups[g] > tick;
+        if (!pending) break;
+        yield("cp.async.wait_group", cur);
+    }
+    const int must = (int)cur->cpa_groups.size() - n;
+    if (must > 0) cur->cpa_groups.erase(cur->cpa_groups.begin(), cur->cpa_groups.begin() + must);
 }
 // cp.async.bulk.global.shared::cta (TMA store) + bulk_group commit / wait_group.read
 void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {

@@ -28,6 +28,7 @@ def _set_stencil(stencil):
     os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
     os.environ["PA_CURV_FUSED"] = {"tma_fused": "1", "tma_fused2": "2", "tma_fused3": "3"}.get(stencil, "0")
+    os.environ["PA_NORMAL_F3"] = "1" if stencil == "tma_n3" else "0"      # flame normal through curv_f3.cu's kernel without its K part
 
 
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
@@ -83,7 +84,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -452,5 +453,10 @@ def test_fused3_strips_match_separate_kernels(gpu, base, mgs, walls):
     a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_fused3")
     assert gpu.curv_fused_launches() > n0                      # the fused kernel ran (no silent fallback)
     b, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma")
+    for c in range(a.shape[0]):
+        assert bit_equal(a[c], b[c]), c
+    n0 = gpu.curv_fused_launches()
+    a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_n3")     # the same kernel without its K part + MODE_DIV
+    assert gpu.curv_fused_launches() > n0
     for c in range(a.shape[0]):
         assert bit_equal(a[c], b[c]), c
