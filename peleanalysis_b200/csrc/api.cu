@@ -107,6 +107,8 @@ struct pa_hier {
     bool f3_ok = false;
     TileTable tiles_n3;                         // work items of its flame-normal-only form (PA_NORMAL_F3): rows x planes x strips of whole boxes
     bool n3_ok = false;
+    TileTable tiles_nw;                         // work items of the barrier-free flame-normal kernel (normal_w.cu, PA_NORMAL_W)
+    bool nw_ok = false;
     int f2_lnxp = -1;                           // log2(width / 2) if every box has the same power-of-two width, else -1
     bool curv_ok = false;
     DevBuf<int> shell_level, shell_box;
@@ -373,6 +375,40 @@ void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int
         }
         h->n3_ok = F.ok && !F.h.empty();
     }
+    {   // normal_w.cu: one warp per row of an x strip of at most normal_w_strip_pairs() pairs (at least two), normal_w_rows() rows per item
+        TileTable& F = h->tiles_nw;
+        F.h.clear();
+        F.ok = true;
+        std::memset(F.begin, 0, sizeof(F.begin));
+        const char* ez = getenv("PA_NW_ZC");
+        const int ZC = ez ? std::max(1, atoi(ez)) : 32;
+        const int ty0 = normal_w_rows(), kq0 = normal_w_strip_pairs();
+        for (int l = 0; l < H.nlev; ++l) {
+            F.begin[0][l] = (long long)F.h.size();
+            const Level& V = H.lev[l];
+            for (size_t lb = 0; lb < V.local.size(); ++lb) {
+                const Box& B = V.boxes[V.local[lb]];
+                const int nx = B.len(0), ny = B.len(1), nz = B.len(2);
+                if (nx < 4 || (nx & 1) || nx > 510) { F.ok = false; continue; }
+                const int nxp = nx / 2;
+                const int nst = (nxp + kq0 - 1) / kq0, kq = (nxp + nst - 1) / nst;
+                const int nzc = (nz + ZC - 1) / ZC, zc = (nz + nzc - 1) / nzc;
+                for (int z0 = 0; z0 < nz; z0 += zc)
+                    for (int y0 = 0; y0 < ny; y0 += ty0)
+                        for (int q0 = 0; q0 < nxp; q0 += kq) {
+                            PaTile t;
+                            t.lev = l | (q0 << 8) | (std::min(kq, nxp - q0) << 16);
+                            t.box = (int)lb;
+                            t.y0 = y0; t.ny = std::min(ty0, ny - y0);
+                            t.z0 = z0; t.nz = std::min(zc, nz - z0);
+                            if ((t.lev >> 16) < 2) F.ok = false;
+                            F.h.push_back(t);
+                        }
+            }
+            F.begin[0][l + 1] = (long long)F.h.size();
+        }
+        h->nw_ok = F.ok && !F.h.empty();
+    }
 }
 
 int ensure_device(pa_hier* h) {
@@ -423,6 +459,7 @@ int ensure_device(pa_hier* h) {
         if (h->f2_ok) CU(h->tiles_f2.d.upload(h->tiles_f2.h, t_stream));
         if (h->f3_ok) CU(h->tiles_f3.d.upload(h->tiles_f3.h, t_stream));
         if (h->n3_ok) CU(h->tiles_n3.d.upload(h->tiles_n3.h, t_stream));
+        if (h->nw_ok) CU(h->tiles_nw.d.upload(h->tiles_nw.h, t_stream));
         if (h->curv_ok) {
             CU(h->tiles_curv.d.upload(h->tiles_curv.h, t_stream));
             CU(h->shell_level.upload(sl, t_stream));
@@ -1264,6 +1301,17 @@ int curv_pass1(const CurvCtx& c) {
             return run_stencil(h, MODE_NORMAL_S, ga, ex, 1, 1, nlev - 1, c.state->ng, c.state);
         }
         CHK(fill_ghosts_impl(c.state, c.comp_S, 1, 0, nlev - 1, false, xf));
+        const char* nw = getenv("PA_NORMAL_W");
+        if (nw && nw[0] == '1' && h->nw_ok && stencil_decide_normal_math(t_stream) == 0) {
+            // S -> Progress, n through the barrier-free kernel of normal_w.cu (opt-in, same results)
+            if (c.state->peers_missing > 0)
+                return fail(PA_ERR_STATE, "this hierarchy uses peer links (PA_HIER_PEER_LINKS): map every rank's slab of the state field first");
+            TileTable& T = h->tiles_nw;
+            const long long a = T.begin[0][0], b = T.begin[0][nlev];
+            CU(launch_normal_w(T.d.p + a, (int)(b - a), ga, ex, t_stream));
+            ++g_fused_launches;
+            return PA_OK;
+        }
         const char* nf3 = getenv("PA_NORMAL_F3");
         if (nf3 && nf3[0] == '1' && h->n3_ok && stencil_decide_normal_math(t_stream) == 0) {
             // S -> Progress, n through the plane-staged kernel of curv_f3.cu without its K part (opt-in, same results)

@@ -130,6 +130,11 @@ cudaError_t launch_normal_f3(const PaTile* tiles, int ntiles, const int* level_e
                              cudaStream_t st);
 int normal_f3_rows();
 int normal_f3_strip_pairs();
+// Barrier-free flame normal (normal_w.cu, PA_NORMAL_W=1): the work of MODE_NORMAL_S, one warp per row of an x strip, no shared
+// memory.  tiles: at most normal_w_rows() rows x planes x a strip of 2 .. normal_w_strip_pairs() pairs, strip encoded as above.
+cudaError_t launch_normal_w(const PaTile* tiles, int ntiles, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st);
+int normal_w_rows();
+int normal_w_strip_pairs();
 // K on the outermost cell layer of the boxes (the cells the fused kernel leaves out), from the ghost-filled flame normal:
 // MODE_DIV's arithmetic, one thread per cell.  GridArgs: in = n (3 comps), out = K.
 cudaError_t launch_div_shell(const int* box_level, const int* box_index, int nboxes, int blocks_per_box, const GridArgs& ga,

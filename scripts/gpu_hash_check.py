@@ -24,9 +24,10 @@ o.prog_max = max(float(h[0].max()) for h in host)
 res = {}
 for thr in (0, 1):
     o.do_threshold, o.threshold = thr, 0.05
-    for fused in ("n3", "3", "2", "1", "0"):
-        os.environ["PA_CURV_FUSED"] = "0" if fused == "n3" else fused
+    for fused in ("nw", "n3", "3", "2", "1", "0"):
+        os.environ["PA_CURV_FUSED"] = "0" if fused in ("n3", "nw") else fused
         os.environ["PA_NORMAL_F3"] = "1" if fused == "n3" else "0"
+        os.environ["PA_NORMAL_W"] = "1" if fused == "nw" else "0"
         out = capi.Field(H, 5, 1)
         out.set_val(-3.0)
         f0 = capi.curv_fused_launches()
@@ -39,4 +40,5 @@ for thr in (0, 1):
     assert res[(thr, "2")] == res[(thr, "0")], "second fused kernel and unfused curvature differ (threshold %d)" % thr
     assert res[(thr, "3")] == res[(thr, "0")], "third fused kernel and unfused curvature differ (threshold %d)" % thr
     assert res[(thr, "n3")] == res[(thr, "0")], "plane-staged flame-normal kernel and MODE_NORMAL_S differ (threshold %d)" % thr
+    assert res[(thr, "nw")] == res[(thr, "0")], "barrier-free flame-normal kernel and MODE_NORMAL_S differ (threshold %d)" % thr
 print("HASH CHECK OK: fused == unfused on config3(%d, %d), with and without threshold_prog" % (base, mgs))

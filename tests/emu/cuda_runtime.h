@@ -124,6 +124,7 @@ void mbar_wait(uint64_t* bar, uint32_t parity);
 void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
 void cp_async_8(void* dst, const void* src);
 void cp_async_16(void* dst, const void* src);                    // cp.async.cg.shared.global 16 (no mbarrier: commit / wait groups)
+void cp_async_n(void* dst, const void* src, int bytes);           // cp.async 4 / 8 / 16 bytes in the same groups
 void cp_async_commit();                                           // cp.async.commit_group
 void cp_async_wait(int n);                                        // cp.async.wait_group n
 void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes);   // cp.async.bulk.global.shared::cta.bulk_group

@@ -325,13 +325,17 @@ void cp_async_8(void* dst, const void* src) {
     asyncq.push_back(Async{1, dst, src, 8, nullptr, due});
     ++progress;
 }
-void cp_async_16(void* dst, const void* src) {
-    if (((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u)) { std::fprintf(stderr, "[cuemu] cp.async 16: misaligned\n"); std::abort(); }
+void cp_async_n(void* dst, const void* src, int bytes) {
+    const uintptr_t m = (uintptr_t)bytes - 1;
+    if ((bytes != 4 && bytes != 8 && bytes != 16) || ((uintptr_t)dst & m) || ((uintptr_t)src & m)) {
+        std::fprintf(stderr, "[cuemu] cp.async %d: bad size or misaligned\n", bytes); std::abort();
+    }
     const unsigned long long due = tick + delay();
     cur->cpa_open = std::max(cur->cpa_open, due + 1);             // lands in run_async once tick >= due, visible from tick due + 1
-    asyncq.push_back(Async{1, dst, src, 16, nullptr, due});
+    asyncq.push_back(Async{1, dst, src, (uint32_t)bytes, nullptr, due});
     ++progress;
 }
+void cp_async_16(void* dst, const void* src) { cp_async_n(dst, src, 16); }
 void cp_async_commit() { cur->cpa_groups.push_back(cur->cpa_open); cur->cpa_open = 0; ++progress; }
 void cp_async_wait(int n) {
     // all committed groups of this thread except the n most recent are complete

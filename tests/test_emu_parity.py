@@ -29,7 +29,7 @@ def emu():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     m.LIB_PATH = lib                     # a private module instance: the product binding itself is untouched
-    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "PA_CURV_FUSED", "PA_NORMAL_F3", "CUEMU_SEED")}
+    old = {k: os.environ.get(k) for k in ("PA_NORMAL_MATH", "PA_STENCIL", "PA_TMA_SMALL", "PA_CURV_FUSED", "PA_NORMAL_F3", "PA_NORMAL_W", "CUEMU_SEED")}
     os.environ["PA_NORMAL_MATH"] = "fast"   # no device self-test: the emulator has no MUFU (sqrt_fast == sqrt there)
     m.init(0)
     yield m
@@ -58,9 +58,9 @@ def _thin_out(schedule, stencil, links):
     only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
     if schedule and (stencil == "simple" or links == "nolinks"):
         pytest.skip("combination not in the thinned-out matrix")
-    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3"):
+    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw"):
         pytest.skip("combination not in the thinned-out matrix")
-    if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "simple"):
+    if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "simple"):
         pytest.skip("combination not in the thinned-out matrix")
 
 
@@ -77,7 +77,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "tma_big", "simple"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
     _thin_out(schedule, stencil, links)

@@ -29,6 +29,7 @@ def _set_stencil(stencil):
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
     os.environ["PA_CURV_FUSED"] = {"tma_fused": "1", "tma_fused2": "2", "tma_fused3": "3"}.get(stencil, "0")
     os.environ["PA_NORMAL_F3"] = "1" if stencil == "tma_n3" else "0"      # flame normal through curv_f3.cu's kernel without its K part
+    os.environ["PA_NORMAL_W"] = "1" if stencil == "tma_nw" else "0"       # ... through the barrier-free kernel of normal_w.cu
 
 
 def _gpu_grad(capi, pf, is_per, sym, names=("temp",), stencil="tma", flags=0):
@@ -84,7 +85,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -455,8 +456,9 @@ def test_fused3_strips_match_separate_kernels(gpu, base, mgs, walls):
     b, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma")
     for c in range(a.shape[0]):
         assert bit_equal(a[c], b[c]), c
-    n0 = gpu.curv_fused_launches()
-    a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_n3")     # the same kernel without its K part + MODE_DIV
-    assert gpu.curv_fused_launches() > n0
-    for c in range(a.shape[0]):
-        assert bit_equal(a[c], b[c]), c
+    for variant in ("tma_n3", "tma_nw"):                       # the same kernel without its K part / the barrier-free kernel, + MODE_DIV
+        n0 = gpu.curv_fused_launches()
+        a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, variant)
+        assert gpu.curv_fused_launches() > n0
+        for c in range(a.shape[0]):
+            assert bit_equal(a[c], b[c]), (variant, c)
