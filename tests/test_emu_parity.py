@@ -58,8 +58,10 @@ def _thin_out(schedule, stencil, links):
     only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
     if schedule and (stencil == "simple" or links == "nolinks"):
         pytest.skip("combination not in the thinned-out matrix")
-    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw"):
-        pytest.skip("combination not in the thinned-out matrix")
+    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2"):
+        pytest.skip("combination not in the thinned-out matrix")       # starved warps matter for the mbarrier protocols only
+    if schedule and stencil in ("tma_fused3", "tma_nw"):
+        pytest.skip("combination not in the thinned-out matrix")       # block barriers / plain loads only; the cp.async staging is tma_n3's
     if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "simple"):
         pytest.skip("combination not in the thinned-out matrix")
 
@@ -257,6 +259,6 @@ def test_emulated_fused2_power_of_two_widths(emu, base, mgs, walls):
     G.test_fused2_power_of_two_widths_match_separate_kernels(emu, base, mgs, walls)
 
 
-@pytest.mark.parametrize("base,mgs,walls", [(32, 16, True), (96, 96, False)])
+@pytest.mark.parametrize("base,mgs,walls", [(32, 16, True), (72, 72, False)])
 def test_emulated_fused3_strips(emu, base, mgs, walls):
     G.test_fused3_strips_match_separate_kernels(emu, base, mgs, walls)
