@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpelestencil_b200.so")
-SOURCES = ["api.cu", "kernels.cu", "stencil_tma.cu", "curv_fused.cu", "curv_f2.cu", "curv_f3.cu", "normal_w.cu", "filter.cu", "hier.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "stencil_tma.cu", "curv_fused.cu", "curv_f3.cu", "normal_w.cu", "filter.cu", "hier.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false".replace("--use_fast_math=false", "-Xptxas=-v")]

@@ -101,15 +101,12 @@ struct pa_hier {
     // fused curvature (curv_fused.cu): K-block work items of every level (class 0 only) and the (level, box) list of the
     // shell pass; curv_ok = every local box is eligible (>= 3 cells in every direction, <= 128 wide, plane fits)
     TileTable tiles_curv;
-    TileTable tiles_f2;                         // work items of the second fused kernel (curv_f2.cu); f2_ok = every box eligible
-    bool f2_ok = false;
     TileTable tiles_f3;                         // work items of the third fused kernel (curv_f3.cu): K rows x K planes x an x strip
     bool f3_ok = false;
     TileTable tiles_n3;                         // work items of its flame-normal-only form (PA_NORMAL_F3): rows x planes x strips of whole boxes
     bool n3_ok = false;
     TileTable tiles_nw;                         // work items of the barrier-free flame-normal kernel (normal_w.cu, PA_NORMAL_W)
     bool nw_ok = false;
-    int f2_lnxp = -1;                           // log2(width / 2) if every box has the same power-of-two width, else -1
     bool curv_ok = false;
     DevBuf<int> shell_level, shell_box;
     long long shell_begin[PA_MAX_LEVELS + 1] = {0};
@@ -266,45 +263,6 @@ void build_curv_tiles(pa_hier* h, std::vector<int>& shell_level, std::vector<int
     }
     if (T.max_plane_doubles > curv_fused_max_plane_doubles()) T.ok = false;
     h->curv_ok = T.ok;
-    {   // second fused kernel: same K-row / K-plane items with its own row count; boxes need an even width
-        TileTable& F = h->tiles_f2;
-        F.h.clear();
-        F.ok = true;
-        std::memset(F.begin, 0, sizeof(F.begin));
-        const char* ez2 = getenv("PA_CF2_ZC");
-        const int ZC2 = ez2 ? std::max(1, atoi(ez2)) : 63;
-        const int ty2 = curv_f2_rows();
-        for (int l = 0; l < H.nlev; ++l) {
-            F.begin[0][l] = (long long)F.h.size();
-            const Level& V = H.lev[l];
-            for (size_t lb = 0; lb < V.local.size(); ++lb) {
-                const Box& B = V.boxes[V.local[lb]];
-                const int nx = B.len(0), ny = B.len(1), nz = B.len(2);
-                if (nx < 4 || (nx & 1) || nx > curv_f2_max_nx() || ny < 3 || nz < 3) { F.ok = false; continue; }
-                const int nky = ny - 2, nkz = nz - 2;
-                const int nty = (nky + ty2 - 1) / ty2, ty = (nky + nty - 1) / nty;
-                const int nzc = (nkz + ZC2 - 1) / ZC2, zc = (nkz + nzc - 1) / nzc;
-                for (int z0 = 1; z0 < nz - 1; z0 += zc)
-                    for (int y0 = 1; y0 < ny - 1; y0 += ty) {
-                        PaTile t;
-                        t.lev = l; t.box = (int)lb;
-                        t.y0 = y0; t.ny = std::min(ty, ny - 1 - y0);
-                        t.z0 = z0; t.nz = std::min(zc, nz - 1 - z0);
-                        F.h.push_back(t);
-                    }
-            }
-            F.begin[0][l + 1] = (long long)F.h.size();
-        }
-        h->f2_ok = F.ok && !F.h.empty();
-        int w = -2;
-        for (int l = 0; l < H.nlev; ++l)
-            for (size_t lb = 0; lb < H.lev[l].local.size(); ++lb) {
-                const int nx = H.lev[l].boxes[H.lev[l].local[lb]].len(0);
-                w = (w == -2 || w == nx) ? nx : -1;
-            }
-        h->f2_lnxp = -1;
-        for (int k = 3; k <= 6; ++k) if (w == (2 << k)) h->f2_lnxp = k;
-    }
     {   // third fused kernel: the same K rows / K planes cut into x strips of at most curv_f3_strip_pairs() pairs as well; the
         // strip (first pair, pairs) rides in the upper bits of PaTile::lev.  Strips of a row block are consecutive items.
         TileTable& F = h->tiles_f3;
@@ -456,7 +414,6 @@ int ensure_device(pa_hier* h) {
     {
         std::vector<int> sl, sb;
         build_curv_tiles(h, sl, sb);
-        if (h->f2_ok) CU(h->tiles_f2.d.upload(h->tiles_f2.h, t_stream));
         if (h->f3_ok) CU(h->tiles_f3.d.upload(h->tiles_f3.h, t_stream));
         if (h->n3_ok) CU(h->tiles_n3.d.upload(h->tiles_n3.h, t_stream));
         if (h->nw_ok) CU(h->tiles_nw.d.upload(h->tiles_nw.h, t_stream));
@@ -1219,15 +1176,15 @@ struct CurvCtx {
 // It is OPT-IN (PA_CURV_FUSED=1): measured on a B200 it moves a third less data than the separate NORMAL_S / DIV kernels
 // (21.7 GB against 32.5 GB per step on the target hierarchy) but is bound by FP64 latency and per-SM store drain, not by HBM,
 // and ends up slower (7.1 ms against 6.5 ms; DESIGN.md section 6 has the ablation).  The separate kernels are the default.
-// PA_CURV_FUSED=2 selects the second fused kernel (curv_f2.cu: one CTA per item, planes in shared memory) where every box is
-// eligible for it (even width); the shell pass and the ghost fills are the same.  Returns 0 (separate kernels), 1 or 2.
+// PA_CURV_FUSED=3 selects the later fused kernel (curv_f3.cu: x strips, planes in shared memory) where every box is eligible
+// for it (even width); the shell pass and the ghost fills are the same.  (PA_CURV_FUSED=2, curv_f2.cu, was its predecessor:
+// measured 7.17 ms, superseded and removed.)  Returns 0 (separate kernels), 1 or 3.
 int curv_fused_mode(const CurvCtx& c) {
     const char* e = getenv("PA_CURV_FUSED");
     const char* no_fuse = getenv("PA_CURV_UNFUSED");
     const char* es = getenv("PA_STENCIL");
-    if (!(e && (e[0] == '1' || e[0] == '2' || e[0] == '3')) || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return 0;
+    if (!(e && (e[0] == '1' || e[0] == '3')) || (no_fuse && no_fuse[0] == '1') || (es && !strcmp(es, "simple"))) return 0;
     if (!(c.state->ng == 1 && c.h->curv_ok && !overlap_enabled(c.h))) return 0;
-    if (e[0] == '2') return (c.h->f2_ok && stencil_decide_normal_math(t_stream) == 0) ? 2 : 0;
     if (e[0] == '3') return (c.h->f3_ok && stencil_decide_normal_math(t_stream) == 0) ? 3 : 0;
     return 1;
 }
@@ -1268,13 +1225,6 @@ int curv_pass1(const CurvCtx& c) {
             int lend[PA_MAX_LEVELS];
             for (int l = 0; l < nlev; ++l) lend[l] = (int)(T.begin[0][l + 1] - a);
             CU(launch_curv_f3(T.d.p + a, (int)(b - a), lend, nlev, ga, ex, t_stream));
-            ++g_fused_launches;
-            return PA_OK;
-        }
-        if (curv_fused_mode(c) == 2) {
-            TileTable& T = h->tiles_f2;
-            const long long a = T.begin[0][0], b = T.begin[0][nlev];
-            CU(launch_curv_f2(T.d.p + a, (int)(b - a), h->f2_lnxp, ga, ex, t_stream));
             ++g_fused_launches;
             return PA_OK;
         }

@@ -1,7 +1,7 @@
 // curv_f3.cu -- third fused curvature kernel (PA_CURV_FUSED=3): S -> Progress, flame normal and K in one sweep.
 //
 // Reference data flow (curvature.cpp:310-567): c = (S - pmin) * inv; G = grad c; n = G / -max(1e-14, |G|); FillBoundary(n);
-// K = 0.5 * div n.  curv_f2.cu (one 512-thread CTA per SM, two block barriers per plane) was measured on a B200 at 259
+// K = 0.5 * div n.  Its predecessor curv_f2.cu (one 512-thread CTA per SM, two block barriers per plane; removed) was measured at 259
 // instructions per cell, of which only 30 % are FP64, and 18 % of the warp time at the barriers.
 // This kernel keeps its data flow -- progress planes and flame-normal planes in shared memory, nothing carried in registers
 // along z -- and changes what that profile blamed:

@@ -110,12 +110,6 @@ cudaError_t launch_curv_fused(const PaTile* tiles, int ntiles, int max_plane_dou
 int curv_fused_consumer_warps();
 int curv_fused_max_rows();           // staged rows per item (K rows + 4)
 int curv_fused_max_plane_doubles();
-// Second fused curvature kernel (curv_f2.cu, PA_CURV_FUSED=2): one CTA per item, progress / normal planes in shared memory.
-// tiles: K rows (at most curv_f2_rows()) x K planes of boxes with an even width <= curv_f2_max_nx(), >= 3 cells in y and z.
-// lnxp: log2(width / 2) when every box of the launch has that (power-of-two) width, else -1
-cudaError_t launch_curv_f2(const PaTile* tiles, int ntiles, int lnxp, const GridArgs& ga, const StencilExtra& ex, cudaStream_t st);
-int curv_f2_rows();
-int curv_f2_max_nx();
 // Third fused curvature kernel (curv_f3.cu, PA_CURV_FUSED=3): 256-thread CTAs, two per SM, one block barrier per plane.
 // tiles: K rows (at most curv_f3_rows()) x K planes x an x strip; PaTile::lev = level | first K pair << 8 | K pairs << 16 with
 // at most curv_f3_strip_pairs() pairs; boxes of even width >= 4, >= 3 cells in y and z.

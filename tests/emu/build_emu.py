@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "peleanalysis_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libpelestencil_emu.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("api.cu", "kernels.cu", "stencil_tma.cu", "curv_fused.cu", "curv_f2.cu", "curv_f3.cu", "normal_w.cu", "filter.cu", "hier.cpp")] + [os.path.join(HERE, "cuemu.cpp")]
+SOURCES = [os.path.join(CSRC, f) for f in ("api.cu", "kernels.cu", "stencil_tma.cu", "curv_fused.cu", "curv_f3.cu", "normal_w.cu", "filter.cu", "hier.cpp")] + [os.path.join(HERE, "cuemu.cpp")]
 FLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-DPA_HOST_EMULATION=1", "-I", HERE,
          "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable", "-Wno-unused-but-set-variable"]
 

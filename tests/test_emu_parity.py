@@ -58,11 +58,11 @@ def _thin_out(schedule, stencil, links):
     only; materialised ghosts (nolinks) are a property of the fill, not of the CTA shape or of the prefetch warp."""
     if schedule and (stencil == "simple" or links == "nolinks"):
         pytest.skip("combination not in the thinned-out matrix")
-    if schedule < 0 and stencil not in ("tma", "tma_fused", "tma_fused2"):
+    if schedule < 0 and stencil not in ("tma", "tma_fused"):
         pytest.skip("combination not in the thinned-out matrix")       # starved warps matter for the mbarrier protocols only
     if schedule and stencil in ("tma_fused3", "tma_nw"):
         pytest.skip("combination not in the thinned-out matrix")       # block barriers / plain loads only; the cp.async staging is tma_n3's
-    if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "simple"):
+    if links == "nolinks" and stencil not in ("tma", "tma_fused", "tma_fused3", "tma_n3", "tma_nw", "simple"):
         pytest.skip("combination not in the thinned-out matrix")
 
 
@@ -79,7 +79,7 @@ def test_emulated_grad_matches_reference_golden(emu, schedule, name, stencil, li
 
 
 @pytest.mark.parametrize("links", list(G.LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused3", "tma_n3", "tma_nw", "tma_big", "simple"])
 @pytest.mark.parametrize("name", CURV_CASES)
 def test_emulated_curvature_matches_reference_golden(emu, schedule, name, stencil, links):
     _thin_out(schedule, stencil, links)
@@ -252,11 +252,6 @@ def test_emulated_recv_slab_has_one_owner(emu):
     P.check(L.pa_exchange_mark_received(a.f, 0, 1))       # marking a again takes the slab away from b
     with pytest.raises(P.PaError):
         b.fill_ghosts(0, 1)
-
-
-@pytest.mark.parametrize("base,mgs,walls", [(32, 16, False), (32, 16, True)])
-def test_emulated_fused2_power_of_two_widths(emu, base, mgs, walls):
-    G.test_fused2_power_of_two_widths_match_separate_kernels(emu, base, mgs, walls)
 
 
 @pytest.mark.parametrize("base,mgs,walls", [(32, 16, True), (72, 72, False)])

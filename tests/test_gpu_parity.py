@@ -24,10 +24,10 @@ def _flat(pf, name):
 def _set_stencil(stencil):
     """tma: TMA pipeline, CTA shape by tile size (small boxes -> 2 / 4 consumer warps); tma_big: TMA pipeline in the 8 /
     16-warp shapes whatever the tile size; tma_fused: curvature through the fused kernel + shell pass where the hierarchy is
-    eligible (PA_CURV_FUSED=1, opt-in; tma_fused2 / tma_fused3: the later fused kernels); simple: the plain-load kernels."""
+    eligible (PA_CURV_FUSED=1, opt-in; tma_fused3: the later fused kernel); simple: the plain-load kernels."""
     os.environ["PA_STENCIL"] = "simple" if stencil == "simple" else "tma"
     os.environ["PA_TMA_SMALL"] = "0" if stencil.startswith("tma_big") else "1"
-    os.environ["PA_CURV_FUSED"] = {"tma_fused": "1", "tma_fused2": "2", "tma_fused3": "3"}.get(stencil, "0")
+    os.environ["PA_CURV_FUSED"] = {"tma_fused": "1", "tma_fused3": "3"}.get(stencil, "0")
     os.environ["PA_NORMAL_F3"] = "1" if stencil == "tma_n3" else "0"      # flame normal through curv_f3.cu's kernel without its K part
     os.environ["PA_NORMAL_W"] = "1" if stencil == "tma_nw" else "0"       # ... through the barrier-free kernel of normal_w.cu
 
@@ -85,7 +85,7 @@ def test_grad_matches_reference_golden(gpu, name, stencil, links):
 
 
 @pytest.mark.parametrize("links", list(LINK_MODES))
-@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused2", "tma_fused3", "tma_n3", "tma_nw", "tma_big", "simple"])
+@pytest.mark.parametrize("stencil", ["tma", "tma_fused", "tma_fused3", "tma_n3", "tma_nw", "tma_big", "simple"])
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if "curvature" in c[3]])
 def test_curvature_matches_reference_golden(gpu, name, stencil, links):
     pf, z = load_golden(name)
@@ -424,22 +424,6 @@ def test_field_hash_matches_its_definition(gpu):
     assert f.hash(1, 1) != f.hash(0, 1)
     f.fill_ghosts(0, 1)                                    # ghost cells change, the fingerprint does not
     assert f.hash(0, 2) == int(want)
-
-
-@pytest.mark.parametrize("base,mgs,walls", [(32, 16, False), (64, 32, True), (32, 16, True)])
-def test_fused2_power_of_two_widths_match_separate_kernels(gpu, base, mgs, walls):
-    """the second fused kernel's shift-based instantiations (all boxes 16 / 32 cells wide: row and pair of a flattened index
-    by shift and mask) against the separate kernels, bit for bit, threshold clip included; three levels, with and without walls"""
-    from peleanalysis_b200 import synth
-    pf = synth.config3(base, mgs)
-    per = (0, 0, 0) if walls else (1, 1, 1)
-    kw = dict(threshold_prog=1, threshold_value=0.02)
-    n0 = gpu.curv_fused_launches()
-    a, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma_fused2")
-    assert gpu.curv_fused_launches() > n0                      # the fused kernel ran (no silent fallback)
-    b, _ = _gpu_curv(gpu, pf, per, (0, 0, 0), 300.0, 1800.0, kw, "tma")
-    for c in range(a.shape[0]):
-        assert bit_equal(a[c], b[c]), c
 
 
 @pytest.mark.parametrize("base,mgs,walls", [(32, 16, True), (96, 96, False), (128, 128, True)])
