@@ -219,7 +219,7 @@ def test_emulated_multi_rank_curvature_options(emu, name, nranks, transport):  #
         os.environ["CUEMU_SEED"] = "0"
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("fused", ["0", "1", "3", "n3", "nw"])
 @pytest.mark.parametrize("transport", ["peer", "slab"])
 @pytest.mark.parametrize("nranks", [2, 3])
 def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport, fused):  # noqa: F811
@@ -233,7 +233,12 @@ def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport, 
     os.environ["CUEMU_SEED"] = "5"
     os.environ["PA_STENCIL"] = "tma"
     os.environ["PA_TMA_SMALL"] = "1"
-    os.environ["PA_CURV_FUSED"] = fused                        # "1": the fused kernel + shell pass on every rank
+    # "1" / "3": a fused kernel + shell pass on every rank; "n3" / "nw": the plane-staged / barrier-free flame-normal kernels
+    os.environ["PA_CURV_FUSED"] = fused if fused in ("0", "1", "3") else "0"
+    os.environ["PA_NORMAL_F3"] = "1" if fused == "n3" else "0"
+    os.environ["PA_NORMAL_W"] = "1" if fused == "nw" else "0"
+    if nranks == 3 and fused in ("3", "n3", "nw"):
+        pytest.skip("combination not in the thinned-out matrix")
     try:
         pf = synth.config3(16, 8)
         for lv in pf.levels:                                    # off-centre blob + a z-dependent ripple
@@ -271,3 +276,5 @@ def test_emulated_multi_rank_threshold_off_centre_field(emu, nranks, transport, 
     finally:
         os.environ["CUEMU_SEED"] = "0"
         os.environ["PA_CURV_FUSED"] = "0"
+        os.environ["PA_NORMAL_F3"] = "0"
+        os.environ["PA_NORMAL_W"] = "0"
