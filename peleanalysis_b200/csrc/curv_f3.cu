@@ -155,12 +155,17 @@ template <int D> __device__ __forceinline__ char* sm_ldp(SmA a) { return reinter
 #ifdef PA_HOST_EMULATION
 __device__ __forceinline__ void stg2b(char* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
 __device__ __forceinline__ void stg1b(char* p, double x) { *reinterpret_cast<double*>(p) = x; }
+__device__ __forceinline__ void stg2b_cs(char* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
 #else
 __device__ __forceinline__ void stg2b(char* p, double x, double y) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory"); }
 __device__ __forceinline__ void stg1b(char* p, double x) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory"); }
+__device__ __forceinline__ void stg2b_cs(char* p, double x, double y) { asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory"); }
 #endif
 
-template <bool FK, int MINB>
+// ABL != 0: timing experiments, WRONG RESULTS (PA_NF3_ABLATE, K-less form only) -- bit 0: n = G instead of the sqrt -> reciprocal
+// -> quotient chain, bit 1: no global stores (the values stay live behind a condition that is never true); bit 2 (results stay
+// right): streaming stores (st.global.cs) for Progress and n
+template <bool FK, int MINB, int ABL = 0>
 __global__ void __launch_bounds__(F3_THREADS, MINB) k_curv_f3(const PaTile* __restrict__ tiles, F3Levels lv, GridArgs ga, StencilExtra ex, int depth) {
     using G = F3Geo<FK>;
     constexpr int F3_PW = G::PW, F3_NW = G::NW, F3_CPL = G::CPL, F3_NPL = G::NPL, F3_SL = G::SL;
@@ -394,8 +399,13 @@ __global__ void __launch_bounds__(F3_THREADS, MINB) k_curv_f3(const PaTile* __re
                 gz[2 * j] = cdiff(dzi, zm.x, c.x, zp.x); gz[2 * j + 1] = cdiff(dzi, zm.y, c.y, zp.y);
                 cc[j] = c;
             }
-            normal_quad(gx, gy, gz, n0, n1, n2);                 // curvature.cpp:467-502
-            const bool wplane = (m >= mw0) & (m <= mw1);
+            if (ABL & 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { n0[i] = gx[i]; n1[i] = gy[i]; n2[i] = gz[i]; }
+            } else {
+                normal_quad(gx, gy, gz, n0, n1, n2);             // curvature.cpp:467-502
+            }
+            const bool wplane = (ABL & 2) ? depth == 12345 : (m >= mw0) & (m <= mw1);
 #pragma unroll
             for (int j = 0; j < F3_NL; ++j) {
                 if (FK && (fl & (1u << j))) {
@@ -407,10 +417,17 @@ __global__ void __launch_bounds__(F3_THREADS, MINB) k_curv_f3(const PaTile* __re
                     const long long ob = 8ll * oe[j];
                     char* const pn = sm_ldp<IC_PN>(IC) + ob;
                     const long long csn = sm_ldq<IC_CSN>(IC);
-                    stg2b(sm_ldp<IC_PC>(IC) + ob, cc[j].x, cc[j].y);                     // Progress (curvature.cpp:310-321)
-                    stg2b(pn, n0[2 * j], n0[2 * j + 1]);
-                    stg2b(pn + csn, n1[2 * j], n1[2 * j + 1]);
-                    stg2b(pn + 2 * csn, n2[2 * j], n2[2 * j + 1]);
+                    if (ABL & 4) {
+                        stg2b_cs(sm_ldp<IC_PC>(IC) + ob, cc[j].x, cc[j].y);
+                        stg2b_cs(pn, n0[2 * j], n0[2 * j + 1]);
+                        stg2b_cs(pn + csn, n1[2 * j], n1[2 * j + 1]);
+                        stg2b_cs(pn + 2 * csn, n2[2 * j], n2[2 * j + 1]);
+                    } else {
+                        stg2b(sm_ldp<IC_PC>(IC) + ob, cc[j].x, cc[j].y);                 // Progress (curvature.cpp:310-321)
+                        stg2b(pn, n0[2 * j], n0[2 * j + 1]);
+                        stg2b(pn + csn, n1[2 * j], n1[2 * j + 1]);
+                        stg2b(pn + 2 * csn, n2[2 * j], n2[2 * j + 1]);
+                    }
                     char* const pa = sm_ldp<IC_PA>(IC);
                     if (pa) {
                         const long long csa = sm_ldq<IC_CSA>(IC);
@@ -463,7 +480,7 @@ int curv_f3_strip_pairs() { return F3Geo<true>::KQ; }
 int normal_f3_rows() { return F3Geo<false>::KR; }
 int normal_f3_strip_pairs() { return F3Geo<false>::KQ; }
 
-template <bool FK, int MINB>
+template <bool FK, int MINB, int ABL = 0>
 static cudaError_t launch_f3(const PaTile* tiles, int ntiles, const int* level_end, int nlev, const GridArgs& ga, const StencilExtra& ex,
                              int depth, cudaStream_t st) {
     if (ntiles <= 0) return cudaSuccess;
@@ -476,16 +493,16 @@ static cudaError_t launch_f3(const PaTile* tiles, int ntiles, const int* level_e
     {
         std::lock_guard<std::mutex> lock(mu);
         if (!configured[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(k_curv_f3<FK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem<FK>());
+            cudaError_t e = cudaFuncSetAttribute(k_curv_f3<FK, MINB, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem<FK>());
             if (e != cudaSuccess) return e;
 #ifndef PA_HOST_EMULATION
-            e = cudaFuncSetAttribute(k_curv_f3<FK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // FK: two CTAs per SM need 195 KB
+            e = cudaFuncSetAttribute(k_curv_f3<FK, MINB, ABL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // FK: two CTAs per SM need 195 KB
             if (e != cudaSuccess) return e;
 #endif
             configured[dev] = true;
         }
     }
-    PA_LAUNCH(ntiles, F3_THREADS, f3_smem<FK>(), st, k_curv_f3<FK, MINB>)(tiles, lv, ga, ex, depth);
+    PA_LAUNCH(ntiles, F3_THREADS, f3_smem<FK>(), st, k_curv_f3<FK, MINB, ABL>)(tiles, lv, ga, ex, depth);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -499,6 +516,12 @@ cudaError_t launch_normal_f3(const PaTile* tiles, int ntiles, const int* level_e
     const char* e = getenv("PA_NF3_CTAS");                      // 3: 80-register build, three CTAs per SM (spills 160 bytes)
     const char* ed = getenv("PA_NF3_DEPTH");                    // planes in flight per CTA (1 .. 4)
     const int depth = ed ? std::min(4, std::max(1, atoi(ed))) : 3;
+    const char* ea = getenv("PA_NF3_ABLATE");                   // timing experiments (wrong results): 1 no chain, 2 no stores, 3 both
+    if (ea && ea[0] == '1') return launch_f3<false, 2, 1>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
+    if (ea && ea[0] == '2') return launch_f3<false, 2, 2>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
+    if (ea && ea[0] == '3') return launch_f3<false, 2, 3>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
+    if (ea && ea[0] == '4') return launch_f3<false, 2, 4>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
+    if (ea && ea[0] == '5') return launch_f3<false, 2, 5>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
     if (e && e[0] == '3') return launch_f3<false, 3>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
     return launch_f3<false, 2>(tiles, ntiles, level_end, nlev, ga, ex, depth, st);
 }
