@@ -486,10 +486,12 @@ cudaError_t launch_mode(const PaTile* tiles, int ntiles, int stage_doubles, cons
     const char* eps = getenv("PA_TMA_PSLEEP");
     // L2 eviction hints (bit 0: evict_last on the staged loads, bit 1: streaming stores).  Measured on a B200
     // (profiles/r02_ab_l2_hints.txt): the bandwidth-bound gradient modes gain 2.5 % with both (config 2: 92.4 -> 95.0 % of the
-    // roofline, DRAM reads 7.04 -> 6.48 GB for 5.6 GB of input: fewer halo rows shared by neighbouring tiles are fetched twice); the FP64-bound
-    // flame-normal pass and the divergence do not (curvature 6.58 -> 6.65 ms), so they keep the default policy.
+    // roofline, DRAM reads 7.04 -> 6.48 GB for 5.6 GB of input: fewer halo rows shared by neighbouring tiles are fetched twice).  The
+    // curvature step as a whole does not (6.58 -> 6.65 ms) -- but kernel by kernel (ncu launch list, end of round 2,
+    // profiles/r02_ablate_normal_f3.txt) the flame-normal pass loses (3.73 -> 3.87 ms) and the read-dominated divergence wins
+    // (2.22 -> 2.13 ms, DRAM reads 11.2 -> 10.4 GB), so the divergence takes the hints and the flame-normal pass does not.
     const char* eh = getenv("PA_TMA_L2HINT");
-    const int hints = eh ? atoi(eh) : ((MODE == MODE_GRAD || MODE == MODE_GRAD3) ? 3 : 0);
+    const int hints = eh ? atoi(eh) : ((MODE == MODE_GRAD || MODE == MODE_GRAD3 || MODE == MODE_DIV) ? 3 : 0);
     const int psleep = (eps ? std::min(std::max(0, atoi(eps)), 0xffff) : 0) | ((hints & 1) << 30) | (((hints >> 1) & 1) << 29);
     PA_LAUNCH(grid, THREADS, smem, st, k_stencil_tma<MODE, CW, PLAIN>)(tiles, ntiles, (int)nwork, ga, ex, stage_doubles, S, T.dev, T.base, psleep);
     T.base += (unsigned long long)nwork + (unsigned long long)grid;
