@@ -13,6 +13,9 @@
 //     set up once per item, the plane loop only advances pointers (f2 re-derived them per pair and plane: 54 + 65 of its 259
 //     instructions per cell);
 //   * the two (row, pair) slots of a thread run through ONE basic block (four sqrt -> reciprocal -> quotient chains in flight).
+// Measured on a B200: 5.87 ms (curvature step 7.31 ms against 6.52 ms for the separate kernels); its K-less form (FK = false,
+// PA_NORMAL_F3) 3.85 ms against 3.73 ms for MODE_NORMAL_S, and 2.0 ms with its global stores removed (PA_NF3_ABLATE, DESIGN.md
+// section 6): the pass is paced by its memory traffic.  Both are opt-in.
 // Cells whose K stencil leaves the box are left to k_div_shell, exactly as with the other fused kernels.  Arithmetic is the
 // reference's expression order with separate IEEE multiplies and adds (-fmad=false): bit-identical to the separate kernels.
 #include <algorithm>

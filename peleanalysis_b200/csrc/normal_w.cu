@@ -19,7 +19,9 @@
 // Result on a B200 (profiles/r02_ncu_normal_w_summary.txt): 275 instructions per pair and plane, 23 warps per SM, and 4.27 ms
 // against 3.73 ms for MODE_NORMAL_S -- the warps wait for their loads (long scoreboard 9-13 cycles per issued instruction)
 // whether the operands are requested in the same step, one step ahead, prefetched into L2 eight planes ahead or kept four
-// steps in flight by cp.async.  Opt-in, parity-tested; not the default.
+// steps in flight by cp.async.  Opt-in, parity-tested; not the default.  (The ablation of the plane-staged kernel at the end of
+// round 2 explains it: the pass is paced by its write-heavy memory traffic, not by arithmetic or by how its loads are issued --
+// profiles/r02_ablate_normal_f3.txt)
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
