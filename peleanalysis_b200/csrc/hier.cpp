@@ -136,6 +136,15 @@ std::string Hier::init(int nlev_, const pa_level_desc_host* L, const int* per, c
     return "";
 }
 
+static int row_align_doubles() {
+    static const int v = [] {
+        const char* e = getenv("PA_ROW_ALIGN");
+        const int b = e ? atoi(e) : 32;
+        return (b == 16 || b == 32 || b == 64 || b == 128) ? b / 8 : 4;
+    }();
+    return v;
+}
+
 const Layout& Hier::layout(int l, int ng) {
     auto key = std::make_pair(l, ng);
     auto it = layouts_.find(key);
@@ -151,9 +160,15 @@ const Layout& Hier::layout(int l, int ng) {
         long long& off = Y.rank_comp_stride[V.owner[gb]];
         PaLayDev e;
         e.ng = ng;
-        e.xoff = ng & 1;                                   // (xoff + ng) even -> first valid cell 16-byte aligned
+        // The first valid cell of every row is aligned to `ra` doubles and the pitch is a multiple of it.  ra = 4 (32 bytes, one
+        // DRAM / L2 sector): with 16-byte alignment a full-row store of a field with one ghost cell wrote HALF of its first and
+        // last sector, and ncu counted 25 M partial-sector (ECC read-modify-write) operations and 0.8 GB of extra DRAM reads per
+        // flame-normal pass -- two per row and component -- against 62 for the gradient kernel, whose output field has no ghost
+        // cells (profiles/r02_ablate_normal_f3.txt).  PA_ROW_ALIGN=16|32|64|128 (bytes) overrides.
+        const int ra = row_align_doubles();
+        e.xoff = (ra - ng % ra) % ra;
         int w = e.xoff + B.len(0) + 2 * ng;
-        e.P = (w + 1) & ~1;
+        e.P = (w + ra - 1) / ra * ra;
         e.PS = e.P * (B.len(1) + 2 * ng);
         e.off = off;
         long long sz = (long long)e.PS * (B.len(2) + 2 * ng);
