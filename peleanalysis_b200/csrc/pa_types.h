@@ -18,9 +18,9 @@ struct PaBoxDev {
 // element (i,j,k) lives at off + (k-lo2+ng)*PS + (j-lo1+ng)*P + (i-lo0+ng+xoff)
 struct PaLayDev {
     long long off;    // element offset inside one component's level slab
-    int P;            // row pitch in doubles (even, so every row starts 16-byte aligned)
+    int P;            // row pitch in doubles (a multiple of 4 by default: every row starts on a 32-byte sector; PA_ROW_ALIGN)
     int PS;           // plane stride = P * (ny + 2 ng)
-    int xoff;         // lead pad so that the first VALID cell of each row is 16-byte aligned
+    int xoff;         // lead pad so that the first VALID cell of each row is 32-byte aligned (at least 16: 128-bit accesses)
     int ng;
 };
 
