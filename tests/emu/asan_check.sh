@@ -8,10 +8,10 @@ ROOT=$(cd "$(dirname "$0")/../.." && pwd)
 OUT=$ROOT/tests/emu/_build/asan
 mkdir -p "$OUT"
 FLAGS="-std=c++17 -O1 -g -fPIC -fsanitize=address -fno-omit-frame-pointer -ffp-contract=off -DPA_HOST_EMULATION=1 -I $ROOT/tests/emu"
-for f in api.cu kernels.cu stencil_tma.cu hier.cpp; do g++ $FLAGS -x c++ -c "$ROOT/peleanalysis_b200/csrc/$f" -o "$OUT/${f%.*}.o" & done
+for f in api.cu kernels.cu stencil_tma.cu curv_fused.cu curv_f3.cu normal_w.cu filter.cu hier.cpp; do g++ $FLAGS -x c++ -c "$ROOT/peleanalysis_b200/csrc/$f" -o "$OUT/${f%.*}.o" & done
 g++ $FLAGS -c "$ROOT/tests/emu/cuemu.cpp" -o "$OUT/cuemu.o"
 wait
-g++ -shared -fsanitize=address -o "$OUT/libpelestencil_emu.so" "$OUT"/api.o "$OUT"/kernels.o "$OUT"/stencil_tma.o "$OUT"/hier.o "$OUT"/cuemu.o
+g++ -shared -fsanitize=address -o "$OUT/libpelestencil_emu.so" "$OUT"/api.o "$OUT"/kernels.o "$OUT"/stencil_tma.o "$OUT"/curv_fused.o "$OUT"/curv_f3.o "$OUT"/normal_w.o "$OUT"/filter.o "$OUT"/hier.o "$OUT"/cuemu.o
 cat > "$OUT/run.py" <<PY
 import importlib.util, os, sys
 sys.path.insert(0, "$ROOT"); sys.path.insert(0, "$ROOT/tests")
@@ -22,12 +22,22 @@ spec = importlib.util.spec_from_file_location("capi_emulated", pc.__file__); emu
 emu.LIB_PATH = "$OUT/libpelestencil_emu.so"; os.environ["PA_NORMAL_MATH"] = "fast"; emu.init(0)
 n = 0
 for name in CASES:
-    for st in ("tma", "tma_big", "simple", "tma_pf"):
+    for st in ("tma", "tma_big", "simple"):
         for bc in ("0", "1"):
             os.environ["PA_BCFILL_V2"] = bc
             if "grad" in CASES[name][3]: G.test_grad_matches_reference_golden(emu, name, st, "links"); n += 1
             if "curvature" in CASES[name][3]: G.test_curvature_matches_reference_golden(emu, name, st, "links"); n += 1
+    os.environ["PA_BCFILL_V2"] = "1"
+    for st in ("tma_fused", "tma_fused3", "tma_n3", "tma_nw"):      # the opt-in curvature kernels, linked and materialised ghosts
+        for links in ("links", "nolinks"):
+            if "curvature" in CASES[name][3]: G.test_curvature_matches_reference_golden(emu, name, st, links); n += 1
     G.test_ghost_cells_match_oracle(emu, name); n += 1
+for args in ((32, 16, True), (72, 72, False)):                       # x strips of the later kernels, threshold clip
+    G.test_fused3_strips_match_separate_kernels(emu, *args); n += 1
+for ring in ("0", "1"):
+    os.environ["PA_NW_RING"] = ring
+    G.test_curvature_matches_reference_golden(emu, "c3_three_levels", "tma_nw", "links"); n += 1
+os.environ["PA_NW_RING"] = "0"
 print("asan check: %d runs, no error" % n)
 PY
 ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python "$OUT/run.py"
