@@ -688,7 +688,8 @@ def main():
                         world, "read in place over NVLink (CUDA-IPC peer links, no exchange step)" if r["flags"] & capi.PEER_LINKS
                         else "NCCL send/recv of packed slabs (%s cells/step recv on rank 0)" % r["slab_cells_rank0"])),
                     "ghosts": "materialised (PA_HIER_NO_LINKS)" if args.no_links else "same-level neighbours read in place by the stencil (neighbour links)",
-                    "stencil": os.environ.get("PA_STENCIL", "tma"), "hier_build_s": r["hier_build_s"]},
+                    "stencil": os.environ.get("PA_STENCIL", "tma"), "hier_build_s": r["hier_build_s"],
+                    "row_align_bytes": int(os.environ.get("PA_ROW_ALIGN", "32"))},
         "e2e": r.get("e2e"),
         "gpu_launches": int(r["launches"]),
         "clocks": sampler.summary(),
